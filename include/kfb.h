@@ -1,0 +1,262 @@
+/*
+ * kfb.h — C ABI of libkfb.so, the B200-native (sm_100a) EK-FAC influence hot path that drops in
+ * behind kronfluence's tracked-module math.
+ *
+ * The reference (pomonam/kronfluence v1.0.1) has no FFI of its own: its hot path is PyTorch ATen
+ * calls made from Python hooks.  Each entry point below names the reference function(s) it
+ * replaces (file:line under /root/reference/kronfluence).  INTEGRATION.md shows the ctypes stub a
+ * kronfluence maintainer would add to bind them.
+ *
+ * Conventions
+ *   - every function returns KFB_OK (0) or a negative kfb_status; kfb_last_error() gives the text;
+ *   - all tensor arguments are raw DEVICE pointers (tensor.data_ptr()), row-major, contiguous
+ *     unless a leading dimension is given; the caller owns every buffer;
+ *   - no allocation happens inside: scratch comes from a caller-provided workspace whose size is
+ *     returned by the matching *_workspace_bytes() query;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     (hooks run on the autograd thread on the forward stream: tracker/factor.py:99-121);
+ *   - dtype codes are kfb_dtype; accumulators and outputs are fp32;
+ *   - dense contractions run on tcgen05 tensor cores with bf16 operands.  KFB_PREC_FP32 splits
+ *     every fp32 operand into bf16 hi+lo and issues three MMAs (hi*hi + hi*lo + lo*hi, fp32
+ *     accumulate in TMEM): ~1e-5 relative error, i.e. fp32-parity.  KFB_PREC_BF16 issues one MMA
+ *     on the bf16-rounded operands (for the reference's bf16 `score_dtype` configurations).
+ *   - there is NO CPU path: on a machine without an sm_100 GPU every compute entry point fails
+ *     with KFB_ERR_NO_DEVICE.
+ */
+#ifndef KFB_H_
+#define KFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KFB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  KFB_OK = 0,
+  KFB_ERR_INVALID = -1,   /* bad argument / unsupported shape -> ValueError                     */
+  KFB_ERR_CUDA = -2,      /* CUDA runtime error                -> RuntimeError                   */
+  KFB_ERR_OOM = -3,       /* -> RuntimeError("CUDA out of memory. ...") so that                  */
+                          /*    utils/dataset.py:66-101 find_executable_batch_size keeps working */
+  KFB_ERR_NO_DEVICE = -4, /* no sm_100 device / driver                                           */
+  KFB_ERR_WORKSPACE = -5, /* workspace too small                                                 */
+  KFB_ERR_NOT_CONVERGED = -6
+} kfb_status;
+
+typedef enum { KFB_F32 = 0, KFB_BF16 = 1, KFB_F16 = 2, KFB_F64 = 3 } kfb_dtype;
+typedef enum { KFB_PREC_FP32 = 0, KFB_PREC_BF16 = 1 } kfb_precision;
+typedef enum { KFB_LINEAR = 0, KFB_CONV2D = 1 } kfb_layer_kind;
+
+/* How the query gradient is preconditioned (factor/config.py strategies).                       */
+typedef enum {
+  KFB_PRECOND_IDENTITY = 0, /* Identity.precondition_gradient  factor/config.py:159-165          */
+  KFB_PRECOND_DIAGONAL = 1, /* Diagonal.precondition_gradient  factor/config.py:210-216          */
+  KFB_PRECOND_EIGEN = 2     /* Kfac/Ekfac.precondition_gradient factor/config.py:273-285,341-353 */
+} kfb_precond_mode;
+
+/* Geometry of one tracked module.  d_in counts the flattened input features WITHOUT the bias
+ * column (Linear: in_features; Conv2d: C_in/groups*k_h*k_w); with has_bias the activation
+ * operand gets a literal ones column appended (module/linear.py:39-43, module/conv2d.py:119-126),
+ * so the factor dimension is d_in + has_bias.                                                   */
+typedef struct {
+  int32_t kind; /* kfb_layer_kind */
+  int32_t d_in;
+  int32_t d_out;
+  int32_t has_bias;
+  /* Conv2d only (NCHW input [B, c_in, h_in, w_in]; output [B, d_out, h_out, w_out]).  The
+   * reference averages the input over `groups` before unfolding (module/conv2d.py:55-56).       */
+  int32_t c_in, h_in, w_in, groups;
+  int32_t k_h, k_w, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int32_t h_out, w_out;
+} kfb_layer;
+
+/* A batch of matrices stored as two bf16 planes (hi, lo) in tensor-core operand layout:
+ * row-major, `cols` contiguous (the contraction index of an NT GEMM), row stride `ld` elements
+ * (multiple of 8 so TMA can address it), `batch` matrices `batch_stride` elements apart.  With
+ * KFB_PREC_BF16 the lo plane is unused and may be NULL.                                          */
+typedef struct {
+  void* hi;
+  void* lo;
+  int64_t rows;
+  int64_t cols;
+  int64_t ld;
+  int64_t batch;
+  int64_t batch_stride;
+} kfb_split;
+
+/* Epilogue selector of the generic NT GEMM (kfb_gemm_nt).                                        */
+typedef enum { KFB_EPI_STORE = 0, KFB_EPI_ROWDOT = 1, KFB_EPI_SQACC = 2 } kfb_epilogue_kind;
+
+typedef struct {
+  int32_t kind; /* kfb_epilogue_kind */
+  /* STORE: D = alpha * (A B^T) [* mul] [^2]; written to any of out_f32 / out_split.
+   *        transpose_out swaps the roles of m and n in the output index.                         */
+  float* out_f32;
+  int64_t ldo;
+  int64_t out_batch_stride;
+  kfb_split out_split; /* hi==NULL -> no split output */
+  const float* mul;    /* optional [M,N] fp32 elementwise factor shared by the batch              */
+  int64_t ldmul;
+  int32_t transpose_out;
+  int32_t square;
+  int32_t accumulate; /* out_f32 += ... instead of = ...                                         */
+  float alpha;
+  /* ROWDOT: out_f32[b*out_batch_stride + m] (+)= alpha * sum_n D[b][m][n] * g[m*ldg + n]        */
+  const float* g;
+  int64_t ldg;
+  /* SQACC: out_f32[m*ldo + n] += alpha * sum_b D[b][m][n]^2   (atomic adds)                     */
+} kfb_epilogue;
+
+/* ---------------------------------------------------------------------------------------------
+ * Library / device
+ * ------------------------------------------------------------------------------------------ */
+int kfb_version(void);
+const char* kfb_last_error(void);
+/* sm count and compute capability of the current device; KFB_ERR_NO_DEVICE if there is none.    */
+int kfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* 0 = tcgen05 (default and only product path), 1 = SIMT debug kernels (tests only).             */
+int kfb_set_gemm_backend(int backend);
+/* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
+int64_t kfb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Operand preparation (fused flatten / ones column / mask / im2col / group-mean / bf16 split).
+ * Replaces module/linear.py:30-54, module/conv2d.py:15-64,106-132 (K3 in SURVEY.md).
+ * ------------------------------------------------------------------------------------------ */
+/* Generic strided gather.  desc9 = {sb, sr, sc1, sc2, rows, c1, c2, ones_mode, flags}:
+ *   dst[b][r][c1i*c2 + c2i] = src[b*sb + r*sr + c1i*sc1 + c2i*sc2]
+ * ones_mode 1 appends a column of ones, 2 appends a row of ones (the bias column of
+ * module/linear.py:39-43 in either orientation); flags bits 0-1: scale mode (1 = scale[b*rows+r]
+ * per row, 2 = scale[b*cols+c] per column — the attention mask of linear.py:34-38), bit 2: square.
+ * Padding up to dst.ld is zero-filled.                                                          */
+int kfb_split_gather(const void* src, int src_dtype, const int64_t* desc9, const float* scale,
+                     const kfb_split* dst, int precision, void* stream);
+
+/* Conv2d im2col with group-mean.  x is NCHW [batch, c_in*groups?]. Layouts of dst:
+ *   layout 0: dst[b][s][i]   (rows = S=h_out*w_out, cols = d_in+bias)  — rotation operand
+ *   layout 1: dst[b][i][s]   (rows = d_in+bias, cols = S)              — per-sample outer product
+ *   layout 2: dst[0][i][b*S+s] (rows = d_in+bias, cols = batch*S)      — covariance operand        */
+int kfb_split_im2col(const kfb_layer* layer, const void* x, int x_dtype, int64_t batch,
+                     int32_t layout, const kfb_split* dst, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The tensor-core engine: batched NT GEMM  D[b] = A[b] * B[b]^T  on tcgen05 with TMA-fed
+ * 128B-swizzled shared memory and fp32 TMEM accumulators.  A.cols == B.cols is the contraction
+ * length; a batch of 1 on either side broadcasts.
+ * ------------------------------------------------------------------------------------------ */
+int kfb_gemm_nt(const kfb_split* A, const kfb_split* B, const kfb_epilogue* epi, int precision,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1 — covariance accumulation (K1-K3).
+ *   activation: CovarianceTracker._update_activation_covariance_matrix  tracker/factor.py:31-58
+ *               + TrackedLinear/Conv2d.get_flattened_activation        linear.py:30-46, conv2d.py:106-128
+ *   gradient:   CovarianceTracker._update_gradient_covariance_matrix    tracker/factor.py:60-93
+ *               + get_flattened_gradient                                linear.py:48-54, conv2d.py:130-132
+ * x: Linear [batch, seq, d_in] (seq=1 for 2-D inputs), Conv2d NCHW.  mask: optional fp32
+ * [batch*seq] (Linear only; rows AND the ones column are multiplied by it).  C: fp32
+ * [d_in+bias]^2 (activation) or [d_out]^2 (gradient), accumulated in place: C += alpha * X^T X.
+ * Counts (N or mask.sum()) are kept by the caller.
+ * ------------------------------------------------------------------------------------------ */
+size_t kfb_cov_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_cov_accum_activation(const kfb_layer* layer, const void* x, int x_dtype, int64_t batch,
+                             int64_t seq, const float* mask, float* C, void* ws, size_t ws_bytes,
+                             int precision, void* stream);
+int kfb_cov_accum_gradient(const kfb_layer* layer, const void* g, int g_dtype, int64_t batch,
+                           int64_t seq, float alpha, float* C, void* ws, size_t ws_bytes,
+                           int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2 — eigendecomposition (K4).  perform_eigendecomposition  factor/eigen.py:140-224:
+ * C/count, 0.5(C+C^T), symmetric eigendecomposition in fp64, eigenvalues ascending,
+ * eigenvectors as COLUMNS of a row-major [d,d] matrix, both cast back to fp32.
+ * Batched one-sided Jacobi in fp64 for d <= kfb_eigh_jacobi_max_dim(); cuSOLVER syevd above it.
+ * ------------------------------------------------------------------------------------------ */
+int kfb_eigh_jacobi_max_dim(void);
+size_t kfb_eigh_workspace_bytes(int32_t d);
+int kfb_eigh_sym(const float* C, double count, int32_t d, float* evals, float* evecs, void* ws,
+                 size_t ws_bytes, void* stream);
+/* Optional: absolute path of the libcusolver.so to dlopen for d > kfb_eigh_jacobi_max_dim().     */
+int kfb_set_cusolver_path(const char* path);
+
+/* ---------------------------------------------------------------------------------------------
+ * Eigenbasis operands.  Splits Q (columns = eigenvectors, as stored by kfb_eigh_sym /
+ * activation_eigenvectors) into the two tensor-core operands the later stages need:
+ * q (row-major copy) and qt (its transpose).  Each kfb_split has rows=cols=d.
+ * Replaces the per-call `.to(device)` of factor/config.py:347-349 and tracker/factor.py:191-201.
+ * ------------------------------------------------------------------------------------------ */
+int kfb_eigen_operands(const float* Q, int32_t d, const kfb_split* q, const kfb_split* qt,
+                       int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3 — Lambda sweep (K5-K6).  LambdaTracker._update_lambda_matrix  tracker/factor.py:162-230
+ * + compute_per_sample_gradient  linear.py:68-77, conv2d.py:164-177.
+ *   with_eigen=1:  Lambda += sum_b (Q_G^T G_b Q_A)^2     (ekfac)    tracker/factor.py:218-226
+ *   with_eigen=0:  Lambda += sum_b G_b^2                 (diagonal) tracker/factor.py:227-230
+ * computed rotate-first: (Q_G^T g)(Q_A^T a)^T summed over the positions of one example, squared,
+ * summed over examples.  a: [batch, seq, d_in] / NCHW; g: [batch, seq, d_out] / [batch,d_out,h,w].
+ * lambda: fp32 [d_out, d_in+bias], accumulated in place.  scale multiplies per-sample gradients
+ * (GradScaler, tracker/factor.py:270-271).
+ * ------------------------------------------------------------------------------------------ */
+size_t kfb_lambda_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_lambda_accum(const kfb_layer* layer, const void* a, int a_dtype, const void* g,
+                     int g_dtype, int64_t batch, int64_t seq, int32_t with_eigen,
+                     const kfb_split* qa_t, const kfb_split* qg_t, float scale, float* lambda,
+                     void* ws, size_t ws_bytes, int precision, void* stream);
+
+/* Ekfac/Diagonal.prepare  factor/config.py:193-203,322-339: out = 1 / (lambda/n + damping) in
+ * fp64, stored fp32.  damping < 0 selects the heuristic 0.1 * mean(lambda/n).  ws: >= 8 bytes.  */
+int kfb_lambda_invert(const float* lambda, int64_t numel, double n, double damping, float* out,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 4 — query side: per-sample gradient + preconditioning (K5, K7).
+ * PreconditionTracker backward hook  tracker/precondition.py:102-123 and
+ * {Identity,Diagonal,Kfac,Ekfac}.precondition_gradient  factor/config.py:159-165,210-216,273-285,341-353.
+ *   P_q = scale * Q_G [ (Q_G^T G_q Q_A) o lambda_inv ] Q_A^T          (KFB_PRECOND_EIGEN)
+ * P is written in tensor-core operand layout (kfb_split with rows=d_out, cols=d_in+bias,
+ * batch = total query capacity) at batch offset q_offset .. q_offset+batch-1, so accumulating
+ * query batches (tracker/precondition.py:216-240) is an append, not a torch.cat.  p_f32, if not
+ * NULL, also receives the fp32 values [batch, d_out, d_in+bias] (for inspection / parity tests).
+ * ------------------------------------------------------------------------------------------ */
+size_t kfb_precondition_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_precondition(const kfb_layer* layer, const void* a, int a_dtype, const void* g,
+                     int g_dtype, int64_t batch, int64_t seq, int32_t mode,
+                     const kfb_split* qa, const kfb_split* qa_t, const kfb_split* qg,
+                     const kfb_split* qg_t, const float* lambda_inv, float scale,
+                     const kfb_split* P, int64_t q_offset, float* p_f32, void* ws, size_t ws_bytes,
+                     int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 5 — train side: pairwise contraction (K8-K9).
+ * TrackedLinear/Conv2d.compute_pairwise_score  linear.py:79-122, conv2d.py:179-209 and the module
+ * sum of compute_dot_products_with_loader  score/dot_product.py:105-118.
+ *   scores[q, t_offset + t] (+)= scale * sum_{s,o,i} P[q,o,i] g[t,s,o] a[t,s,i]
+ * seq==1 (Linear on 2-D inputs): one fused kernel — (a P_q^T) on tensor cores, row-dot with g in
+ * the epilogue; no [T,d_out,d_in] intermediate.  seq>1 / Conv2d: per-sample gradients are formed
+ * by a batched tensor-core GEMM into the workspace and contracted against P by a second GEMM.
+ * scores: fp32 [num_queries, ld_scores]; accumulate=1 adds (module sum), 0 overwrites.
+ * ------------------------------------------------------------------------------------------ */
+size_t kfb_pairwise_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
+                        const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
+                        int64_t seq, float scale, float* scores, int64_t ld_scores,
+                        int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes,
+                        int precision, void* stream);
+
+/* Same contraction through HOST buffers (pinned or pageable): a, g are host pointers, scores_host
+ * receives [num_queries, batch] fp32.  dev_a / dev_g / dev_scores are caller-provided device
+ * staging buffers of at least the same sizes.  Used for the end-to-end measurement.             */
+int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
+                             const void* a_host, int a_dtype, const void* g_host, int g_dtype,
+                             int64_t batch, int64_t seq, float scale, float* scores_host,
+                             void* dev_a, void* dev_g, float* dev_scores, void* ws,
+                             size_t ws_bytes, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFB_H_ */

@@ -1,0 +1,820 @@
+// The tensor-core engine of libkfb: a persistent, warp-specialised, batched NT GEMM for sm_100a.
+//
+//   D[b] (128 x BLOCK_N fp32 tile in TMEM)  =  sum_k  A[b][m,k] * B[b][n,k]
+//
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor.3d loads of the bf16 hi/lo planes of A
+//                      and B into a ring of 128B/64B-swizzled shared-memory stages (mbarrier
+//                      complete_tx signalling)
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16;
+//                      with KFB_PREC_FP32 three MMAs per k-step (lo*hi + hi*lo + hi*hi) into the
+//                      same fp32 accumulator; tcgen05.commit releases smem stages / publishes the
+//                      accumulator
+//   warp 2             TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the
+//                      MMAs of tile i+1)
+//   warps 4-7          epilogue: tcgen05.ld 32x32b (thread == accumulator row), then one of
+//                        STORE   fp32 and/or bf16 hi/lo store, optional transpose / square /
+//                                elementwise factor / accumulate / split-K atomics
+//                        ROWDOT  out[b,m] = sum_n D[m,n] g[m,n]   (fused pairwise-score epilogue:
+//                                module/linear.py:112-122 "qio,bi,bo->qb" without the [T,d_out]
+//                                intermediate), looping over all n-tiles of a (b, m-tile) unit
+//                        REGACC  fp32 register accumulation across TMEM passes: either over a chunk
+//                                of the batch with squaring, out[m,n] += sum_b D[b][m,n]^2 (Lambda
+//                                sweep, tracker/factor.py:218-226), or over k-chunks of one long
+//                                contraction (see kMaxPassK), finished by the STORE options
+//
+// A second, trivially simple SIMT implementation of the same contract exists for debugging the
+// host logic (kfb_set_gemm_backend(1)); it is never selected implicitly.
+#include "kfb_gemm.cuh"
+
+#include <atomic>
+#include <mutex>
+
+namespace kfb {
+
+// Kernel-level epilogue families.  The public KFB_EPI_STORE maps to EPI_STORE when the contraction
+// fits one TMEM accumulation pass and to EPI_REGACC (k-chunk mode) when it does not; KFB_EPI_SQACC
+// maps to EPI_REGACC (batch mode).
+enum : int { EPI_STORE = 0, EPI_ROWDOT = 1, EPI_REGACC = 2 };
+enum : int { REGACC_BATCH = 0, REGACC_KCHUNK = 1 };
+
+// The tensor core adds each MMA's partial products into the fp32 TMEM accumulator with truncation,
+// so a long accumulation chain acquires a relative bias of ~(K/16)*nsplit_mmas*2^-25.  One TMEM pass
+// is therefore limited to kMaxPassK contraction elements (~8e-6 relative with the 3-MMA split);
+// longer contractions are cut into passes that are summed in fp32 registers (round-to-nearest).
+static const int kMaxPassK = 2048;
+
+struct GemmParams {
+  int M, N, K, batch;
+  int a_batched, b_batched;
+  int m_blocks, n_blocks, k_blocks;
+  int k_splits, kb_per_split;  // contraction split ACROSS CTAs (atomics)
+  int k_chunks, kb_per_chunk;  // contraction passes INSIDE a unit (register accumulation)
+  int inner;                   // REGACC_BATCH: batches per chunk
+  int regacc_mode;
+  long long num_units;
+  // outputs
+  float* out_f32;
+  long long ldo, out_bs;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ldo_s, out_bs_s;
+  const float* mul;
+  long long ldmul;
+  int transpose_out, square, accumulate, use_atomic, vec_ok, zero_pad;
+  float alpha;
+  const float* g;
+  long long ldg;
+  int g_vec4;
+};
+
+struct Tile {
+  int b, m_blk, n_blk, kb0, kb1;
+};
+
+template <int EPI>
+__device__ __forceinline__ int unit_inner_count(const GemmParams& p, long long unit) {
+  if (EPI == EPI_ROWDOT) return p.n_blocks * p.k_chunks;
+  if (EPI == EPI_REGACC) {
+    if (p.regacc_mode == REGACC_BATCH) {
+      const long long chunk = unit / ((long long)p.m_blocks * p.n_blocks);
+      const long long rem = (long long)p.batch - chunk * p.inner;
+      return rem < p.inner ? (int)rem : p.inner;
+    }
+    const int ks = (int)((unit / ((long long)p.m_blocks * p.n_blocks)) % p.k_splits);
+    const int kb0 = ks * p.kb_per_split;
+    const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+    return (kb1 - kb0 + p.kb_per_chunk - 1) / p.kb_per_chunk;
+  }
+  return 1;
+}
+
+template <int EPI>
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit, int j) {
+  Tile t;
+  t.m_blk = (int)(unit % p.m_blocks);
+  long long r = unit / p.m_blocks;
+  if (EPI == EPI_ROWDOT) {
+    t.b = (int)r;
+    t.n_blk = j / p.k_chunks;
+    const int kc = j - t.n_blk * p.k_chunks;
+    t.kb0 = kc * p.kb_per_chunk;
+    t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_chunk);
+  } else if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH) {
+    t.n_blk = (int)(r % p.n_blocks);
+    const long long chunk = r / p.n_blocks;
+    t.b = (int)(chunk * p.inner + j);
+    t.kb0 = 0;
+    t.kb1 = p.k_blocks;
+  } else {
+    t.n_blk = (int)(r % p.n_blocks);
+    r /= p.n_blocks;
+    const int ks = (int)(r % p.k_splits);
+    t.b = (int)(r / p.k_splits);
+    const int split0 = ks * p.kb_per_split;
+    const int split1 = min(p.k_blocks, split0 + p.kb_per_split);
+    if (EPI == EPI_REGACC) {
+      t.kb0 = split0 + j * p.kb_per_chunk;
+      t.kb1 = min(split1, t.kb0 + p.kb_per_chunk);
+    } else {
+      t.kb0 = split0;
+      t.kb1 = split1;
+    }
+  }
+  return t;
+}
+
+// Writes 32 consecutive accumulator columns of one row through every STORE option.
+__device__ __forceinline__ void store_values(const GemmParams& p, int b, long long row, int col0,
+                                             const float (&acc)[32]) {
+  float x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float val = p.alpha * acc[i];
+    if (p.mul != nullptr && col0 + i < p.N) val *= __ldg(p.mul + row * p.ldmul + col0 + i);
+    if (p.square) val *= val;
+    x[i] = val;
+  }
+  const bool full = col0 + 32 <= p.N;
+  if (p.out_f32 != nullptr) {
+    float* ob = p.out_f32 + (long long)b * p.out_bs;
+    if (!p.transpose_out && full && p.vec_ok && !p.use_atomic) {
+      float4* o4 = reinterpret_cast<float4*>(ob + row * p.ldo + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 w = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        if (p.accumulate) {
+          const float4 old = o4[i];
+          w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+        }
+        o4[i] = w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i < p.N) {
+          float* o = p.transpose_out ? ob + (long long)(col0 + i) * p.ldo + row : ob + row * p.ldo + col0 + i;
+          if (p.use_atomic) atomicAdd(o, x[i]);
+          else if (p.accumulate) *o += x[i];
+          else *o = x[i];
+        }
+      }
+    }
+  }
+  if (p.out_hi != nullptr) {
+    __nv_bfloat16* oh = p.out_hi + (long long)b * p.out_bs_s;
+    __nv_bfloat16* ol = p.out_lo != nullptr ? p.out_lo + (long long)b * p.out_bs_s : nullptr;
+    if (!p.transpose_out && full && p.vec_ok) {
+      uint4* h4 = reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0);
+      uint4* l4 = ol ? reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0) : nullptr;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(x[8 * i + e], h[e], l[e]);
+        h4[i] = *reinterpret_cast<uint4*>(h);
+        if (l4) l4[i] = *reinterpret_cast<uint4*>(l);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i < p.N) {
+          const long long idx = p.transpose_out ? (long long)(col0 + i) * p.ldo_s + row : row * p.ldo_s + col0 + i;
+          __nv_bfloat16 h, l;
+          split_bf16(x[i], h, l);
+          oh[idx] = h;
+          if (ol) ol[idx] = l;
+        }
+      }
+    }
+  }
+}
+
+// keep the [N, ld) padding of non-transposed split outputs finite (zero): they may be re-read as part
+// of a flattened contraction dimension.
+__device__ __forceinline__ void store_zero_pad(const GemmParams& p, int b, long long row) {
+  __nv_bfloat16* oh = p.out_hi + (long long)b * p.out_bs_s + row * p.ldo_s;
+  __nv_bfloat16* ol = p.out_lo != nullptr ? p.out_lo + (long long)b * p.out_bs_s + row * p.ldo_s : nullptr;
+  for (long long c = p.N; c < p.ldo_s; ++c) {
+    oh[c] = __float2bfloat16_rn(0.f);
+    if (ol) ol[c] = __float2bfloat16_rn(0.f);
+  }
+}
+
+template <int BLOCK_N, int BLOCK_K, int NSPLIT>
+struct GemmCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int SWIZZLE = BLOCK_K * 2;  // bytes per smem row == swizzle span
+  static constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_PLANE = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = NSPLIT * (A_PLANE + B_PLANE);
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS_RAW = ACC_STAGES * BLOCK_N;
+  static constexpr int TMEM_COLS =
+      TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                 : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
+  static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K must match a 128B or 64B swizzle span");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+};
+
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT>;
+  constexpr int BLOCK_M = Cfg::BLOCK_M;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+  constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES +
+                                           8 * (2 * STAGES + 2 * ACC_STAGES));
+
+  auto smem_a = [&](int s, int plane) {
+    return smem_base + s * Cfg::STAGE_BYTES + plane * Cfg::A_PLANE;
+  };
+  auto smem_b = [&](int s, int plane) {
+    return smem_base + s * Cfg::STAGE_BYTES + NSPLIT * Cfg::A_PLANE + plane * Cfg::B_PLANE;
+  };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_b_hi);
+    if (NSPLIT == 2) {
+      tma_prefetch_desc(&tm_a_lo);
+      tma_prefetch_desc(&tm_b_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(tmem_full_bar(s), 1);
+      mbar_init(tmem_empty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================== TMA producer ======================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const int inner = unit_inner_count<EPI>(p, unit);
+      for (int j = 0; j < inner; ++j) {
+        const Tile t = decode_tile<EPI>(p, unit, j);
+        const int row_a = t.m_blk * BLOCK_M;
+        const int row_b = t.n_blk * BLOCK_N;
+        const int ba = p.a_batched ? t.b : 0;
+        const int bb = p.b_batched ? t.b : 0;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          tma_load_3d(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
+          tma_load_3d(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
+          if (NSPLIT == 2) {
+            tma_load_3d(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
+            tma_load_3d(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ====================================== MMA issuer =======================================
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;
+    for (long long unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const int inner = unit_inner_count<EPI>(p, unit);
+      for (int j = 0; j < inner; ++j, ++it) {
+        const Tile t = decode_tile<EPI>(p, unit, j);
+        const uint32_t as = it % ACC_STAGES;
+        const uint32_t aphase = (it / ACC_STAGES) & 1u;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t a_hi = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, 0));
+          const uint64_t b_hi = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, 0));
+          const uint64_t a_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, NSPLIT - 1));
+          const uint64_t b_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, NSPLIT - 1));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advancing 16 bf16 (32 bytes) along K inside the swizzle span: +2 in 16-byte units
+            const uint64_t koff = (uint64_t)(2 * k);
+            const uint32_t acc = (kb > t.kb0 || k > 0) ? 1u : 0u;
+            if (NSPLIT == 2) {
+              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, IDESC, acc);
+              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1u);
+            } else {
+              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, acc);
+            }
+          }
+          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          if (kb == t.kb1 - 1) umma_commit(tmem_full_bar(as));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue ========================================
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int lane_row = quarter * 32 + lane;  // accumulator row owned by this thread
+    constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N : 1;
+    uint32_t it = 0;
+    for (long long unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const int inner = unit_inner_count<EPI>(p, unit);
+      float rowdot = 0.f;
+      float racc[NACC];
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) racc[i] = 0.f;
+      Tile t = decode_tile<EPI>(p, unit, 0);
+      for (int j = 0; j < inner; ++j, ++it) {
+        t = decode_tile<EPI>(p, unit, j);
+        const uint32_t as = it % ACC_STAGES;
+        const uint32_t aphase = (it / ACC_STAGES) & 1u;
+        mbar_wait(tmem_full_bar(as), aphase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + as * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
+        const long long row = (long long)t.m_blk * BLOCK_M + lane_row;
+        const bool row_ok = row < p.M;
+        const int n0 = t.n_blk * BLOCK_N;
+#pragma unroll
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N && EPI != EPI_REGACC) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (EPI == EPI_ROWDOT) {
+            if (row_ok) {
+              const float* gp = p.g + row * p.ldg + col0;
+              if (p.g_vec4 && col0 + 32 <= p.N) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 gv = __ldg(reinterpret_cast<const float4*>(gp) + i);
+                  rowdot = fmaf(__uint_as_float(v[4 * i + 0]), gv.x, rowdot);
+                  rowdot = fmaf(__uint_as_float(v[4 * i + 1]), gv.y, rowdot);
+                  rowdot = fmaf(__uint_as_float(v[4 * i + 2]), gv.z, rowdot);
+                  rowdot = fmaf(__uint_as_float(v[4 * i + 3]), gv.w, rowdot);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) rowdot = fmaf(__uint_as_float(v[i]), __ldg(gp + i), rowdot);
+              }
+            }
+          } else if (EPI == EPI_REGACC) {
+            if (p.regacc_mode == REGACC_BATCH) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = __uint_as_float(v[i]);
+                racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += x * x;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[i]);
+            }
+          } else {
+            if (row_ok) {
+              float x[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+              store_values(p, t.b, row, col0, x);
+            }
+          }
+        }
+        if (EPI == EPI_STORE && p.zero_pad && row_ok && t.n_blk == p.n_blocks - 1) store_zero_pad(p, t.b, row);
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty_bar(as));
+      }
+      // ---- per-unit finalisation ----
+      if (EPI == EPI_ROWDOT) {
+        const long long row = (long long)t.m_blk * BLOCK_M + lane_row;
+        if (row < p.M) {
+          float* o = p.out_f32 + (long long)t.b * p.out_bs + row;
+          const float val = p.alpha * rowdot;
+          if (p.accumulate) *o += val;
+          else *o = val;
+        }
+      } else if (EPI == EPI_REGACC) {
+        const long long row = (long long)t.m_blk * BLOCK_M + lane_row;
+        if (row < p.M) {
+          const int n0 = t.n_blk * BLOCK_N;
+          const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
+#pragma unroll
+          for (int c = 0; c < NACC / 32; ++c) {
+            if (n0 + c * 32 < p.N) {
+              float x[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = racc[(EPI == EPI_REGACC ? c * 32 + i : 0)];
+              store_values(p, ob, row, n0 + c * 32, x);
+            }
+          }
+          if (p.zero_pad && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// SIMT debug implementation of the same contract (kfb_set_gemm_backend(1)).  One thread per output.
+// -------------------------------------------------------------------------------------------------
+struct SimtOperand {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;
+  long long ld, bs;
+};
+
+__device__ __forceinline__ float simt_dot(const SimtOperand& A, const SimtOperand& B, long long ab,
+                                          long long bb, long long m, long long n, int K) {
+  const __nv_bfloat16* ah = A.hi + ab * A.bs + m * A.ld;
+  const __nv_bfloat16* bh = B.hi + bb * B.bs + n * B.ld;
+  const __nv_bfloat16* al = A.lo ? A.lo + ab * A.bs + m * A.ld : nullptr;
+  const __nv_bfloat16* bl = B.lo ? B.lo + bb * B.bs + n * B.ld : nullptr;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float a_h = __bfloat162float(ah[k]), b_h = __bfloat162float(bh[k]);
+    const float a_l = al ? __bfloat162float(al[k]) : 0.f;
+    const float b_l = bl ? __bfloat162float(bl[k]) : 0.f;
+    acc += a_l * b_h + a_h * b_l + a_h * b_h;
+  }
+  return acc;
+}
+
+__global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int epi) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (epi == KFB_EPI_STORE) {
+    const long long total = (long long)p.batch * p.M * p.N;
+    if (tid >= total) return;
+    const long long n = tid % p.N, m = (tid / p.N) % p.M, b = tid / ((long long)p.N * p.M);
+    float val = p.alpha * simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K);
+    if (p.mul) val *= p.mul[m * p.ldmul + n];
+    if (p.square) val *= val;
+    if (p.out_f32) {
+      float* o = p.out_f32 + b * p.out_bs + (p.transpose_out ? n * p.ldo + m : m * p.ldo + n);
+      if (p.accumulate) *o += val;
+      else *o = val;
+    }
+    if (p.out_hi) {
+      const long long idx = b * p.out_bs_s + (p.transpose_out ? n * p.ldo_s + m : m * p.ldo_s + n);
+      __nv_bfloat16 h, l;
+      split_bf16(val, h, l);
+      p.out_hi[idx] = h;
+      if (p.out_lo) p.out_lo[idx] = l;
+      if (p.zero_pad && !p.transpose_out && n == p.N - 1) {
+        for (long long c = p.N; c < p.ldo_s; ++c) {
+          p.out_hi[b * p.out_bs_s + m * p.ldo_s + c] = __float2bfloat16_rn(0.f);
+          if (p.out_lo) p.out_lo[b * p.out_bs_s + m * p.ldo_s + c] = __float2bfloat16_rn(0.f);
+        }
+      }
+    }
+  } else if (epi == KFB_EPI_ROWDOT) {
+    const long long total = (long long)p.batch * p.M;
+    if (tid >= total) return;
+    const long long m = tid % p.M, b = tid / p.M;
+    float sum = 0.f;
+    for (int n = 0; n < p.N; ++n)
+      sum += simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K) * p.g[m * p.ldg + n];
+    float* o = p.out_f32 + b * p.out_bs + m;
+    if (p.accumulate) *o += p.alpha * sum;
+    else *o = p.alpha * sum;
+  } else {
+    const long long total = (long long)p.M * p.N;
+    if (tid >= total) return;
+    const long long n = tid % p.N, m = tid / p.N;
+    float sum = 0.f;
+    for (int b = 0; b < p.batch; ++b) {
+      const float d = simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K);
+      sum += d * d;
+    }
+    p.out_f32[m * p.ldo + n] += p.alpha * sum;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Host side
+// -------------------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_backend{0};
+void count_launch(int n) { g_launches += n; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long long rows,
+                     long long batch, long long ld, long long bs, int box_k, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return KFB_ERR_NO_DEVICE;
+  }
+  KFB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "operand base must be 16-byte aligned");
+  KFB_REQUIRE(ld % 8 == 0, "operand leading dimension (%lld) must be a multiple of 8", ld);
+  KFB_REQUIRE(batch == 1 || bs % 8 == 0, "operand batch stride (%lld) must be a multiple of 8", bs);
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  long long bs_bytes = (batch > 1 ? bs : rows * ld) * 2;
+  if (bs_bytes < 16) bs_bytes = 16;
+  cuuint64_t gstride[2] = {(cuuint64_t)(ld * 2), (cuuint64_t)bs_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): cols=%lld rows=%lld batch=%lld ld=%lld bs=%lld",
+              (int)r, cols, rows, batch, ld, bs);
+    return KFB_ERR_CUDA;
+  }
+  return KFB_OK;
+}
+
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI>
+static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT>;
+  p.m_blocks = (int)ceil_div_ll(p.M, 128);
+  p.n_blocks = (int)ceil_div_ll(p.N, BLOCK_N);
+  p.k_blocks = (int)ceil_div_ll(p.K, BLOCK_K);
+  const int max_pass_kb = kMaxPassK / BLOCK_K;
+  const long long tiles = (long long)p.m_blocks * p.n_blocks;
+  if (EPI == EPI_ROWDOT) {
+    p.k_splits = 1;
+    p.kb_per_split = p.k_blocks;
+    p.k_chunks = (int)ceil_div_ll(p.k_blocks, max_pass_kb);
+    p.kb_per_chunk = (int)ceil_div_ll(p.k_blocks, p.k_chunks);
+    p.k_chunks = (int)ceil_div_ll(p.k_blocks, p.kb_per_chunk);
+    p.num_units = (long long)p.m_blocks * p.batch;
+  } else if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH) {
+    // cut the batch into chunks so that there are enough units to fill the machine
+    long long chunks = ceil_div_ll(2LL * sm_count(), tiles);
+    if (chunks > p.batch) chunks = p.batch;
+    if (chunks < 1) chunks = 1;
+    p.inner = (int)ceil_div_ll(p.batch, chunks);
+    chunks = ceil_div_ll(p.batch, p.inner);
+    p.k_splits = 1;
+    p.kb_per_split = p.k_blocks;
+    p.k_chunks = 1;
+    p.kb_per_chunk = p.k_blocks;
+    p.num_units = tiles * chunks;
+  } else {
+    if (p.k_splits < 1) p.k_splits = 1;
+    if (p.k_splits > p.k_blocks) p.k_splits = p.k_blocks;
+    p.kb_per_split = (int)ceil_div_ll(p.k_blocks, p.k_splits);
+    p.k_splits = (int)ceil_div_ll(p.k_blocks, p.kb_per_split);
+    p.use_atomic = p.k_splits > 1 ? 1 : 0;
+    if (EPI == EPI_REGACC) {
+      p.k_chunks = (int)ceil_div_ll(p.kb_per_split, max_pass_kb);
+      p.kb_per_chunk = (int)ceil_div_ll(p.kb_per_split, p.k_chunks);
+    } else {
+      p.k_chunks = 1;
+      p.kb_per_chunk = p.kb_per_split;
+    }
+    p.num_units = tiles * p.k_splits * p.batch;
+  }
+  if (p.num_units == 0) return KFB_OK;
+
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  KFB_TRY(make_tmap(&ta_hi, A.hi, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
+  KFB_TRY(make_tmap(&tb_hi, B.hi, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, BLOCK_N));
+  if (NSPLIT == 2) {
+    KFB_TRY(make_tmap(&ta_lo, A.lo, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
+    KFB_TRY(make_tmap(&tb_lo, B.lo, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, BLOCK_N));
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    KFB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  long long grid = p.num_units < sm_count() ? p.num_units : sm_count();
+  kernel<<<(unsigned)grid, 256, Cfg::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  count_launch();
+  KFB_CUDA_TRY(cudaGetLastError());
+  return KFB_OK;
+}
+
+static inline int pick_bn(int N, int cap) {
+  int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  return bn > cap ? cap : bn;
+}
+
+template <int EPI>
+static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams& p, int nsplit,
+                       cudaStream_t stream) {
+  // Tile width: as wide as N allows (wider tiles = more reuse of the A stage per MMA), except for
+  // REGACC whose per-thread register accumulators limit it to 128.
+  const int bn = pick_bn(p.N, EPI == EPI_REGACC ? 128 : 256);
+  if (nsplit == 2) {
+    if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 32, 2, EPI>(A, B, p, stream);
+    if (bn == 128) return launch_tc<128, 64, 2, EPI>(A, B, p, stream);
+    return launch_tc<64, 64, 2, EPI>(A, B, p, stream);
+  }
+  if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 64, 1, EPI>(A, B, p, stream);
+  if (bn == 128) return launch_tc<128, 64, 1, EPI>(A, B, p, stream);
+  return launch_tc<64, 64, 1, EPI>(A, B, p, stream);
+}
+
+static int launch_simt(const kfb_split& A, const kfb_split& B, GemmParams p, int epi, int nsplit,
+                       cudaStream_t stream) {
+  SimtOperand a{(const __nv_bfloat16*)A.hi, nsplit == 2 ? (const __nv_bfloat16*)A.lo : nullptr, A.ld,
+                A.batch_stride};
+  SimtOperand b{(const __nv_bfloat16*)B.hi, nsplit == 2 ? (const __nv_bfloat16*)B.lo : nullptr, B.ld,
+                B.batch_stride};
+  long long total = epi == KFB_EPI_STORE    ? (long long)p.batch * p.M * p.N
+                    : epi == KFB_EPI_ROWDOT ? (long long)p.batch * p.M
+                                            : (long long)p.M * p.N;
+  if (total == 0) return KFB_OK;
+  gemm_simt_kernel<<<(unsigned)ceil_div_ll(total, 128), 128, 0, stream>>>(a, b, p, epi);
+  count_launch();
+  KFB_CUDA_TRY(cudaGetLastError());
+  return KFB_OK;
+}
+
+int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int precision,
+            int k_splits, cudaStream_t stream) {
+  KFB_REQUIRE(A.hi != nullptr && B.hi != nullptr, "gemm_nt: null operand");
+  KFB_REQUIRE(A.cols == B.cols, "gemm_nt: contraction lengths differ (%lld vs %lld)",
+              (long long)A.cols, (long long)B.cols);
+  KFB_REQUIRE(A.batch >= 1 && B.batch >= 1 && (A.batch == B.batch || A.batch == 1 || B.batch == 1),
+              "gemm_nt: incompatible batch counts %lld / %lld", (long long)A.batch, (long long)B.batch);
+  KFB_REQUIRE(A.rows < (1LL << 31) && B.rows < (1LL << 31) && A.cols < (1LL << 31),
+              "gemm_nt: dimension too large");
+  const int nsplit = precision == KFB_PREC_FP32 ? 2 : 1;
+  KFB_REQUIRE(nsplit == 1 || (A.lo != nullptr && B.lo != nullptr),
+              "gemm_nt: KFB_PREC_FP32 needs lo planes");
+  GemmParams p{};
+  p.M = (int)A.rows;
+  p.N = (int)B.rows;
+  p.K = (int)A.cols;
+  p.batch = (int)(A.batch > B.batch ? A.batch : B.batch);
+  p.a_batched = A.batch > 1;
+  p.b_batched = B.batch > 1;
+  p.out_f32 = epi.out_f32;
+  p.ldo = epi.ldo;
+  p.out_bs = epi.out_batch_stride;
+  p.out_hi = (__nv_bfloat16*)epi.out_split.hi;
+  p.out_lo = (__nv_bfloat16*)epi.out_split.lo;
+  p.ldo_s = epi.out_split.ld;
+  p.out_bs_s = epi.out_split.batch_stride;
+  p.mul = epi.mul;
+  p.ldmul = epi.ldmul;
+  p.transpose_out = epi.transpose_out;
+  p.square = epi.square;
+  p.accumulate = epi.accumulate;
+  p.alpha = epi.alpha;
+  p.g = epi.g;
+  p.ldg = epi.ldg;
+  p.k_splits = 1;
+  p.k_chunks = 1;
+  if (p.M == 0 || p.N == 0 || p.batch == 0) return KFB_OK;
+  KFB_REQUIRE(p.K > 0, "gemm_nt: empty contraction");
+
+  if (epi.kind == KFB_EPI_STORE) {
+    KFB_REQUIRE(p.out_f32 != nullptr || p.out_hi != nullptr, "gemm_nt: STORE without an output");
+    p.vec_ok = 1;
+    if (p.out_f32 && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) || p.ldo % 4 || p.out_bs % 4))
+      p.vec_ok = 0;
+    if (p.out_hi && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) || p.ldo_s % 8 || p.out_bs_s % 8 ||
+                     (p.out_lo && (reinterpret_cast<uintptr_t>(p.out_lo) & 15))))
+      p.vec_ok = 0;
+    p.zero_pad = (p.out_hi != nullptr && !p.transpose_out) ? 1 : 0;
+  } else if (epi.kind == KFB_EPI_ROWDOT) {
+    KFB_REQUIRE(p.out_f32 != nullptr && p.g != nullptr, "gemm_nt: ROWDOT needs out_f32 and g");
+    KFB_REQUIRE(A.batch == 1 || A.batch == p.batch, "gemm_nt: ROWDOT batch mismatch");
+    p.g_vec4 = ((reinterpret_cast<uintptr_t>(p.g) & 15) == 0 && p.ldg % 4 == 0) ? 1 : 0;
+  } else if (epi.kind == KFB_EPI_SQACC) {
+    KFB_REQUIRE(p.out_f32 != nullptr, "gemm_nt: SQACC needs out_f32");
+    // sum over the batch of squares: register accumulation, atomically added to the target
+    p.regacc_mode = REGACC_BATCH;
+    p.use_atomic = 1;
+    p.out_hi = nullptr;
+    p.out_lo = nullptr;
+    p.mul = nullptr;
+    p.square = 0;
+    p.transpose_out = 0;
+    p.out_bs = 0;
+  } else {
+    KFB_REQUIRE(false, "gemm_nt: unknown epilogue %d", epi.kind);
+  }
+
+  if (g_backend.load() == 1) return launch_simt(A, B, p, epi.kind, nsplit, stream);
+  if (epi.kind == KFB_EPI_ROWDOT) return dispatch_tc<EPI_ROWDOT>(A, B, p, nsplit, stream);
+  if (epi.kind == KFB_EPI_SQACC) return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
+
+  // STORE: one TMEM pass if the contraction is short, register-accumulated passes otherwise; the
+  // contraction is additionally split across CTAs (atomic adds into an accumulated fp32 target) when
+  // there are too few output tiles to fill the machine.
+  const bool long_k = p.K > kMaxPassK;
+  const bool splittable = p.out_hi == nullptr && p.mul == nullptr && !p.square && p.accumulate;
+  if (splittable) {
+    if (k_splits == 0) {
+      const int bn = pick_bn(p.N, long_k ? 128 : 256);
+      const long long tiles = ceil_div_ll(p.M, 128) * ceil_div_ll(p.N, bn) * p.batch;
+      const long long passes = ceil_div_ll(p.K, kMaxPassK);
+      long long want = ceil_div_ll(sm_count(), tiles);
+      if (want > passes) want = passes;  // never make a split shorter than one full pass
+      k_splits = want < 1 ? 1 : (int)want;
+    }
+    p.k_splits = k_splits;
+  }
+  if (long_k) {
+    p.regacc_mode = REGACC_KCHUNK;
+    return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
+  }
+  return dispatch_tc<EPI_STORE>(A, B, p, nsplit, stream);
+}
+
+}  // namespace kfb
+
+extern "C" {
+
+int kfb_gemm_nt(const kfb_split* A, const kfb_split* B, const kfb_epilogue* epi, int precision,
+                void* stream) {
+  if (A == nullptr || B == nullptr || epi == nullptr) {
+    kfb::set_error("kfb_gemm_nt: null argument");
+    return KFB_ERR_INVALID;
+  }
+  return kfb::gemm_nt(*A, *B, *epi, precision, 0, static_cast<cudaStream_t>(stream));
+}
+
+int kfb_set_gemm_backend(int backend) {
+  if (backend != 0 && backend != 1) {
+    kfb::set_error("kfb_set_gemm_backend: backend must be 0 (tcgen05) or 1 (simt debug)");
+    return KFB_ERR_INVALID;
+  }
+  kfb::g_backend.store(backend);
+  return KFB_OK;
+}
+
+int64_t kfb_launch_count(void) { return kfb::g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,659 @@
+// Stage-level operations of the EK-FAC influence hot path, composed from the operand-preparation
+// kernels (kfb_prep.cu) and the tcgen05 NT-GEMM engine (kfb_gemm.cu).  Each function restates one
+// piece of kronfluence's tracked-module math (file:line cited per function) in a formulation that
+// keeps every dense contraction on tensor cores and never materialises what the reference does
+// (ones-column concatenations, im2col buffers, [B, d_out, d_in] per-sample gradients on the
+// Lambda / pairwise S=1 paths).
+#include "kfb_gemm.cuh"
+#include "kfb_prep.cuh"
+
+namespace kfb {
+
+static inline long long ld8(long long c) { return round_up_ll(c, 8); }
+
+static inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case KFB_F32: return 4;
+    case KFB_BF16: return 2;
+    case KFB_F16: return 2;
+    case KFB_F64: return 8;
+    default: return 0;
+  }
+}
+static inline const void* advance(const void* p, int dt, long long elems) {
+  return static_cast<const char*>(p) + elems * (long long)dtype_size(dt);
+}
+
+// Bump allocator over the caller's workspace.  In "dry" mode it only measures.
+struct Ws {
+  char* base;
+  size_t cap;
+  size_t off;
+  bool dry;
+  void* take(size_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    void* p = dry ? nullptr : base + off;
+    off += n;
+    return p;
+  }
+  bool fits() const { return dry || off <= cap; }
+};
+
+static kfb_split ws_split(Ws& ws, long long rows, long long cols, long long batch, int precision) {
+  kfb_split s;
+  s.rows = rows;
+  s.cols = cols;
+  s.ld = ld8(cols);
+  s.batch = batch;
+  s.batch_stride = rows * s.ld;
+  const size_t plane = (size_t)(rows * s.ld * batch) * 2;
+  s.hi = ws.take(plane);
+  s.lo = precision == KFB_PREC_FP32 ? ws.take(plane) : nullptr;
+  return s;
+}
+
+static kfb_split split_batch_view(const kfb_split& s, long long b0, long long nb) {
+  kfb_split v = s;
+  v.hi = static_cast<char*>(s.hi) + b0 * s.batch_stride * 2;
+  v.lo = s.lo ? static_cast<char*>(s.lo) + b0 * s.batch_stride * 2 : nullptr;
+  v.batch = nb;
+  return v;
+}
+
+// Scratch budget per intermediate family; larger batches are processed in chunks.
+static const long long kChunkBudgetBytes = 1LL << 31;
+
+static long long chunk_count(long long batch, long long bytes_per_sample) {
+  long long c = bytes_per_sample > 0 ? kChunkBudgetBytes / bytes_per_sample : batch;
+  if (c < 1) c = 1;
+  if (c > batch) c = batch;
+  return c < 1 ? 1 : c;
+}
+
+static kfb_epilogue store_epilogue() {
+  kfb_epilogue e{};
+  e.kind = KFB_EPI_STORE;
+  e.alpha = 1.f;
+  return e;
+}
+
+static int check_layer(const kfb_layer* L) {
+  KFB_REQUIRE(L != nullptr, "null layer");
+  KFB_REQUIRE(L->kind == KFB_LINEAR || L->kind == KFB_CONV2D, "unknown layer kind %d", L->kind);
+  KFB_REQUIRE(L->d_in > 0 && L->d_out > 0, "layer dimensions must be positive");
+  if (L->kind == KFB_CONV2D)
+    KFB_REQUIRE(L->h_out > 0 && L->w_out > 0 && L->groups > 0 && L->c_in % L->groups == 0 &&
+                    L->d_in == (L->c_in / L->groups) * L->k_h * L->k_w,
+                "inconsistent Conv2d geometry");
+  return KFB_OK;
+}
+
+static inline long long positions(const kfb_layer& L, long long seq) {
+  return L.kind == KFB_CONV2D ? (long long)L.h_out * L.w_out : seq;
+}
+
+// =================================================================================================
+// Stage 1: covariance accumulation.  tracker/factor.py:31-93, linear.py:30-54, conv2d.py:106-132.
+//   C += alpha * X^T X  with X = [N, d]; computed as Xt Xt^T where Xt = X^T is produced directly by
+//   the gather (K-major in the sample index), so the GEMM is the generic NT engine with K = N.
+// =================================================================================================
+static int cov_run(const kfb_layer& L, bool activation, const void* x, int dt, long long batch,
+                   long long seq, const float* mask, float alpha, float* C, Ws& ws, int precision,
+                   cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long d = activation ? L.d_in + L.has_bias : L.d_out;
+  // chunk over samples so that the transposed operand stays within the scratch budget
+  const long long per_sample = d * S * 2 * (precision == KFB_PREC_FP32 ? 2 : 1);
+  const long long cb = chunk_count(batch, per_sample);
+  kfb_split Xt = ws_split(ws, d, cb * S, 1, precision);
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("covariance workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    kfb_split v = Xt;
+    v.cols = nb * S;  // ld stays that of the full chunk
+    if (L.kind == KFB_LINEAR) {
+      const long long feat = activation ? L.d_in : L.d_out;
+      GatherDesc g{};
+      g.sb = 0;
+      g.sr = 1;
+      g.sc1 = 0;
+      g.sc2 = feat;
+      g.rows = feat;
+      g.c1 = 1;
+      g.c2 = nb * S;
+      g.ones_mode = (activation && L.has_bias) ? 2 : 0;
+      g.scale_mode = (activation && mask != nullptr) ? 2 : 0;
+      g.scale = mask != nullptr ? mask + b0 * S : nullptr;
+      KFB_TRY(split_gather(advance(x, dt, b0 * S * feat), dt, g, v, precision, stream));
+    } else if (activation) {
+      KFB_TRY(split_im2col(L, advance(x, dt, b0 * (long long)L.c_in * L.h_in * L.w_in), dt, nb, 2, v,
+                           precision, stream));
+    } else {
+      GatherDesc g{};
+      g.sb = 0;
+      g.sr = S;
+      g.sc1 = (long long)L.d_out * S;
+      g.sc2 = 1;
+      g.rows = L.d_out;
+      g.c1 = nb;
+      g.c2 = S;
+      KFB_TRY(split_gather(advance(x, dt, b0 * (long long)L.d_out * S), dt, g, v, precision, stream));
+    }
+    kfb_epilogue e = store_epilogue();
+    e.out_f32 = C;
+    e.ldo = d;
+    e.accumulate = 1;
+    e.alpha = alpha;
+    KFB_TRY(gemm_nt(v, v, e, precision, 0, stream));
+  }
+  return KFB_OK;
+}
+
+// =================================================================================================
+// Per-sample outer-product operands.  For samples [b0, b0+nb):
+//   Lt[b] = [d_out, S]  and  Rt[b] = [d_in+bias, S]   (S = positions per sample, contiguous)
+// so that  G_b = Lt[b] Rt[b]^T  is the per-sample gradient of linear.py:68-77 / conv2d.py:164-177
+// (rotate == 0) or its eigenbasis image Q_G^T G_b Q_A (rotate == 1: the rotation is applied to
+// the [S, d] operands FIRST, 2 N (d_in^2 + d_out^2) flops instead of the reference's
+// 2 B D (d_in + d_out)).
+// =================================================================================================
+struct OuterBufs {
+  kfb_split Lt, Rt;        // outputs
+  kfb_split tmp_a, tmp_g;  // [nb][S][d] K-major-in-feature operands for the rotation (rotate only)
+};
+
+static OuterBufs outer_alloc(Ws& ws, const kfb_layer& L, long long nb, long long S, bool rotate,
+                             int precision) {
+  OuterBufs o{};
+  const long long di = L.d_in + L.has_bias;
+  o.Lt = ws_split(ws, L.d_out, S, nb, precision);
+  o.Rt = ws_split(ws, di, S, nb, precision);
+  if (rotate) {
+    o.tmp_a = ws_split(ws, S, di, nb, precision);
+    o.tmp_g = ws_split(ws, S, L.d_out, nb, precision);
+  }
+  return o;
+}
+
+static long long outer_bytes_per_sample(const kfb_layer& L, long long S, bool rotate, int precision) {
+  const long long di = L.d_in + L.has_bias;
+  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
+  long long b = (L.d_out + di) * ld8(S) * 2 * planes;
+  if (rotate) b += S * (ld8(di) + ld8(L.d_out)) * 2 * planes;
+  return b;
+}
+
+static int outer_fill(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt,
+                      long long b0, long long nb, long long seq, bool rotate, const kfb_split* qa_t,
+                      const kfb_split* qg_t, OuterBufs& o, int precision, cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  kfb_split Lt = split_batch_view(o.Lt, 0, nb), Rt = split_batch_view(o.Rt, 0, nb);
+  const void* a0 = L.kind == KFB_LINEAR ? advance(a, a_dt, b0 * S * L.d_in)
+                                        : advance(a, a_dt, b0 * (long long)L.c_in * L.h_in * L.w_in);
+  const void* g0 = advance(g, g_dt, b0 * S * L.d_out);
+  if (!rotate) {
+    if (L.kind == KFB_LINEAR) {
+      GatherDesc ga{};
+      ga.sb = S * L.d_in; ga.sr = 1; ga.sc2 = L.d_in; ga.rows = L.d_in; ga.c1 = 1; ga.c2 = S;
+      ga.ones_mode = L.has_bias ? 2 : 0;
+      KFB_TRY(split_gather(a0, a_dt, ga, Rt, precision, stream));
+      GatherDesc gg{};
+      gg.sb = S * L.d_out; gg.sr = 1; gg.sc2 = L.d_out; gg.rows = L.d_out; gg.c1 = 1; gg.c2 = S;
+      KFB_TRY(split_gather(g0, g_dt, gg, Lt, precision, stream));
+    } else {
+      KFB_TRY(split_im2col(L, a0, a_dt, nb, 1, Rt, precision, stream));
+      GatherDesc gg{};
+      gg.sb = (long long)L.d_out * S; gg.sr = S; gg.sc2 = 1; gg.rows = L.d_out; gg.c1 = 1; gg.c2 = S;
+      KFB_TRY(split_gather(g0, g_dt, gg, Lt, precision, stream));
+    }
+    return KFB_OK;
+  }
+  KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->hi != nullptr && qg_t->hi != nullptr,
+              "eigenbasis operands are required");
+  KFB_REQUIRE(qa_t->rows == di && qa_t->cols == di && qg_t->rows == L.d_out && qg_t->cols == L.d_out,
+              "eigenbasis operand shapes do not match the layer");
+  kfb_split ta = split_batch_view(o.tmp_a, 0, nb), tg = split_batch_view(o.tmp_g, 0, nb);
+  if (L.kind == KFB_LINEAR) {
+    GatherDesc ga{};
+    ga.sb = S * L.d_in; ga.sr = L.d_in; ga.sc2 = 1; ga.rows = S; ga.c1 = 1; ga.c2 = L.d_in;
+    ga.ones_mode = L.has_bias ? 1 : 0;
+    KFB_TRY(split_gather(a0, a_dt, ga, ta, precision, stream));
+    GatherDesc gg{};
+    gg.sb = S * L.d_out; gg.sr = L.d_out; gg.sc2 = 1; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
+    KFB_TRY(split_gather(g0, g_dt, gg, tg, precision, stream));
+  } else {
+    KFB_TRY(split_im2col(L, a0, a_dt, nb, 0, ta, precision, stream));
+    GatherDesc gg{};
+    gg.sb = (long long)L.d_out * S; gg.sr = 1; gg.sc2 = S; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
+    KFB_TRY(split_gather(g0, g_dt, gg, tg, precision, stream));
+  }
+  // Rt[b] = Q_A^T a_b^T : M = d_in+bias (eigen index), N = S, K = d_in+bias
+  kfb_epilogue e = store_epilogue();
+  e.out_split = Rt;
+  KFB_TRY(gemm_nt(*qa_t, ta, e, precision, 1, stream));
+  e.out_split = Lt;
+  KFB_TRY(gemm_nt(*qg_t, tg, e, precision, 1, stream));
+  return KFB_OK;
+}
+
+// =================================================================================================
+// Stage 3: Lambda sweep.  tracker/factor.py:162-230.
+// =================================================================================================
+static int lambda_run(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt,
+                      long long batch, long long seq, bool with_eigen, const kfb_split* qa_t,
+                      const kfb_split* qg_t, float scale, float* lambda, Ws& ws, int precision,
+                      cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
+  if (with_eigen && L.kind == KFB_LINEAR && S == 1) {
+    // One position per example: (Q_G^T g_b)(Q_A^T a_b)^T is rank one, so
+    //   Lambda += (Gr o Gr)^T (Ar o Ar)     with Ar = A Q_A, Gr = G Q_G        (K = batch)
+    // i.e. two rotations with a squaring epilogue and one accumulate-GEMM.
+    const long long per = (ld8(di) + ld8(L.d_out)) * 2 * planes * 2;
+    const long long cb = chunk_count(batch, per);
+    kfb_split a_sp = ws_split(ws, cb, di, 1, precision);
+    kfb_split g_sp = ws_split(ws, cb, L.d_out, 1, precision);
+    kfb_split At2 = ws_split(ws, di, cb, 1, precision);
+    kfb_split Gt2 = ws_split(ws, L.d_out, cb, 1, precision);
+    if (ws.dry) return KFB_OK;
+    if (!ws.fits()) {
+      set_error("lambda workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+      return KFB_ERR_WORKSPACE;
+    }
+    KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr, "eigenbasis operands are required");
+    for (long long b0 = 0; b0 < batch; b0 += cb) {
+      const long long nb = batch - b0 < cb ? batch - b0 : cb;
+      kfb_split av = a_sp, gv = g_sp, at = At2, gt = Gt2;
+      av.rows = nb; gv.rows = nb; at.cols = nb; gt.cols = nb;
+      GatherDesc ga{};
+      ga.sr = L.d_in; ga.sc2 = 1; ga.rows = nb; ga.c1 = 1; ga.c2 = L.d_in;
+      ga.ones_mode = L.has_bias ? 1 : 0;
+      KFB_TRY(split_gather(advance(a, a_dt, b0 * L.d_in), a_dt, ga, av, precision, stream));
+      GatherDesc gg{};
+      gg.sr = L.d_out; gg.sc2 = 1; gg.rows = nb; gg.c1 = 1; gg.c2 = L.d_out;
+      KFB_TRY(split_gather(advance(g, g_dt, b0 * L.d_out), g_dt, gg, gv, precision, stream));
+      kfb_epilogue e = store_epilogue();
+      e.square = 1;
+      e.out_split = at;
+      KFB_TRY(gemm_nt(*qa_t, av, e, precision, 1, stream));
+      e.out_split = gt;
+      e.alpha = scale;  // squared by the epilogue -> scale^2, as tracker/factor.py:270-271 then :223
+      KFB_TRY(gemm_nt(*qg_t, gv, e, precision, 1, stream));
+      kfb_epilogue acc = store_epilogue();
+      acc.out_f32 = lambda;
+      acc.ldo = di;
+      acc.accumulate = 1;
+      KFB_TRY(gemm_nt(gt, at, acc, precision, 0, stream));
+    }
+    return KFB_OK;
+  }
+  const long long per = outer_bytes_per_sample(L, S, with_eigen, precision);
+  const long long cb = chunk_count(batch, per);
+  OuterBufs o = outer_alloc(ws, L, cb, S, with_eigen, precision);
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("lambda workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, with_eigen, qa_t, qg_t, o, precision, stream));
+    kfb_epilogue e{};
+    e.kind = KFB_EPI_SQACC;
+    e.out_f32 = lambda;
+    e.ldo = di;
+    e.alpha = scale * scale;
+    KFB_TRY(gemm_nt(split_batch_view(o.Lt, 0, nb), split_batch_view(o.Rt, 0, nb), e, precision, 1, stream));
+  }
+  return KFB_OK;
+}
+
+// =================================================================================================
+// Stage 4: query-side per-sample gradient + preconditioning.  tracker/precondition.py:102-123,
+// factor/config.py:341-353.
+// =================================================================================================
+static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt,
+                            long long batch, long long seq, int mode, const kfb_split* qa,
+                            const kfb_split* qa_t, const kfb_split* qg, const kfb_split* qg_t,
+                            const float* lambda_inv, float scale, const kfb_split* P,
+                            long long q_offset, float* p_f32, Ws& ws, int precision,
+                            cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
+  const bool eigen = mode == KFB_PRECOND_EIGEN;
+  long long per = outer_bytes_per_sample(L, S, eigen, precision);
+  if (eigen) per += (L.d_out * ld8(di) + di * ld8(L.d_out)) * 2 * planes;
+  const long long cb = chunk_count(batch, per);
+  OuterBufs o = outer_alloc(ws, L, cb, S, eigen, precision);
+  kfb_split Mp{}, Rt2{};
+  if (eigen) {
+    Mp = ws_split(ws, L.d_out, di, cb, precision);
+    Rt2 = ws_split(ws, di, L.d_out, cb, precision);
+  }
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("precondition workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  KFB_REQUIRE(P != nullptr && P->hi != nullptr, "precondition: null destination");
+  KFB_REQUIRE(P->rows == L.d_out && P->cols == di && P->ld >= di && P->ld % 8 == 0,
+              "precondition: destination layout does not match the layer");
+  KFB_REQUIRE(q_offset >= 0 && q_offset + batch <= P->batch,
+              "precondition: queries [%lld, %lld) exceed the destination capacity %lld", q_offset,
+              q_offset + batch, (long long)P->batch);
+  KFB_REQUIRE(mode == KFB_PRECOND_IDENTITY || lambda_inv != nullptr, "precondition: lambda_inv is required");
+  if (eigen)
+    KFB_REQUIRE(qa != nullptr && qg != nullptr && qa->rows == di && qg->rows == L.d_out,
+                "precondition: eigenbasis operands do not match the layer");
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, eigen, qa_t, qg_t, o, precision, stream));
+    kfb_split Lt = split_batch_view(o.Lt, 0, nb), Rt = split_batch_view(o.Rt, 0, nb);
+    kfb_split Pv = split_batch_view(*P, q_offset + b0, nb);
+    float* pf = p_f32 != nullptr ? p_f32 + b0 * L.d_out * di : nullptr;
+    if (!eigen) {
+      kfb_epilogue e = store_epilogue();
+      e.out_split = Pv;
+      e.out_f32 = pf;
+      e.ldo = di;
+      e.out_batch_stride = L.d_out * di;
+      e.mul = mode == KFB_PRECOND_DIAGONAL ? lambda_inv : nullptr;
+      e.ldmul = di;
+      e.alpha = scale;
+      KFB_TRY(gemm_nt(Lt, Rt, e, precision, 1, stream));
+      continue;
+    }
+    // M' = (Q_G^T G Q_A) o lambda_inv                         [nb][d_out][d_in+bias]
+    kfb_epilogue e1 = store_epilogue();
+    e1.out_split = split_batch_view(Mp, 0, nb);
+    e1.mul = lambda_inv;
+    e1.ldmul = di;
+    KFB_TRY(gemm_nt(Lt, Rt, e1, precision, 1, stream));
+    // R^T = Q_A M'^T                                          [nb][d_in+bias][d_out]
+    kfb_epilogue e2 = store_epilogue();
+    e2.out_split = split_batch_view(Rt2, 0, nb);
+    KFB_TRY(gemm_nt(*qa, split_batch_view(Mp, 0, nb), e2, precision, 1, stream));
+    // P = scale * Q_G R                                       [nb][d_out][d_in+bias]
+    kfb_epilogue e3 = store_epilogue();
+    e3.out_split = Pv;
+    e3.out_f32 = pf;
+    e3.ldo = di;
+    e3.out_batch_stride = L.d_out * di;
+    e3.alpha = scale;
+    KFB_TRY(gemm_nt(*qg, split_batch_view(Rt2, 0, nb), e3, precision, 1, stream));
+  }
+  return KFB_OK;
+}
+
+// =================================================================================================
+// Stage 5: pairwise contraction.  linear.py:79-122, conv2d.py:179-209, score/dot_product.py:105-118.
+// =================================================================================================
+__global__ void zero_strided_kernel(float* p, long long rows, long long cols, long long ld) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[(i / cols) * ld + (i % cols)] = 0.f;
+}
+
+static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, const void* a, int a_dt,
+                        const void* g, int g_dt, long long batch, long long seq, float scale,
+                        float* scores, long long ld_scores, long long t_offset, int accumulate,
+                        Ws& ws, int precision, cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
+  if (L.kind == KFB_LINEAR && S == 1) {
+    // Fused path: scores[q, t] = sum_o g[t,o] * (sum_i a[t,i] P[q,o,i]); the inner GEMM is the
+    // tensor-core tile (M = t, N = o, K = i, batched over q), the outer sum is the ROWDOT epilogue.
+    kfb_split a_sp = ws_split(ws, batch, di, 1, precision);
+    float* g32 = g_dt == KFB_F32 ? nullptr : static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
+    if (ws.dry) return KFB_OK;
+    if (!ws.fits()) {
+      set_error("pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+      return KFB_ERR_WORKSPACE;
+    }
+    GatherDesc ga{};
+    ga.sr = L.d_in; ga.sc2 = 1; ga.rows = batch; ga.c1 = 1; ga.c2 = L.d_in;
+    ga.ones_mode = L.has_bias ? 1 : 0;
+    KFB_TRY(split_gather(a, a_dt, ga, a_sp, precision, stream));
+    const float* gp = static_cast<const float*>(g);
+    if (g32 != nullptr) {
+      KFB_TRY(cast_to_f32(g, g_dt, g32, batch * L.d_out, 1.f, stream));
+      gp = g32;
+    }
+    kfb_epilogue e{};
+    e.kind = KFB_EPI_ROWDOT;
+    e.out_f32 = scores + t_offset;
+    e.out_batch_stride = ld_scores;
+    e.g = gp;
+    e.ldg = L.d_out;
+    e.alpha = scale;
+    e.accumulate = accumulate;
+    return gemm_nt(a_sp, split_batch_view(*P, 0, nq), e, precision, 1, stream);
+  }
+  // General path (sequences, Conv2d): per-sample gradients G_t = g_t^T a_t via a batched GEMM
+  // (K = S) written straight in P's operand layout, then scores = P_flat G_flat^T (K = d_out*ld).
+  const long long ldp = P != nullptr ? P->ld : ld8(di);
+  const long long per = outer_bytes_per_sample(L, S, false, precision) + L.d_out * ldp * 2 * planes;
+  const long long cb = chunk_count(batch, per);
+  OuterBufs o = outer_alloc(ws, L, cb, S, false, precision);
+  kfb_split G{};
+  G.rows = L.d_out; G.cols = di; G.ld = ldp; G.batch = cb; G.batch_stride = L.d_out * ldp;
+  G.hi = ws.take((size_t)(cb * G.batch_stride) * 2);
+  G.lo = precision == KFB_PREC_FP32 ? ws.take((size_t)(cb * G.batch_stride) * 2) : nullptr;
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  KFB_REQUIRE(P->batch_stride >= L.d_out * ldp, "pairwise: P batch stride is smaller than one matrix");
+  if (!accumulate) {
+    zero_strided_kernel<<<296, 256, 0, stream>>>(scores + t_offset, nq, batch, ld_scores);
+    count_launch();
+  }
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, false, nullptr, nullptr, o, precision, stream));
+    kfb_epilogue e1 = store_epilogue();
+    e1.out_split = split_batch_view(G, 0, nb);
+    KFB_TRY(gemm_nt(split_batch_view(o.Lt, 0, nb), split_batch_view(o.Rt, 0, nb), e1, precision, 1, stream));
+    kfb_split Pf{};
+    Pf.hi = P->hi; Pf.lo = P->lo; Pf.rows = nq; Pf.cols = L.d_out * ldp; Pf.ld = P->batch_stride;
+    Pf.batch = 1; Pf.batch_stride = 0;
+    kfb_split Gf{};
+    Gf.hi = G.hi; Gf.lo = G.lo; Gf.rows = nb; Gf.cols = L.d_out * ldp; Gf.ld = G.batch_stride;
+    Gf.batch = 1; Gf.batch_stride = 0;
+    kfb_epilogue e2 = store_epilogue();
+    e2.out_f32 = scores + t_offset + b0;
+    e2.ldo = ld_scores;
+    e2.accumulate = 1;
+    e2.alpha = scale;
+    KFB_TRY(gemm_nt(Pf, Gf, e2, precision, 0, stream));
+  }
+  return KFB_OK;
+}
+
+}  // namespace kfb
+
+// =================================================================================================
+// C ABI wrappers
+// =================================================================================================
+using namespace kfb;
+
+#define KFB_WS(ws_ptr, ws_bytes, dryflag) \
+  Ws w { static_cast<char*>(ws_ptr), (ws_bytes), 0, (dryflag) }
+
+extern "C" {
+
+size_t kfb_cov_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  size_t best = 0;
+  for (int act = 0; act < 2; ++act) {
+    KFB_WS(nullptr, 0, true);
+    cov_run(*layer, act == 1, nullptr, KFB_F32, batch, seq, nullptr, 1.f, nullptr, w, KFB_PREC_FP32, nullptr);
+    if (w.off > best) best = w.off;
+  }
+  return best + 256;
+}
+
+int kfb_cov_accum_activation(const kfb_layer* layer, const void* x, int x_dtype, int64_t batch,
+                             int64_t seq, const float* mask, float* C, void* ws, size_t ws_bytes,
+                             int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(x != nullptr && C != nullptr, "cov_accum_activation: null tensor");
+  KFB_REQUIRE(mask == nullptr || layer->kind == KFB_LINEAR, "attention masks apply to Linear layers only");
+  if (batch <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return cov_run(*layer, true, x, x_dtype, batch, seq, mask, 1.f, C, w, precision, (cudaStream_t)stream);
+}
+
+int kfb_cov_accum_gradient(const kfb_layer* layer, const void* g, int g_dtype, int64_t batch,
+                           int64_t seq, float alpha, float* C, void* ws, size_t ws_bytes,
+                           int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(g != nullptr && C != nullptr, "cov_accum_gradient: null tensor");
+  if (batch <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return cov_run(*layer, false, g, g_dtype, batch, seq, nullptr, alpha, C, w, precision, (cudaStream_t)stream);
+}
+
+int kfb_eigen_operands(const float* Q, int32_t d, const kfb_split* q, const kfb_split* qt,
+                       int precision, void* stream) {
+  KFB_REQUIRE(Q != nullptr && d > 0 && q != nullptr && qt != nullptr, "eigen_operands: bad argument");
+  GatherDesc gq{};
+  gq.sr = d; gq.sc2 = 1; gq.rows = d; gq.c1 = 1; gq.c2 = d;
+  KFB_TRY(split_gather(Q, KFB_F32, gq, *q, precision, (cudaStream_t)stream));
+  GatherDesc gt{};
+  gt.sr = 1; gt.sc2 = d; gt.rows = d; gt.c1 = 1; gt.c2 = d;
+  return split_gather(Q, KFB_F32, gt, *qt, precision, (cudaStream_t)stream);
+}
+
+size_t kfb_lambda_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  size_t best = 0;
+  for (int eig = 0; eig < 2; ++eig) {
+    KFB_WS(nullptr, 0, true);
+    lambda_run(*layer, nullptr, KFB_F32, nullptr, KFB_F32, batch, seq, eig == 1, nullptr, nullptr, 1.f,
+               nullptr, w, KFB_PREC_FP32, nullptr);
+    if (w.off > best) best = w.off;
+  }
+  return best + 256;
+}
+
+int kfb_lambda_accum(const kfb_layer* layer, const void* a, int a_dtype, const void* g,
+                     int g_dtype, int64_t batch, int64_t seq, int32_t with_eigen,
+                     const kfb_split* qa_t, const kfb_split* qg_t, float scale, float* lambda,
+                     void* ws, size_t ws_bytes, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(a != nullptr && g != nullptr && lambda != nullptr, "lambda_accum: null tensor");
+  if (batch <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return lambda_run(*layer, a, a_dtype, g, g_dtype, batch, seq, with_eigen != 0, qa_t, qg_t, scale,
+                    lambda, w, precision, (cudaStream_t)stream);
+}
+
+int kfb_lambda_invert(const float* lambda, int64_t numel, double n, double damping, float* out,
+                      void* ws, size_t ws_bytes, void* stream) {
+  KFB_REQUIRE(lambda != nullptr && out != nullptr, "lambda_invert: null tensor");
+  return lambda_invert(lambda, numel, n, damping, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t kfb_precondition_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  precondition_run(*layer, nullptr, KFB_F32, nullptr, KFB_F32, batch, seq, KFB_PRECOND_EIGEN, nullptr,
+                   nullptr, nullptr, nullptr, nullptr, 1.f, nullptr, 0, nullptr, w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_precondition(const kfb_layer* layer, const void* a, int a_dtype, const void* g,
+                     int g_dtype, int64_t batch, int64_t seq, int32_t mode, const kfb_split* qa,
+                     const kfb_split* qa_t, const kfb_split* qg, const kfb_split* qg_t,
+                     const float* lambda_inv, float scale, const kfb_split* P, int64_t q_offset,
+                     float* p_f32, void* ws, size_t ws_bytes, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(a != nullptr && g != nullptr, "precondition: null tensor");
+  KFB_REQUIRE(mode >= KFB_PRECOND_IDENTITY && mode <= KFB_PRECOND_EIGEN, "precondition: bad mode %d", mode);
+  if (batch <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return precondition_run(*layer, a, a_dtype, g, g_dtype, batch, seq, mode, qa, qa_t, qg, qg_t,
+                          lambda_inv, scale, P, q_offset, p_f32, w, precision, (cudaStream_t)stream);
+}
+
+size_t kfb_pairwise_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  // g may need an fp32 staging copy: measure with a non-fp32 dtype
+  pairwise_run(*layer, nullptr, 0, nullptr, KFB_F32, nullptr, KFB_BF16, batch, seq, 1.f, nullptr, 0, 0, 1,
+               w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
+                        const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
+                        int64_t seq, float scale, float* scores, int64_t ld_scores,
+                        int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes,
+                        int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(P != nullptr && P->hi != nullptr && a != nullptr && g != nullptr && scores != nullptr,
+              "pairwise_scores: null tensor");
+  KFB_REQUIRE(P->rows == layer->d_out && P->cols == layer->d_in + layer->has_bias,
+              "pairwise_scores: P layout does not match the layer");
+  KFB_REQUIRE(num_queries >= 0 && num_queries <= P->batch, "pairwise_scores: num_queries exceeds P");
+  KFB_REQUIRE(t_offset >= 0 && t_offset + batch <= ld_scores, "pairwise_scores: columns out of range");
+  if (batch <= 0 || num_queries == 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return pairwise_run(*layer, P, num_queries, a, a_dtype, g, g_dtype, batch, seq, scale, scores,
+                      ld_scores, t_offset, accumulate, w, precision, (cudaStream_t)stream);
+}
+
+int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
+                             const void* a_host, int a_dtype, const void* g_host, int g_dtype,
+                             int64_t batch, int64_t seq, float scale, float* scores_host,
+                             void* dev_a, void* dev_g, float* dev_scores, void* ws,
+                             size_t ws_bytes, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(a_host && g_host && scores_host && dev_a && dev_g && dev_scores,
+              "pairwise_scores_host: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long S = positions(*layer, seq);
+  const size_t a_bytes = (layer->kind == KFB_LINEAR
+                              ? (size_t)batch * S * layer->d_in
+                              : (size_t)batch * layer->c_in * layer->h_in * layer->w_in) * dtype_size(a_dtype);
+  const size_t g_bytes = (size_t)batch * S * layer->d_out * dtype_size(g_dtype);
+  KFB_CUDA_TRY(cudaMemcpyAsync(dev_a, a_host, a_bytes, cudaMemcpyHostToDevice, st));
+  KFB_CUDA_TRY(cudaMemcpyAsync(dev_g, g_host, g_bytes, cudaMemcpyHostToDevice, st));
+  KFB_TRY(kfb_pairwise_scores(layer, P, num_queries, dev_a, a_dtype, dev_g, g_dtype, batch, seq, scale,
+                              dev_scores, batch, 0, 0, ws, ws_bytes, precision, stream));
+  KFB_CUDA_TRY(cudaMemcpyAsync(scores_host, dev_scores, (size_t)num_queries * batch * 4,
+                               cudaMemcpyDeviceToHost, st));
+  return KFB_OK;
+}
+
+int kfb_split_gather(const void* src, int src_dtype, const int64_t* desc9, const float* scale,
+                     const kfb_split* dst, int precision, void* stream) {
+  KFB_REQUIRE(src != nullptr && desc9 != nullptr && dst != nullptr, "split_gather: null argument");
+  GatherDesc g{};
+  g.sb = desc9[0]; g.sr = desc9[1]; g.sc1 = desc9[2]; g.sc2 = desc9[3];
+  g.rows = desc9[4]; g.c1 = desc9[5]; g.c2 = desc9[6];
+  g.ones_mode = (int)desc9[7];
+  g.scale_mode = scale != nullptr ? (int)desc9[8] & 3 : 0;
+  g.square = (int)(desc9[8] >> 2) & 1;
+  g.scale = scale;
+  return split_gather(src, src_dtype, g, *dst, precision, (cudaStream_t)stream);
+}
+
+int kfb_split_im2col(const kfb_layer* layer, const void* x, int x_dtype, int64_t batch,
+                     int32_t layout, const kfb_split* dst, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(x != nullptr && dst != nullptr && layout >= 0 && layout <= 2, "split_im2col: bad argument");
+  return split_im2col(*layer, x, x_dtype, batch, layout, *dst, precision, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+"""Tensor-level entry points of the EK-FAC hot path: thin, typed wrappers over the C ABI (include/kfb.h).
+
+Each function takes torch CUDA tensors, passes their device pointers to libkfb on the current stream
+and returns / updates torch tensors.  They are what the tracked-module hooks call, and what the parity
+tests drive directly with the golden fixtures.  No arithmetic happens in Python.
+"""
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from kronfluence_b200 import engine
+from kronfluence_b200.engine import (
+    PREC_BF16,
+    PREC_FP32,
+    PRECOND_DIAGONAL,
+    PRECOND_EIGEN,
+    PRECOND_IDENTITY,
+    KfbLayer,
+    Split,
+    Workspace,
+    check,
+    dtype_code,
+    ptr,
+    stream_ptr,
+)
+
+_WORKSPACES = {}
+
+
+def workspace(device: torch.device) -> Workspace:
+    key = (device.type, device.index)
+    if key not in _WORKSPACES:
+        _WORKSPACES[key] = Workspace(device)
+    return _WORKSPACES[key]
+
+
+def release_workspaces() -> None:
+    for ws in _WORKSPACES.values():
+        ws.release()
+
+
+def layer_of(module: nn.Module, input_shape: Optional[Tuple[int, ...]] = None) -> KfbLayer:
+    """Geometry of an nn.Linear / nn.Conv2d as the C ABI wants it (include/kfb.h kfb_layer)."""
+    if isinstance(module, nn.Linear):
+        return KfbLayer(kind=engine.LINEAR, d_in=module.in_features, d_out=module.out_features,
+                        has_bias=int(module.bias is not None))
+    if isinstance(module, nn.Conv2d):
+        if input_shape is None:
+            raise ValueError("Conv2d geometry needs the input shape")
+        if module.padding_mode != "zeros":
+            raise ValueError("only zero padding is supported for Conv2d")
+        k_h, k_w = module.kernel_size
+        s_h, s_w = module.stride
+        d_h, d_w = module.dilation
+        padding = module.padding
+        if isinstance(padding, str):
+            # module/conv2d.py:46-53: string paddings must resolve to symmetric integers
+            if padding == "valid":
+                padding = (0, 0)
+            else:
+                total = (d_h * (k_h - 1), d_w * (k_w - 1))
+                if total[0] % 2 or total[1] % 2:
+                    raise ValueError("Unequal padding not supported in unfold.")
+                padding = (total[0] // 2, total[1] // 2)
+        p_h, p_w = padding
+        h_in, w_in = int(input_shape[-2]), int(input_shape[-1])
+        h_out = (h_in + 2 * p_h - d_h * (k_h - 1) - 1) // s_h + 1
+        w_out = (w_in + 2 * p_w - d_w * (k_w - 1) - 1) // s_w + 1
+        return KfbLayer(kind=engine.CONV2D, d_in=(module.in_channels // module.groups) * k_h * k_w,
+                        d_out=module.out_channels, has_bias=int(module.bias is not None),
+                        c_in=module.in_channels, h_in=h_in, w_in=w_in, groups=module.groups, k_h=k_h, k_w=k_w,
+                        stride_h=s_h, stride_w=s_w, pad_h=p_h, pad_w=p_w, dil_h=d_h, dil_w=d_w,
+                        h_out=h_out, w_out=w_out)
+    raise ValueError(f"unsupported module type {type(module)}")
+
+
+def _batch_seq(layer: KfbLayer, x: torch.Tensor) -> Tuple[int, int]:
+    """(batch, positions per example) as the C ABI counts them."""
+    if layer.kind == engine.CONV2D:
+        return x.shape[0], layer.h_out * layer.w_out
+    if x.dim() == 1:
+        return 1, 1
+    batch = x.shape[0]
+    seq = 1
+    for s in x.shape[1:-1]:
+        seq *= s
+    return batch, seq
+
+
+def factor_dims(layer: KfbLayer) -> Tuple[int, int]:
+    return layer.d_in + layer.has_bias, layer.d_out
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage 1: covariance (tracker/factor.py:31-93)
+# --------------------------------------------------------------------------------------------------
+def cov_accum_activation(layer: KfbLayer, x: torch.Tensor, cov: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                         precision: int = PREC_FP32) -> None:
+    lib = engine.load_library()
+    x = _contig(x)
+    batch, seq = _batch_seq(layer, x)
+    mask_f = None
+    if mask is not None:
+        mask_f = _contig(mask.reshape(-1).to(dtype=torch.float32))
+    ws_ptr, ws_size = workspace(x.device).get(lib.kfb_cov_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_cov_accum_activation(ctypes.byref(layer), x.data_ptr(), dtype_code(x.dtype), batch, seq,
+                                       ptr(mask_f), cov.data_ptr(), ws_ptr, ws_size, precision, stream_ptr(x.device)))
+
+
+def cov_accum_gradient(layer: KfbLayer, g: torch.Tensor, cov: torch.Tensor, alpha: float = 1.0,
+                       precision: int = PREC_FP32) -> None:
+    lib = engine.load_library()
+    g = _contig(g)
+    batch, seq = _batch_seq(layer, g)
+    ws_ptr, ws_size = workspace(g.device).get(lib.kfb_cov_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_cov_accum_gradient(ctypes.byref(layer), g.data_ptr(), dtype_code(g.dtype), batch, seq,
+                                     float(alpha), cov.data_ptr(), ws_ptr, ws_size, precision, stream_ptr(g.device)))
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage 2: eigendecomposition (factor/eigen.py:140-224)
+# --------------------------------------------------------------------------------------------------
+def eigh_sym(cov: torch.Tensor, count: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (eigenvalues ascending [d], eigenvectors as columns [d, d]) in fp32 on cov's device."""
+    lib = engine.load_library()
+    cov = _contig(cov.to(dtype=torch.float32))
+    d = cov.shape[0]
+    evals = torch.empty(d, dtype=torch.float32, device=cov.device)
+    evecs = torch.empty(d, d, dtype=torch.float32, device=cov.device)
+    ws_ptr, ws_size = workspace(cov.device).get(lib.kfb_eigh_workspace_bytes(d))
+    check(lib.kfb_eigh_sym(cov.data_ptr(), float(count), d, evals.data_ptr(), evecs.data_ptr(), ws_ptr, ws_size,
+                           stream_ptr(cov.device)))
+    return evals, evecs
+
+
+class EigenOperands:
+    """Q and Q^T of one Kronecker factor in tensor-core operand layout (kfb_eigen_operands)."""
+
+    def __init__(self, q: torch.Tensor, precision: int = PREC_FP32):
+        lib = engine.load_library()
+        q = _contig(q.to(dtype=torch.float32))
+        d = q.shape[0]
+        self.d = d
+        self.q = Split(d, d, 1, device=q.device, precision=precision)
+        self.qt = Split(d, d, 1, device=q.device, precision=precision)
+        sq, sqt = self.q.struct(), self.qt.struct()
+        check(lib.kfb_eigen_operands(q.data_ptr(), d, ctypes.byref(sq), ctypes.byref(sqt), precision,
+                                     stream_ptr(q.device)))
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage 3: Lambda (tracker/factor.py:162-230)
+# --------------------------------------------------------------------------------------------------
+def lambda_accum(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, lam: torch.Tensor,
+                 qa: Optional[EigenOperands] = None, qg: Optional[EigenOperands] = None, scale: float = 1.0,
+                 precision: int = PREC_FP32) -> None:
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    with_eigen = int(qa is not None)
+    sa = qa.qt.struct() if qa is not None else None
+    sg = qg.qt.struct() if qg is not None else None
+    ws_ptr, ws_size = workspace(a.device).get(lib.kfb_lambda_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_lambda_accum(ctypes.byref(layer), a.data_ptr(), dtype_code(a.dtype), g.data_ptr(),
+                               dtype_code(g.dtype), batch, seq, with_eigen,
+                               ctypes.byref(sa) if sa is not None else None,
+                               ctypes.byref(sg) if sg is not None else None, float(scale), lam.data_ptr(),
+                               ws_ptr, ws_size, precision, stream_ptr(a.device)))
+
+
+def lambda_invert(lam: torch.Tensor, n: float, damping: Optional[float]) -> torch.Tensor:
+    """1 / (Lambda / n + damping), factor/config.py:322-339; damping None -> 0.1 * mean(Lambda / n)."""
+    lib = engine.load_library()
+    lam = _contig(lam.to(dtype=torch.float32))
+    out = torch.empty_like(lam)
+    ws_ptr, ws_size = workspace(lam.device).get(256)
+    check(lib.kfb_lambda_invert(lam.data_ptr(), lam.numel(), float(n), -1.0 if damping is None else float(damping),
+                                out.data_ptr(), ws_ptr, ws_size, stream_ptr(lam.device)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage 4: query gradients (tracker/precondition.py:102-123, factor/config.py:341-353)
+# --------------------------------------------------------------------------------------------------
+def make_query_store(layer: KfbLayer, capacity: int, device, precision: int = PREC_FP32) -> Split:
+    """Device storage for `capacity` preconditioned query gradients of one module."""
+    di, do = factor_dims(layer)
+    return Split(do, di, capacity, device=device, precision=precision, zero=True)
+
+
+def precondition(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, store: Split, q_offset: int, mode: int,
+                 qa: Optional[EigenOperands] = None, qg: Optional[EigenOperands] = None,
+                 lambda_inv: Optional[torch.Tensor] = None, scale: float = 1.0,
+                 out_f32: Optional[torch.Tensor] = None, precision: int = PREC_FP32) -> None:
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    structs = [op.struct() if op is not None else None for op in
+               ((qa.q if qa else None), (qa.qt if qa else None), (qg.q if qg else None), (qg.qt if qg else None))]
+    refs = [ctypes.byref(s) if s is not None else None for s in structs]
+    dst = store.struct(0, store.batch)
+    ws_ptr, ws_size = workspace(a.device).get(lib.kfb_precondition_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_precondition(ctypes.byref(layer), a.data_ptr(), dtype_code(a.dtype), g.data_ptr(),
+                               dtype_code(g.dtype), batch, seq, mode, refs[0], refs[1], refs[2], refs[3],
+                               ptr(lambda_inv), float(scale), ctypes.byref(dst), int(q_offset), ptr(out_f32),
+                               ws_ptr, ws_size, precision, stream_ptr(a.device)))
+
+
+# --------------------------------------------------------------------------------------------------
+# Stage 5: pairwise scores (linear.py:79-122, conv2d.py:179-209, score/dot_product.py:105-118)
+# --------------------------------------------------------------------------------------------------
+def pairwise_scores(layer: KfbLayer, store: Split, num_queries: int, a: torch.Tensor, g: torch.Tensor,
+                    scores: torch.Tensor, t_offset: int = 0, accumulate: bool = False, scale: float = 1.0,
+                    precision: int = PREC_FP32) -> None:
+    """scores[:num_queries, t_offset:t_offset+B] (+)= <P_q, per-sample gradient of example t>."""
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    assert scores.dtype == torch.float32 and scores.stride(-1) == 1
+    src = store.struct(0, store.batch)
+    ws_ptr, ws_size = workspace(a.device).get(lib.kfb_pairwise_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_pairwise_scores(ctypes.byref(layer), ctypes.byref(src), int(num_queries), a.data_ptr(),
+                                  dtype_code(a.dtype), g.data_ptr(), dtype_code(g.dtype), batch, seq, float(scale),
+                                  scores.data_ptr(), scores.stride(0), int(t_offset), int(accumulate), ws_ptr,
+                                  ws_size, precision, stream_ptr(a.device)))
+
+
+__all__ = [
+    "PREC_FP32", "PREC_BF16", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
+    "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
+    "make_query_store", "precondition", "pairwise_scores", "layer_of", "factor_dims", "workspace",
+]
+
+
+def load_query_store(store: Split, p: torch.Tensor, q_offset: int = 0, precision: int = PREC_FP32) -> None:
+    """Writes fp32 preconditioned gradients [q, d_out, d_in(+1)] into the operand store at q_offset."""
+    lib = engine.load_library()
+    p = _contig(p)
+    q, rows, cols = p.shape
+    assert rows == store.rows and cols == store.cols and q_offset + q <= store.batch
+    desc = (ctypes.c_int64 * 9)(rows * cols, cols, 0, 1, rows, 1, cols, 0, 0)
+    dst = store.struct(q_offset, q)
+    check(lib.kfb_split_gather(p.data_ptr(), dtype_code(p.dtype), desc, None, ctypes.byref(dst), precision,
+                               stream_ptr(p.device)))

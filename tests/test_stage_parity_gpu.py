@@ -1,0 +1,192 @@
+"""Stage-by-stage parity of the CUDA path (through the C ABI) with the reference's own outputs
+(tests/golden/stage_*.npz) and with the numpy oracle on larger seeded problems.
+
+Tolerances (relative Frobenius norm, stated per stage):
+  covariance 2e-5, Lambda 5e-5, Lambda^-1 1e-6, preconditioned gradient 1e-4, pairwise scores 1e-4
+against the reference's float64 path; the reference's own float32 path sits 1e-6..1e-5 away from it.
+"""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ekfac_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[len("stage_"):-4] for p in glob.glob(os.path.join(GOLDEN, "stage_*.npz")))
+
+
+def rel(a, b):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def cuda(x, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(x), dtype=dtype).cuda()
+
+
+def setup_case(case):
+    from kronfluence_b200 import engine, ops
+
+    engine.require_device()
+    g = dict(np.load(os.path.join(GOLDEN, f"stage_{case}.npz")))
+    if "conv_geometry" in g:
+        c_in, c_out, k1, k2, s1, s2, p1, p2, d1, d2, groups, bias = [int(v) for v in g["conv_geometry"]]
+        module = torch.nn.Conv2d(c_in, c_out, (k1, k2), stride=(s1, s2), padding=(p1, p2), dilation=(d1, d2),
+                                 groups=groups, bias=bool(bias))
+    else:
+        d_in, d_out, bias = [int(v) for v in g["linear_geometry"]]
+        module = torch.nn.Linear(d_in, d_out, bias=bool(bias))
+    layer = ops.layer_of(module, g["x_train"].shape)
+    return ops, g, layer
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_covariance(case):
+    ops, g, layer = setup_case(case)
+    di, do = ops.factor_dims(layer)
+    cov_a = torch.zeros(di, di, device="cuda")
+    cov_g = torch.zeros(do, do, device="cuda")
+    x, grad = cuda(g["x_train"]), cuda(g["g_train"])
+    mask = cuda(g["mask"]) if "mask" in g else None
+    for _ in range(2):
+        ops.cov_accum_activation(layer, x, cov_a, mask)
+        ops.cov_accum_gradient(layer, grad, cov_g)
+    torch.cuda.synchronize()
+    assert rel(cov_a, g["cov_a"]) < 2e-5
+    assert rel(cov_g, g["cov_g"]) < 2e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_eigendecomposition(case):
+    ops, g, _ = setup_case(case)
+    for side, num in (("activation", "num_a"), ("gradient", "num_g")):
+        cov = g["cov_a" if side == "activation" else "cov_g"]
+        evals, evecs = ops.eigh_sym(cuda(cov), float(g[num]))
+        torch.cuda.synchronize()
+        ref = g[f"{side}_eigenvalues"]
+        e = evals.double().cpu().numpy()
+        q = evecs.double().cpu().numpy()
+        assert np.all(np.diff(e) >= -1e-6 * abs(ref).max())          # ascending like torch.linalg.eigh
+        assert np.abs(e - ref).max() < 2e-6 * abs(ref).max()
+        sym = 0.5 * (cov / g[num] + (cov / g[num]).T)
+        assert rel(q @ np.diag(e) @ q.T, sym) < 5e-6                  # basis-invariant residual
+        assert np.abs(q.T @ q - np.eye(len(e))).max() < 5e-6         # orthonormal columns
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_lambda_precondition_scores(case):
+    ops, g, layer = setup_case(case)
+    di, do = ops.factor_dims(layer)
+    x, grad = cuda(g["x_train"]), cuda(g["g_train"])
+    xq, gq = cuda(g["x_query"]), cuda(g["g_query"])
+    qa = ops.EigenOperands(cuda(g["activation_eigenvectors"]))
+    qg = ops.EigenOperands(cuda(g["gradient_eigenvectors"]))
+
+    lam = torch.zeros(do, di, device="cuda")
+    for _ in range(2):
+        ops.lambda_accum(layer, x, grad, lam, qa, qg)
+    torch.cuda.synchronize()
+    assert rel(lam, g["lambda"]) < 5e-5
+
+    lam_inv = ops.lambda_invert(cuda(g["lambda"]), float(g["num_lambda"]), float(g["damping"]))
+    assert rel(lam_inv, g["lambda_inv"]) < 1e-6
+
+    nq = xq.shape[0]
+    store = ops.make_query_store(layer, nq + 2, "cuda")
+    p32 = torch.empty(nq, do, di, device="cuda")
+    ops.precondition(layer, xq, gq, store, 1, ops.PRECOND_EIGEN, qa, qg, cuda(g["lambda_inv"]), out_f32=p32)
+    torch.cuda.synchronize()
+    assert rel(p32, g["p"]) < 1e-4
+    assert rel(store.to_float()[1 : 1 + nq], g["p"]) < 1e-4
+
+    # pairwise from OUR preconditioned gradients ...
+    n_train = x.shape[0]
+    scores = torch.zeros(nq + 2, n_train + 3, device="cuda")
+    ops.pairwise_scores(layer, store, nq + 2, x, grad, scores, t_offset=2)
+    torch.cuda.synchronize()
+    assert rel(scores[1 : 1 + nq, 2 : 2 + n_train], g["scores"]) < 1e-4
+    assert rel(scores[1 : 1 + nq, 2 : 2 + n_train], g["scores_f32"]) < 1e-4
+    assert (scores[:, :2] == 0).all() and (scores[:, 2 + n_train :] == 0).all() and (scores[0] == 0).all()
+    # ... and in isolation from the reference's own P, accumulating on top of existing values
+    ops.load_query_store(store, cuda(g["p"]), 1)
+    ops.pairwise_scores(layer, store, nq + 2, x, grad, scores, t_offset=2, accumulate=True, scale=2.0)
+    torch.cuda.synchronize()
+    assert rel(scores[1 : 1 + nq, 2 : 2 + n_train], 3.0 * g["scores"]) < 1e-4
+
+
+def test_diagonal_and_identity_modes():
+    ops, g, layer = setup_case("linear3d_nobias")
+    di, do = ops.factor_dims(layer)
+    x, grad = cuda(g["x_train"]), cuda(g["g_train"])
+    lam = torch.zeros(do, di, device="cuda")
+    ops.lambda_accum(layer, x, grad, lam, None, None, scale=0.5)
+    torch.cuda.synchronize()
+    want = 0.25 * orc.lambda_update(None, g["psg_train"])
+    assert rel(lam, want) < 5e-5
+    xq, gq = cuda(g["x_query"]), cuda(g["g_query"])
+    nq = xq.shape[0]
+    store = ops.make_query_store(layer, nq, "cuda")
+    inv = torch.rand(do, di, device="cuda") + 0.5
+    ops.precondition(layer, xq, gq, store, 0, ops.PRECOND_DIAGONAL, lambda_inv=inv, scale=3.0)
+    torch.cuda.synchronize()
+    assert rel(store.to_float(), 3.0 * g["psg_query"] * inv.double().cpu().numpy()) < 2e-5
+    ops.precondition(layer, xq, gq, store, 0, ops.PRECOND_IDENTITY)
+    torch.cuda.synchronize()
+    assert rel(store.to_float(), g["psg_query"]) < 2e-5
+
+
+LARGE = [
+    # (d_in, d_out, bias, T, Q, S)
+    (300, 200, True, 500, 70, 1),
+    (1030, 520, True, 260, 33, 1),
+    (96, 130, False, 40, 9, 50),
+    (257, 64, True, 12, 5, 300),
+]
+
+
+@pytest.mark.parametrize("cfg", LARGE)
+def test_linear_layer_against_oracle(cfg):
+    """Whole layer (covariance -> Lambda -> precondition -> scores) at sizes with ragged tiles,
+    several k-blocks and k-chunks, checked against the float64 oracle with the oracle's eigenvectors
+    injected (eigenbases are only unique up to sign/rotation: SURVEY.md 'Hard parts')."""
+    from kronfluence_b200 import engine, ops
+
+    engine.require_device()
+    d_in, d_out, bias, T, Q, S = cfg
+    rng = np.random.default_rng(7)
+    shape = (T, d_in) if S == 1 else (T, S, d_in)
+    a_tr = np.maximum(rng.standard_normal(shape), 0.0)
+    g_tr = rng.standard_normal(shape[:-1] + (d_out,)) / np.sqrt(d_out)
+    a_q = np.maximum(rng.standard_normal((Q,) + shape[1:]), 0.0)
+    g_q = rng.standard_normal((Q,) + shape[1:-1] + (d_out,)) / np.sqrt(d_out)
+    ref = orc.linear_ekfac_layer(a_tr, g_tr, a_q, g_q, bias, damping=1e-6)
+
+    layer = ops.layer_of(torch.nn.Linear(d_in, d_out, bias=bias))
+    di, do = ops.factor_dims(layer)
+    x, grad, xq, gq = cuda(a_tr), cuda(g_tr), cuda(a_q), cuda(g_q)
+    cov_a = torch.zeros(di, di, device="cuda")
+    cov_g = torch.zeros(do, do, device="cuda")
+    ops.cov_accum_activation(layer, x, cov_a)
+    ops.cov_accum_gradient(layer, grad, cov_g)
+    torch.cuda.synchronize()
+    assert rel(cov_a, ref["cov_a"]) < 2e-5
+    assert rel(cov_g, ref["cov_g"]) < 2e-5
+    qa, qg = ops.EigenOperands(cuda(ref["q_a"])), ops.EigenOperands(cuda(ref["q_g"]))
+    lam = torch.zeros(do, di, device="cuda")
+    ops.lambda_accum(layer, x, grad, lam, qa, qg)
+    torch.cuda.synchronize()
+    assert rel(lam, ref["lambda"]) < 5e-5
+    store = ops.make_query_store(layer, Q, "cuda")
+    ops.precondition(layer, xq, gq, store, 0, ops.PRECOND_EIGEN, qa, qg, cuda(ref["lambda_inv"]))
+    scores = torch.empty(Q, T, device="cuda")
+    ops.pairwise_scores(layer, store, Q, x, grad, scores)
+    torch.cuda.synchronize()
+    assert rel(store.to_float(), ref["p"]) < 1e-4
+    assert rel(scores, ref["scores"]) < 1e-4
