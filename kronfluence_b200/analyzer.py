@@ -1,0 +1,741 @@
+"""`prepare_model` and `Analyzer`: the public facade, call-compatible with kronfluence's
+(analyzer.py:20-195, computer/factor_computer.py:159-701, computer/score_computer.py:218-464 of the
+reference) for the EK-FAC hot path: fit_all_factors / fit_covariance_matrices /
+perform_eigendecomposition / fit_lambda_matrices / compute_pairwise_scores and their load_* twins.
+
+What stays Python: the data loaders, the model's forward/backward, the module hooks, file IO.
+What does not: every contraction behind the hooks (libkfb, see kronfluence_b200/ops.py).  Differences in
+execution model that follow from that, all invisible in the results:
+  * factors and scores stay on the device for a whole stage; there is one device->host copy at the end
+    of a stage instead of one per module per batch (score/dot_product.py:105-118 of the reference);
+  * query gradients are appended to a preallocated operand store instead of torch.cat'ed;
+  * the model is not wrapped in DDP (nothing to all-reduce: parameters are frozen); ranks exchange one
+    flat all-reduce of the factor sums, one all-gather of query gradients per query batch and one
+    gather of score columns per query chunk, over NCCL.
+"""
+
+import logging
+import math
+import time
+from pathlib import Path
+from typing import Any, Callable, Dict, List, Optional, Sequence, Union
+
+import torch
+import torch.distributed as dist
+from torch import nn
+from torch.utils import data
+
+from kronfluence_b200 import ops
+from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+from kronfluence_b200.module.tracked_module import ModuleMode, TrackedModule, strategy_config
+from kronfluence_b200.module.utils import (
+    collect_factors,
+    finalize_iteration,
+    get_tracked_module_names,
+    make_modules_partition,
+    set_attention_mask,
+    set_factors,
+    set_gradient_scale,
+    set_mode,
+    tracked_modules,
+    update_factor_args,
+    update_score_args,
+    wrap_tracked_modules,
+)
+from kronfluence_b200.task import Task
+from kronfluence_b200.utils import save as io
+from kronfluence_b200.utils.constants import (
+    ACTIVATION_COVARIANCE_MATRIX_NAME,
+    ACTIVATION_EIGENVALUES_NAME,
+    ACTIVATION_EIGENVECTORS_NAME,
+    ALL_MODULE_NAME,
+    COVARIANCE_FACTOR_NAMES,
+    EIGENDECOMPOSITION_FACTOR_NAMES,
+    FACTOR_ARGUMENTS_NAME,
+    FACTOR_SAVE_PREFIX,
+    GRADIENT_COVARIANCE_MATRIX_NAME,
+    GRADIENT_EIGENVALUES_NAME,
+    GRADIENT_EIGENVECTORS_NAME,
+    LAMBDA_FACTOR_NAMES,
+    LAMBDA_MATRIX_NAME,
+    NUM_ACTIVATION_COVARIANCE_PROCESSED,
+    NUM_GRADIENT_COVARIANCE_PROCESSED,
+    NUM_LAMBDA_PROCESSED,
+    PAIRWISE_SCORE_MATRIX_NAME,
+    SCORE_ARGUMENTS_NAME,
+    SCORE_SAVE_PREFIX,
+)
+from kronfluence_b200.utils.dataset import (
+    DataLoaderKwargs,
+    DistributedEvalSampler,
+    DistributedQuerySampler,
+    DistributedSamplerWithStack,
+    find_executable_batch_size,
+    make_indices_partition,
+)
+from kronfluence_b200.utils.exceptions import FactorsNotFoundError
+from kronfluence_b200.utils.state import State, release_memory
+
+FACTOR_TYPE = Dict[str, Dict[str, torch.Tensor]]
+
+
+def prepare_model(model: nn.Module, task: Task) -> nn.Module:
+    """eval mode, every parameter and buffer frozen, supported leaves wrapped in place
+    (analyzer.py:20-45 of the reference).  Call before DDP / torch.compile."""
+    model.eval()
+    for params in model.parameters():
+        params.requires_grad = False
+    for buffers in model.buffers():
+        buffers.requires_grad = False
+    return wrap_tracked_modules(model=model, task=task)
+
+
+def _send_to_device(batch: Any, device: torch.device) -> Any:
+    if isinstance(batch, torch.Tensor):
+        return batch.to(device, non_blocking=True)
+    if isinstance(batch, (list, tuple)):
+        return type(batch)(_send_to_device(b, device) for b in batch)
+    if isinstance(batch, dict):
+        return {k: _send_to_device(v, device) for k, v in batch.items()}
+    return batch
+
+
+def _find_batch_size(batch: Any) -> Optional[int]:
+    if isinstance(batch, torch.Tensor):
+        return batch.shape[0]
+    if isinstance(batch, (list, tuple)):
+        for item in batch:
+            size = _find_batch_size(item)
+            if size is not None:
+                return size
+    if isinstance(batch, dict):
+        for item in batch.values():
+            size = _find_batch_size(item)
+            if size is not None:
+                return size
+    return None
+
+
+class Profiler:
+    """Wall-clock per named action, synchronised on the device (utils/logger.py:57-154 of the reference)."""
+
+    def __init__(self, state: State, enabled: bool) -> None:
+        self.state, self.enabled = state, enabled
+        self.durations: Dict[str, List[float]] = {}
+
+    class _Span:
+        def __init__(self, prof: "Profiler", name: str) -> None:
+            self.prof, self.name = prof, name
+
+        def __enter__(self):
+            if self.prof.enabled and self.prof.state.device.type == "cuda":
+                torch.cuda.synchronize(self.prof.state.device)
+            self.start = time.monotonic()
+            return self
+
+        def __exit__(self, *exc):
+            if self.prof.enabled and self.prof.state.device.type == "cuda":
+                torch.cuda.synchronize(self.prof.state.device)
+            self.prof.durations.setdefault(self.name, []).append(time.monotonic() - self.start)
+            return False
+
+    def profile(self, name: str) -> "Profiler._Span":
+        return Profiler._Span(self, name)
+
+    def summary(self) -> str:
+        lines = ["Action | Total time (s) | Calls"]
+        for name, values in sorted(self.durations.items(), key=lambda kv: -sum(kv[1])):
+            lines.append(f"{name} | {sum(values):.4f} | {len(values)}")
+        return "\n".join(lines)
+
+
+class Analyzer:
+    """Fits EK-FAC factors and computes pairwise influence scores for a prepared model."""
+
+    def __init__(self, analysis_name: str, model: nn.Module, task: Task, cpu: bool = False,
+                 log_level: Optional[int] = None, log_main_process_only: bool = True, profile: bool = False,
+                 disable_tqdm: bool = False, output_dir: str = "./influence_results",
+                 disable_model_save: bool = True) -> None:
+        del log_main_process_only, disable_model_save
+        get_tracked_module_names(model)  # raises TrackedModuleNotFoundError if prepare_model was skipped
+        self.state = State(cpu=cpu)
+        if self.state.device.type != "cuda" and ops.BACKEND == "cuda":
+            raise RuntimeError(
+                "kronfluence_b200 computes factors and scores with sm_100a CUDA kernels only; there is no CPU "
+                "path (cpu=True / no visible GPU is not supported).")
+        self.model = model
+        self.task = task
+        self.logger = logging.getLogger("kronfluence_b200")
+        if log_level is not None:
+            self.logger.setLevel(log_level)
+        self.disable_tqdm = disable_tqdm
+        self.model.to(self.state.device)
+        self.output_dir = Path(output_dir).joinpath(analysis_name).resolve()
+        if self.state.is_main_process:
+            self.output_dir.mkdir(parents=True, exist_ok=True)
+        self.profiler = Profiler(self.state, profile)
+        self._dataloader_params = DataLoaderKwargs()
+
+    # ------------------------------------------------------------------------------------------
+    # small helpers
+    # ------------------------------------------------------------------------------------------
+    def set_dataloader_kwargs(self, dataloader_kwargs: DataLoaderKwargs) -> None:
+        self._dataloader_params = dataloader_kwargs
+
+    def factors_output_dir(self, factors_name: str) -> Path:
+        return (self.output_dir / (FACTOR_SAVE_PREFIX + factors_name)).resolve()
+
+    def scores_output_dir(self, scores_name: str) -> Path:
+        return (self.output_dir / (SCORE_SAVE_PREFIX + scores_name)).resolve()
+
+    def _save_arguments(self, name: str, args: Optional[Any], out_dir: Path, overwrite: bool) -> None:
+        """JSON-saves the arguments; refuses to reuse a directory created with different ones
+        (computer/computer.py:135-163 of the reference)."""
+        path = out_dir / f"{name}_arguments.json"
+        current = None if args is None else args.to_dict()
+        if path.exists() and not overwrite:
+            if io.load_json(path) != current:
+                raise ValueError(f"Attempting to use arguments that differ from the ones saved at `{path}`. "
+                                 "Use a different name or set `overwrite_output_dir=True`.")
+        elif self.state.is_main_process:
+            io.save_json(current, path)
+        self.state.wait_for_everyone()
+
+    def _save_dataset_metadata(self, dataset_name: str, dataset: data.Dataset, out_dir: Path,
+                               indices: Optional[Sequence[int]], overwrite: bool) -> None:
+        """Records which dataset a directory was computed on and refuses silent reuse with another one
+        (computer/computer.py:165-191 of the reference; same file name and fields)."""
+        path = out_dir / f"{dataset_name}_dataset_metadata.json"
+        meta = {"type": type(dataset).__name__, "dataset_size": len(dataset),
+                "indices": None if indices is None else list(indices)}
+        if path.exists() and not overwrite:
+            if io.load_json(path) != meta:
+                raise ValueError("Attempting to use the dataset that differs from the one already saved. "
+                                 f"Please set `overwrite_output_dir=True`.\nNew metadata: {meta}.")
+        elif self.state.is_main_process:
+            io.save_json(meta, path)
+        self.state.wait_for_everyone()
+
+    def _load_factor_args(self, factors_name: str) -> FactorArguments:
+        path = self.factors_output_dir(factors_name) / f"{FACTOR_ARGUMENTS_NAME}_arguments.json"
+        if not path.exists():
+            raise FactorsNotFoundError(f"Factors with name `{factors_name}` not found at `{path.parent}`.")
+        return FactorArguments(**io.load_json(path))
+
+    def _loader(self, dataset: data.Dataset, batch_size: int, indices: Optional[Sequence[int]], kind: str,
+                dataloader_kwargs: Optional[DataLoaderKwargs]) -> data.DataLoader:
+        """kind: 'eval' (strided, unpadded), 'stack' (contiguous chunks, padded), 'query' (strided, padded)."""
+        if indices is not None:
+            dataset = data.Subset(dataset, list(indices))
+        sampler: Optional[data.Sampler] = None
+        if self.state.use_distributed:
+            cls = {"eval": DistributedEvalSampler, "stack": DistributedSamplerWithStack,
+                   "query": DistributedQuerySampler}[kind]
+            sampler = cls(dataset, self.state.num_processes, self.state.process_index)
+        params = (dataloader_kwargs or self._dataloader_params).to_kwargs()
+        return data.DataLoader(dataset, batch_size=batch_size, sampler=sampler, shuffle=False, drop_last=False, **params)
+
+    def _amp(self, amp_dtype: Optional[torch.dtype], amp_scale: float):
+        enable_amp = amp_dtype is not None
+        scaler = torch.amp.GradScaler(self.state.device.type, init_scale=amp_scale,
+                                      enabled=enable_amp and amp_dtype == torch.float16)
+        if scaler.is_enabled():
+            set_gradient_scale(self.model, 1.0 / scaler.get_scale())
+        autocast = lambda: torch.autocast(device_type=self.state.device.type, enabled=enable_amp, dtype=amp_dtype)  # noqa: E731
+        return scaler, autocast
+
+    def _all_reduce_factors(self, factor_names: List[str], module_names: List[str]) -> None:
+        """ONE NCCL all-reduce for every module's sums and ONE for the counts (the reference reduces each
+        tensor separately, tracker/factor.py:132-142,311-321)."""
+        if not self.state.use_distributed:
+            return
+        floats, ints = [], []
+        for module in tracked_modules(self.model, module_names):
+            for name in factor_names:
+                value = module.storage[name]
+                if value is None:
+                    continue
+                if value.device != self.state.device:
+                    value = value.to(self.state.device)
+                    module.storage[name] = value
+                (floats if value.is_floating_point() else ints).append(value)
+        for group in (floats, ints):
+            if not group:
+                continue
+            flat = torch.cat([t.reshape(-1) for t in group])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            offset = 0
+            for t in group:
+                t.copy_(flat[offset : offset + t.numel()].view_as(t))
+                offset += t.numel()
+
+    def _fit_loop(self, loader: data.DataLoader, mode: ModuleMode, module_names: List[str],
+                  factor_args: FactorArguments, desc: str) -> torch.Tensor:
+        """One pass over `loader` with the trackers of `mode` live: forward, (sampled) loss, backward
+        (the loop of factor/covariance.py:205-236 and factor/eigen.py:404-433 of the reference)."""
+        del desc
+        scaler, autocast = self._amp(factor_args.amp_dtype, factor_args.amp_scale)
+        num_processed = torch.zeros(1, dtype=torch.int64)
+        for batch in loader:
+            batch = _send_to_device(batch, self.state.device)
+            set_attention_mask(self.model, self.task.get_attention_mask(batch))
+            self.model.zero_grad(set_to_none=True)
+            with autocast():
+                loss = self.task.compute_train_loss(batch=batch, model=self.model,
+                                                    sample=not factor_args.use_empirical_fisher)
+            scaler.scale(loss).backward()
+            if factor_args.has_shared_parameters:
+                finalize_iteration(self.model, module_names)
+            num_processed += _find_batch_size(batch)
+            del loss
+        self.model.zero_grad(set_to_none=True)
+        set_attention_mask(self.model, None)
+        if scaler.is_enabled():
+            set_gradient_scale(self.model, 1.0)
+        if self.state.use_distributed:
+            count = num_processed.to(self.state.device)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM)
+            num_processed = count.cpu()
+        return num_processed
+
+    def _resolve_batch_size(self, run: Callable[[int], Any], per_device_batch_size: Optional[int],
+                            initial_attempt: int, total: int) -> int:
+        if per_device_batch_size is not None:
+            return per_device_batch_size
+        if self.state.use_distributed:
+            raise ValueError("`per_device_batch_size` must be given when running on several GPUs "
+                             "(automatic search is single-device, factor_computer.py:120-126 of the reference).")
+        return find_executable_batch_size(run, min(initial_attempt, total))
+
+    # ------------------------------------------------------------------------------------------
+    # Stage 1: covariance matrices
+    # ------------------------------------------------------------------------------------------
+    def fit_covariance_matrices(self, factors_name: str, dataset: data.Dataset,
+                                per_device_batch_size: Optional[int] = None,
+                                initial_per_device_batch_size_attempt: int = 4096,
+                                dataloader_kwargs: Optional[DataLoaderKwargs] = None,
+                                factor_args: Optional[FactorArguments] = None,
+                                target_data_partitions: Optional[Union[Sequence[int], int]] = None,
+                                target_module_partitions: Optional[Union[Sequence[int], int]] = None,
+                                overwrite_output_dir: bool = False) -> None:
+        del target_data_partitions, target_module_partitions
+        factor_args = FactorArguments() if factor_args is None else factor_args
+        out_dir = self.factors_output_dir(factors_name)
+        if self.state.is_main_process:
+            out_dir.mkdir(parents=True, exist_ok=True)
+        self.state.wait_for_everyone()
+        self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
+        if not strategy_config(factor_args.strategy)["covariance"]:
+            return
+        if io.factors_exist(out_dir, COVARIANCE_FACTOR_NAMES) and not overwrite_output_dir:
+            return
+        self._save_dataset_metadata("covariance", dataset, out_dir, None, overwrite_output_dir)
+        update_factor_args(self.model, factor_args)
+        total = len(dataset) if factor_args.covariance_max_examples is None else min(
+            factor_args.covariance_max_examples, len(dataset))
+        all_names = get_tracked_module_names(self.model)
+        data_parts = make_indices_partition(total, factor_args.covariance_data_partitions)
+        module_parts = make_modules_partition(all_names, factor_args.covariance_module_partitions)
+
+        merged: FACTOR_TYPE = {name: {} for name in COVARIANCE_FACTOR_NAMES}
+        with self.profiler.profile("Fit Covariance"):
+            for start, end in data_parts:
+                for names in module_parts:
+                    def run(batch_size: int) -> torch.Tensor:
+                        set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                        set_mode(self.model, ModuleMode.COVARIANCE, names, release_memory=True)
+                        loader = self._loader(dataset, batch_size, range(start, end), "eval", dataloader_kwargs)
+                        return self._fit_loop(loader, ModuleMode.COVARIANCE, names, factor_args, "covariance")
+
+                    batch_size = self._resolve_batch_size(run, per_device_batch_size,
+                                                          initial_per_device_batch_size_attempt, end - start)
+                    if per_device_batch_size is not None:
+                        run(batch_size)
+                    self._all_reduce_factors(COVARIANCE_FACTOR_NAMES, names)
+                    for fname in COVARIANCE_FACTOR_NAMES:
+                        dtype = None
+                        if fname == ACTIVATION_COVARIANCE_MATRIX_NAME:
+                            dtype = factor_args.activation_covariance_dtype
+                        elif fname == GRADIENT_COVARIANCE_MATRIX_NAME:
+                            dtype = factor_args.gradient_covariance_dtype
+                        part = collect_factors(self.model, fname, names, cpu=True, dtype=dtype)
+                        for mname, tensor in part.items():
+                            merged[fname][mname] = tensor if mname not in merged[fname] else merged[fname][mname] + tensor
+                    set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+        with self.profiler.profile("Save Covariance"):
+            if self.state.is_main_process:
+                io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
+            self.state.wait_for_everyone()
+
+    def load_covariance_matrices(self, factors_name: str) -> Optional[FACTOR_TYPE]:
+        out_dir = self.factors_output_dir(factors_name)
+        if not io.factors_exist(out_dir, COVARIANCE_FACTOR_NAMES):
+            return None
+        return io.load_factors(out_dir, COVARIANCE_FACTOR_NAMES)
+
+    # ------------------------------------------------------------------------------------------
+    # Stage 2: eigendecomposition
+    # ------------------------------------------------------------------------------------------
+    def perform_eigendecomposition(self, factors_name: str, factor_args: Optional[FactorArguments] = None,
+                                   overwrite_output_dir: bool = False,
+                                   load_from_factors_name: Optional[str] = None) -> None:
+        factor_args = FactorArguments() if factor_args is None else factor_args
+        out_dir = self.factors_output_dir(factors_name)
+        if self.state.is_main_process:
+            out_dir.mkdir(parents=True, exist_ok=True)
+        self.state.wait_for_everyone()
+        self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
+        if not strategy_config(factor_args.strategy)["eigen"]:
+            return
+        if io.factors_exist(out_dir, EIGENDECOMPOSITION_FACTOR_NAMES) and not overwrite_output_dir:
+            return
+        source = factors_name if load_from_factors_name is None else load_from_factors_name
+        with self.profiler.profile("Load Covariance"):
+            covariance = self.load_covariance_matrices(source)
+        if covariance is None:
+            raise FactorsNotFoundError(f"Covariance matrices not found at `{self.factors_output_dir(source)}`. "
+                                       "To perform eigendecomposition, covariance matrices need to be fitted first.")
+        eigen: FACTOR_TYPE = {name: {} for name in EIGENDECOMPOSITION_FACTOR_NAMES}
+        with self.profiler.profile("Perform Eigendecomposition"):
+            if self.state.is_main_process:  # factor_computer.py:449 of the reference
+                for mname in covariance[ACTIVATION_COVARIANCE_MATRIX_NAME]:
+                    for cov_name, num_name, vec_name, val_name in (
+                        (ACTIVATION_COVARIANCE_MATRIX_NAME, NUM_ACTIVATION_COVARIANCE_PROCESSED,
+                         ACTIVATION_EIGENVECTORS_NAME, ACTIVATION_EIGENVALUES_NAME),
+                        (GRADIENT_COVARIANCE_MATRIX_NAME, NUM_GRADIENT_COVARIANCE_PROCESSED,
+                         GRADIENT_EIGENVECTORS_NAME, GRADIENT_EIGENVALUES_NAME),
+                    ):
+                        cov = covariance[cov_name][mname]
+                        count = float(covariance[num_name][mname].item())
+                        evals, evecs = ops.eigh_sym(cov.to(device=self.state.device, dtype=torch.float32), count)
+                        eigen[val_name][mname] = evals.to(dtype=cov.dtype, device="cpu")
+                        eigen[vec_name][mname] = evecs.to(dtype=cov.dtype, device="cpu")
+        with self.profiler.profile("Save Eigendecomposition"):
+            if self.state.is_main_process:
+                io.save_factors(out_dir, eigen, metadata=factor_args.to_str_dict())
+            self.state.wait_for_everyone()
+
+    def load_eigendecomposition(self, factors_name: str) -> Optional[FACTOR_TYPE]:
+        out_dir = self.factors_output_dir(factors_name)
+        if not io.factors_exist(out_dir, EIGENDECOMPOSITION_FACTOR_NAMES):
+            return None
+        return io.load_factors(out_dir, EIGENDECOMPOSITION_FACTOR_NAMES)
+
+    # ------------------------------------------------------------------------------------------
+    # Stage 3: Lambda matrices
+    # ------------------------------------------------------------------------------------------
+    def fit_lambda_matrices(self, factors_name: str, dataset: data.Dataset,
+                            per_device_batch_size: Optional[int] = None,
+                            initial_per_device_batch_size_attempt: int = 4096,
+                            dataloader_kwargs: Optional[DataLoaderKwargs] = None,
+                            factor_args: Optional[FactorArguments] = None,
+                            target_data_partitions: Optional[Union[Sequence[int], int]] = None,
+                            target_module_partitions: Optional[Union[Sequence[int], int]] = None,
+                            overwrite_output_dir: bool = False,
+                            load_from_factors_name: Optional[str] = None) -> None:
+        del target_data_partitions, target_module_partitions
+        factor_args = FactorArguments() if factor_args is None else factor_args
+        out_dir = self.factors_output_dir(factors_name)
+        if self.state.is_main_process:
+            out_dir.mkdir(parents=True, exist_ok=True)
+        self.state.wait_for_everyone()
+        self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
+        config = strategy_config(factor_args.strategy)
+        if not config["lambda_"]:
+            return
+        if io.factors_exist(out_dir, LAMBDA_FACTOR_NAMES) and not overwrite_output_dir:
+            return
+        self._save_dataset_metadata("lambda", dataset, out_dir, None, overwrite_output_dir)
+        update_factor_args(self.model, factor_args)
+        eigen = None
+        if config["lambda_eigen"]:
+            source = factors_name if load_from_factors_name is None else load_from_factors_name
+            with self.profiler.profile("Load Eigendecomposition"):
+                eigen = self.load_eigendecomposition(source)
+            if eigen is None:
+                raise FactorsNotFoundError(
+                    f"Eigendecomposition results not found at `{self.factors_output_dir(source)}`. To fit Lambda "
+                    f"matrices for `{factor_args.strategy}`, eigendecomposition must be performed first.")
+        total = len(dataset) if factor_args.lambda_max_examples is None else min(
+            factor_args.lambda_max_examples, len(dataset))
+        all_names = get_tracked_module_names(self.model)
+        data_parts = make_indices_partition(total, factor_args.lambda_data_partitions)
+        module_parts = make_modules_partition(all_names, factor_args.lambda_module_partitions)
+
+        merged: FACTOR_TYPE = {name: {} for name in LAMBDA_FACTOR_NAMES}
+        with self.profiler.profile("Fit Lambda"):
+            for start, end in data_parts:
+                for names in module_parts:
+                    def run(batch_size: int) -> torch.Tensor:
+                        set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                        if eigen is not None:
+                            for fname in (ACTIVATION_EIGENVECTORS_NAME, GRADIENT_EIGENVECTORS_NAME):
+                                set_factors(self.model, fname, {k: v for k, v in eigen[fname].items() if k in names},
+                                            device=self.state.device)
+                        set_mode(self.model, ModuleMode.LAMBDA, names, release_memory=False)
+                        loader = self._loader(dataset, batch_size, range(start, end), "eval", dataloader_kwargs)
+                        return self._fit_loop(loader, ModuleMode.LAMBDA, names, factor_args, "lambda")
+
+                    batch_size = self._resolve_batch_size(run, per_device_batch_size,
+                                                          initial_per_device_batch_size_attempt, end - start)
+                    if per_device_batch_size is not None:
+                        run(batch_size)
+                    self._all_reduce_factors(LAMBDA_FACTOR_NAMES, names)
+                    for fname in LAMBDA_FACTOR_NAMES:
+                        dtype = factor_args.lambda_dtype if fname == LAMBDA_MATRIX_NAME else None
+                        part = collect_factors(self.model, fname, names, cpu=True, dtype=dtype)
+                        for mname, tensor in part.items():
+                            merged[fname][mname] = tensor if mname not in merged[fname] else merged[fname][mname] + tensor
+                    set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+        with self.profiler.profile("Save Lambda"):
+            if self.state.is_main_process:
+                io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
+            self.state.wait_for_everyone()
+
+    def load_lambda_matrices(self, factors_name: str) -> Optional[FACTOR_TYPE]:
+        out_dir = self.factors_output_dir(factors_name)
+        if not io.factors_exist(out_dir, LAMBDA_FACTOR_NAMES):
+            return None
+        return io.load_factors(out_dir, LAMBDA_FACTOR_NAMES)
+
+    def fit_all_factors(self, factors_name: str, dataset: data.Dataset, per_device_batch_size: Optional[int] = None,
+                        initial_per_device_batch_size_attempt: int = 4096,
+                        dataloader_kwargs: Optional[DataLoaderKwargs] = None,
+                        factor_args: Optional[FactorArguments] = None, overwrite_output_dir: bool = False) -> None:
+        """Covariance -> eigendecomposition -> Lambda (analyzer.py:144-195 of the reference)."""
+        self.fit_covariance_matrices(factors_name, dataset, per_device_batch_size, initial_per_device_batch_size_attempt,
+                                     dataloader_kwargs, factor_args, overwrite_output_dir=overwrite_output_dir)
+        self.perform_eigendecomposition(factors_name, factor_args, overwrite_output_dir=overwrite_output_dir)
+        self.fit_lambda_matrices(factors_name, dataset, per_device_batch_size, initial_per_device_batch_size_attempt,
+                                 dataloader_kwargs, factor_args, overwrite_output_dir=overwrite_output_dir)
+
+    def load_all_factors(self, factors_name: str) -> FACTOR_TYPE:
+        """Every factor the strategy produced (computer/computer.py:387-434 of the reference)."""
+        factor_args = self._load_factor_args(factors_name)
+        config = strategy_config(factor_args.strategy)
+        out: FACTOR_TYPE = {}
+        for needed, loader in ((config["covariance"], self.load_covariance_matrices),
+                               (config["eigen"], self.load_eigendecomposition),
+                               (config["lambda_"], self.load_lambda_matrices)):
+            if needed:
+                part = loader(factors_name)
+                if part is None:
+                    raise FactorsNotFoundError(f"Factors `{factors_name}` are incomplete at "
+                                               f"`{self.factors_output_dir(factors_name)}`.")
+                out.update(part)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # Stage 4+5: pairwise scores
+    # ------------------------------------------------------------------------------------------
+    def _prepare_for_scores(self, factors: FACTOR_TYPE, factor_args: FactorArguments, score_args: ScoreArguments,
+                            names: List[str]) -> None:
+        """`prepare_modules`: eigenvectors to operand layout, Lambda -> (Lambda/n + damping)^-1
+        ({Diagonal,Kfac,Ekfac}.prepare, factor/config.py:193-203,252-271,322-339 of the reference)."""
+        config = strategy_config(factor_args.strategy)
+        device = self.state.device
+        for module in tracked_modules(self.model, names):
+            mname = module.name
+            if config["eigen"]:
+                module.set_factor(ACTIVATION_EIGENVECTORS_NAME, factors[ACTIVATION_EIGENVECTORS_NAME][mname].to(device))
+                module.set_factor(GRADIENT_EIGENVECTORS_NAME, factors[GRADIENT_EIGENVECTORS_NAME][mname].to(device))
+            if factor_args.strategy == "kfac":
+                lam = torch.outer(factors[GRADIENT_EIGENVALUES_NAME][mname].to(device=device, dtype=torch.float32),
+                                  factors[ACTIVATION_EIGENVALUES_NAME][mname].to(device=device, dtype=torch.float32))
+                module.set_factor(LAMBDA_MATRIX_NAME, ops.lambda_invert(lam, 1.0, score_args.damping_factor))
+            elif config["lambda_"]:
+                lam = factors[LAMBDA_MATRIX_NAME][mname].to(device=device, dtype=torch.float32)
+                count = float(factors[NUM_LAMBDA_PROCESSED][mname].item())
+                module.set_factor(LAMBDA_MATRIX_NAME, ops.lambda_invert(lam, count, score_args.damping_factor))
+
+    def _gather_queries(self, names: List[str], base: int, local_batch: int) -> None:
+        """All-gathers this batch's preconditioned query gradients and re-interleaves them to dataset
+        order (tracker/precondition.py:166-201 of the reference).  rank r's j-th local query is global
+        query j*world + r of the batch."""
+        world = self.state.num_processes
+        for module in tracked_modules(self.model, names):
+            store = module.storage["accumulated_preconditioned_gradient"]
+            local = store.storage[:, base : base + local_batch].contiguous()
+            gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(gathered, local)
+            # [world, planes, j, rows, ld] -> [planes, j, world, rows, ld] -> [planes, j*world, rows, ld]
+            inter = gathered.permute(1, 2, 0, 3, 4).reshape(local.shape[0], local_batch * world, *local.shape[2:])
+            store.storage[:, base : base + local_batch * world].copy_(inter)
+            module.query_count = base + local_batch * world
+
+    def _pairwise(self, query_dataset: data.Dataset, train_dataset: data.Dataset, query_bs: int, train_bs: int,
+                  query_indices: Optional[Sequence[int]], train_indices: Optional[Sequence[int]],
+                  factor_args: FactorArguments, score_args: ScoreArguments, names: List[str],
+                  dataloader_kwargs: Optional[DataLoaderKwargs]) -> Dict[str, torch.Tensor]:
+        """compute_pairwise_scores_with_loaders + compute_dot_products_with_loader
+        (score/pairwise.py:133-293, score/dot_product.py:39-153 of the reference)."""
+        device = self.state.device
+        world = self.state.num_processes
+        query_loader = self._loader(query_dataset, query_bs, query_indices, "query", dataloader_kwargs)
+        train_loader = self._loader(train_dataset, train_bs, train_indices, "stack", dataloader_kwargs)
+        n_query = len(query_indices) if query_indices is not None else len(query_dataset)
+        n_train = len(train_indices) if train_indices is not None else len(train_dataset)
+        t_local = len(train_loader.sampler) if self.state.use_distributed else n_train
+        scaler, autocast = self._amp(score_args.amp_dtype, factor_args.amp_scale)
+        steps = score_args.query_gradient_accumulation_steps
+        capacity = query_bs * world * steps
+        modules = tracked_modules(self.model, names)
+        per_module = score_args.compute_per_module_scores
+        out_chunks: Dict[str, List[torch.Tensor]] = {m.name: [] for m in modules} if per_module else {ALL_MODULE_NAME: []}
+
+        def train_sweep(num_queries: int) -> None:
+            set_mode(self.model, ModuleMode.PAIRWISE_SCORE, names, release_memory=False)
+            if per_module:
+                sinks = {m.name: torch.zeros(num_queries, t_local, dtype=torch.float32, device=device) for m in modules}
+            else:
+                shared = torch.zeros(num_queries, t_local, dtype=torch.float32, device=device)
+                sinks = {m.name: shared for m in modules}
+            for module in modules:
+                module.storage[PAIRWISE_SCORE_MATRIX_NAME] = sinks[module.name]
+            offset = 0
+            for batch in train_loader:
+                batch = _send_to_device(batch, device)
+                for module in modules:
+                    module.score_offset = offset
+                self.model.zero_grad(set_to_none=True)
+                with autocast():
+                    loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
+                scaler.scale(loss).backward()
+                if factor_args.has_shared_parameters:
+                    finalize_iteration(self.model, names)
+                offset += _find_batch_size(batch)
+                del loss
+            self.model.zero_grad(set_to_none=True)
+            results = {m.name: sinks[m.name] for m in modules} if per_module else {ALL_MODULE_NAME: shared}
+            for key, local_scores in results.items():
+                if self.state.use_distributed:
+                    gathered = [torch.empty_like(local_scores) for _ in range(world)] if self.state.is_main_process else None
+                    dist.gather(local_scores, gathered, dst=0)
+                    if self.state.is_main_process:
+                        local_scores = torch.cat(gathered, dim=1)[:, :n_train]
+                out_chunks[key].append(local_scores.to(dtype=score_args.score_dtype, device="cpu"))
+            for module in modules:
+                module.storage[PAIRWISE_SCORE_MATRIX_NAME] = None
+            set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
+
+        set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
+        for module in modules:
+            module.allocate_query_store(capacity, device)
+        remaining = n_query
+        step = 0
+        for batch in query_loader:
+            batch = _send_to_device(batch, device)
+            base = modules[0].query_count
+            self.model.zero_grad(set_to_none=True)
+            with autocast():
+                measurement = self.task.compute_measurement(batch=batch, model=self.model)
+            scaler.scale(measurement).backward()
+            if factor_args.has_shared_parameters:
+                finalize_iteration(self.model, names)
+            del measurement
+            local_batch = _find_batch_size(batch)
+            if self.state.use_distributed:
+                self._gather_queries(names, base, local_batch)
+            # drop the wrap-padded duplicates of the last, ragged batch (score/pairwise.py:244-246)
+            valid = min(local_batch * world, remaining)
+            for module in modules:
+                module.query_count = base + valid
+            remaining -= valid
+            step += 1
+            if step % steps == 0 or remaining == 0:
+                train_sweep(modules[0].query_count)
+                for module in modules:
+                    module.query_count = 0
+            if remaining == 0:
+                break
+        self.model.zero_grad(set_to_none=True)
+        set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+        if scaler.is_enabled():
+            set_gradient_scale(self.model, 1.0)
+        return {key: torch.cat(chunks, dim=0) for key, chunks in out_chunks.items() if chunks}
+
+    def compute_pairwise_scores(self, scores_name: str, factors_name: str, query_dataset: data.Dataset,
+                                train_dataset: data.Dataset, per_device_query_batch_size: int,
+                                per_device_train_batch_size: Optional[int] = None,
+                                initial_per_device_train_batch_size_attempt: int = 4096,
+                                query_indices: Optional[Sequence[int]] = None,
+                                train_indices: Optional[Sequence[int]] = None,
+                                dataloader_kwargs: Optional[DataLoaderKwargs] = None,
+                                score_args: Optional[ScoreArguments] = None,
+                                target_data_partitions: Optional[Union[Sequence[int], int]] = None,
+                                target_module_partitions: Optional[Union[Sequence[int], int]] = None,
+                                overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
+        del target_data_partitions, target_module_partitions
+        score_args = ScoreArguments() if score_args is None else score_args
+        for flag in ("compute_per_token_scores", "aggregate_query_gradients", "aggregate_train_gradients"):
+            if getattr(score_args, flag):
+                raise NotImplementedError(f"`{flag}` is not part of the B200 hot path yet (SURVEY.md §8f).")
+        if score_args.query_gradient_low_rank is not None:
+            raise NotImplementedError("Low-rank query batching is not part of the B200 hot path yet (SURVEY.md §8f).")
+        if self.task.enable_post_process_per_sample_gradient:
+            raise NotImplementedError("`post_process_per_sample_gradient` needs materialised gradients; unsupported.")
+        factor_args = self._load_factor_args(factors_name)
+        out_dir = self.scores_output_dir(scores_name)
+        if self.state.is_main_process:
+            out_dir.mkdir(parents=True, exist_ok=True)
+        self.state.wait_for_everyone()
+        if io.scores_path(out_dir).exists() and not overwrite_output_dir:
+            return None
+        self._save_arguments(SCORE_ARGUMENTS_NAME, score_args, out_dir, overwrite_output_dir)
+        self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
+        self._save_dataset_metadata("query", query_dataset, out_dir, query_indices, overwrite_output_dir)
+        self._save_dataset_metadata("train", train_dataset, out_dir, train_indices, overwrite_output_dir)
+        with self.profiler.profile("Load All Factors"):
+            factors = self.load_all_factors(factors_name)
+        update_factor_args(self.model, factor_args)
+        update_score_args(self.model, score_args)
+
+        n_train = len(train_indices) if train_indices is not None else len(train_dataset)
+        all_names = get_tracked_module_names(self.model)
+        data_parts = make_indices_partition(n_train, score_args.data_partitions)
+        module_parts = make_modules_partition(all_names, score_args.module_partitions)
+        base_train = list(train_indices) if train_indices is not None else list(range(n_train))
+
+        with self.profiler.profile("Compute Pairwise Score"):
+            column_blocks: List[Dict[str, torch.Tensor]] = []
+            for start, end in data_parts:
+                block: Dict[str, torch.Tensor] = {}
+                for names in module_parts:
+                    set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                    self._prepare_for_scores(factors, factor_args, score_args, names)
+
+                    def run(batch_size: int) -> Dict[str, torch.Tensor]:
+                        return self._pairwise(query_dataset, train_dataset, per_device_query_batch_size, batch_size,
+                                              query_indices, base_train[start:end], factor_args, score_args, names,
+                                              dataloader_kwargs)
+
+                    if per_device_train_batch_size is None:
+                        holder: Dict[str, Any] = {}
+
+                        def probe(batch_size: int) -> None:
+                            holder["scores"] = run(batch_size)
+
+                        self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, end - start)
+                        part = holder["scores"]
+                    else:
+                        part = run(per_device_train_batch_size)
+                    for key, value in part.items():
+                        block[key] = value if key not in block else block[key] + value
+                column_blocks.append(block)
+            scores = {key: torch.cat([blk[key] for blk in column_blocks], dim=1) for key in column_blocks[0]}
+        with self.profiler.profile("Save Pairwise Score"):
+            if self.state.is_main_process:
+                io.save_scores(out_dir, scores, metadata=score_args.to_str_dict())
+            self.state.wait_for_everyone()
+        release_memory()
+        return scores
+
+    def load_pairwise_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:
+        path = io.scores_path(self.scores_output_dir(scores_name))
+        return io.load_file(path) if path.exists() else None
+
+    def get_module_summary(self) -> str:
+        lines = ["Tracked modules:"]
+        for module in tracked_modules(self.model):
+            lines.append(f"  {module.name}: {module.original_module}")
+        return "\n".join(lines)

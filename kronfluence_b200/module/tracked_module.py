@@ -1,0 +1,469 @@
+"""`TrackedModule`: the wrapper that `prepare_model` installs around every nn.Linear / nn.Conv2d.
+
+Same contract as kronfluence's module/tracked_module.py:49-318 — a mode switch selects which tracker's
+forward / tensor-backward hooks are live, statistics live in `module.storage[...]` under the reference's
+key names — but the trackers do no arithmetic themselves: they hand raw activations and output
+gradients to libkfb (kronfluence_b200.ops), which accumulates covariances, the Lambda matrix,
+preconditioned query gradients and pairwise scores with TMA/tcgen05 kernels on the hook's stream.
+"""
+
+from enum import Enum
+from typing import Any, Callable, Dict, List, Optional, Tuple, Type
+
+import torch
+from torch import nn
+
+from kronfluence_b200 import ops
+from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+from kronfluence_b200.utils.constants import (
+    ACCUMULATED_PRECONDITIONED_GRADIENT_NAME,
+    ACTIVATION_COVARIANCE_MATRIX_NAME,
+    ACTIVATION_EIGENVECTORS_NAME,
+    COVARIANCE_FACTOR_NAMES,
+    EIGENDECOMPOSITION_FACTOR_NAMES,
+    GRADIENT_COVARIANCE_MATRIX_NAME,
+    GRADIENT_EIGENVECTORS_NAME,
+    LAMBDA_FACTOR_NAMES,
+    LAMBDA_MATRIX_NAME,
+    NUM_ACTIVATION_COVARIANCE_PROCESSED,
+    NUM_GRADIENT_COVARIANCE_PROCESSED,
+    NUM_LAMBDA_PROCESSED,
+    PAIRWISE_SCORE_MATRIX_NAME,
+    PRECONDITIONED_GRADIENT_NAME,
+)
+from kronfluence_b200.utils.exceptions import FactorsNotFoundError
+
+
+class ModuleMode(str, Enum):
+    """What a tracked module computes during forward/backward (tracked_module.py:32-46 of the reference)."""
+
+    DEFAULT = "default"
+    COVARIANCE = "covariance"
+    LAMBDA = "lambda"
+    PRECONDITION_GRADIENT = "precondition_gradient"
+    PAIRWISE_SCORE = "pairwise_score"
+
+    def __str__(self) -> str:
+        return self.value
+
+
+def precision_of(dtype: torch.dtype) -> int:
+    """float32/float64 -> fp32-parity 3-MMA split; bfloat16/float16 -> single bf16 MMA."""
+    return ops.PREC_BF16 if dtype in (torch.bfloat16, torch.float16) else ops.PREC_FP32
+
+
+# Which statistics each strategy needs (factor/config.py:127-353 of the reference, as a table).
+STRATEGIES: Dict[str, Dict[str, Any]] = {
+    "identity": dict(covariance=False, eigen=False, lambda_=False, lambda_eigen=False, mode=ops.PRECOND_IDENTITY),
+    "diagonal": dict(covariance=False, eigen=False, lambda_=True, lambda_eigen=False, mode=ops.PRECOND_DIAGONAL),
+    "kfac": dict(covariance=True, eigen=True, lambda_=False, lambda_eigen=False, mode=ops.PRECOND_EIGEN),
+    "ekfac": dict(covariance=True, eigen=True, lambda_=True, lambda_eigen=True, mode=ops.PRECOND_EIGEN),
+}
+
+
+def strategy_config(name: str) -> Dict[str, Any]:
+    if name not in STRATEGIES:
+        raise ValueError(f"Unknown factor strategy {name!r}; expected one of {sorted(STRATEGIES)}.")
+    return STRATEGIES[name]
+
+
+class BaseTracker:
+    """Hook manager for one mode of one module (tracker/base.py:8-88 of the reference)."""
+
+    def __init__(self, module: "TrackedModule") -> None:
+        self.module = module
+        self.registered_hooks: List[Any] = []
+        self.cached_hooks: List[Any] = []
+        self.cached_activations: List[torch.Tensor] = []
+        self.cached_gradients: List[torch.Tensor] = []
+
+    def release_hooks(self) -> None:
+        self.clear_all_cache()
+        while self.registered_hooks:
+            self.registered_hooks.pop().remove()
+
+    def clear_all_cache(self) -> None:
+        self.cached_activations = []
+        self.cached_gradients = []
+        while self.cached_hooks:
+            self.cached_hooks.pop().remove()
+
+    def _no_cache_error(self) -> None:
+        raise RuntimeError(
+            f"Module '{self.module.name}' has no cached activations. This can occur if:\n"
+            f"1. The module was not used during the forward pass, or\n"
+            f"2. The module was encountered multiple times in the forward pass.\n"
+            f"For case 2, set 'has_shared_parameters=True' to enable parameter sharing."
+        )
+
+    def _cache_input(self, inputs: Tuple[torch.Tensor, ...]) -> None:
+        # A private copy, like the reference's `.to(copy=True)`: later in-place ops on the activation
+        # (residual adds, in-place ReLU on a shared buffer) must not change what backward sees.
+        cached = inputs[0].detach().clone()
+        if self.module.factor_args.has_shared_parameters:
+            self.cached_activations.append(cached)
+        else:
+            self.cached_activations = [cached]
+
+    def _stacked_uses(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Activations / output gradients of every use of a shared module in one iteration, stacked
+        along the position axis: sum_uses sum_s g a^T is one longer sum over positions."""
+        acts = self.cached_activations
+        grads = list(reversed(self.cached_gradients))  # backward visits the uses in reverse order
+        if len(acts) != len(grads) or not acts:
+            self._no_cache_error()
+        if len(acts) == 1:
+            return acts[0], grads[0]
+        if self.module.is_conv:
+            raise NotImplementedError("has_shared_parameters is not supported for shared Conv2d modules.")
+        flat_a = [a.reshape(a.shape[0], -1, a.shape[-1]) for a in acts]
+        flat_g = [g.reshape(g.shape[0], -1, g.shape[-1]) for g in grads]
+        return torch.cat(flat_a, dim=1), torch.cat(flat_g, dim=1)
+
+    # --- protocol ---
+    def register_hooks(self) -> None: ...
+
+    def finalize_iteration(self) -> None: ...
+
+    def exist(self) -> bool:
+        return False
+
+    def release_memory(self) -> None: ...
+
+
+class CovarianceTracker(BaseTracker):
+    """A^T A and G^T G accumulation (tracker/factor.py:25-152 of the reference)."""
+
+    def register_hooks(self) -> None:
+        module = self.module
+
+        @torch.no_grad()
+        def forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
+            x = inputs[0].detach()
+            layer = module.layer_for(x)
+            d_in, _ = ops.factor_dims(layer)
+            storage = module.storage
+            if storage[ACTIVATION_COVARIANCE_MATRIX_NAME] is None:
+                storage[ACTIVATION_COVARIANCE_MATRIX_NAME] = torch.zeros(d_in, d_in, dtype=torch.float32, device=x.device)
+                storage[NUM_ACTIVATION_COVARIANCE_PROCESSED] = torch.zeros(1, dtype=torch.int64, device=x.device)
+            rows = x.numel() // x.shape[-1] if not module.is_conv else x.shape[0] * layer.h_out * layer.w_out
+            mask = None
+            if not module.is_conv and module.attention_mask is not None and module.attention_mask.numel() == rows:
+                mask = module.attention_mask  # linear.py:34 of the reference: only if it covers every row
+            ops.cov_accum_activation(layer, x, storage[ACTIVATION_COVARIANCE_MATRIX_NAME], mask,
+                                     precision_of(module.factor_args.activation_covariance_dtype))
+            storage[NUM_ACTIVATION_COVARIANCE_PROCESSED].add_(rows if mask is None else mask.sum().to(torch.int64))
+            self.cached_hooks.append(outputs.register_hook(lambda grad: backward_hook(grad, layer, rows, mask)))
+
+        @torch.no_grad()
+        def backward_hook(grad: torch.Tensor, layer, rows: int, mask: Optional[torch.Tensor]) -> None:
+            self.cached_hooks.pop().remove()
+            grad = grad.detach()
+            _, d_out = ops.factor_dims(layer)
+            storage = module.storage
+            if storage[GRADIENT_COVARIANCE_MATRIX_NAME] is None:
+                storage[GRADIENT_COVARIANCE_MATRIX_NAME] = torch.zeros(d_out, d_out, dtype=torch.float32, device=grad.device)
+                storage[NUM_GRADIENT_COVARIANCE_PROCESSED] = torch.zeros(1, dtype=torch.int64, device=grad.device)
+            alpha = module.gradient_scale**2.0 if module.gradient_scale != 1.0 else 1.0
+            ops.cov_accum_gradient(layer, grad, storage[GRADIENT_COVARIANCE_MATRIX_NAME], alpha,
+                                   precision_of(module.factor_args.gradient_covariance_dtype))
+            storage[NUM_GRADIENT_COVARIANCE_PROCESSED].add_(rows if mask is None else mask.sum().to(torch.int64))
+
+        self.registered_hooks.append(module.register_forward_hook(forward_hook))
+
+    def exist(self) -> bool:
+        return all(self.module.storage[name] is not None for name in COVARIANCE_FACTOR_NAMES)
+
+    def release_memory(self) -> None:
+        for name in COVARIANCE_FACTOR_NAMES:
+            self.module.storage[name] = None
+
+
+class LambdaTracker(BaseTracker):
+    """Lambda += sum_b (Q_G^T G_b Q_A)^2 (tracker/factor.py:155-327 of the reference)."""
+
+    def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
+        module = self.module
+        layer = module.layer_for(a)
+        d_in, d_out = ops.factor_dims(layer)
+        storage = module.storage
+        if storage[LAMBDA_MATRIX_NAME] is None:
+            storage[LAMBDA_MATRIX_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
+            storage[NUM_LAMBDA_PROCESSED] = torch.zeros(1, dtype=torch.int64)
+        qa = qg = None
+        if strategy_config(module.factor_args.strategy)["lambda_eigen"]:
+            qa, qg = module.eigen_operands(g.device)
+        ops.lambda_accum(layer, a, g, storage[LAMBDA_MATRIX_NAME], qa, qg, module.gradient_scale,
+                         precision_of(module.factor_args.lambda_dtype))
+        storage[NUM_LAMBDA_PROCESSED].add_(a.shape[0])
+
+    def register_hooks(self) -> None:
+        module = self.module
+
+        @torch.no_grad()
+        def forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
+            self._cache_input(inputs)
+            self.cached_hooks.append(outputs.register_hook(backward_hook))
+
+        @torch.no_grad()
+        def backward_hook(grad: torch.Tensor) -> None:
+            if not self.cached_activations:
+                self._no_cache_error()
+            self.cached_hooks.pop().remove()
+            if module.factor_args.has_shared_parameters:
+                self.cached_gradients.append(grad.detach().clone())
+                return
+            self._update(self.cached_activations[0], grad.detach())
+            self.clear_all_cache()
+
+        self.registered_hooks.append(module.register_forward_hook(forward_hook))
+
+    @torch.no_grad()
+    def finalize_iteration(self) -> None:
+        if self.module.factor_args.has_shared_parameters and self.cached_gradients:
+            a, g = self._stacked_uses()
+            self._update(a, g)
+        self.clear_all_cache()
+
+    def exist(self) -> bool:
+        return all(self.module.storage[name] is not None for name in LAMBDA_FACTOR_NAMES)
+
+    def release_memory(self) -> None:
+        self.clear_all_cache()
+        for name in LAMBDA_FACTOR_NAMES:
+            self.module.storage[name] = None
+
+
+class PreconditionTracker(BaseTracker):
+    """Query side: per-sample gradient -> Q_G[(Q_G^T G Q_A) o Lambda^-1]Q_A^T, appended to the module's
+    query store (tracker/precondition.py:16-261 of the reference; the append replaces its torch.cat)."""
+
+    def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
+        module = self.module
+        layer = module.layer_for(a)
+        store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
+        if store is None:
+            raise RuntimeError(f"Module '{module.name}': the query store has not been allocated.")
+        mode = strategy_config(module.factor_args.strategy)["mode"]
+        qa = qg = None
+        if mode == ops.PRECOND_EIGEN:
+            qa, qg = module.eigen_operands(g.device)
+        lam_inv = module.storage[LAMBDA_MATRIX_NAME] if mode != ops.PRECOND_IDENTITY else None
+        ops.precondition(layer, a, g, store, module.query_count, mode, qa, qg, lam_inv, module.gradient_scale,
+                         precision=precision_of(module.score_args.precondition_dtype))
+        module.last_query_batch = a.shape[0]
+        module.query_count += a.shape[0]
+
+    def register_hooks(self) -> None:
+        module = self.module
+
+        @torch.no_grad()
+        def forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
+            self._cache_input(inputs)
+            self.cached_hooks.append(outputs.register_hook(backward_hook))
+
+        @torch.no_grad()
+        def backward_hook(grad: torch.Tensor) -> None:
+            if not self.cached_activations:
+                self._no_cache_error()
+            self.cached_hooks.pop().remove()
+            if module.factor_args.has_shared_parameters:
+                self.cached_gradients.append(grad.detach().clone())
+                return
+            self._update(self.cached_activations[0], grad.detach())
+            self.clear_all_cache()
+
+        self.registered_hooks.append(module.register_forward_hook(forward_hook))
+
+    @torch.no_grad()
+    def finalize_iteration(self) -> None:
+        if self.module.factor_args.has_shared_parameters and self.cached_gradients:
+            a, g = self._stacked_uses()
+            self._update(a, g)
+        self.clear_all_cache()
+
+    def exist(self) -> bool:
+        return self.module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] is not None and self.module.query_count > 0
+
+    def release_memory(self) -> None:
+        self.clear_all_cache()
+        self.module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = None
+        self.module.storage[PRECONDITIONED_GRADIENT_NAME] = None
+        self.module.query_count = 0
+
+
+class PairwiseScoreTracker(BaseTracker):
+    """Train side: adds this module's <P_q, grad_t> into the shared [Q, T] score buffer
+    (tracker/pairwise_score.py:16-137 + the module sum of score/dot_product.py:105-118 of the reference)."""
+
+    def register_hooks(self) -> None:
+        module = self.module
+
+        @torch.no_grad()
+        def forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
+            self._cache_input(inputs)
+            self.cached_hooks.append(outputs.register_hook(backward_hook))
+
+        @torch.no_grad()
+        def backward_hook(grad: torch.Tensor) -> None:
+            if not self.cached_activations:
+                self._no_cache_error()
+            self.cached_hooks.pop().remove()
+            a = self.cached_activations.pop() if module.factor_args.has_shared_parameters else self.cached_activations[0]
+            sink = module.storage[PAIRWISE_SCORE_MATRIX_NAME]
+            store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
+            if sink is None or store is None:
+                raise RuntimeError(f"Module '{module.name}': pairwise scoring was not set up.")
+            layer = module.layer_for(a)
+            # Every use of a shared module adds its own term (the mathematically correct sum; the
+            # reference keeps only the last use).
+            ops.pairwise_scores(layer, store, module.query_count, a, grad.detach(), sink, module.score_offset,
+                                accumulate=True, scale=module.gradient_scale,
+                                precision=precision_of(module.score_args.score_dtype))
+            if not module.factor_args.has_shared_parameters:
+                self.clear_all_cache()
+
+        self.registered_hooks.append(module.register_forward_hook(forward_hook))
+
+    def finalize_iteration(self) -> None:
+        self.clear_all_cache()
+
+    def exist(self) -> bool:
+        return self.module.storage[PAIRWISE_SCORE_MATRIX_NAME] is not None
+
+    def release_memory(self) -> None:
+        self.clear_all_cache()
+        self.module.storage[PAIRWISE_SCORE_MATRIX_NAME] = None
+
+
+class TrackedModule(nn.Module):
+    """Wraps one nn.Linear / nn.Conv2d; behaves exactly like it in forward/backward."""
+
+    SUPPORTED_MODULES: Dict[Type[nn.Module], Any] = {}
+    is_conv = False
+
+    def __init_subclass__(cls, module_type: Optional[Type[nn.Module]] = None, **kwargs: Any) -> None:
+        super().__init_subclass__(**kwargs)
+        if module_type is not None:
+            cls.SUPPORTED_MODULES[module_type] = cls
+
+    def __init__(self, name: str, original_module: nn.Module, factor_args: Optional[FactorArguments] = None,
+                 score_args: Optional[ScoreArguments] = None,
+                 per_sample_gradient_process_fnc: Optional[Callable] = None) -> None:
+        super().__init__()
+        self.name = name
+        self.original_module = original_module
+        # Frozen models still need a gradient path to this module's output so that the tensor hook on
+        # `outputs` fires (tracked_module.py:97-103,165-168 of the reference).
+        self._constant = nn.Parameter(torch.zeros(1, dtype=original_module.weight.dtype, requires_grad=True))
+        self.current_mode = ModuleMode.DEFAULT
+        self.factor_args = FactorArguments() if factor_args is None else factor_args
+        self.score_args = ScoreArguments() if score_args is None else score_args
+        self.per_sample_gradient_process_fnc = per_sample_gradient_process_fnc
+        self._trackers = {
+            ModuleMode.DEFAULT: BaseTracker(self),
+            ModuleMode.COVARIANCE: CovarianceTracker(self),
+            ModuleMode.LAMBDA: LambdaTracker(self),
+            ModuleMode.PRECONDITION_GRADIENT: PreconditionTracker(self),
+            ModuleMode.PAIRWISE_SCORE: PairwiseScoreTracker(self),
+        }
+        self.attention_mask: Optional[torch.Tensor] = None
+        self.gradient_scale: float = 1.0
+        self.storage: Dict[str, Any] = {}
+        for key in (COVARIANCE_FACTOR_NAMES + EIGENDECOMPOSITION_FACTOR_NAMES + LAMBDA_FACTOR_NAMES +
+                    [PRECONDITIONED_GRADIENT_NAME, ACCUMULATED_PRECONDITIONED_GRADIENT_NAME,
+                     PAIRWISE_SCORE_MATRIX_NAME]):
+            self.storage[key] = None
+        self.query_count = 0
+        self.last_query_batch = 0
+        self.score_offset = 0
+        self._layers: Dict[Tuple[int, ...], Any] = {}
+        self._eigen_ops: Optional[Tuple[Any, Any]] = None
+
+    def forward(self, inputs: torch.Tensor, *args: Any, **kwargs: Any) -> torch.Tensor:
+        outputs = self.original_module(inputs, *args, **kwargs)
+        if outputs.requires_grad:
+            return outputs
+        return outputs + self._constant
+
+    # ---- geometry / operands ----
+    def layer_for(self, x: torch.Tensor):
+        key = tuple(x.shape[-2:]) if self.is_conv else ()
+        if key not in self._layers:
+            self._layers[key] = ops.layer_of(self.original_module, tuple(x.shape))
+        return self._layers[key]
+
+    def eigen_operands(self, device: torch.device):
+        """Q_A / Q_G in tensor-core operand layout, built once per set of factors (the reference moves
+        the fp32 eigenvectors to the device on every call: factor/config.py:347-349)."""
+        if self._eigen_ops is None:
+            qa, qg = self.storage[ACTIVATION_EIGENVECTORS_NAME], self.storage[GRADIENT_EIGENVECTORS_NAME]
+            if qa is None or qg is None:
+                raise FactorsNotFoundError(
+                    f"The strategy {self.factor_args.strategy} requires eigendecomposition results for module "
+                    f"'{self.name}', but they are not found."
+                )
+            self._eigen_ops = (ops.make_eigen_operands(qa.to(device)), ops.make_eigen_operands(qg.to(device)))
+        return self._eigen_ops
+
+    # ---- factor plumbing (names follow tracked_module.py:170-240 of the reference) ----
+    def update_factor_args(self, factor_args: FactorArguments) -> None:
+        self.factor_args = factor_args
+
+    def update_score_args(self, score_args: ScoreArguments) -> None:
+        self.score_args = score_args
+
+    def get_factor(self, factor_name: str) -> Optional[Any]:
+        return self.storage.get(factor_name)
+
+    def release_factor(self, factor_name: str) -> None:
+        if factor_name in self.storage:
+            self.storage[factor_name] = None
+        if factor_name in EIGENDECOMPOSITION_FACTOR_NAMES:
+            self._eigen_ops = None
+
+    def set_factor(self, factor_name: str, factor: Any) -> None:
+        if factor_name in self.storage:
+            self.storage[factor_name] = factor
+        if factor_name in EIGENDECOMPOSITION_FACTOR_NAMES:
+            self._eigen_ops = None
+
+    def set_mode(self, mode: ModuleMode, release_memory: bool = False) -> None:
+        self._trackers[self.current_mode].release_hooks()
+        self.current_mode = mode
+        if release_memory:
+            for tracker in self._trackers.values():
+                tracker.release_memory()
+            for name in EIGENDECOMPOSITION_FACTOR_NAMES:
+                self.storage[name] = None
+            self._eigen_ops = None
+        self._trackers[self.current_mode].register_hooks()
+
+    def set_attention_mask(self, attention_mask: Optional[torch.Tensor] = None) -> None:
+        self.attention_mask = attention_mask
+
+    def set_gradient_scale(self, scale: float = 1.0) -> None:
+        self.gradient_scale = scale
+
+    def finalize_iteration(self) -> None:
+        self._trackers[self.current_mode].finalize_iteration()
+
+    def exist(self) -> bool:
+        return self._trackers[self.current_mode].exist()
+
+    # ---- score plumbing ----
+    def allocate_query_store(self, capacity: int, device: torch.device) -> None:
+        d_in_total, d_out = ops.module_factor_dims(self.original_module)
+        self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = ops.make_query_store(
+            d_out, d_in_total, capacity, device, precision_of(self.score_args.score_dtype))
+        self.query_count = 0
+
+
+class TrackedLinear(TrackedModule, module_type=nn.Linear):
+    """nn.Linear: factors are [in_features (+1 bias column)]^2 and [out_features]^2."""
+
+
+class TrackedConv2d(TrackedModule, module_type=nn.Conv2d):
+    """nn.Conv2d: the activation factor is over unfolded patches C_in/groups * k_h * k_w (+1)."""
+
+    is_conv = True

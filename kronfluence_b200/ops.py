@@ -27,6 +27,10 @@ from kronfluence_b200.engine import (
     stream_ptr,
 )
 
+# "cuda": the real library.  Tests of the host logic may swap the functions of this module for an
+# oracle-backed double and set this to something else; the product never does.
+BACKEND = "cuda"
+
 _WORKSPACES = {}
 
 
@@ -189,10 +193,23 @@ def lambda_invert(lam: torch.Tensor, n: float, damping: Optional[float]) -> torc
 # --------------------------------------------------------------------------------------------------
 # Stage 4: query gradients (tracker/precondition.py:102-123, factor/config.py:341-353)
 # --------------------------------------------------------------------------------------------------
-def make_query_store(layer: KfbLayer, capacity: int, device, precision: int = PREC_FP32) -> Split:
-    """Device storage for `capacity` preconditioned query gradients of one module."""
-    di, do = factor_dims(layer)
-    return Split(do, di, capacity, device=device, precision=precision, zero=True)
+def module_factor_dims(module: nn.Module) -> Tuple[int, int]:
+    """(activation factor dimension incl. bias column, gradient factor dimension) of a module."""
+    if isinstance(module, nn.Linear):
+        return module.in_features + int(module.bias is not None), module.out_features
+    if isinstance(module, nn.Conv2d):
+        k_h, k_w = module.kernel_size
+        return (module.in_channels // module.groups) * k_h * k_w + int(module.bias is not None), module.out_channels
+    raise ValueError(f"unsupported module type {type(module)}")
+
+
+def make_query_store(d_out: int, d_in_total: int, capacity: int, device, precision: int = PREC_FP32) -> Split:
+    """Device storage for `capacity` preconditioned query gradients [d_out, d_in(+1)] of one module."""
+    return Split(d_out, d_in_total, capacity, device=device, precision=precision, zero=True)
+
+
+def make_eigen_operands(q: torch.Tensor, precision: int = PREC_FP32) -> "EigenOperands":
+    return EigenOperands(q, precision)
 
 
 def precondition(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, store: Split, q_offset: int, mode: int,
@@ -235,7 +252,7 @@ def pairwise_scores(layer: KfbLayer, store: Split, num_queries: int, a: torch.Te
 __all__ = [
     "PREC_FP32", "PREC_BF16", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
     "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
-    "make_query_store", "precondition", "pairwise_scores", "layer_of", "factor_dims", "workspace",
+    "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "layer_of", "factor_dims", "workspace",
 ]
 
 

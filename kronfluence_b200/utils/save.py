@@ -1,0 +1,70 @@
+"""safetensors / JSON IO with kronfluence's file layout (factor/covariance.py:35-150, factor/eigen.py:46-137,
+227-342, score/pairwise.py:38-130, utils/save.py of the reference): factors fitted by either engine can be
+consumed by the other."""
+
+import json
+from pathlib import Path
+from typing import Any, Dict, Optional
+
+import torch
+from safetensors import safe_open
+from safetensors.torch import save_file
+
+FACTOR_TYPE = Dict[str, Dict[str, torch.Tensor]]
+
+
+def load_file(path: Path) -> Dict[str, torch.Tensor]:
+    if not Path(path).exists():
+        raise FileNotFoundError(f"File not found: {path}.")
+    with safe_open(str(path), framework="pt", device="cpu") as f:
+        return {key: f.get_tensor(key) for key in f.keys()}
+
+
+def save_json(obj: Any, path: Path) -> None:
+    Path(path).parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(obj, f, indent=4, ensure_ascii=False)
+
+
+def load_json(path: Path) -> Dict[str, Any]:
+    if not Path(path).exists():
+        raise FileNotFoundError(f"File not found: {path}.")
+    with open(path, "r", encoding="utf-8") as f:
+        return json.load(f)
+
+
+def factor_path(output_dir: Path, factor_name: str, partition: Optional[tuple] = None) -> Path:
+    if partition is not None:
+        data_partition, module_partition = partition
+        return Path(output_dir) / f"{factor_name}_data_partition{data_partition}_module_partition{module_partition}.safetensors"
+    return Path(output_dir) / f"{factor_name}.safetensors"
+
+
+def save_factors(output_dir: Path, factors: FACTOR_TYPE, partition: Optional[tuple] = None,
+                 metadata: Optional[Dict[str, str]] = None) -> None:
+    Path(output_dir).mkdir(parents=True, exist_ok=True)
+    for factor_name, per_module in factors.items():
+        tensors = {k: v.contiguous() for k, v in per_module.items()}
+        save_file(tensors=tensors, filename=str(factor_path(output_dir, factor_name, partition)), metadata=metadata)
+
+
+def load_factors(output_dir: Path, factor_names, partition: Optional[tuple] = None) -> FACTOR_TYPE:
+    return {name: load_file(factor_path(output_dir, name, partition)) for name in factor_names}
+
+
+def factors_exist(output_dir: Path, factor_names, partition: Optional[tuple] = None) -> bool:
+    return all(factor_path(output_dir, name, partition).exists() for name in factor_names)
+
+
+def scores_path(output_dir: Path, partition: Optional[tuple] = None) -> Path:
+    if partition is not None:
+        data_partition, module_partition = partition
+        return Path(output_dir) / f"pairwise_scores_data_partition{data_partition}_module_partition{module_partition}.safetensors"
+    return Path(output_dir) / "pairwise_scores.safetensors"
+
+
+def save_scores(output_dir: Path, scores: Dict[str, torch.Tensor], partition: Optional[tuple] = None,
+                metadata: Optional[Dict[str, str]] = None) -> None:
+    Path(output_dir).mkdir(parents=True, exist_ok=True)
+    save_file(tensors={k: v.contiguous() for k, v in scores.items()}, filename=str(scores_path(output_dir, partition)),
+              metadata=metadata)

@@ -226,3 +226,15 @@ def linear_ekfac_layer(a_train, g_train, a_query, g_query, has_bias, damping=1e-
     scores = pairwise_scores_from_gradients(p, grads)
     return {"cov_a": cov_a, "cov_g": cov_g, "q_a": q_a, "q_g": q_g, "lambda": lam, "lambda_inv": lam_inv,
             "p": p, "scores": scores}
+
+
+def linear_pairwise_scores_2d(p: np.ndarray, a: np.ndarray, g: np.ndarray, has_bias: bool) -> np.ndarray:
+    """The same 'qio,bi,bo->qb' contraction for 2-D inputs in the flop-optimal order the reference
+    executes (module/linear.py:112-122: opt_einsum's path for S=1 is (P x a) first, then the reduction
+    with g), without materialising [B, d_out, d_in] per-sample gradients.  Used for CPU timing."""
+    if has_bias:
+        a = np.concatenate([a, np.ones((a.shape[0], 1), dtype=a.dtype)], axis=-1)
+    q, d_out, d_in = p.shape
+    inner = p.reshape(q * d_out, d_in) @ a.T  # [q*d_out, B]
+    inner = inner.reshape(q, d_out, a.shape[0])
+    return np.einsum("qob,bo->qb", inner, g)

@@ -84,7 +84,7 @@ def stage_case(name, dtype):
         per_sample_gradient_dtype=dtype, lambda_dtype=dtype,
     )
     score_args = ScoreArguments(
-        damping_factor=1e-3, per_sample_gradient_dtype=dtype, precondition_dtype=dtype, score_dtype=dtype,
+        damping_factor=None, per_sample_gradient_dtype=dtype, precondition_dtype=dtype, score_dtype=dtype,
     )
     wrapper_cls = TrackedModule.SUPPORTED_MODULES[type(module)]
     tracked = wrapper_cls(name="layer", original_module=module, factor_args=factor_args, score_args=score_args)
@@ -154,7 +154,7 @@ def stage_case(name, dtype):
     config = FactorConfig.CONFIGS["ekfac"]
     config.prepare(storage=tracked.storage, score_args=score_args, device=torch.device("cpu"))
     out["lambda_inv"] = npy(tracked.storage[LAMBDA_MATRIX_NAME])
-    out["damping"] = score_args.damping_factor
+    out["damping"] = -1.0  # None: heuristic 0.1 * mean(Lambda / n), factor/config.py:331-337
     p = config.precondition_gradient(gradient=psg_query.clone(), storage=tracked.storage)
     out["p"] = npy(p)
 
@@ -199,7 +199,7 @@ def run_reference(case, dtype, strategy="ekfac"):
         analyzer = Analyzer(analysis_name="golden", model=model, task=task, cpu=True, output_dir=tmp,
                             disable_tqdm=True, disable_model_save=True)
         factor_args = FactorArguments(strategy=strategy, use_empirical_fisher=True)
-        score_args = ScoreArguments(damping_factor=1e-4)
+        score_args = ScoreArguments(damping_factor=None)
         if dtype == torch.float64:
             for key in ("activation_covariance_dtype", "gradient_covariance_dtype", "per_sample_gradient_dtype",
                         "lambda_dtype"):

@@ -1,0 +1,134 @@
+"""A CPU test double for `kronfluence_b200.ops`, backed by the numpy oracle.
+
+TEST INFRASTRUCTURE ONLY.  The product has no CPU path; this double exists so that the HOST logic
+(trackers, Analyzer orchestration, samplers, file layout, multi-process sharding over gloo) can be
+exercised in the GPU-less build container.  It swaps the functions of the `ops` module for oracle-backed
+equivalents operating on CPU tensors, for the duration of a `with oracle_backend():` block.
+"""
+
+import contextlib
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+from torch import nn
+
+from kronfluence_b200 import ops
+from oracle import ekfac_oracle as orc
+
+
+def _np(t):
+    return t.detach().cpu().double().numpy()
+
+
+def layer_of(module, input_shape=None):
+    if isinstance(module, nn.Linear):
+        return SimpleNamespace(kind=0, d_in=module.in_features, d_out=module.out_features,
+                               has_bias=int(module.bias is not None), h_out=1, w_out=1, conv=None)
+    k, s, p, d = module.kernel_size, module.stride, module.padding, module.dilation
+    h_out, w_out = orc.conv2d_output_size(input_shape[-2], input_shape[-1], k, s, p, d)
+    return SimpleNamespace(kind=1, d_in=(module.in_channels // module.groups) * k[0] * k[1], d_out=module.out_channels,
+                           has_bias=int(module.bias is not None), h_out=h_out, w_out=w_out,
+                           conv=dict(kernel=k, stride=s, padding=p, dilation=d, groups=module.groups))
+
+
+def factor_dims(layer):
+    return layer.d_in + layer.has_bias, layer.d_out
+
+
+def _flat_activation(layer, x, mask):
+    if layer.conv is not None:
+        return orc.conv2d_flatten_activation(_np(x), has_bias=bool(layer.has_bias), **layer.conv)[0]
+    return orc.linear_flatten_activation(_np(x), bool(layer.has_bias), None if mask is None else _np(mask))[0]
+
+
+def _per_sample(layer, a, g):
+    if layer.conv is not None:
+        return orc.conv2d_per_sample_gradient(_np(a), _np(g), has_bias=bool(layer.has_bias), **layer.conv)
+    return orc.linear_per_sample_gradient(_np(a), _np(g), bool(layer.has_bias))
+
+
+def cov_accum_activation(layer, x, cov, mask=None, precision=0):
+    flat = _flat_activation(layer, x, mask)
+    cov.add_(torch.from_numpy(flat.T @ flat).to(cov.dtype))
+
+
+def cov_accum_gradient(layer, g, cov, alpha=1.0, precision=0):
+    flat = orc.conv2d_flatten_gradient(_np(g))[0] if layer.conv is not None else orc.linear_flatten_gradient(_np(g))[0]
+    cov.add_(torch.from_numpy(alpha * (flat.T @ flat)).to(cov.dtype))
+
+
+def eigh_sym(cov, count):
+    evals, evecs = orc.eigendecompose(_np(cov), count)
+    return torch.from_numpy(evals).float(), torch.from_numpy(evecs).float()
+
+
+def make_eigen_operands(q, precision=0):
+    return SimpleNamespace(q=_np(q))
+
+
+def lambda_accum(layer, a, g, lam, qa=None, qg=None, scale=1.0, precision=0):
+    grads = _per_sample(layer, a, g) * scale
+    upd = orc.lambda_update(None, grads, None if qa is None else qa.q, None if qg is None else qg.q)
+    lam.add_(torch.from_numpy(upd).to(lam.dtype))
+
+
+def lambda_invert(lam, n, damping):
+    return torch.from_numpy(orc.lambda_inverse(_np(lam), n, damping)).float()
+
+
+class FakeStore:
+    def __init__(self, d_out, d_in_total, capacity):
+        self.rows, self.cols, self.batch = d_out, d_in_total, capacity
+        self.storage = torch.zeros(1, capacity, d_out, d_in_total, dtype=torch.float64)
+
+    def to_float(self):
+        return self.storage[0]
+
+
+def make_query_store(d_out, d_in_total, capacity, device, precision=0):
+    return FakeStore(d_out, d_in_total, capacity)
+
+
+def precondition(layer, a, g, store, q_offset, mode, qa=None, qg=None, lambda_inv=None, scale=1.0, out_f32=None,
+                 precision=0):
+    grads = _per_sample(layer, a, g)
+    if mode == ops.PRECOND_EIGEN:
+        p = orc.precondition(grads, _np(lambda_inv), qa.q, qg.q)
+    elif mode == ops.PRECOND_DIAGONAL:
+        p = orc.precondition(grads, _np(lambda_inv))
+    else:
+        p = grads
+    p = torch.from_numpy(p * scale)
+    store.storage[0, q_offset : q_offset + p.shape[0]] = p
+    if out_f32 is not None:
+        out_f32.copy_(p.to(out_f32.dtype))
+
+
+def pairwise_scores(layer, store, num_queries, a, g, scores, t_offset=0, accumulate=False, scale=1.0, precision=0):
+    grads = _per_sample(layer, a, g)
+    block = torch.from_numpy(orc.pairwise_scores_from_gradients(store.storage[0, :num_queries].numpy(), grads) * scale)
+    view = scores[:num_queries, t_offset : t_offset + grads.shape[0]]
+    if accumulate:
+        view.add_(block.to(scores.dtype))
+    else:
+        view.copy_(block.to(scores.dtype))
+
+
+_PATCHED = ["layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
+            "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores"]
+
+
+@contextlib.contextmanager
+def oracle_backend():
+    saved = {name: getattr(ops, name) for name in _PATCHED}
+    saved_backend = ops.BACKEND
+    try:
+        for name in _PATCHED:
+            setattr(ops, name, globals()[name])
+        ops.BACKEND = "oracle-test-double"
+        yield
+    finally:
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
+        ops.BACKEND = saved_backend

@@ -1,0 +1,168 @@
+"""Host-logic tests of the public API on CPU.  The CUDA ops are replaced by the oracle-backed test
+double (tests/cpu_backend.py); everything else — prepare_model, trackers, Analyzer orchestration, file
+layout — is the product code.  Results are compared with the reference's own Analyzer outputs
+(tests/golden/e2e_*.npz)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from kronfluence_b200.analyzer import Analyzer, prepare_model
+from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+from kronfluence_b200.task import Task
+from kronfluence_b200.utils.exceptions import IllegalTaskConfigurationError, TrackedModuleNotFoundError
+from tests import fixtures
+from tests.cpu_backend import oracle_backend
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def run_case(case, tmp_path, factor_kwargs=None, score_kwargs=None, inject_eigen=None, train_bs=None, query_bs=None):
+    tasks = fixtures.make_tasks(Task)
+    model, train_set, query_set = fixtures.make_case(case)
+    _, _, _, _, d_train_bs, d_query_bs = fixtures.CASES[case]
+    task = tasks[case]()
+    model = prepare_model(model, task)
+    analyzer = Analyzer("cpu", model, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+    factor_args = FactorArguments(strategy="ekfac", use_empirical_fisher=True, **(factor_kwargs or {}))
+    score_args = ScoreArguments(damping_factor=None, **(score_kwargs or {}))
+    bs = train_bs or d_train_bs
+    analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=bs, factor_args=factor_args)
+    analyzer.perform_eigendecomposition("f", factor_args)
+    if inject_eigen is not None:
+        from kronfluence_b200.utils import save as io
+
+        eig = analyzer.load_eigendecomposition("f")
+        for fname in eig:
+            for mname in eig[fname]:
+                eig[fname][mname] = torch.from_numpy(inject_eigen[f"f32/{fname}/{mname}"])
+        io.save_factors(analyzer.factors_output_dir("f"), eig)
+    analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=bs, factor_args=factor_args)
+    scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set,
+                                              per_device_query_batch_size=query_bs or d_query_bs,
+                                              per_device_train_batch_size=bs, score_args=score_args)
+    return analyzer, scores
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_end_to_end_matches_reference(case, tmp_path):
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    with oracle_backend():
+        analyzer, scores = run_case(case, tmp_path, inject_eigen=golden)
+        factors = analyzer.load_all_factors("f")
+    for key, ref in golden.items():
+        if not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files"):
+            continue
+        _, fname, mname = key.split("/", 2)
+        got = factors[fname][mname].numpy()
+        if "eigen" in fname:
+            continue  # injected
+        assert rel(got, ref) < 2e-5, key
+    assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
+    # same file layout as the reference
+    files = sorted(os.listdir(analyzer.factors_output_dir("f")))
+    assert files == sorted(golden["f32/files_factors"].tolist())
+    assert sorted(os.listdir(analyzer.scores_output_dir("s"))) == sorted(golden["f32/files_scores"].tolist())
+    loaded = analyzer.load_pairwise_scores("s")
+    assert torch.equal(loaded["all_modules"], scores["all_modules"])
+
+
+def test_batch_size_and_accumulation_invariance(tmp_path):
+    """tests/scores/test_pairwise_scores.py:169-269,572-649 of the reference: scores do not depend on batch
+    sizes or on query_gradient_accumulation_steps."""
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_mlp.npz")))
+    with oracle_backend():
+        _, a = run_case("mlp", tmp_path / "a", inject_eigen=golden)
+        _, b = run_case("mlp", tmp_path / "b", inject_eigen=golden, train_bs=41, query_bs=1,
+                        score_kwargs=dict(query_gradient_accumulation_steps=3))
+    assert rel(a["all_modules"].numpy(), b["all_modules"].numpy()) < 1e-6
+
+
+def test_per_module_scores_sum_and_partitions(tmp_path):
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_conv.npz")))
+    with oracle_backend():
+        _, total = run_case("conv", tmp_path / "t", inject_eigen=golden)
+        _, per = run_case("conv", tmp_path / "p", inject_eigen=golden,
+                          score_kwargs=dict(compute_per_module_scores=True, data_partitions=2, module_partitions=3),
+                          factor_kwargs=dict(covariance_data_partitions=2, lambda_module_partitions=3))
+    assert set(per) == {"0", "2", "5"}
+    for key, value in per.items():
+        assert rel(value.numpy(), golden[f"f32/scores/{key}"]) < 5e-5
+    assert rel(sum(per.values()).numpy(), total["all_modules"].numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("strategy", ["identity", "diagonal", "kfac"])
+def test_other_strategies_run(strategy, tmp_path):
+    tasks = fixtures.make_tasks(Task)
+    model, train_set, query_set = fixtures.make_case("mlp")
+    task = tasks["mlp"]()
+    model = prepare_model(model, task)
+    with oracle_backend():
+        analyzer = Analyzer("s", model, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        factor_args = FactorArguments(strategy=strategy, use_empirical_fisher=True)
+        analyzer.fit_all_factors("f", train_set, per_device_batch_size=16, factor_args=factor_args)
+        scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=4,
+                                                  per_device_train_batch_size=16,
+                                                  score_args=ScoreArguments(damping_factor=None))
+    assert scores["all_modules"].shape == (7, 41)
+    assert torch.isfinite(scores["all_modules"]).all()
+    if strategy == "identity":
+        # independent ground truth: <grad m(z_q), grad L(z_t)> from plain autograd
+        plain, tr, qs = fixtures.make_case("mlp")
+        params = [p for p in plain.parameters()]
+
+        def flat_grad(fn, sample):
+            loss = fn(tuple(t.unsqueeze(0) for t in sample), plain)
+            return torch.cat([g.reshape(-1) for g in torch.autograd.grad(loss, params)])
+
+        plain_task = tasks["mlp"]()
+        gq = torch.stack([flat_grad(plain_task.compute_measurement, qs[i]) for i in range(len(qs))])
+        gt = torch.stack([flat_grad(plain_task.compute_train_loss, tr[i]) for i in range(len(tr))])
+        assert rel(scores["all_modules"].numpy(), (gq @ gt.T).detach().numpy()) < 1e-5
+
+
+def test_api_errors_and_defaults(tmp_path):
+    tasks = fixtures.make_tasks(Task)
+    task = tasks["mlp"]()
+    with pytest.raises(TrackedModuleNotFoundError):
+        Analyzer("x", fixtures.make_mlp(), task, cpu=True, output_dir=str(tmp_path))
+    model = prepare_model(fixtures.make_mlp(), task)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        Analyzer("x", model, task, cpu=True, output_dir=str(tmp_path))  # real backend: there is no CPU path
+
+    class Named(tasks["mlp"]):
+        def get_influence_tracked_modules(self):
+            return ["0", "does.not.exist"]
+
+    with pytest.raises(IllegalTaskConfigurationError):
+        prepare_model(fixtures.make_mlp(), Named())
+    # defaults pinned by the reference's tests/test_analyzer.py:101-151
+    fa, sa = FactorArguments(), ScoreArguments()
+    assert (fa.strategy, fa.use_empirical_fisher, fa.amp_dtype, fa.amp_scale) == ("ekfac", False, None, 2.0**16)
+    assert fa.covariance_max_examples == 100_000 and fa.lambda_max_examples == 100_000
+    assert fa.eigendecomposition_dtype == torch.float64 and fa.lambda_dtype == torch.float32
+    assert sa.damping_factor == 1e-08 and sa.query_gradient_accumulation_steps == 1 and sa.score_dtype == torch.float32
+    assert FactorArguments(**fa.to_dict()) == fa  # dtype strings round-trip through JSON
+    with pytest.raises(ValueError):
+        FactorArguments(covariance_data_partitions=0)
+
+
+def test_prepared_model_is_transparent():
+    """tests/modules/test_modules.py:15-137 of the reference: wrapping changes neither outputs nor grads."""
+    tasks = fixtures.make_tasks(Task)
+    plain = fixtures.make_conv()
+    wrapped = prepare_model(fixtures.make_conv(), tasks["conv"]())
+    x = torch.rand(3, 3, 8, 8, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    out_a, out_b = plain(x), wrapped(x2)
+    assert torch.allclose(out_a, out_b)
+    out_a.sum().backward()
+    out_b.sum().backward()
+    assert torch.allclose(x.grad, x2.grad)

@@ -1,0 +1,82 @@
+"""End-to-end parity on the GPU through the public API: Analyzer.fit_all_factors /
+compute_pairwise_scores on the fixture models against the reference Analyzer's outputs
+(tests/golden/e2e_*.npz, float32 reference defaults, EKFAC, empirical Fisher, heuristic damping)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def run(case, tmp_path, golden, inject, **score_kwargs):
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+    from kronfluence_b200.utils import save as io
+    from tests import fixtures
+
+    tasks = fixtures.make_tasks(Task)
+    model, train_set, query_set = fixtures.make_case(case)
+    _, _, _, _, train_bs, query_bs = fixtures.CASES[case]
+    task = tasks[case]()
+    model = prepare_model(model, task)
+    analyzer = Analyzer("gpu", model, task, output_dir=str(tmp_path), disable_tqdm=True, profile=True)
+    factor_args = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+    analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=train_bs, factor_args=factor_args)
+    analyzer.perform_eigendecomposition("f", factor_args)
+    own_eigen = analyzer.load_eigendecomposition("f")
+    if inject:
+        eig = {f: {m: torch.from_numpy(golden[f"f32/{f}/{m}"]) for m in own_eigen[f]} for f in own_eigen}
+        io.save_factors(analyzer.factors_output_dir("f"), eig)
+    analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=train_bs, factor_args=factor_args)
+    scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=query_bs,
+                                              per_device_train_batch_size=train_bs,
+                                              score_args=ScoreArguments(damping_factor=None, **score_kwargs))
+    return analyzer, scores, own_eigen
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_end_to_end_with_reference_eigenbasis(case, tmp_path):
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    analyzer, scores, own_eigen = run(case, tmp_path, golden, inject=True)
+    factors = analyzer.load_all_factors("f")
+    for key, ref in golden.items():
+        if not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files") or "eigen" in key:
+            continue
+        _, fname, mname = key.split("/", 2)
+        tol = 1e-4 if fname == "lambda_matrix" else 2e-5
+        assert rel(factors[fname][mname].numpy(), ref) < tol, key
+    # eigendecomposition: basis-invariant checks of our own Jacobi solver
+    for side in ("activation", "gradient"):
+        for mname, q in own_eigen[f"{side}_eigenvectors"].items():
+            cov = golden[f"f32/{side}_covariance/{mname}"].astype(np.float64)
+            n = float(golden[f"f32/num_{side}_covariance_processed/{mname}"][0])
+            sym = 0.5 * (cov + cov.T) / n
+            w = own_eigen[f"{side}_eigenvalues"][mname].double().numpy()
+            q = q.double().numpy()
+            assert rel(q @ np.diag(w) @ q.T, sym) < 1e-5
+            assert np.abs(w - golden[f"f32/{side}_eigenvalues/{mname}"]).max() < 1e-5 * max(np.abs(w).max(), 1e-30)
+    assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 1e-4
+    assert rel(scores["all_modules"].numpy(), golden["f64/scores"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["mlp", "conv"])
+def test_end_to_end_with_own_eigenbasis(case, tmp_path):
+    """Everything from our own kernels, including the Jacobi eigenvectors.  Eigenbases are unique only up
+    to sign / rotations inside (near-)degenerate subspaces, where Lambda differs too, so the bar is looser."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    _, scores, _ = run(case, tmp_path, golden, inject=False)
+    assert rel(scores["all_modules"].numpy(), golden["f64/scores"]) < 5e-3
+    per_module = run(case, tmp_path / "pm", golden, inject=True, compute_per_module_scores=True)[1]
+    for key, value in per_module.items():
+        assert rel(value.numpy(), golden[f"f32/scores/{key}"]) < 1e-4, key
