@@ -119,6 +119,8 @@ const char* kfb_last_error(void);
 int kfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* 0 = tcgen05 (default and only product path), 1 = SIMT debug kernels (tests only).             */
 int kfb_set_gemm_backend(int backend);
+/* 1 (default): large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles); 0: single CTAs.  */
+int kfb_set_cta_pairs(int enable);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 int64_t kfb_launch_count(void);
 

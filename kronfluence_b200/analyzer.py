@@ -556,8 +556,9 @@ class Analyzer:
         for module in tracked_modules(self.model, names):
             store = module.storage["accumulated_preconditioned_gradient"]
             local = store.storage[:, base : base + local_batch].contiguous()
-            gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-            dist.all_gather_into_tensor(gathered, local)
+            flat = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(flat, local)  # concatenated along dim 0 (the form gloo and nccl share)
+            gathered = flat.view((world,) + tuple(local.shape))
             # [world, planes, j, rows, ld] -> [planes, j, world, rows, ld] -> [planes, j*world, rows, ld]
             inter = gathered.permute(1, 2, 0, 3, 4).reshape(local.shape[0], local_batch * world, *local.shape[2:])
             store.storage[:, base : base + local_batch * world].copy_(inter)

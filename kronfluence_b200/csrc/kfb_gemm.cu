@@ -200,12 +200,17 @@ __device__ __forceinline__ void store_zero_pad(const GemmParams& p, int b, long 
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, int NSPLIT>
+// CG = 1: one CTA per tile (M = 128).  CG = 2: a CTA PAIR per tile (tcgen05 cta_group::2, M = 256):
+// each CTA stages its own 128 rows of A and HALF of the B tile, the pair's tensor cores read both B
+// halves, so shared-memory and L2 operand traffic per MMA drop by a third.
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int CG>
 struct GemmCfg {
-  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_M = 128;          // accumulator rows per CTA
+  static constexpr int TILE_M = BLOCK_M * CG;  // rows of one scheduled tile
+  static constexpr int LOAD_N = BLOCK_N / CG;  // B rows staged by one CTA
   static constexpr int SWIZZLE = BLOCK_K * 2;  // bytes per smem row == swizzle span
   static constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_PLANE = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_PLANE = LOAD_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PLANE + B_PLANE);
   static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
@@ -219,18 +224,19 @@ struct GemmCfg {
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K must match a 128B or 64B swizzle span");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+  static_assert(CG == 1 || CG == 2, "cta_group must be 1 or 2");
 };
 
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI>
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG>;
   constexpr int BLOCK_M = Cfg::BLOCK_M;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
-  constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc_bf16(Cfg::TILE_M, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
@@ -255,7 +261,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the pair's MMAs)
+  const long long unit0 = CG == 2 ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long unit_stride = CG == 2 ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
 
+  if (CG == 2) cluster_sync_all();  // both CTAs of the pair are resident before the paired TMEM allocation
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_b_hi);
@@ -266,21 +276,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), CG);   // one producer arrival (+tx bytes) per CTA of the group
+      mbar_init(empty_bar(s), 1);   // one tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tmem_full_bar(s), 1);
-      mbar_init(tmem_empty_bar(s), 128);
+      mbar_init(tmem_empty_bar(s), 4 * CG);  // one arrival per epilogue warp of the group
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must exist before anyone signals them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -288,23 +304,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // ===================================== TMA producer ======================================
     int stage = 0;
     uint32_t phase = 0;
-    for (long long unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+    for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
       const int inner = unit_inner_count<EPI>(p, unit);
       for (int j = 0; j < inner; ++j) {
         const Tile t = decode_tile<EPI>(p, unit, j);
-        const int row_a = t.m_blk * BLOCK_M;
-        const int row_b = t.n_blk * BLOCK_N;
+        const int row_a = t.m_blk * Cfg::TILE_M + (int)cta_rank * BLOCK_M;
+        const int row_b = t.n_blk * BLOCK_N + (int)cta_rank * Cfg::LOAD_N;
         const int ba = p.a_batched ? t.b : 0;
         const int bb = p.b_batched ? t.b : 0;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const int k0 = kb * BLOCK_K;
-          tma_load_3d(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
-          tma_load_3d(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
-          if (NSPLIT == 2) {
-            tma_load_3d(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
-            tma_load_3d(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
+          if (CG == 2) {
+            // both CTAs credit the LEADER's full barrier: its MMA thread consumes the pair's stage
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            else mbar_arrive_expect_tx_cluster(full_bar(stage), 0, Cfg::STAGE_BYTES);
+            tma_load_3d_2sm(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
+            tma_load_3d_2sm(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
+            if (NSPLIT == 2) {
+              tma_load_3d_2sm(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
+              tma_load_3d_2sm(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
+            }
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_3d(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
+            tma_load_3d(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
+            if (NSPLIT == 2) {
+              tma_load_3d(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
+              tma_load_3d(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -313,12 +341,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
     // ====================================== MMA issuer =======================================
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;
-    for (long long unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+    for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
       const int inner = unit_inner_count<EPI>(p, unit);
       for (int j = 0; j < inner; ++j, ++it) {
         const Tile t = decode_tile<EPI>(p, unit, j);
@@ -339,7 +367,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             // advancing 16 bf16 (32 bytes) along K inside the swizzle span: +2 in 16-byte units
             const uint64_t koff = (uint64_t)(2 * k);
             const uint32_t acc = (kb > t.kb0 || k > 0) ? 1u : 0u;
-            if (NSPLIT == 2) {
+            if (CG == 2) {
+              if (NSPLIT == 2) {
+                umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, IDESC, acc);
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1u);
+              } else {
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, IDESC, acc);
+              }
+            } else if (NSPLIT == 2) {
               umma_bf16(d_tmem, a_lo + koff, b_hi + koff, IDESC, acc);
               umma_bf16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
               umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1u);
@@ -347,8 +383,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, acc);
             }
           }
-          umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
-          if (kb == t.kb1 - 1) umma_commit(tmem_full_bar(as));
+          // smem stage reusable (in both CTAs) once these MMAs retire; accumulator published at the end
+          if (CG == 2) {
+            umma_commit_2sm(empty_bar(stage));
+            if (kb == t.kb1 - 1) umma_commit_2sm(tmem_full_bar(as));
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == t.kb1 - 1) umma_commit(tmem_full_bar(as));
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -362,7 +404,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int lane_row = quarter * 32 + lane;  // accumulator row owned by this thread
     constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N : 1;
     uint32_t it = 0;
-    for (long long unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+    for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
       const int inner = unit_inner_count<EPI>(p, unit);
       float rowdot = 0.f;
       float racc[NACC];
@@ -376,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(tmem_full_bar(as), aphase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + as * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
-        const long long row = (long long)t.m_blk * BLOCK_M + lane_row;
+        const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
         const bool row_ok = row < p.M;
         const int n0 = t.n_blk * BLOCK_N;
 #pragma unroll
@@ -425,12 +467,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           }
         }
         if (EPI == EPI_STORE && p.zero_pad && row_ok && t.n_blk == p.n_blocks - 1) store_zero_pad(p, t.b, row);
+        // hand the accumulator stage back to the (leader's) MMA thread: one arrival per warp
         tcgen05_fence_before();
-        mbar_arrive(tmem_empty_bar(as));
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+          else mbar_arrive(tmem_empty_bar(as));
+        }
       }
       // ---- per-unit finalisation ----
       if (EPI == EPI_ROWDOT) {
-        const long long row = (long long)t.m_blk * BLOCK_M + lane_row;
+        const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
         if (row < p.M) {
           float* o = p.out_f32 + (long long)t.b * p.out_bs + row;
           const float val = p.alpha * rowdot;
@@ -438,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           else *o = val;
         }
       } else if (EPI == EPI_REGACC) {
-        const long long row = (long long)t.m_blk * BLOCK_M + lane_row;
+        const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
         if (row < p.M) {
           const int n0 = t.n_blk * BLOCK_N;
           const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
@@ -458,10 +505,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer may still be reading operands / signalling our barriers
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -545,6 +594,7 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
 // -------------------------------------------------------------------------------------------------
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_backend{0};
+static std::atomic<int> g_cta_pairs{1};
 void count_launch(int n) { g_launches += n; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -594,10 +644,10 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
   return KFB_OK;
 }
 
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI>
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG = 1>
 static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT>;
-  p.m_blocks = (int)ceil_div_ll(p.M, 128);
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG>;
+  p.m_blocks = (int)ceil_div_ll(p.M, Cfg::TILE_M);
   p.n_blocks = (int)ceil_div_ll(p.N, BLOCK_N);
   p.k_blocks = (int)ceil_div_ll(p.K, BLOCK_K);
   const int max_pass_kb = kMaxPassK / BLOCK_K;
@@ -640,23 +690,36 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   KFB_TRY(make_tmap(&ta_hi, A.hi, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
-  KFB_TRY(make_tmap(&tb_hi, B.hi, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, BLOCK_N));
+  KFB_TRY(make_tmap(&tb_hi, B.hi, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
   if (NSPLIT == 2) {
     KFB_TRY(make_tmap(&ta_lo, A.lo, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
-    KFB_TRY(make_tmap(&tb_lo, B.lo, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, BLOCK_N));
+    KFB_TRY(make_tmap(&tb_lo, B.lo, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
   }
-  auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI>;
+  auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     KFB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  long long grid = p.num_units < sm_count() ? p.num_units : sm_count();
-  kernel<<<(unsigned)grid, 256, Cfg::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  const long long groups = sm_count() / CG;  // CTA (pairs) resident at once: one per SM (TPC)
+  const long long grid = (p.num_units < groups ? p.num_units : groups) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  KFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, p));
   count_launch();
   KFB_CUDA_TRY(cudaGetLastError());
   return KFB_OK;
@@ -673,11 +736,15 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
   // Tile width: as wide as N allows (wider tiles = more reuse of the A stage per MMA), except for
   // REGACC whose per-thread register accumulators limit it to 128.
   const int bn = pick_bn(p.N, EPI == EPI_REGACC ? 128 : 256);
+  // CTA pairs (M = 256 tiles) whenever the problem has at least two full 128-row tiles to pair up
+  const bool pair = g_cta_pairs.load() != 0 && bn == 256 && p.M > 128;
   if (nsplit == 2) {
+    if (EPI != EPI_REGACC && bn == 256 && pair) return launch_tc<256, 64, 2, EPI, 2>(A, B, p, stream);
     if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 32, 2, EPI>(A, B, p, stream);
     if (bn == 128) return launch_tc<128, 64, 2, EPI>(A, B, p, stream);
     return launch_tc<64, 64, 2, EPI>(A, B, p, stream);
   }
+  if (EPI != EPI_REGACC && bn == 256 && pair) return launch_tc<256, 64, 1, EPI, 2>(A, B, p, stream);
   if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 64, 1, EPI>(A, B, p, stream);
   if (bn == 128) return launch_tc<128, 64, 1, EPI>(A, B, p, stream);
   return launch_tc<64, 64, 1, EPI>(A, B, p, stream);
@@ -816,5 +883,10 @@ int kfb_set_gemm_backend(int backend) {
 }
 
 int64_t kfb_launch_count(void) { return kfb::g_launches.load(); }
+
+int kfb_set_cta_pairs(int enable) {
+  kfb::g_cta_pairs.store(enable ? 1 : 0);
+  return KFB_OK;
+}
 
 }  // extern "C"

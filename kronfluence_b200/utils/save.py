@@ -17,7 +17,9 @@ def load_file(path: Path) -> Dict[str, torch.Tensor]:
     if not Path(path).exists():
         raise FileNotFoundError(f"File not found: {path}.")
     with safe_open(str(path), framework="pt", device="cpu") as f:
-        return {key: f.get_tensor(key) for key in f.keys()}
+        # cloned: the returned tensors must not alias the (possibly memory-mapped) file, which a later save
+        # with overwrite_output_dir=True may rewrite
+        return {key: f.get_tensor(key).clone() for key in f.keys()}
 
 
 def save_json(obj: Any, path: Path) -> None:

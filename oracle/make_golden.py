@@ -217,6 +217,7 @@ def run_reference(case, dtype, strategy="ekfac"):
                                          score_args=score_args_pm, overwrite_output_dir=True)
         out = {}
         factors = analyzer.load_all_factors("f")
+        factors.update(analyzer.load_covariance_matrices("f"))
         for fname, per_module in factors.items():
             for mname, tensor in per_module.items():
                 out[f"{fname}/{mname}"] = npy(tensor)

@@ -1,0 +1,51 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/kfb.h declares; compute
+entry points refuse to run without a device (there is no CPU path)."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+from kronfluence_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "kfb.h"), encoding="utf-8").read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kfb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in kfb.h but not exported by libkfb.so"
+    # and the ctypes binding types every one of them
+    assert set(names) == set(engine.SIGNATURES), set(names) ^ set(engine.SIGNATURES)
+    assert lib.kfb_version() == 100
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(engine.KfbLayer) == 18 * 4
+    assert ctypes.sizeof(engine.KfbSplit) == 7 * 8
+    # kfb_epilogue: int32 kind (+pad), ptr, 2x int64, kfb_split, ptr, int64, 3x int32, float, ptr, int64
+    assert ctypes.sizeof(engine.KfbEpilogue) == 8 + 8 + 16 + 56 + 8 + 8 + 16 + 8 + 8
+
+
+def test_no_cpu_path():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(engine.KfbError, match="no CPU path"):
+        engine.require_device()
+    lib = engine.load_library()
+    # pure host-side queries still work without a device
+    layer = engine.KfbLayer(kind=0, d_in=64, d_out=32, has_bias=1)
+    assert lib.kfb_pairwise_workspace_bytes(ctypes.byref(layer), 16, 1) > 0
+    assert lib.kfb_eigh_workspace_bytes(128) > 2 * 128 * 128 * 8
+    assert lib.kfb_eigh_jacobi_max_dim() == 1024

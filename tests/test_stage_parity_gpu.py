@@ -149,7 +149,7 @@ def test_diagonal_and_identity_modes():
 LARGE = [
     # (d_in, d_out, bias, T, Q, S)
     (300, 200, True, 500, 70, 1),
-    (1030, 520, True, 260, 33, 1),
+    (520, 1030, True, 1300, 33, 1),
     (96, 130, False, 40, 9, 50),
     (257, 64, True, 12, 5, 300),
 ]
