@@ -239,10 +239,18 @@ def main() -> None:
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     achieved_tf = alg_flops / kernel_s / 1e12
     issued = 3.0 if precision == engine.PREC_FP32 else 1.0
+    # DRAM bytes per launch from the committed ncu capture (profiles/r01_summary.md: 20.305 GB + 5.8 MB at Q=128,
+    # i.e. 2.4x the P planes read once), scaled by Q; only meaningful for the profiled target layer / fp32 mode.
+    traffic = None
+    if args.workload == "target" and precision == engine.PREC_FP32 and t_batch == 2048:
+        traffic = (20.305108e9 + 5.805568e6) * n_query / 128.0
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained", "kernel_ms": kernel_s * 1e3,
-                "kernel": "gemm_tc_kernel<BLOCK_N=256,BLOCK_K=32,NSPLIT=2,ROWDOT>" if precision == engine.PREC_FP32
-                else "gemm_tc_kernel<256,64,1,ROWDOT>",
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write, profiles/r01_summary.md, scaled Q/128",
+                "algorithmic_bytes": float(n_query) * do * store.ld * 2 * (2 if precision == engine.PREC_FP32 else 1)
+                + t_batch * (di + do) * 4.0,
+                "peak_source": f"{peak_kind} bf16_tflops_sustained", "kernel_ms": kernel_s * 1e3,
+                "kernel": "gemm_tc_kernel<BLOCK_N=256,BLOCK_K=64,NSPLIT=2,ROWDOT,cta_group=2>" if precision == engine.PREC_FP32
+                else "gemm_tc_kernel<256,64,1,ROWDOT,cta_group=2>",
                 "issued_tflops": achieved_tf * issued, "issued_frac": achieved_tf * issued / peak_tf,
                 "kernel_share_of_step": kernel_s / (elapsed_s / args.steps)}
 

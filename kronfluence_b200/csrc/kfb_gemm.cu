@@ -123,24 +123,24 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit,
   return t;
 }
 
-// Writes 32 consecutive accumulator columns of one row through every STORE option.
-__device__ __forceinline__ void store_values(const GemmParams& p, int b, long long row, int col0,
-                                             const float (&acc)[32]) {
-  float x[32];
+// Writes 8 consecutive accumulator columns of one row through every STORE option (kept to 8 values at a
+// time so that the register-accumulating epilogue does not spill).
+__device__ __forceinline__ void store8(const GemmParams& p, int b, long long row, int col0, const float (&a)[8]) {
+  float x[8];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float val = p.alpha * acc[i];
+  for (int i = 0; i < 8; ++i) {
+    float val = p.alpha * a[i];
     if (p.mul != nullptr && col0 + i < p.N) val *= __ldg(p.mul + row * p.ldmul + col0 + i);
     if (p.square) val *= val;
     x[i] = val;
   }
-  const bool full = col0 + 32 <= p.N;
+  const bool full = col0 + 8 <= p.N;
   if (p.out_f32 != nullptr) {
     float* ob = p.out_f32 + (long long)b * p.out_bs;
     if (!p.transpose_out && full && p.vec_ok && !p.use_atomic) {
       float4* o4 = reinterpret_cast<float4*>(ob + row * p.ldo + col0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 2; ++i) {
         float4 w = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
         if (p.accumulate) {
           const float4 old = o4[i];
@@ -150,7 +150,7 @@ __device__ __forceinline__ void store_values(const GemmParams& p, int b, long lo
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 8; ++i) {
         if (col0 + i < p.N) {
           float* o = p.transpose_out ? ob + (long long)(col0 + i) * p.ldo + row : ob + row * p.ldo + col0 + i;
           if (p.use_atomic) atomicAdd(o, x[i]);
@@ -164,19 +164,14 @@ __device__ __forceinline__ void store_values(const GemmParams& p, int b, long lo
     __nv_bfloat16* oh = p.out_hi + (long long)b * p.out_bs_s;
     __nv_bfloat16* ol = p.out_lo != nullptr ? p.out_lo + (long long)b * p.out_bs_s : nullptr;
     if (!p.transpose_out && full && p.vec_ok) {
-      uint4* h4 = reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0);
-      uint4* l4 = ol ? reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0) : nullptr;
+      __nv_bfloat16 h[8], l[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 h[8], l[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16(x[8 * i + e], h[e], l[e]);
-        h4[i] = *reinterpret_cast<uint4*>(h);
-        if (l4) l4[i] = *reinterpret_cast<uint4*>(l);
-      }
+      for (int e = 0; e < 8; ++e) split_bf16(x[e], h[e], l[e]);
+      *reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0) = *reinterpret_cast<uint4*>(h);
+      if (ol) *reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0) = *reinterpret_cast<uint4*>(l);
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 8; ++i) {
         if (col0 + i < p.N) {
           const long long idx = p.transpose_out ? (long long)(col0 + i) * p.ldo_s + row : row * p.ldo_s + col0 + i;
           __nv_bfloat16 h, l;
@@ -185,6 +180,21 @@ __device__ __forceinline__ void store_values(const GemmParams& p, int b, long lo
           if (ol) ol[idx] = l;
         }
       }
+    }
+  }
+}
+
+// 32 columns starting at compile-time offset OFF of a register array.
+template <int OFF, int N>
+__device__ __forceinline__ void store_values(const GemmParams& p, int b, long long row, int col0,
+                                             const float (&acc)[N]) {
+#pragma unroll
+  for (int grp = 0; grp < 4; ++grp) {
+    if (col0 + grp * 8 < p.N) {
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = acc[OFF + grp * 8 + i];
+      store8(p, b, row, col0 + grp * 8, a);
     }
   }
 }
@@ -462,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               float x[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-              store_values(p, t.b, row, col0, x);
+              store_values<0>(p, t.b, row, col0, x);
             }
           }
         }
@@ -489,15 +499,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (row < p.M) {
           const int n0 = t.n_blk * BLOCK_N;
           const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
-#pragma unroll
-          for (int c = 0; c < NACC / 32; ++c) {
-            if (n0 + c * 32 < p.N) {
-              float x[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = racc[(EPI == EPI_REGACC ? c * 32 + i : 0)];
-              store_values(p, ob, row, n0 + c * 32, x);
-            }
-          }
+          if (NACC >= 32 && n0 < p.N) store_values<0>(p, ob, row, n0, racc);
+          if (NACC >= 64 && n0 + 32 < p.N) store_values<(NACC >= 64 ? 32 : 0)>(p, ob, row, n0 + 32, racc);
+          if (NACC >= 128 && n0 + 64 < p.N) store_values<(NACC >= 128 ? 64 : 0)>(p, ob, row, n0 + 64, racc);
+          if (NACC >= 128 && n0 + 96 < p.N) store_values<(NACC >= 128 ? 96 : 0)>(p, ob, row, n0 + 96, racc);
           if (p.zero_pad && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
         }
       }
