@@ -47,7 +47,11 @@ typedef enum {
 } kfb_status;
 
 typedef enum { KFB_F32 = 0, KFB_BF16 = 1, KFB_F16 = 2, KFB_F64 = 3 } kfb_dtype;
-typedef enum { KFB_PREC_FP32 = 0, KFB_PREC_BF16 = 1 } kfb_precision;
+/* KFB_PREC_FP32: fp32 parity.  Large contractions split operands into bf16 hi+lo (3 MMAs, ~1e-5 relative
+ * to the operand norms); the small eigenbasis ROTATIONS, whose errors would be amplified by Lambda^-1, run
+ * in KFB_PREC_STRICT.  KFB_PREC_BF16: one MMA on bf16-rounded operands.  KFB_PREC_STRICT: bf16 hi+mid+lo
+ * (24 mantissa bits), 6 MMAs, TMEM drained into fp32 registers every 64 contraction elements (~1e-6). */
+typedef enum { KFB_PREC_FP32 = 0, KFB_PREC_BF16 = 1, KFB_PREC_STRICT = 2 } kfb_precision;
 typedef enum { KFB_LINEAR = 0, KFB_CONV2D = 1 } kfb_layer_kind;
 
 /* How the query gradient is preconditioned (factor/config.py strategies).                       */
@@ -76,10 +80,11 @@ typedef struct {
 /* A batch of matrices stored as two bf16 planes (hi, lo) in tensor-core operand layout:
  * row-major, `cols` contiguous (the contraction index of an NT GEMM), row stride `ld` elements
  * (multiple of 8 so TMA can address it), `batch` matrices `batch_stride` elements apart.  With
- * KFB_PREC_BF16 the lo plane is unused and may be NULL.                                          */
+ * KFB_PREC_BF16 the lo plane is unused and may be NULL; KFB_PREC_STRICT adds a third plane lo2.   */
 typedef struct {
   void* hi;
   void* lo;
+  void* lo2; /* third plane, KFB_PREC_STRICT operands only (else NULL) */
   int64_t rows;
   int64_t cols;
   int64_t ld;
@@ -219,6 +224,9 @@ int kfb_lambda_invert(const float* lambda, int64_t numel, double n, double dampi
  * PreconditionTracker backward hook  tracker/precondition.py:102-123 and
  * {Identity,Diagonal,Kfac,Ekfac}.precondition_gradient  factor/config.py:159-165,210-216,273-285,341-353.
  *   P_q = scale * Q_G [ (Q_G^T G_q Q_A) o lambda_inv ] Q_A^T          (KFB_PRECOND_EIGEN)
+ * With KFB_PRECOND_EIGEN the STORE keeps the eigenbasis image  Pt_q = scale * (Q_G^T G_q Q_A) o lambda_inv
+ * (no back-rotation: kfb_pairwise_scores rotates the train operands instead, see kfb_ops.cu for why this
+ * is both cheaper and much better conditioned); p_f32 still receives the reference-layout P_q.
  * P is written in tensor-core operand layout (kfb_split with rows=d_out, cols=d_in+bias,
  * batch = total query capacity) at batch offset q_offset .. q_offset+batch-1, so accumulating
  * query batches (tracker/precondition.py:216-240) is an append, not a torch.cat.  p_f32, if not
@@ -237,6 +245,9 @@ int kfb_precondition(const kfb_layer* layer, const void* a, int a_dtype, const v
  * TrackedLinear/Conv2d.compute_pairwise_score  linear.py:79-122, conv2d.py:179-209 and the module
  * sum of compute_dot_products_with_loader  score/dot_product.py:105-118.
  *   scores[q, t_offset + t] (+)= scale * sum_{s,o,i} P[q,o,i] g[t,s,o] a[t,s,i]
+ * `mode` says how the store was filled: with KFB_PRECOND_EIGEN it holds eigenbasis images and the train
+ * operands are rotated by qa_t / qg_t (built by kfb_eigen_operands with KFB_PREC_STRICT) first; with
+ * IDENTITY / DIAGONAL the eigen operands are ignored (may be NULL).
  * seq==1 (Linear on 2-D inputs): one fused kernel — (a P_q^T) on tensor cores, row-dot with g in
  * the epilogue; no [T,d_out,d_in] intermediate.  seq>1 / Conv2d: per-sample gradients are formed
  * by a batched tensor-core GEMM into the workspace and contracted against P by a second GEMM.
@@ -245,16 +256,17 @@ int kfb_precondition(const kfb_layer* layer, const void* a, int a_dtype, const v
 size_t kfb_pairwise_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
 int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
                         const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
-                        int64_t seq, float scale, float* scores, int64_t ld_scores,
-                        int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes,
-                        int precision, void* stream);
+                        int64_t seq, int32_t mode, const kfb_split* qa_t, const kfb_split* qg_t,
+                        float scale, float* scores, int64_t ld_scores, int64_t t_offset,
+                        int32_t accumulate, void* ws, size_t ws_bytes, int precision, void* stream);
 
 /* Same contraction through HOST buffers (pinned or pageable): a, g are host pointers, scores_host
  * receives [num_queries, batch] fp32.  dev_a / dev_g / dev_scores are caller-provided device
  * staging buffers of at least the same sizes.  Used for the end-to-end measurement.             */
 int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
                              const void* a_host, int a_dtype, const void* g_host, int g_dtype,
-                             int64_t batch, int64_t seq, float scale, float* scores_host,
+                             int64_t batch, int64_t seq, int32_t mode, const kfb_split* qa_t,
+                             const kfb_split* qg_t, float scale, float* scores_host,
                              void* dev_a, void* dev_g, float* dev_scores, void* ws,
                              size_t ws_bytes, int precision, void* stream);
 

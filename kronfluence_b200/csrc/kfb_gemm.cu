@@ -51,6 +51,7 @@ struct GemmParams {
   int k_chunks, kb_per_chunk;  // contraction passes INSIDE a unit (register accumulation)
   int inner;                   // REGACC_BATCH: batches per chunk
   int regacc_mode;
+  int max_pass_k;              // longest TMEM accumulation chain (contraction elements) of this launch
   long long num_units;
   // outputs
   float* out_f32;
@@ -241,8 +242,11 @@ template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+               const __grid_constant__ CUtensorMap tm_a_lo2, const __grid_constant__ CUtensorMap tm_b_lo2,
                const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG>;
+  static_assert(NSPLIT >= 1 && NSPLIT <= 3, "1 (bf16), 2 (hi/lo) or 3 (hi/mid/lo) operand planes");
+  static_assert(NSPLIT < 3 || CG == 1, "the strict 3-plane mode runs on single CTAs");
   constexpr int BLOCK_M = Cfg::BLOCK_M;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
@@ -279,9 +283,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_b_hi);
-    if (NSPLIT == 2) {
+    if (NSPLIT >= 2) {
       tma_prefetch_desc(&tm_a_lo);
       tma_prefetch_desc(&tm_b_lo);
+    }
+    if (NSPLIT == 3) {
+      tma_prefetch_desc(&tm_a_lo2);
+      tma_prefetch_desc(&tm_b_lo2);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -339,9 +347,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             tma_load_3d(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
             tma_load_3d(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
-            if (NSPLIT == 2) {
+            if (NSPLIT >= 2) {
               tma_load_3d(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
               tma_load_3d(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
+            }
+            if (NSPLIT == 3) {
+              tma_load_3d(&tm_a_lo2, full_bar(stage), smem_a(stage, 2), k0, row_a, ba);
+              tma_load_3d(&tm_b_lo2, full_bar(stage), smem_b(stage, 2), k0, row_b, bb);
             }
           }
           if (++stage == STAGES) {
@@ -370,8 +382,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           tcgen05_fence_after();
           const uint64_t a_hi = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, 0));
           const uint64_t b_hi = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, 0));
-          const uint64_t a_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, NSPLIT - 1));
-          const uint64_t b_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, NSPLIT - 1));
+          const uint64_t a_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, NSPLIT >= 2 ? 1 : 0));
+          const uint64_t b_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, NSPLIT >= 2 ? 1 : 0));
+          const uint64_t a_l2 = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, NSPLIT == 3 ? 2 : 0));
+          const uint64_t b_l2 = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, NSPLIT == 3 ? 2 : 0));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advancing 16 bf16 (32 bytes) along K inside the swizzle span: +2 in 16-byte units
@@ -385,6 +399,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               } else {
                 umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, IDESC, acc);
               }
+            } else if (NSPLIT == 3) {
+              // hi/mid/lo planes (orders 0/1/2): every cross term of total order <= 2, smallest first
+              umma_bf16(d_tmem, a_l2 + koff, b_hi + koff, IDESC, acc);
+              umma_bf16(d_tmem, a_hi + koff, b_l2 + koff, IDESC, 1u);
+              umma_bf16(d_tmem, a_lo + koff, b_lo + koff, IDESC, 1u);
+              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1u);
             } else if (NSPLIT == 2) {
               umma_bf16(d_tmem, a_lo + koff, b_hi + koff, IDESC, acc);
               umma_bf16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
@@ -525,6 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 struct SimtOperand {
   const __nv_bfloat16* hi;
   const __nv_bfloat16* lo;
+  const __nv_bfloat16* lo2;
   long long ld, bs;
 };
 
@@ -534,12 +557,19 @@ __device__ __forceinline__ float simt_dot(const SimtOperand& A, const SimtOperan
   const __nv_bfloat16* bh = B.hi + bb * B.bs + n * B.ld;
   const __nv_bfloat16* al = A.lo ? A.lo + ab * A.bs + m * A.ld : nullptr;
   const __nv_bfloat16* bl = B.lo ? B.lo + bb * B.bs + n * B.ld : nullptr;
+  const __nv_bfloat16* al2 = A.lo2 ? A.lo2 + ab * A.bs + m * A.ld : nullptr;
+  const __nv_bfloat16* bl2 = B.lo2 ? B.lo2 + bb * B.bs + n * B.ld : nullptr;
   float acc = 0.f;
   for (int k = 0; k < K; ++k) {
     const float a_h = __bfloat162float(ah[k]), b_h = __bfloat162float(bh[k]);
     const float a_l = al ? __bfloat162float(al[k]) : 0.f;
     const float b_l = bl ? __bfloat162float(bl[k]) : 0.f;
-    acc += a_l * b_h + a_h * b_l + a_h * b_h;
+    if (al2 != nullptr) {
+      const float a_2 = __bfloat162float(al2[k]), b_2 = __bfloat162float(bl2[k]);
+      acc += (a_h + a_l + a_2) * (b_h + b_l + b_2);
+    } else {
+      acc += a_l * b_h + a_h * b_l + a_h * b_h;
+    }
   }
   return acc;
 }
@@ -655,7 +685,8 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   p.m_blocks = (int)ceil_div_ll(p.M, Cfg::TILE_M);
   p.n_blocks = (int)ceil_div_ll(p.N, BLOCK_N);
   p.k_blocks = (int)ceil_div_ll(p.K, BLOCK_K);
-  const int max_pass_kb = kMaxPassK / BLOCK_K;
+  const int max_pass_kb = (p.max_pass_k > 0 ? p.max_pass_k : kMaxPassK) / BLOCK_K > 0
+                              ? (p.max_pass_k > 0 ? p.max_pass_k : kMaxPassK) / BLOCK_K : 1;
   const long long tiles = (long long)p.m_blocks * p.n_blocks;
   if (EPI == EPI_ROWDOT) {
     p.k_splits = 1;
@@ -696,12 +727,17 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   KFB_TRY(make_tmap(&ta_hi, A.hi, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
   KFB_TRY(make_tmap(&tb_hi, B.hi, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
-  if (NSPLIT == 2) {
+  if (NSPLIT >= 2) {
     KFB_TRY(make_tmap(&ta_lo, A.lo, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
     KFB_TRY(make_tmap(&tb_lo, B.lo, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
+  }
+  CUtensorMap ta_lo2 = ta_hi, tb_lo2 = tb_hi;
+  if (NSPLIT == 3) {
+    KFB_TRY(make_tmap(&ta_lo2, A.lo2, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
+    KFB_TRY(make_tmap(&tb_lo2, B.lo2, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
   }
   auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG>;
   static bool attr_set = false;
@@ -724,7 +760,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  KFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, p));
+  KFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, ta_lo2, tb_lo2, p));
   count_launch();
   KFB_CUDA_TRY(cudaGetLastError());
   return KFB_OK;
@@ -743,6 +779,15 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
   const int bn = pick_bn(p.N, EPI == EPI_REGACC ? 128 : 256);
   // CTA pairs (M = 256 tiles) whenever the problem has at least two full 128-row tiles to pair up
   const bool pair = g_cta_pairs.load() != 0 && bn == 256 && p.M > 128;
+  if (nsplit == 3) {
+    if (EPI == EPI_ROWDOT) {
+      set_error("gemm_nt: the strict (3-plane) mode has no ROWDOT epilogue");
+      return KFB_ERR_INVALID;
+    } else {
+      if (pick_bn(p.N, 128) == 128) return launch_tc<128, 64, 3, EPI>(A, B, p, stream);
+      return launch_tc<64, 64, 3, EPI>(A, B, p, stream);
+    }
+  }
   if (nsplit == 2) {
     if (EPI != EPI_REGACC && bn == 256 && pair) return launch_tc<256, 64, 2, EPI, 2>(A, B, p, stream);
     if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 32, 2, EPI>(A, B, p, stream);
@@ -757,10 +802,10 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
 
 static int launch_simt(const kfb_split& A, const kfb_split& B, GemmParams p, int epi, int nsplit,
                        cudaStream_t stream) {
-  SimtOperand a{(const __nv_bfloat16*)A.hi, nsplit == 2 ? (const __nv_bfloat16*)A.lo : nullptr, A.ld,
-                A.batch_stride};
-  SimtOperand b{(const __nv_bfloat16*)B.hi, nsplit == 2 ? (const __nv_bfloat16*)B.lo : nullptr, B.ld,
-                B.batch_stride};
+  SimtOperand a{(const __nv_bfloat16*)A.hi, nsplit >= 2 ? (const __nv_bfloat16*)A.lo : nullptr,
+                nsplit == 3 ? (const __nv_bfloat16*)A.lo2 : nullptr, A.ld, A.batch_stride};
+  SimtOperand b{(const __nv_bfloat16*)B.hi, nsplit >= 2 ? (const __nv_bfloat16*)B.lo : nullptr,
+                nsplit == 3 ? (const __nv_bfloat16*)B.lo2 : nullptr, B.ld, B.batch_stride};
   long long total = epi == KFB_EPI_STORE    ? (long long)p.batch * p.M * p.N
                     : epi == KFB_EPI_ROWDOT ? (long long)p.batch * p.M
                                             : (long long)p.M * p.N;
@@ -780,9 +825,9 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
               "gemm_nt: incompatible batch counts %lld / %lld", (long long)A.batch, (long long)B.batch);
   KFB_REQUIRE(A.rows < (1LL << 31) && B.rows < (1LL << 31) && A.cols < (1LL << 31),
               "gemm_nt: dimension too large");
-  const int nsplit = precision == KFB_PREC_FP32 ? 2 : 1;
-  KFB_REQUIRE(nsplit == 1 || (A.lo != nullptr && B.lo != nullptr),
-              "gemm_nt: KFB_PREC_FP32 needs lo planes");
+  const int nsplit = precision == KFB_PREC_FP32 ? 2 : (precision == KFB_PREC_STRICT ? 3 : 1);
+  KFB_REQUIRE(nsplit == 1 || (A.lo != nullptr && B.lo != nullptr), "gemm_nt: missing lo planes");
+  KFB_REQUIRE(nsplit < 3 || (A.lo2 != nullptr && B.lo2 != nullptr), "gemm_nt: KFB_PREC_STRICT needs lo2 planes");
   GemmParams p{};
   p.M = (int)A.rows;
   p.N = (int)B.rows;
@@ -807,6 +852,8 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   p.ldg = epi.ldg;
   p.k_splits = 1;
   p.k_chunks = 1;
+  // strict mode: 6 truncating accumulations per k-step, so drain TMEM every 64 contraction elements
+  p.max_pass_k = nsplit == 3 ? 64 : kMaxPassK;
   if (p.M == 0 || p.N == 0 || p.batch == 0) return KFB_OK;
   KFB_REQUIRE(p.K > 0, "gemm_nt: empty contraction");
 
@@ -845,13 +892,13 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   // STORE: one TMEM pass if the contraction is short, register-accumulated passes otherwise; the
   // contraction is additionally split across CTAs (atomic adds into an accumulated fp32 target) when
   // there are too few output tiles to fill the machine.
-  const bool long_k = p.K > kMaxPassK;
+  const bool long_k = p.K > p.max_pass_k;
   const bool splittable = p.out_hi == nullptr && p.mul == nullptr && !p.square && p.accumulate;
   if (splittable) {
     if (k_splits == 0) {
       const int bn = pick_bn(p.N, long_k ? 128 : 256);
       const long long tiles = ceil_div_ll(p.M, 128) * ceil_div_ll(p.N, bn) * p.batch;
-      const long long passes = ceil_div_ll(p.K, kMaxPassK);
+      const long long passes = ceil_div_ll(p.K, nsplit == 3 ? 1024 : kMaxPassK);
       long long want = ceil_div_ll(sm_count(), tiles);
       if (want > passes) want = passes;  // never make a split shorter than one full pass
       k_splits = want < 1 ? 1 : (int)want;

@@ -39,8 +39,15 @@ struct Ws {
   bool fits() const { return dry || off <= cap; }
 };
 
+static inline int planes_of(int precision) {
+  return precision == KFB_PREC_BF16 ? 1 : (precision == KFB_PREC_STRICT ? 3 : 2);
+}
+// Precision of the eigenbasis rotations: their component-wise errors are what Lambda^-1 amplifies, so the
+// fp32-parity mode runs them in the strict 3-plane mode (DESIGN.md "Precision model").
+static inline int rot_prec(int precision) { return precision == KFB_PREC_FP32 ? KFB_PREC_STRICT : precision; }
+
 static kfb_split ws_split(Ws& ws, long long rows, long long cols, long long batch, int precision) {
-  kfb_split s;
+  kfb_split s{};
   s.rows = rows;
   s.cols = cols;
   s.ld = ld8(cols);
@@ -48,7 +55,8 @@ static kfb_split ws_split(Ws& ws, long long rows, long long cols, long long batc
   s.batch_stride = rows * s.ld;
   const size_t plane = (size_t)(rows * s.ld * batch) * 2;
   s.hi = ws.take(plane);
-  s.lo = precision == KFB_PREC_FP32 ? ws.take(plane) : nullptr;
+  s.lo = precision != KFB_PREC_BF16 ? ws.take(plane) : nullptr;
+  s.lo2 = precision == KFB_PREC_STRICT ? ws.take(plane) : nullptr;
   return s;
 }
 
@@ -56,6 +64,7 @@ static kfb_split split_batch_view(const kfb_split& s, long long b0, long long nb
   kfb_split v = s;
   v.hi = static_cast<char*>(s.hi) + b0 * s.batch_stride * 2;
   v.lo = s.lo ? static_cast<char*>(s.lo) + b0 * s.batch_stride * 2 : nullptr;
+  v.lo2 = s.lo2 ? static_cast<char*>(s.lo2) + b0 * s.batch_stride * 2 : nullptr;
   v.batch = nb;
   return v;
 }
@@ -103,7 +112,7 @@ static int cov_run(const kfb_layer& L, bool activation, const void* x, int dt, l
   const long long S = positions(L, seq);
   const long long d = activation ? L.d_in + L.has_bias : L.d_out;
   // chunk over samples so that the transposed operand stays within the scratch budget
-  const long long per_sample = d * S * 2 * (precision == KFB_PREC_FP32 ? 2 : 1);
+  const long long per_sample = d * S * 2 * planes_of(precision);
   const long long cb = chunk_count(batch, per_sample);
   kfb_split Xt = ws_split(ws, d, cb * S, 1, precision);
   if (ws.dry) return KFB_OK;
@@ -173,17 +182,16 @@ static OuterBufs outer_alloc(Ws& ws, const kfb_layer& L, long long nb, long long
   o.Lt = ws_split(ws, L.d_out, S, nb, precision);
   o.Rt = ws_split(ws, di, S, nb, precision);
   if (rotate) {
-    o.tmp_a = ws_split(ws, S, di, nb, precision);
-    o.tmp_g = ws_split(ws, S, L.d_out, nb, precision);
+    o.tmp_a = ws_split(ws, S, di, nb, rot_prec(precision));
+    o.tmp_g = ws_split(ws, S, L.d_out, nb, rot_prec(precision));
   }
   return o;
 }
 
 static long long outer_bytes_per_sample(const kfb_layer& L, long long S, bool rotate, int precision) {
   const long long di = L.d_in + L.has_bias;
-  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
-  long long b = (L.d_out + di) * ld8(S) * 2 * planes;
-  if (rotate) b += S * (ld8(di) + ld8(L.d_out)) * 2 * planes;
+  long long b = (L.d_out + di) * ld8(S) * 2 * planes_of(precision);
+  if (rotate) b += S * (ld8(di) + ld8(L.d_out)) * 2 * planes_of(rot_prec(precision));
   return b;
 }
 
@@ -217,27 +225,30 @@ static int outer_fill(const kfb_layer& L, const void* a, int a_dt, const void* g
               "eigenbasis operands are required");
   KFB_REQUIRE(qa_t->rows == di && qa_t->cols == di && qg_t->rows == L.d_out && qg_t->cols == L.d_out,
               "eigenbasis operand shapes do not match the layer");
+  const int rp = rot_prec(precision);
+  KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+              "eigenbasis operands must be built with KFB_PREC_STRICT for the fp32-parity mode");
   kfb_split ta = split_batch_view(o.tmp_a, 0, nb), tg = split_batch_view(o.tmp_g, 0, nb);
   if (L.kind == KFB_LINEAR) {
     GatherDesc ga{};
     ga.sb = S * L.d_in; ga.sr = L.d_in; ga.sc2 = 1; ga.rows = S; ga.c1 = 1; ga.c2 = L.d_in;
     ga.ones_mode = L.has_bias ? 1 : 0;
-    KFB_TRY(split_gather(a0, a_dt, ga, ta, precision, stream));
+    KFB_TRY(split_gather(a0, a_dt, ga, ta, rp, stream));
     GatherDesc gg{};
     gg.sb = S * L.d_out; gg.sr = L.d_out; gg.sc2 = 1; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
-    KFB_TRY(split_gather(g0, g_dt, gg, tg, precision, stream));
+    KFB_TRY(split_gather(g0, g_dt, gg, tg, rp, stream));
   } else {
-    KFB_TRY(split_im2col(L, a0, a_dt, nb, 0, ta, precision, stream));
+    KFB_TRY(split_im2col(L, a0, a_dt, nb, 0, ta, rp, stream));
     GatherDesc gg{};
     gg.sb = (long long)L.d_out * S; gg.sr = 1; gg.sc2 = S; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
-    KFB_TRY(split_gather(g0, g_dt, gg, tg, precision, stream));
+    KFB_TRY(split_gather(g0, g_dt, gg, tg, rp, stream));
   }
   // Rt[b] = Q_A^T a_b^T : M = d_in+bias (eigen index), N = S, K = d_in+bias
   kfb_epilogue e = store_epilogue();
   e.out_split = Rt;
-  KFB_TRY(gemm_nt(*qa_t, ta, e, precision, 1, stream));
+  KFB_TRY(gemm_nt(*qa_t, ta, e, rp, 1, stream));
   e.out_split = Lt;
-  KFB_TRY(gemm_nt(*qg_t, tg, e, precision, 1, stream));
+  KFB_TRY(gemm_nt(*qg_t, tg, e, rp, 1, stream));
   return KFB_OK;
 }
 
@@ -250,15 +261,16 @@ static int lambda_run(const kfb_layer& L, const void* a, int a_dt, const void* g
                       cudaStream_t stream) {
   const long long S = positions(L, seq);
   const long long di = L.d_in + L.has_bias;
-  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
+  const long long planes = planes_of(precision);
   if (with_eigen && L.kind == KFB_LINEAR && S == 1) {
     // One position per example: (Q_G^T g_b)(Q_A^T a_b)^T is rank one, so
     //   Lambda += (Gr o Gr)^T (Ar o Ar)     with Ar = A Q_A, Gr = G Q_G        (K = batch)
     // i.e. two rotations with a squaring epilogue and one accumulate-GEMM.
-    const long long per = (ld8(di) + ld8(L.d_out)) * 2 * planes * 2;
+    const int rp = rot_prec(precision);
+    const long long per = (ld8(di) + ld8(L.d_out)) * 2 * (planes + planes_of(rp));
     const long long cb = chunk_count(batch, per);
-    kfb_split a_sp = ws_split(ws, cb, di, 1, precision);
-    kfb_split g_sp = ws_split(ws, cb, L.d_out, 1, precision);
+    kfb_split a_sp = ws_split(ws, cb, di, 1, rp);
+    kfb_split g_sp = ws_split(ws, cb, L.d_out, 1, rp);
     kfb_split At2 = ws_split(ws, di, cb, 1, precision);
     kfb_split Gt2 = ws_split(ws, L.d_out, cb, 1, precision);
     if (ws.dry) return KFB_OK;
@@ -274,17 +286,17 @@ static int lambda_run(const kfb_layer& L, const void* a, int a_dt, const void* g
       GatherDesc ga{};
       ga.sr = L.d_in; ga.sc2 = 1; ga.rows = nb; ga.c1 = 1; ga.c2 = L.d_in;
       ga.ones_mode = L.has_bias ? 1 : 0;
-      KFB_TRY(split_gather(advance(a, a_dt, b0 * L.d_in), a_dt, ga, av, precision, stream));
+      KFB_TRY(split_gather(advance(a, a_dt, b0 * L.d_in), a_dt, ga, av, rp, stream));
       GatherDesc gg{};
       gg.sr = L.d_out; gg.sc2 = 1; gg.rows = nb; gg.c1 = 1; gg.c2 = L.d_out;
-      KFB_TRY(split_gather(advance(g, g_dt, b0 * L.d_out), g_dt, gg, gv, precision, stream));
+      KFB_TRY(split_gather(advance(g, g_dt, b0 * L.d_out), g_dt, gg, gv, rp, stream));
       kfb_epilogue e = store_epilogue();
       e.square = 1;
       e.out_split = at;
-      KFB_TRY(gemm_nt(*qa_t, av, e, precision, 1, stream));
+      KFB_TRY(gemm_nt(*qa_t, av, e, rp, 1, stream));
       e.out_split = gt;
       e.alpha = scale;  // squared by the epilogue -> scale^2, as tracker/factor.py:270-271 then :223
-      KFB_TRY(gemm_nt(*qg_t, gv, e, precision, 1, stream));
+      KFB_TRY(gemm_nt(*qg_t, gv, e, rp, 1, stream));
       kfb_epilogue acc = store_epilogue();
       acc.out_f32 = lambda;
       acc.ldo = di;
@@ -317,6 +329,17 @@ static int lambda_run(const kfb_layer& L, const void* a, int a_dt, const void* g
 // =================================================================================================
 // Stage 4: query-side per-sample gradient + preconditioning.  tracker/precondition.py:102-123,
 // factor/config.py:341-353.
+//
+// KFB_PRECOND_EIGEN keeps the result IN THE EIGENBASIS:
+//     Pt_q = scale * (Q_G^T G_q Q_A) o Lambda^-1                      (stored; "M'" below)
+// instead of the reference's P_q = Q_G Pt_q Q_A^T, and stage 5 rotates the TRAIN operands instead:
+//     <P_q, G_t> = <Pt_q, Q_G^T G_t Q_A> = sum_{s} (Q_G^T g_ts)^T Pt_q (Q_A^T a_ts).
+// Same number up to rounding, but far better conditioned: Lambda^-1 spans many orders of magnitude, and
+// rotating Pt_q back mixes its huge (nearly-null-direction) entries into every parameter, so that the
+// final dot product with G_t relies on cancellation.  In the eigenbasis every term of the score is a plain
+// product, and the only error Lambda^-1 can amplify is that of the rotated vectors, which are computed in
+// the strict 3-plane mode.  It also saves the two back-rotation GEMMs per query.  p_f32, if requested,
+// still receives the reference-layout P_q (two extra GEMMs; inspection / parity tests only).
 // =================================================================================================
 static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt,
                             long long batch, long long seq, int mode, const kfb_split* qa,
@@ -326,17 +349,15 @@ static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const v
                             cudaStream_t stream) {
   const long long S = positions(L, seq);
   const long long di = L.d_in + L.has_bias;
-  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
+  const long long planes = planes_of(precision);
   const bool eigen = mode == KFB_PRECOND_EIGEN;
+  const bool back_rotate = eigen && (p_f32 != nullptr || ws.dry);
   long long per = outer_bytes_per_sample(L, S, eigen, precision);
-  if (eigen) per += (L.d_out * ld8(di) + di * ld8(L.d_out)) * 2 * planes;
+  if (back_rotate) per += di * ld8(L.d_out) * 2 * planes;
   const long long cb = chunk_count(batch, per);
   OuterBufs o = outer_alloc(ws, L, cb, S, eigen, precision);
-  kfb_split Mp{}, Rt2{};
-  if (eigen) {
-    Mp = ws_split(ws, L.d_out, di, cb, precision);
-    Rt2 = ws_split(ws, di, L.d_out, cb, precision);
-  }
+  kfb_split Rt2{};
+  if (back_rotate) Rt2 = ws_split(ws, di, L.d_out, cb, precision);
   if (ws.dry) return KFB_OK;
   if (!ws.fits()) {
     set_error("precondition workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
@@ -349,7 +370,7 @@ static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const v
               "precondition: queries [%lld, %lld) exceed the destination capacity %lld", q_offset,
               q_offset + batch, (long long)P->batch);
   KFB_REQUIRE(mode == KFB_PRECOND_IDENTITY || lambda_inv != nullptr, "precondition: lambda_inv is required");
-  if (eigen)
+  if (back_rotate)
     KFB_REQUIRE(qa != nullptr && qg != nullptr && qa->rows == di && qg->rows == L.d_out,
                 "precondition: eigenbasis operands do not match the layer");
   for (long long b0 = 0; b0 < batch; b0 += cb) {
@@ -358,36 +379,29 @@ static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const v
     kfb_split Lt = split_batch_view(o.Lt, 0, nb), Rt = split_batch_view(o.Rt, 0, nb);
     kfb_split Pv = split_batch_view(*P, q_offset + b0, nb);
     float* pf = p_f32 != nullptr ? p_f32 + b0 * L.d_out * di : nullptr;
+    // Pt = scale * (Lt Rt^T) [o lambda_inv]                    [nb][d_out][d_in+bias]
+    kfb_epilogue e = store_epilogue();
+    e.out_split = Pv;
+    e.mul = mode == KFB_PRECOND_IDENTITY ? nullptr : lambda_inv;
+    e.ldmul = di;
+    e.alpha = scale;
     if (!eigen) {
-      kfb_epilogue e = store_epilogue();
-      e.out_split = Pv;
       e.out_f32 = pf;
       e.ldo = di;
       e.out_batch_stride = L.d_out * di;
-      e.mul = mode == KFB_PRECOND_DIAGONAL ? lambda_inv : nullptr;
-      e.ldmul = di;
-      e.alpha = scale;
-      KFB_TRY(gemm_nt(Lt, Rt, e, precision, 1, stream));
-      continue;
     }
-    // M' = (Q_G^T G Q_A) o lambda_inv                         [nb][d_out][d_in+bias]
-    kfb_epilogue e1 = store_epilogue();
-    e1.out_split = split_batch_view(Mp, 0, nb);
-    e1.mul = lambda_inv;
-    e1.ldmul = di;
-    KFB_TRY(gemm_nt(Lt, Rt, e1, precision, 1, stream));
-    // R^T = Q_A M'^T                                          [nb][d_in+bias][d_out]
-    kfb_epilogue e2 = store_epilogue();
-    e2.out_split = split_batch_view(Rt2, 0, nb);
-    KFB_TRY(gemm_nt(*qa, split_batch_view(Mp, 0, nb), e2, precision, 1, stream));
-    // P = scale * Q_G R                                       [nb][d_out][d_in+bias]
-    kfb_epilogue e3 = store_epilogue();
-    e3.out_split = Pv;
-    e3.out_f32 = pf;
-    e3.ldo = di;
-    e3.out_batch_stride = L.d_out * di;
-    e3.alpha = scale;
-    KFB_TRY(gemm_nt(*qg, split_batch_view(Rt2, 0, nb), e3, precision, 1, stream));
+    KFB_TRY(gemm_nt(Lt, Rt, e, precision, 1, stream));
+    if (eigen && pf != nullptr) {
+      // reference layout on request:  R^T = Q_A Pt^T  [nb][d_in+bias][d_out],  P = Q_G R  [nb][d_out][d_in+bias]
+      kfb_epilogue e2 = store_epilogue();
+      e2.out_split = split_batch_view(Rt2, 0, nb);
+      KFB_TRY(gemm_nt(*qa, Pv, e2, precision, 1, stream));
+      kfb_epilogue e3 = store_epilogue();
+      e3.out_f32 = pf;
+      e3.ldo = di;
+      e3.out_batch_stride = L.d_out * di;
+      KFB_TRY(gemm_nt(*qg, split_batch_view(Rt2, 0, nb), e3, precision, 1, stream));
+    }
   }
   return KFB_OK;
 }
@@ -402,17 +416,28 @@ __global__ void zero_strided_kernel(float* p, long long rows, long long cols, lo
 }
 
 static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, const void* a, int a_dt,
-                        const void* g, int g_dt, long long batch, long long seq, float scale,
-                        float* scores, long long ld_scores, long long t_offset, int accumulate,
-                        Ws& ws, int precision, cudaStream_t stream) {
+                        const void* g, int g_dt, long long batch, long long seq, int mode,
+                        const kfb_split* qa_t, const kfb_split* qg_t, float scale, float* scores,
+                        long long ld_scores, long long t_offset, int accumulate, Ws& ws, int precision,
+                        cudaStream_t stream) {
   const long long S = positions(L, seq);
   const long long di = L.d_in + L.has_bias;
-  const long long planes = precision == KFB_PREC_FP32 ? 2 : 1;
+  const long long planes = planes_of(precision);
+  const bool eigen = mode == KFB_PRECOND_EIGEN;  // P is stored in the eigenbasis: rotate the train operands
+  const int rp = rot_prec(precision);
   if (L.kind == KFB_LINEAR && S == 1) {
     // Fused path: scores[q, t] = sum_o g[t,o] * (sum_i a[t,i] P[q,o,i]); the inner GEMM is the
     // tensor-core tile (M = t, N = o, K = i, batched over q), the outer sum is the ROWDOT epilogue.
-    kfb_split a_sp = ws_split(ws, batch, di, 1, precision);
-    float* g32 = g_dt == KFB_F32 ? nullptr : static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
+    kfb_split a_sp = ws_split(ws, batch, di, 1, eigen ? rp : precision);
+    kfb_split g_sp{}, a_rot{};
+    float* g32 = nullptr;
+    if (eigen) {
+      g_sp = ws_split(ws, batch, L.d_out, 1, rp);
+      a_rot = ws_split(ws, batch, di, 1, precision);
+      g32 = static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
+    } else if (g_dt != KFB_F32) {
+      g32 = static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
+    }
     if (ws.dry) return KFB_OK;
     if (!ws.fits()) {
       set_error("pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
@@ -421,9 +446,28 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
     GatherDesc ga{};
     ga.sr = L.d_in; ga.sc2 = 1; ga.rows = batch; ga.c1 = 1; ga.c2 = L.d_in;
     ga.ones_mode = L.has_bias ? 1 : 0;
-    KFB_TRY(split_gather(a, a_dt, ga, a_sp, precision, stream));
+    KFB_TRY(split_gather(a, a_dt, ga, a_sp, eigen ? rp : precision, stream));
     const float* gp = static_cast<const float*>(g);
-    if (g32 != nullptr) {
+    const kfb_split* a_operand = &a_sp;
+    if (eigen) {
+      KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
+                  "pairwise: eigenbasis operands do not match the layer");
+      KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+                  "pairwise: eigenbasis operands must be built with KFB_PREC_STRICT");
+      GatherDesc gg{};
+      gg.sr = L.d_out; gg.sc2 = 1; gg.rows = batch; gg.c1 = 1; gg.c2 = L.d_out;
+      KFB_TRY(split_gather(g, g_dt, gg, g_sp, rp, stream));
+      // a~[t, n] = sum_k a[t,k] Q_A[k,n]  (operand planes for the fused kernel);  g~[t, n] likewise (fp32)
+      kfb_epilogue ea = store_epilogue();
+      ea.out_split = a_rot;
+      KFB_TRY(gemm_nt(a_sp, *qa_t, ea, rp, 1, stream));
+      kfb_epilogue eg = store_epilogue();
+      eg.out_f32 = g32;
+      eg.ldo = L.d_out;
+      KFB_TRY(gemm_nt(g_sp, *qg_t, eg, rp, 1, stream));
+      a_operand = &a_rot;
+      gp = g32;
+    } else if (g32 != nullptr) {
       KFB_TRY(cast_to_f32(g, g_dt, g32, batch * L.d_out, 1.f, stream));
       gp = g32;
     }
@@ -435,18 +479,19 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
     e.ldg = L.d_out;
     e.alpha = scale;
     e.accumulate = accumulate;
-    return gemm_nt(a_sp, split_batch_view(*P, 0, nq), e, precision, 1, stream);
+    return gemm_nt(*a_operand, split_batch_view(*P, 0, nq), e, precision, 1, stream);
   }
-  // General path (sequences, Conv2d): per-sample gradients G_t = g_t^T a_t via a batched GEMM
-  // (K = S) written straight in P's operand layout, then scores = P_flat G_flat^T (K = d_out*ld).
+  // General path (sequences, Conv2d): per-sample gradients G_t = g_t^T a_t (rotated into the eigenbasis
+  // first when P is) via a batched GEMM (K = S) written straight in P's operand layout, then
+  // scores = P_flat G_flat^T (K = d_out*ld).
   const long long ldp = P != nullptr ? P->ld : ld8(di);
-  const long long per = outer_bytes_per_sample(L, S, false, precision) + L.d_out * ldp * 2 * planes;
+  const long long per = outer_bytes_per_sample(L, S, eigen, precision) + L.d_out * ldp * 2 * planes;
   const long long cb = chunk_count(batch, per);
-  OuterBufs o = outer_alloc(ws, L, cb, S, false, precision);
+  OuterBufs o = outer_alloc(ws, L, cb, S, eigen, precision);
   kfb_split G{};
   G.rows = L.d_out; G.cols = di; G.ld = ldp; G.batch = cb; G.batch_stride = L.d_out * ldp;
   G.hi = ws.take((size_t)(cb * G.batch_stride) * 2);
-  G.lo = precision == KFB_PREC_FP32 ? ws.take((size_t)(cb * G.batch_stride) * 2) : nullptr;
+  G.lo = precision != KFB_PREC_BF16 ? ws.take((size_t)(cb * G.batch_stride) * 2) : nullptr;
   if (ws.dry) return KFB_OK;
   if (!ws.fits()) {
     set_error("pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
@@ -459,7 +504,7 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
   }
   for (long long b0 = 0; b0 < batch; b0 += cb) {
     const long long nb = batch - b0 < cb ? batch - b0 : cb;
-    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, false, nullptr, nullptr, o, precision, stream));
+    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, eigen, qa_t, qg_t, o, precision, stream));
     kfb_epilogue e1 = store_epilogue();
     e1.out_split = split_batch_view(G, 0, nb);
     KFB_TRY(gemm_nt(split_batch_view(o.Lt, 0, nb), split_batch_view(o.Rt, 0, nb), e1, precision, 1, stream));
@@ -590,16 +635,16 @@ size_t kfb_pairwise_workspace_bytes(const kfb_layer* layer, int64_t batch, int64
   if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
   KFB_WS(nullptr, 0, true);
   // g may need an fp32 staging copy: measure with a non-fp32 dtype
-  pairwise_run(*layer, nullptr, 0, nullptr, KFB_F32, nullptr, KFB_BF16, batch, seq, 1.f, nullptr, 0, 0, 1,
-               w, KFB_PREC_FP32, nullptr);
+  pairwise_run(*layer, nullptr, 0, nullptr, KFB_F32, nullptr, KFB_BF16, batch, seq, KFB_PRECOND_EIGEN, nullptr,
+               nullptr, 1.f, nullptr, 0, 0, 1, w, KFB_PREC_FP32, nullptr);
   return w.off + 256;
 }
 
 int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
                         const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
-                        int64_t seq, float scale, float* scores, int64_t ld_scores,
-                        int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes,
-                        int precision, void* stream) {
+                        int64_t seq, int32_t mode, const kfb_split* qa_t, const kfb_split* qg_t,
+                        float scale, float* scores, int64_t ld_scores, int64_t t_offset,
+                        int32_t accumulate, void* ws, size_t ws_bytes, int precision, void* stream) {
   KFB_TRY(check_layer(layer));
   KFB_REQUIRE(P != nullptr && P->hi != nullptr && a != nullptr && g != nullptr && scores != nullptr,
               "pairwise_scores: null tensor");
@@ -609,13 +654,15 @@ int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_
   KFB_REQUIRE(t_offset >= 0 && t_offset + batch <= ld_scores, "pairwise_scores: columns out of range");
   if (batch <= 0 || num_queries == 0) return KFB_OK;
   KFB_WS(ws, ws_bytes, false);
-  return pairwise_run(*layer, P, num_queries, a, a_dtype, g, g_dtype, batch, seq, scale, scores,
-                      ld_scores, t_offset, accumulate, w, precision, (cudaStream_t)stream);
+  KFB_REQUIRE(mode >= KFB_PRECOND_IDENTITY && mode <= KFB_PRECOND_EIGEN, "pairwise_scores: bad mode %d", mode);
+  return pairwise_run(*layer, P, num_queries, a, a_dtype, g, g_dtype, batch, seq, mode, qa_t, qg_t, scale,
+                      scores, ld_scores, t_offset, accumulate, w, precision, (cudaStream_t)stream);
 }
 
 int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,
                              const void* a_host, int a_dtype, const void* g_host, int g_dtype,
-                             int64_t batch, int64_t seq, float scale, float* scores_host,
+                             int64_t batch, int64_t seq, int32_t mode, const kfb_split* qa_t,
+                             const kfb_split* qg_t, float scale, float* scores_host,
                              void* dev_a, void* dev_g, float* dev_scores, void* ws,
                              size_t ws_bytes, int precision, void* stream) {
   KFB_TRY(check_layer(layer));
@@ -629,8 +676,8 @@ int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t
   const size_t g_bytes = (size_t)batch * S * layer->d_out * dtype_size(g_dtype);
   KFB_CUDA_TRY(cudaMemcpyAsync(dev_a, a_host, a_bytes, cudaMemcpyHostToDevice, st));
   KFB_CUDA_TRY(cudaMemcpyAsync(dev_g, g_host, g_bytes, cudaMemcpyHostToDevice, st));
-  KFB_TRY(kfb_pairwise_scores(layer, P, num_queries, dev_a, a_dtype, dev_g, g_dtype, batch, seq, scale,
-                              dev_scores, batch, 0, 0, ws, ws_bytes, precision, stream));
+  KFB_TRY(kfb_pairwise_scores(layer, P, num_queries, dev_a, a_dtype, dev_g, g_dtype, batch, seq, mode, qa_t,
+                              qg_t, scale, dev_scores, batch, 0, 0, ws, ws_bytes, precision, stream));
   KFB_CUDA_TRY(cudaMemcpyAsync(scores_host, dev_scores, (size_t)num_queries * batch * 4,
                                cudaMemcpyDeviceToHost, st));
   return KFB_OK;

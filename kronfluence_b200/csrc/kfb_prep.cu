@@ -29,10 +29,29 @@ __device__ __forceinline__ float load_as_float<double>(const double* p, long lon
 struct SplitDst {
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
+  __nv_bfloat16* lo2;
   long long ld, bs;
 };
 
+static SplitDst make_dst(const kfb_split& dst, int precision) {
+  SplitDst d;
+  d.hi = (__nv_bfloat16*)dst.hi;
+  d.lo = precision != KFB_PREC_BF16 ? (__nv_bfloat16*)dst.lo : nullptr;
+  d.lo2 = precision == KFB_PREC_STRICT ? (__nv_bfloat16*)dst.lo2 : nullptr;
+  d.ld = dst.ld;
+  d.bs = dst.batch_stride;
+  return d;
+}
+
 __device__ __forceinline__ void store_split(const SplitDst& d, long long idx, float v) {
+  if (d.lo2 != nullptr) {
+    __nv_bfloat16 h, m, l;
+    split_bf16_3(v, h, m, l);
+    d.hi[idx] = h;
+    d.lo[idx] = m;
+    d.lo2[idx] = l;
+    return;
+  }
   __nv_bfloat16 h, l;
   split_bf16(v, h, l);
   d.hi[idx] = h;
@@ -102,11 +121,11 @@ static int launch_gather(const T* src, const GatherDesc& g, const kfb_split& dst
               (long long)dst.cols, out_rows, out_cols);
   KFB_REQUIRE(dst.ld >= out_cols && dst.ld % 8 == 0, "split_gather: bad destination ld %lld",
               (long long)dst.ld);
-  KFB_REQUIRE(dst.hi != nullptr && (precision == KFB_PREC_BF16 || dst.lo != nullptr),
+  KFB_REQUIRE(dst.hi != nullptr && (precision == KFB_PREC_BF16 || dst.lo != nullptr) &&
+                  (precision != KFB_PREC_STRICT || dst.lo2 != nullptr),
               "split_gather: missing destination plane");
   if (out_rows == 0 || dst.batch == 0) return KFB_OK;
-  SplitDst d{(__nv_bfloat16*)dst.hi, precision == KFB_PREC_FP32 ? (__nv_bfloat16*)dst.lo : nullptr,
-             dst.ld, dst.batch_stride};
+  SplitDst d = make_dst(dst, precision);
   const unsigned gz = (unsigned)(dst.batch < 65535 ? dst.batch : 65535);
   const bool transpose = (g.sr == 1 && g.sc2 != 1 && g.rows > 1);
   if (transpose) {
@@ -195,8 +214,7 @@ static int launch_im2col(const kfb_layer& L, const T* x, long long batch, int la
   KFB_REQUIRE(dst.ld >= cols && dst.ld % 8 == 0, "im2col: bad destination ld");
   KFB_REQUIRE(layout == 2 ? dst.batch == 1 : dst.batch == batch, "im2col: bad destination batch");
   if (batch == 0) return KFB_OK;
-  SplitDst d{(__nv_bfloat16*)dst.hi, precision == KFB_PREC_FP32 ? (__nv_bfloat16*)dst.lo : nullptr,
-             dst.ld, dst.batch_stride};
+  SplitDst d = make_dst(dst, precision);
   dim3 block(128, 2);
   dim3 grid((unsigned)ceil_div_ll(dst.ld, block.x), (unsigned)ceil_div_ll(rows, block.y),
             (unsigned)(layout == 2 ? 1 : (batch < 65535 ? batch : 65535)));

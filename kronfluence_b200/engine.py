@@ -23,7 +23,7 @@ KFB_ERR_WORKSPACE = -5
 KFB_ERR_NOT_CONVERGED = -6
 
 KFB_F32, KFB_BF16, KFB_F16, KFB_F64 = 0, 1, 2, 3
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_STRICT = 0, 1, 2
 LINEAR, CONV2D = 0, 1
 PRECOND_IDENTITY, PRECOND_DIAGONAL, PRECOND_EIGEN = 0, 1, 2
 EPI_STORE, EPI_ROWDOT, EPI_SQACC = 0, 1, 2
@@ -38,7 +38,7 @@ class KfbLayer(ctypes.Structure):
 
 
 class KfbSplit(ctypes.Structure):
-    _fields_ = [("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("rows", ctypes.c_int64),
+    _fields_ = [("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("lo2", ctypes.c_void_p), ("rows", ctypes.c_int64),
                 ("cols", ctypes.c_int64), ("ld", ctypes.c_int64), ("batch", ctypes.c_int64),
                 ("batch_stride", ctypes.c_int64)]
 
@@ -79,8 +79,8 @@ SIGNATURES = {
     "kfb_precondition_workspace_bytes": (_sz, [_LP, _i64, _i64]),
     "kfb_precondition": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _SP, _SP, _vp, _f32, _SP, _i64, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "kfb_pairwise_workspace_bytes": (_sz, [_LP, _i64, _i64]),
-    "kfb_pairwise_scores": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _f32, _vp, _i64, _i64, _i32, _vp, _sz, ctypes.c_int, _vp]),
-    "kfb_pairwise_scores_host": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
+    "kfb_pairwise_scores": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _f32, _vp, _i64, _i64, _i32, _vp, _sz, ctypes.c_int, _vp]),
+    "kfb_pairwise_scores_host": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _f32, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
 }
 
 _lib = None
@@ -183,7 +183,7 @@ class Split:
         self.ld = round_up(max(self.cols, 1), 8)
         self.batch_stride = self.rows * self.ld
         self.precision = precision
-        planes = 2 if precision == PREC_FP32 else 1
+        planes = {PREC_FP32: 2, PREC_BF16: 1, PREC_STRICT: 3}[precision]
         alloc = torch.zeros if zero else torch.empty
         self.storage = alloc((planes, self.batch, self.rows, self.ld), dtype=torch.bfloat16, device=device)
 
@@ -191,14 +191,15 @@ class Split:
         nb = self.batch - batch_offset if batch is None else batch
         off = batch_offset * self.batch_stride * 2
         hi = self.storage[0].data_ptr() + off
-        lo = self.storage[1].data_ptr() + off if self.storage.shape[0] == 2 else None
-        return KfbSplit(hi, lo, self.rows, self.cols, self.ld, nb, self.batch_stride)
+        lo = self.storage[1].data_ptr() + off if self.storage.shape[0] >= 2 else None
+        lo2 = self.storage[2].data_ptr() + off if self.storage.shape[0] == 3 else None
+        return KfbSplit(hi, lo, lo2, self.rows, self.cols, self.ld, nb, self.batch_stride)
 
     def to_float(self) -> torch.Tensor:
         """hi + lo as fp32 [batch, rows, cols] (tests / debugging)."""
         val = self.storage[0].float()
-        if self.storage.shape[0] == 2:
-            val = val + self.storage[1].float()
+        for plane in range(1, self.storage.shape[0]):
+            val = val + self.storage[plane].float()
         return val[:, :, : self.cols]
 
     def nbytes(self) -> int:

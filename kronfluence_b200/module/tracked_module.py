@@ -315,11 +315,14 @@ class PairwiseScoreTracker(BaseTracker):
             if sink is None or store is None:
                 raise RuntimeError(f"Module '{module.name}': pairwise scoring was not set up.")
             layer = module.layer_for(a)
+            qa = qg = None
+            if strategy_config(module.factor_args.strategy)["mode"] == ops.PRECOND_EIGEN:
+                qa, qg = module.eigen_operands(grad.device)  # the store holds eigenbasis images
             # Every use of a shared module adds its own term (the mathematically correct sum; the
             # reference keeps only the last use).
             ops.pairwise_scores(layer, store, module.query_count, a, grad.detach(), sink, module.score_offset,
                                 accumulate=True, scale=module.gradient_scale,
-                                precision=precision_of(module.score_args.score_dtype))
+                                precision=precision_of(module.score_args.score_dtype), qa=qa, qg=qg)
             if not module.factor_args.has_shared_parameters:
                 self.clear_all_cache()
 

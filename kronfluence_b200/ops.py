@@ -15,6 +15,7 @@ from kronfluence_b200 import engine
 from kronfluence_b200.engine import (
     PREC_BF16,
     PREC_FP32,
+    PREC_STRICT,
     PRECOND_DIAGONAL,
     PRECOND_EIGEN,
     PRECOND_IDENTITY,
@@ -145,10 +146,16 @@ def eigh_sym(cov: torch.Tensor, count: float) -> Tuple[torch.Tensor, torch.Tenso
 
 
 class EigenOperands:
-    """Q and Q^T of one Kronecker factor in tensor-core operand layout (kfb_eigen_operands)."""
+    """Q and Q^T of one Kronecker factor in tensor-core operand layout (kfb_eigen_operands).
+
+    In the fp32-parity mode the rotations run in the strict 3-plane precision (their errors are what
+    Lambda^-1 amplifies), so the operands are built with three bf16 planes; the first two double as the
+    ordinary hi/lo pair."""
 
     def __init__(self, q: torch.Tensor, precision: int = PREC_FP32):
         lib = engine.load_library()
+        if precision == PREC_FP32:
+            precision = PREC_STRICT
         q = _contig(q.to(dtype=torch.float32))
         d = q.shape[0]
         self.d = d
@@ -235,22 +242,31 @@ def precondition(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, store: Split
 # --------------------------------------------------------------------------------------------------
 def pairwise_scores(layer: KfbLayer, store: Split, num_queries: int, a: torch.Tensor, g: torch.Tensor,
                     scores: torch.Tensor, t_offset: int = 0, accumulate: bool = False, scale: float = 1.0,
-                    precision: int = PREC_FP32) -> None:
-    """scores[:num_queries, t_offset:t_offset+B] (+)= <P_q, per-sample gradient of example t>."""
+                    precision: int = PREC_FP32, qa: Optional[EigenOperands] = None,
+                    qg: Optional[EigenOperands] = None) -> None:
+    """scores[:num_queries, t_offset:t_offset+B] (+)= <P_q, per-sample gradient of example t>.
+
+    With eigen operands the store holds eigenbasis images (as `precondition(..., PRECOND_EIGEN)` writes them)
+    and the train operands are rotated first; without, the store is in parameter layout."""
     lib = engine.load_library()
     a, g = _contig(a), _contig(g)
     batch, seq = _batch_seq(layer, a)
     assert scores.dtype == torch.float32 and scores.stride(-1) == 1
     src = store.struct(0, store.batch)
+    mode = PRECOND_EIGEN if qa is not None else PRECOND_IDENTITY
+    sa = qa.qt.struct() if qa is not None else None
+    sg = qg.qt.struct() if qg is not None else None
     ws_ptr, ws_size = workspace(a.device).get(lib.kfb_pairwise_workspace_bytes(ctypes.byref(layer), batch, seq))
     check(lib.kfb_pairwise_scores(ctypes.byref(layer), ctypes.byref(src), int(num_queries), a.data_ptr(),
-                                  dtype_code(a.dtype), g.data_ptr(), dtype_code(g.dtype), batch, seq, float(scale),
+                                  dtype_code(a.dtype), g.data_ptr(), dtype_code(g.dtype), batch, seq, mode,
+                                  ctypes.byref(sa) if sa is not None else None,
+                                  ctypes.byref(sg) if sg is not None else None, float(scale),
                                   scores.data_ptr(), scores.stride(0), int(t_offset), int(accumulate), ws_ptr,
                                   ws_size, precision, stream_ptr(a.device)))
 
 
 __all__ = [
-    "PREC_FP32", "PREC_BF16", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
+    "PREC_FP32", "PREC_BF16", "PREC_STRICT", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
     "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
     "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "layer_of", "factor_dims", "workspace",
 ]

@@ -187,7 +187,7 @@ def make_stage_fixtures():
 # --------------------------------------------------------------------------------------------------
 # End-to-end fixtures through the reference Analyzer
 # --------------------------------------------------------------------------------------------------
-def run_reference(case, dtype, strategy="ekfac"):
+def run_reference(case, dtype, strategy="ekfac", damping=None):
     tasks = fixtures.make_tasks(Task)
     model, train_set, query_set = fixtures.make_case(case)
     model = model.to(dtype=dtype)
@@ -199,7 +199,7 @@ def run_reference(case, dtype, strategy="ekfac"):
         analyzer = Analyzer(analysis_name="golden", model=model, task=task, cpu=True, output_dir=tmp,
                             disable_tqdm=True, disable_model_save=True)
         factor_args = FactorArguments(strategy=strategy, use_empirical_fisher=True)
-        score_args = ScoreArguments(damping_factor=None)
+        score_args = ScoreArguments(damping_factor=damping)
         if dtype == torch.float64:
             for key in ("activation_covariance_dtype", "gradient_covariance_dtype", "per_sample_gradient_dtype",
                         "lambda_dtype"):
@@ -238,6 +238,11 @@ def make_e2e_fixtures():
         d64 = run_reference(case, torch.float64)
         merged = {f"f32/{k}": v for k, v in d32.items()}
         merged.update({f"f64/{k}": v for k, v in d64.items()})
+        # the reference's DEFAULT damping (ScoreArguments.damping_factor = 1e-8): ill-conditioned on purpose
+        merged["f32/scores_default_damping"] = run_reference(case, torch.float32, damping=1e-8)["scores"]
+        merged["f64/scores_default_damping"] = run_reference(case, torch.float64, damping=1e-8)["scores"]
+        rel_d = np.linalg.norm(merged["f32/scores_default_damping"] - merged["f64/scores_default_damping"]) / np.linalg.norm(merged["f64/scores_default_damping"])
+        print("e2e", case, "default damping 1e-8: reference fp32-vs-fp64 rel", rel_d)
         np.savez_compressed(os.path.join(GOLDEN, f"e2e_{case}.npz"), **merged)
         rel = np.linalg.norm(d32["scores"] - d64["scores"]) / np.linalg.norm(d64["scores"])
         print("e2e", case, "scores", d32["scores"].shape, "fp32-vs-fp64 rel", rel)

@@ -94,7 +94,11 @@ def precondition(layer, a, g, store, q_offset, mode, qa=None, qg=None, lambda_in
                  precision=0):
     grads = _per_sample(layer, a, g)
     if mode == ops.PRECOND_EIGEN:
-        p = orc.precondition(grads, _np(lambda_inv), qa.q, qg.q)
+        # like the CUDA op, the store keeps the eigenbasis image (Q_G^T G Q_A) o Lambda^-1
+        p = np.matmul(qg.q.T, np.matmul(grads, qa.q)) * _np(lambda_inv)
+        if out_f32 is not None:
+            out_f32.copy_(torch.from_numpy(orc.precondition(grads, _np(lambda_inv), qa.q, qg.q) * scale).to(out_f32.dtype))
+            out_f32 = None
     elif mode == ops.PRECOND_DIAGONAL:
         p = orc.precondition(grads, _np(lambda_inv))
     else:
@@ -105,8 +109,11 @@ def precondition(layer, a, g, store, q_offset, mode, qa=None, qg=None, lambda_in
         out_f32.copy_(p.to(out_f32.dtype))
 
 
-def pairwise_scores(layer, store, num_queries, a, g, scores, t_offset=0, accumulate=False, scale=1.0, precision=0):
+def pairwise_scores(layer, store, num_queries, a, g, scores, t_offset=0, accumulate=False, scale=1.0, precision=0,
+                    qa=None, qg=None):
     grads = _per_sample(layer, a, g)
+    if qa is not None:
+        grads = np.matmul(qg.q.T, np.matmul(grads, qa.q))
     block = torch.from_numpy(orc.pairwise_scores_from_gradients(store.storage[0, :num_queries].numpy(), grads) * scale)
     view = scores[:num_queries, t_offset : t_offset + grads.shape[0]]
     if accumulate:

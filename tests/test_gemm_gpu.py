@@ -164,3 +164,34 @@ def test_long_contraction_passes(shape):
     assert _rel(out, ref) < 1e-5
     assert _rel(acc - 1.0, ref) < 1e-5
     assert _rel(dst.to_float(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 200, 150, 700), (3, 1, 64, 300, 4097), (1, 1, 130, 40, 30)])
+def test_strict_precision(shape):
+    """KFB_PREC_STRICT: hi/mid/lo planes, 6 MMAs, TMEM drained every 64 contraction elements.  Checked against
+    float64 on the ORIGINAL float32 inputs: the whole error (split + truncating accumulation) is ~1e-6."""
+    engine = _engine()
+    ba, bb, m, n, k = shape
+    gen = torch.Generator(device="cuda").manual_seed(23)
+    a = torch.randn(ba, m, k, device="cuda", generator=gen)
+    b = torch.randn(bb, n, k, device="cuda", generator=gen)
+    sa = engine.split_from_tensor(a, engine.PREC_STRICT)
+    sb = engine.split_from_tensor(b, engine.PREC_STRICT)
+    assert (sa.to_float() - a).abs().max() <= 2e-7 * a.abs().max()
+    ref = torch.matmul(a.double(), b.double().transpose(1, 2))
+    batch = max(ba, bb)
+    out = torch.full((batch, m, n), float("nan"), device="cuda")
+    epi = engine.KfbEpilogue(kind=engine.EPI_STORE, out_f32=out.data_ptr(), ldo=n, out_batch_stride=m * n, alpha=1.0)
+    engine.gemm_nt(sa, sb, epi, engine.PREC_STRICT)
+    dst = engine.Split(n, m, batch, device="cuda")
+    epi2 = engine.KfbEpilogue(kind=engine.EPI_STORE, out_split=dst.struct(), alpha=1.0, transpose_out=1)
+    engine.gemm_nt(sa, sb, epi2, engine.PREC_STRICT)
+    # the same operands serve the ordinary 3-MMA mode (their first two planes are the hi/lo pair)
+    out3 = torch.empty_like(out)
+    epi3 = engine.KfbEpilogue(kind=engine.EPI_STORE, out_f32=out3.data_ptr(), ldo=n, out_batch_stride=m * n, alpha=1.0)
+    engine.gemm_nt(sa, sb, epi3, engine.PREC_FP32)
+    torch.cuda.synchronize()
+    err = _rel(out, ref.expand(batch, m, n))
+    assert err < 2e-6, err
+    assert _rel(dst.to_float(), ref.expand(batch, m, n).transpose(1, 2)) < 1e-4
+    assert _rel(out3, ref.expand(batch, m, n)) < 3e-5
