@@ -201,28 +201,29 @@ def test_linear_layer_against_oracle(cfg):
 
 
 def test_ill_conditioned_preconditioning():
-    """T < d (rank-deficient factors) and a tiny absolute damping: Lambda^-1 spans ~8 orders of magnitude.
-    Scoring in the eigenbasis with strict-precision rotations must stay close to the float64 oracle where a
-    parameter-layout P (huge null-space components cancelling in the final dot product) would not."""
+    """A skewed spectrum (ReLU activations: one dominant mean direction, a long tail) with a tiny absolute
+    damping, so that Lambda^-1 spans many orders of magnitude.  Scoring in the eigenbasis with strict-precision
+    rotations must stay within a small multiple of what float32 arithmetic itself loses against float64, where a
+    parameter-layout P (huge small-Lambda components cancelling in the final dot product) would not."""
     from kronfluence_b200 import engine, ops
 
     engine.require_device()
-    d_in, d_out, T, Q = 300, 120, 64, 16
+    d_in, d_out, T, Q = 300, 120, 420, 16
     rng = np.random.default_rng(3)
     a_tr = np.maximum(rng.standard_normal((T, d_in)), 0.0)
     g_tr = rng.standard_normal((T, d_out)) / np.sqrt(d_out)
     a_q = np.maximum(rng.standard_normal((Q, d_in)), 0.0)
     g_q = rng.standard_normal((Q, d_out)) / np.sqrt(d_out)
-    ref = orc.linear_ekfac_layer(a_tr, g_tr, a_q, g_q, True, damping=1e-8)
+    ref = orc.linear_ekfac_layer(a_tr, g_tr, a_q, g_q, True, damping=1e-7)
     ref32 = orc.linear_ekfac_layer(a_tr.astype(np.float32), g_tr.astype(np.float32), a_q.astype(np.float32),
-                                   g_q.astype(np.float32), True, damping=1e-8)
+                                   g_q.astype(np.float32), True, damping=1e-7)
     layer = ops.layer_of(torch.nn.Linear(d_in, d_out, bias=True))
     di, do = ops.factor_dims(layer)
     x, grad, xq, gq = cuda(a_tr), cuda(g_tr), cuda(a_q), cuda(g_q)
     qa, qg = ops.EigenOperands(cuda(ref["q_a"])), ops.EigenOperands(cuda(ref["q_g"]))
     lam = torch.zeros(do, di, device="cuda")
     ops.lambda_accum(layer, x, grad, lam, qa, qg)
-    lam_inv = ops.lambda_invert(lam, float(T), 1e-8)
+    lam_inv = ops.lambda_invert(lam, float(T), 1e-7)
     store = ops.make_query_store(do, di, Q, "cuda")
     ops.precondition(layer, xq, gq, store, 0, ops.PRECOND_EIGEN, qa, qg, lam_inv)
     scores = torch.empty(Q, T, device="cuda")
