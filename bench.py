@@ -93,27 +93,46 @@ class ClockSampler:
 
 
 def cpu_reference(d_in, d_out, bias, steps, warmup, budget_flops=6e11):
-    """Times the CPU restatement of the reference's path (module/linear.py:112-122 contraction order) on a
-    bounded sample of the workload: q_s queries x t_s train examples of the SAME layer shape, fp32, all host
-    threads (numpy/OpenBLAS).  scores/s is invariant to the truncation of Q and T."""
+    """Times the reference's CPU path for this contraction on a bounded sample of the workload: q_s queries x
+    t_s train examples of the SAME layer shape, fp32, all host threads.  It executes exactly what
+    TrackedLinear.compute_pairwise_score does (module/linear.py:112-122): torch's einsum 'qio,bi,bo->qb' along
+    the flop-optimal path opt_einsum finds for S=1 (P x activation first, then the reduction with the output
+    gradient), on the ones-augmented activation.  The numpy oracle is used to check the result.  scores/s is
+    invariant to the truncation of Q and T."""
+    import torch
+    from torch import _VF
+
     from oracle import ekfac_oracle as orc
 
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     di = d_in + int(bias)
     t_s = 256
     q_s = max(1, int(budget_flops / (2.0 * t_s * d_out * di)))
-    rng = np.random.default_rng(0)
-    p = rng.standard_normal((q_s, d_out, di), dtype=np.float32)
-    a = np.maximum(rng.standard_normal((t_s, d_in), dtype=np.float32), 0)
-    g = rng.standard_normal((t_s, d_out), dtype=np.float32) / np.sqrt(d_out).astype(np.float32)
+    gen = torch.Generator().manual_seed(0)
+    p = torch.randn(q_s, d_out, di, generator=gen)
+    a = torch.relu(torch.randn(t_s, d_in, generator=gen))
+    g = torch.randn(t_s, d_out, generator=gen) / d_out**0.5
+    a1 = torch.cat([a, torch.ones(t_s, 1)], dim=-1) if bias else a  # linear.py:56-61
+
+    def run():
+        # operands (preconditioned_gradient, output_gradient, input_activation); path: (0,2) then (0,1)
+        return _VF.einsum("qio,bi,bo->qb", (p, g, a1), path=[0, 2, 0, 1])  # pylint: disable=no-member
+
     for _ in range(warmup):
-        orc.linear_pairwise_scores_2d(p, a, g, bias)
+        out = run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.linear_pairwise_scores_2d(p, a, g, bias)
+        out = run()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": q_s * t_s / dt, "unit": "scores/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"Q={q_s} x T={t_s} of the {di}->{d_out} layer, fp32 numpy (OpenBLAS, {os.cpu_count()} threads), "
-                      f"{steps} timed passes of {dt:.2f} s", "ms_per_step": dt * 1e3}
+    check = orc.linear_pairwise_scores_2d(p[:4].numpy().astype(np.float64), a.numpy().astype(np.float64),
+                                          g.numpy().astype(np.float64), bias)
+    err = float(np.linalg.norm(out[:4].double().numpy() - check) / np.linalg.norm(check))
+    assert err < 1e-4, err
+    return {"value": q_s * t_s / dt, "unit": "scores/s", "cores": threads, "kind": "port",
+            "sample": f"Q={q_s} x T={t_s} of the {di}->{d_out} layer, fp32 torch.einsum along the reference's "
+                      f"opt_einsum path (ATen/MKL, {threads} threads), {steps} timed passes of {dt:.2f} s",
+            "ms_per_step": dt * 1e3}
 
 
 def main() -> None:
@@ -211,22 +230,6 @@ def main() -> None:
     if world > 1:
         gather_scores()  # untimed: NCCL communicator / NVLink connection setup happens on first use
     barrier()
-    launches0 = lib.kfb_launch_count()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        start.record()
-        for i in range(args.steps):
-            step(warmup + i)
-        gathered = gather_scores() if world > 1 else None
-        stop.record()
-        barrier()
-    elapsed_ms = torch.tensor([start.elapsed_time(stop)], device=device)
-    if world > 1:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    elapsed_s = elapsed_ms.item() / 1e3
-    launches = lib.kfb_launch_count() - launches0
-    value = n_query * t_batch * args.steps * world / elapsed_s
 
     # ---- dominant kernel alone (prep excluded): CUDA events around each launch ----
     a_split = engine.Split(t_batch, di, 1, device=device, precision=precision)
@@ -246,6 +249,24 @@ def main() -> None:
         if i >= 2:
             kernel_ms.append(e0.elapsed_time(e1))
     kernel_s = float(np.mean(kernel_ms)) / 1e3
+
+    launches0 = lib.kfb_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for i in range(args.steps):
+            step(warmup + i)
+        gathered = gather_scores() if world > 1 else None
+        stop.record()
+        barrier()
+    elapsed_ms = torch.tensor([start.elapsed_time(stop)], device=device)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_s = elapsed_ms.item() / 1e3
+    launches = lib.kfb_launch_count() - launches0
+    value = n_query * t_batch * args.steps * world / elapsed_s
+
     alg_flops = 2.0 * n_query * t_batch * do * di
     peaks, peak_kind = measured_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
