@@ -298,6 +298,30 @@ class Analyzer:
             num_processed = count.cpu()
         return num_processed
 
+    def _run_factor_partitions(self, out_dir: Path, factor_names: List[str], data_parts, module_parts,
+                               fit_part: Callable[[int, int, List[str]], FACTOR_TYPE], overwrite: bool,
+                               metadata: Dict[str, str]) -> FACTOR_TYPE:
+        """Runs every (data, module) partition, summing the results.  With more than one partition each
+        result is also saved under the reference's partition file names and an existing file is reused
+        instead of recomputed — kronfluence's preemption / resume story (factor_computer.py:57-108,263-274)."""
+        partitioned = len(data_parts) > 1 or len(module_parts) > 1
+        merged: FACTOR_TYPE = {name: {} for name in factor_names}
+        for d_idx, (start, end) in enumerate(data_parts):
+            for m_idx, names in enumerate(module_parts):
+                partition = (d_idx, m_idx)
+                if partitioned and not overwrite and io.factors_exist(out_dir, factor_names, partition):
+                    part = io.load_factors(out_dir, factor_names, partition)
+                else:
+                    part = fit_part(start, end, names)
+                    if partitioned:
+                        if self.state.is_main_process:
+                            io.save_factors(out_dir, part, partition=partition, metadata=metadata)
+                        self.state.wait_for_everyone()
+                for fname in factor_names:
+                    for mname, tensor in part[fname].items():
+                        merged[fname][mname] = tensor if mname not in merged[fname] else merged[fname][mname] + tensor
+        return merged
+
     def _resolve_batch_size(self, run: Callable[[int], Any], per_device_batch_size: Optional[int],
                             initial_attempt: int, total: int) -> int:
         if per_device_batch_size is not None:
@@ -337,31 +361,32 @@ class Analyzer:
         data_parts = make_indices_partition(total, factor_args.covariance_data_partitions)
         module_parts = make_modules_partition(all_names, factor_args.covariance_module_partitions)
 
-        merged: FACTOR_TYPE = {name: {} for name in COVARIANCE_FACTOR_NAMES}
-        with self.profiler.profile("Fit Covariance"):
-            for start, end in data_parts:
-                for names in module_parts:
-                    def run(batch_size: int) -> torch.Tensor:
-                        set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-                        set_mode(self.model, ModuleMode.COVARIANCE, names, release_memory=True)
-                        loader = self._loader(dataset, batch_size, range(start, end), "eval", dataloader_kwargs)
-                        return self._fit_loop(loader, ModuleMode.COVARIANCE, names, factor_args, "covariance")
+        def fit_part(start: int, end: int, names: List[str]) -> FACTOR_TYPE:
+            def run(batch_size: int) -> torch.Tensor:
+                set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                set_mode(self.model, ModuleMode.COVARIANCE, names, release_memory=True)
+                loader = self._loader(dataset, batch_size, range(start, end), "eval", dataloader_kwargs)
+                return self._fit_loop(loader, ModuleMode.COVARIANCE, names, factor_args, "covariance")
 
-                    batch_size = self._resolve_batch_size(run, per_device_batch_size,
-                                                          initial_per_device_batch_size_attempt, end - start)
-                    if per_device_batch_size is not None:
-                        run(batch_size)
-                    self._all_reduce_factors(COVARIANCE_FACTOR_NAMES, names)
-                    for fname in COVARIANCE_FACTOR_NAMES:
-                        dtype = None
-                        if fname == ACTIVATION_COVARIANCE_MATRIX_NAME:
-                            dtype = factor_args.activation_covariance_dtype
-                        elif fname == GRADIENT_COVARIANCE_MATRIX_NAME:
-                            dtype = factor_args.gradient_covariance_dtype
-                        part = collect_factors(self.model, fname, names, cpu=True, dtype=dtype)
-                        for mname, tensor in part.items():
-                            merged[fname][mname] = tensor if mname not in merged[fname] else merged[fname][mname] + tensor
-                    set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            batch_size = self._resolve_batch_size(run, per_device_batch_size, initial_per_device_batch_size_attempt,
+                                                  end - start)
+            if per_device_batch_size is not None:
+                run(batch_size)
+            self._all_reduce_factors(COVARIANCE_FACTOR_NAMES, names)
+            part: FACTOR_TYPE = {}
+            for fname in COVARIANCE_FACTOR_NAMES:
+                dtype = None
+                if fname == ACTIVATION_COVARIANCE_MATRIX_NAME:
+                    dtype = factor_args.activation_covariance_dtype
+                elif fname == GRADIENT_COVARIANCE_MATRIX_NAME:
+                    dtype = factor_args.gradient_covariance_dtype
+                part[fname] = collect_factors(self.model, fname, names, cpu=True, dtype=dtype)
+            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            return part
+
+        with self.profiler.profile("Fit Covariance"):
+            merged = self._run_factor_partitions(out_dir, COVARIANCE_FACTOR_NAMES, data_parts, module_parts, fit_part,
+                                                 overwrite_output_dir, factor_args.to_str_dict())
         with self.profiler.profile("Save Covariance"):
             if self.state.is_main_process:
                 io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
@@ -462,31 +487,32 @@ class Analyzer:
         data_parts = make_indices_partition(total, factor_args.lambda_data_partitions)
         module_parts = make_modules_partition(all_names, factor_args.lambda_module_partitions)
 
-        merged: FACTOR_TYPE = {name: {} for name in LAMBDA_FACTOR_NAMES}
-        with self.profiler.profile("Fit Lambda"):
-            for start, end in data_parts:
-                for names in module_parts:
-                    def run(batch_size: int) -> torch.Tensor:
-                        set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-                        if eigen is not None:
-                            for fname in (ACTIVATION_EIGENVECTORS_NAME, GRADIENT_EIGENVECTORS_NAME):
-                                set_factors(self.model, fname, {k: v for k, v in eigen[fname].items() if k in names},
-                                            device=self.state.device)
-                        set_mode(self.model, ModuleMode.LAMBDA, names, release_memory=False)
-                        loader = self._loader(dataset, batch_size, range(start, end), "eval", dataloader_kwargs)
-                        return self._fit_loop(loader, ModuleMode.LAMBDA, names, factor_args, "lambda")
+        def fit_part(start: int, end: int, names: List[str]) -> FACTOR_TYPE:
+            def run(batch_size: int) -> torch.Tensor:
+                set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                if eigen is not None:
+                    for fname in (ACTIVATION_EIGENVECTORS_NAME, GRADIENT_EIGENVECTORS_NAME):
+                        set_factors(self.model, fname, {k: v for k, v in eigen[fname].items() if k in names},
+                                    device=self.state.device)
+                set_mode(self.model, ModuleMode.LAMBDA, names, release_memory=False)
+                loader = self._loader(dataset, batch_size, range(start, end), "eval", dataloader_kwargs)
+                return self._fit_loop(loader, ModuleMode.LAMBDA, names, factor_args, "lambda")
 
-                    batch_size = self._resolve_batch_size(run, per_device_batch_size,
-                                                          initial_per_device_batch_size_attempt, end - start)
-                    if per_device_batch_size is not None:
-                        run(batch_size)
-                    self._all_reduce_factors(LAMBDA_FACTOR_NAMES, names)
-                    for fname in LAMBDA_FACTOR_NAMES:
-                        dtype = factor_args.lambda_dtype if fname == LAMBDA_MATRIX_NAME else None
-                        part = collect_factors(self.model, fname, names, cpu=True, dtype=dtype)
-                        for mname, tensor in part.items():
-                            merged[fname][mname] = tensor if mname not in merged[fname] else merged[fname][mname] + tensor
-                    set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            batch_size = self._resolve_batch_size(run, per_device_batch_size, initial_per_device_batch_size_attempt,
+                                                  end - start)
+            if per_device_batch_size is not None:
+                run(batch_size)
+            self._all_reduce_factors(LAMBDA_FACTOR_NAMES, names)
+            part: FACTOR_TYPE = {}
+            for fname in LAMBDA_FACTOR_NAMES:
+                dtype = factor_args.lambda_dtype if fname == LAMBDA_MATRIX_NAME else None
+                part[fname] = collect_factors(self.model, fname, names, cpu=True, dtype=dtype)
+            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            return part
+
+        with self.profiler.profile("Fit Lambda"):
+            merged = self._run_factor_partitions(out_dir, LAMBDA_FACTOR_NAMES, data_parts, module_parts, fit_part,
+                                                 overwrite_output_dir, factor_args.to_str_dict())
         with self.profiler.profile("Save Lambda"):
             if self.state.is_main_process:
                 io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
@@ -697,29 +723,39 @@ class Analyzer:
         module_parts = make_modules_partition(all_names, score_args.module_partitions)
         base_train = list(train_indices) if train_indices is not None else list(range(n_train))
 
+        partitioned = len(data_parts) > 1 or len(module_parts) > 1
         with self.profiler.profile("Compute Pairwise Score"):
             column_blocks: List[Dict[str, torch.Tensor]] = []
-            for start, end in data_parts:
+            for d_idx, (start, end) in enumerate(data_parts):
                 block: Dict[str, torch.Tensor] = {}
-                for names in module_parts:
-                    set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-                    self._prepare_for_scores(factors, factor_args, score_args, names)
-
-                    def run(batch_size: int) -> Dict[str, torch.Tensor]:
-                        return self._pairwise(query_dataset, train_dataset, per_device_query_batch_size, batch_size,
-                                              query_indices, base_train[start:end], factor_args, score_args, names,
-                                              dataloader_kwargs)
-
-                    if per_device_train_batch_size is None:
-                        holder: Dict[str, Any] = {}
-
-                        def probe(batch_size: int) -> None:
-                            holder["scores"] = run(batch_size)
-
-                        self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, end - start)
-                        part = holder["scores"]
+                for m_idx, names in enumerate(module_parts):
+                    partition = (d_idx, m_idx)
+                    part_path = io.scores_path(out_dir, partition)
+                    if partitioned and part_path.exists() and not overwrite_output_dir:
+                        part = io.load_file(part_path)  # resume (score_computer.py:77-139 of the reference)
                     else:
-                        part = run(per_device_train_batch_size)
+                        set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                        self._prepare_for_scores(factors, factor_args, score_args, names)
+
+                        def run(batch_size: int) -> Dict[str, torch.Tensor]:
+                            return self._pairwise(query_dataset, train_dataset, per_device_query_batch_size, batch_size,
+                                                  query_indices, base_train[start:end], factor_args, score_args, names,
+                                                  dataloader_kwargs)
+
+                        if per_device_train_batch_size is None:
+                            holder: Dict[str, Any] = {}
+
+                            def probe(batch_size: int) -> None:
+                                holder["scores"] = run(batch_size)
+
+                            self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, end - start)
+                            part = holder["scores"]
+                        else:
+                            part = run(per_device_train_batch_size)
+                        if partitioned:
+                            if self.state.is_main_process:
+                                io.save_scores(out_dir, part, partition=partition, metadata=score_args.to_str_dict())
+                            self.state.wait_for_everyone()
                     for key, value in part.items():
                         block[key] = value if key not in block else block[key] + value
                 column_blocks.append(block)

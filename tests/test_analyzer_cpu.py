@@ -93,6 +93,12 @@ def test_per_module_scores_sum_and_partitions(tmp_path):
                           score_kwargs=dict(compute_per_module_scores=True, data_partitions=2, module_partitions=3),
                           factor_kwargs=dict(covariance_data_partitions=2, lambda_module_partitions=3))
     assert set(per) == {"0", "2", "5"}
+    # partitioned runs leave the reference's per-partition files next to the aggregated ones (resume points)
+    files = set(os.listdir(tmp_path / "p" / "cpu" / "factors_f"))
+    assert "activation_covariance_data_partition1_module_partition0.safetensors" in files
+    assert "lambda_matrix_data_partition0_module_partition2.safetensors" in files
+    assert "pairwise_scores_data_partition1_module_partition2.safetensors" in set(
+        os.listdir(tmp_path / "p" / "cpu" / "scores_s"))
     for key, value in per.items():
         assert rel(value.numpy(), golden[f"f32/scores/{key}"]) < 5e-5
     assert rel(sum(per.values()).numpy(), total["all_modules"].numpy()) < 1e-6

@@ -233,3 +233,32 @@ def test_ill_conditioned_preconditioning():
     ref_noise = rel(ref32["scores"], ref["scores"])  # what float32 arithmetic itself loses here
     print(f"ill-conditioned: ours {ours:.3e}  float32 oracle {ref_noise:.3e}")
     assert ours < max(1e-3, 30 * ref_noise)
+
+
+@pytest.mark.parametrize("d", [257, 1024, 1500])
+def test_eigh_sizes(d):
+    """Jacobi up to kfb_eigh_jacobi_max_dim() = 1024, cuSOLVER syevd (dlopen'ed) above; a rank-deficient
+    covariance (N < d) exercises the null-space handling of the Jacobi sweep."""
+    import time
+
+    from kronfluence_b200 import engine, ops
+
+    engine.require_device()
+    gen = torch.Generator(device="cuda").manual_seed(d)
+    n = d // 2 if d == 257 else 4 * d
+    x = torch.randn(n, d, device="cuda", generator=gen) * torch.linspace(0.05, 2.0, d, device="cuda")
+    cov = x.T @ x
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    evals, evecs = ops.eigh_sym(cov, float(n))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sym = (0.5 * (cov + cov.T) / n).double()
+    q, w = evecs.double(), evals.double()
+    resid = ((q * w) @ q.T - sym).norm() / sym.norm()
+    ortho = (q.T @ q - torch.eye(d, device="cuda", dtype=torch.float64)).abs().max()
+    ref = torch.linalg.eigvalsh(sym)
+    print(f"eigh d={d}: {dt * 1e3:.1f} ms, residual {resid:.2e}, orthogonality {ortho:.2e}")
+    assert resid < 5e-6 and ortho < 5e-6
+    assert (w - ref).abs().max() < 2e-6 * ref.abs().max()
+    assert (w[1:] >= w[:-1] - 1e-6 * ref.abs().max()).all()
