@@ -113,6 +113,10 @@ typedef struct {
   const float* g;
   int64_t ldg;
   /* SQACC: out_f32[m*ldo + n] += alpha * sum_b D[b][m][n]^2   (atomic adds)                     */
+  /* STORE with reduce_sq != 0: nothing is stored element-wise; instead
+   *   out_f32[b*out_batch_stride] += alpha * sum_{m,n} D[b][m][n]^2 * (mul ? mul[m][n] : 1)
+   * (one scalar per batch entry: the self-influence contraction).                                */
+  int32_t reduce_sq;
 } kfb_epilogue;
 
 /* ---------------------------------------------------------------------------------------------
@@ -259,6 +263,22 @@ int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_
                         int64_t seq, int32_t mode, const kfb_split* qa_t, const kfb_split* qg_t,
                         float scale, float* scores, int64_t ld_scores, int64_t t_offset,
                         int32_t accumulate, void* ws, size_t ws_bytes, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-influence scores.  SelfScoreTracker._compute_self_score
+ * tracker/self_score.py:32-60:  out[t_offset + t] (+)= sum_{o,i} P(G_t)[o,i] * G_t[o,i], G_t = scale * per-sample
+ * gradient, P = the strategy's preconditioner.  Evaluated in the eigenbasis as
+ *   sum_{o,i} (Q_G^T G_t Q_A)[o,i]^2 * lambda_inv[o,i]
+ * seq==1: ONE fused ROWDOT launch on squared rotated operands (A = a~^2, B = lambda_inv, g = g~^2);
+ * otherwise a batched K=S GEMM whose epilogue reduces D^2 o lambda_inv to one scalar per example.
+ * lambda_inv must be given (all ones for KFB_PRECOND_IDENTITY).
+ * ------------------------------------------------------------------------------------------ */
+size_t kfb_self_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_self_scores(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype,
+                    int64_t batch, int64_t seq, int32_t mode, const kfb_split* qa_t,
+                    const kfb_split* qg_t, const float* lambda_inv, float scale, float* out,
+                    int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes, int precision,
+                    void* stream);
 
 /* Same contraction through HOST buffers (pinned or pageable): a, g are host pointers, scores_host
  * receives [num_queries, batch] fp32.  dev_a / dev_g / dev_scores are caller-provided device

@@ -62,6 +62,7 @@ from kronfluence_b200.utils.constants import (
     NUM_GRADIENT_COVARIANCE_PROCESSED,
     NUM_LAMBDA_PROCESSED,
     PAIRWISE_SCORE_MATRIX_NAME,
+    SELF_SCORE_VECTOR_NAME,
     SCORE_ARGUMENTS_NAME,
     SCORE_SAVE_PREFIX,
 )
@@ -769,6 +770,111 @@ class Analyzer:
 
     def load_pairwise_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:
         path = io.scores_path(self.scores_output_dir(scores_name))
+        return io.load_file(path) if path.exists() else None
+
+    # ------------------------------------------------------------------------------------------
+    # Self-influence scores
+    # ------------------------------------------------------------------------------------------
+    def compute_self_scores(self, scores_name: str, factors_name: str, train_dataset: data.Dataset,
+                            per_device_train_batch_size: Optional[int] = None,
+                            initial_per_device_train_batch_size_attempt: int = 4096,
+                            train_indices: Optional[Sequence[int]] = None,
+                            dataloader_kwargs: Optional[DataLoaderKwargs] = None,
+                            score_args: Optional[ScoreArguments] = None,
+                            target_data_partitions: Optional[Union[Sequence[int], int]] = None,
+                            target_module_partitions: Optional[Union[Sequence[int], int]] = None,
+                            overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
+        """self[t] = sum_modules <P(grad L(z_t)), grad L(z_t)>  (score_computer.py:558-770, score/self.py:135-290
+        of the reference; the `use_measurement_for_self_influence` variant is not built yet)."""
+        del target_data_partitions, target_module_partitions
+        score_args = ScoreArguments() if score_args is None else score_args
+        if score_args.use_measurement_for_self_influence:
+            raise NotImplementedError("`use_measurement_for_self_influence` is not part of the B200 hot path yet.")
+        if score_args.query_gradient_low_rank is not None or score_args.compute_per_token_scores:
+            raise NotImplementedError("low-rank / per-token options do not apply to self-influence scores here.")
+        factor_args = self._load_factor_args(factors_name)
+        out_dir = self.scores_output_dir(scores_name)
+        if self.state.is_main_process:
+            out_dir.mkdir(parents=True, exist_ok=True)
+        self.state.wait_for_everyone()
+        path = out_dir / "self_scores.safetensors"
+        if path.exists() and not overwrite_output_dir:
+            return None
+        self._save_arguments(SCORE_ARGUMENTS_NAME, score_args, out_dir, overwrite_output_dir)
+        self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
+        self._save_dataset_metadata("train", train_dataset, out_dir, train_indices, overwrite_output_dir)
+        with self.profiler.profile("Load All Factors"):
+            factors = self.load_all_factors(factors_name)
+        update_factor_args(self.model, factor_args)
+        update_score_args(self.model, score_args)
+        n_train = len(train_indices) if train_indices is not None else len(train_dataset)
+        names = get_tracked_module_names(self.model)
+        modules = tracked_modules(self.model, names)
+        device = self.state.device
+
+        def run(batch_size: int) -> Dict[str, torch.Tensor]:
+            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            self._prepare_for_scores(factors, factor_args, score_args, names)
+            loader = self._loader(train_dataset, batch_size, train_indices, "stack", dataloader_kwargs)
+            t_local = len(loader.sampler) if self.state.use_distributed else n_train
+            scaler, autocast = self._amp(score_args.amp_dtype, factor_args.amp_scale)
+            set_mode(self.model, ModuleMode.SELF_SCORE, names, release_memory=False)
+            per_module = score_args.compute_per_module_scores
+            shared = None if per_module else torch.zeros(t_local, dtype=torch.float32, device=device)
+            sinks = {m.name: (torch.zeros(t_local, dtype=torch.float32, device=device) if per_module else shared)
+                     for m in modules}
+            for module in modules:
+                module.storage[SELF_SCORE_VECTOR_NAME] = sinks[module.name]
+            offset = 0
+            for batch in loader:
+                batch = _send_to_device(batch, device)
+                for module in modules:
+                    module.score_offset = offset
+                self.model.zero_grad(set_to_none=True)
+                with autocast():
+                    loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
+                scaler.scale(loss).backward()
+                if factor_args.has_shared_parameters:
+                    finalize_iteration(self.model, names)
+                offset += _find_batch_size(batch)
+                del loss
+            self.model.zero_grad(set_to_none=True)
+            results = {m.name: sinks[m.name] for m in modules} if per_module else {ALL_MODULE_NAME: shared}
+            out: Dict[str, torch.Tensor] = {}
+            for key, local in results.items():
+                if self.state.use_distributed:
+                    gathered = [torch.empty_like(local) for _ in range(self.state.num_processes)] \
+                        if self.state.is_main_process else None
+                    dist.gather(local, gathered, dst=0)
+                    if self.state.is_main_process:
+                        local = torch.cat(gathered, dim=0)[:n_train]
+                out[key] = local.to(dtype=score_args.score_dtype, device="cpu")
+            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            if scaler.is_enabled():
+                set_gradient_scale(self.model, 1.0)
+            return out
+
+        with self.profiler.profile("Compute Self-Influence Score"):
+            if per_device_train_batch_size is None:
+                holder: Dict[str, Any] = {}
+
+                def probe(batch_size: int) -> None:
+                    holder["scores"] = run(batch_size)
+
+                self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, n_train)
+                scores = holder["scores"]
+            else:
+                scores = run(per_device_train_batch_size)
+        with self.profiler.profile("Save Self-Influence Score"):
+            if self.state.is_main_process:
+                from safetensors.torch import save_file
+
+                save_file({k: v.contiguous() for k, v in scores.items()}, str(path), metadata=score_args.to_str_dict())
+            self.state.wait_for_everyone()
+        return scores
+
+    def load_self_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:
+        path = self.scores_output_dir(scores_name) / "self_scores.safetensors"
         return io.load_file(path) if path.exists() else None
 
     def get_module_summary(self) -> str:

@@ -62,6 +62,7 @@ struct GemmParams {
   const float* mul;
   long long ldmul;
   int transpose_out, square, accumulate, use_atomic, vec_ok, zero_pad;
+  int reduce_sq;  // STORE: reduce D^2 (o mul) to one scalar per batch entry instead of storing
   float alpha;
   const float* g;
   long long ldg;
@@ -489,6 +490,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[i]);
             }
+          } else if (p.reduce_sq) {
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (col0 + i < p.N) {
+                  const float x = __uint_as_float(v[i]);
+                  const float w = p.mul != nullptr ? __ldg(p.mul + row * p.ldmul + col0 + i) : 1.f;
+                  rowdot = fmaf(x * x, w, rowdot);
+                }
+              }
+            }
           } else {
             if (row_ok) {
               float x[32];
@@ -498,7 +510,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
           }
         }
-        if (EPI == EPI_STORE && p.zero_pad && row_ok && t.n_blk == p.n_blocks - 1) store_zero_pad(p, t.b, row);
+        if (EPI == EPI_STORE && p.reduce_sq) {
+          // one scalar per batch entry: warp-reduce, then one atomic per warp
+          float part = rowdot;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (lane == 0 && part != 0.f) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs, p.alpha * part);
+          rowdot = 0.f;
+        }
+        if (EPI == EPI_STORE && p.zero_pad && !p.reduce_sq && row_ok && t.n_blk == p.n_blocks - 1) store_zero_pad(p, t.b, row);
         // hand the accumulator stage back to the (leader's) MMA thread: one arrival per warp
         tcgen05_fence_before();
         __syncwarp();
@@ -580,6 +600,11 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
     const long long total = (long long)p.batch * p.M * p.N;
     if (tid >= total) return;
     const long long n = tid % p.N, m = (tid / p.N) % p.M, b = tid / ((long long)p.N * p.M);
+    if (p.reduce_sq) {
+      const float d = simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K);
+      atomicAdd(p.out_f32 + b * p.out_bs, p.alpha * d * d * (p.mul ? p.mul[m * p.ldmul + n] : 1.f));
+      return;
+    }
     float val = p.alpha * simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K);
     if (p.mul) val *= p.mul[m * p.ldmul + n];
     if (p.square) val *= val;
@@ -850,6 +875,7 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   p.alpha = epi.alpha;
   p.g = epi.g;
   p.ldg = epi.ldg;
+  p.reduce_sq = epi.kind == KFB_EPI_STORE ? epi.reduce_sq : 0;
   p.k_splits = 1;
   p.k_chunks = 1;
   // strict mode: 6 truncating accumulations per k-step, so drain TMEM every 64 contraction elements
@@ -866,6 +892,11 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
                      (p.out_lo && (reinterpret_cast<uintptr_t>(p.out_lo) & 15))))
       p.vec_ok = 0;
     p.zero_pad = (p.out_hi != nullptr && !p.transpose_out) ? 1 : 0;
+    if (p.reduce_sq) {
+      KFB_REQUIRE(p.out_f32 != nullptr && p.out_hi == nullptr, "gemm_nt: reduce_sq needs out_f32 only");
+      KFB_REQUIRE(p.K <= p.max_pass_k, "gemm_nt: reduce_sq needs the contraction to fit one TMEM pass (K <= %d)",
+                  p.max_pass_k);
+    }
   } else if (epi.kind == KFB_EPI_ROWDOT) {
     KFB_REQUIRE(p.out_f32 != nullptr && p.g != nullptr, "gemm_nt: ROWDOT needs out_f32 and g");
     KFB_REQUIRE(A.batch == 1 || A.batch == p.batch, "gemm_nt: ROWDOT batch mismatch");

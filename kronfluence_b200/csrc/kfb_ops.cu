@@ -524,6 +524,97 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
   return KFB_OK;
 }
 
+// =================================================================================================
+// Self-influence (next row #3 of SURVEY.md §8f).  tracker/self_score.py:32-60.
+//   self[t] = sum_{o,i} (Q_G^T G_t Q_A)[o,i]^2 * lambda_inv[o,i]      with G_t = scale * per-sample gradient
+// =================================================================================================
+static int self_run(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt, long long batch,
+                    long long seq, int mode, const kfb_split* qa_t, const kfb_split* qg_t,
+                    const float* lambda_inv, float scale, float* out, long long t_offset, int accumulate,
+                    Ws& ws, int precision, cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const bool eigen = mode == KFB_PRECOND_EIGEN;
+  const int rp = rot_prec(precision);
+  if (L.kind == KFB_LINEAR && S == 1) {
+    // rank-one gradients: self[t] = sum_o g~[t,o]^2 * sum_i lambda_inv[o,i] a~[t,i]^2  — the fused ROWDOT kernel
+    // with A = a~^2, B = lambda_inv, g = g~^2 and a single "query".
+    kfb_split a_sp = ws_split(ws, batch, di, 1, eigen ? rp : precision);
+    kfb_split g_sp{}, a_sq{};
+    if (eigen) {
+      g_sp = ws_split(ws, batch, L.d_out, 1, rp);
+      a_sq = ws_split(ws, batch, di, 1, precision);
+    }
+    float* g_sq = static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
+    kfb_split lam = ws_split(ws, L.d_out, di, 1, precision);
+    if (ws.dry) return KFB_OK;
+    if (!ws.fits()) {
+      set_error("self-score workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+      return KFB_ERR_WORKSPACE;
+    }
+    GatherDesc gl{};
+    gl.sr = di; gl.sc2 = 1; gl.rows = L.d_out; gl.c1 = 1; gl.c2 = di;
+    KFB_TRY(split_gather(lambda_inv, KFB_F32, gl, lam, precision, stream));
+    GatherDesc ga{};
+    ga.sr = L.d_in; ga.sc2 = 1; ga.rows = batch; ga.c1 = 1; ga.c2 = L.d_in;
+    ga.ones_mode = L.has_bias ? 1 : 0;
+    const kfb_split* a_operand = &a_sp;
+    if (eigen) {
+      KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
+                  "self_scores: eigenbasis operands do not match the layer");
+      KFB_TRY(split_gather(a, a_dt, ga, a_sp, rp, stream));
+      GatherDesc gg{};
+      gg.sr = L.d_out; gg.sc2 = 1; gg.rows = batch; gg.c1 = 1; gg.c2 = L.d_out;
+      KFB_TRY(split_gather(g, g_dt, gg, g_sp, rp, stream));
+      kfb_epilogue ea = store_epilogue();
+      ea.out_split = a_sq;
+      ea.square = 1;
+      KFB_TRY(gemm_nt(a_sp, *qa_t, ea, rp, 1, stream));
+      kfb_epilogue eg = store_epilogue();
+      eg.out_f32 = g_sq;
+      eg.ldo = L.d_out;
+      eg.square = 1;
+      KFB_TRY(gemm_nt(g_sp, *qg_t, eg, rp, 1, stream));
+      a_operand = &a_sq;
+    } else {
+      ga.square = 1;
+      KFB_TRY(split_gather(a, a_dt, ga, a_sp, precision, stream));
+      KFB_TRY(cast_to_f32(g, g_dt, g_sq, batch * L.d_out, -1.f, stream));
+    }
+    kfb_epilogue e{};
+    e.kind = KFB_EPI_ROWDOT;
+    e.out_f32 = out + t_offset;
+    e.out_batch_stride = 0;
+    e.g = g_sq;
+    e.ldg = L.d_out;
+    e.alpha = scale * scale;
+    e.accumulate = accumulate;
+    return gemm_nt(*a_operand, lam, e, precision, 1, stream);
+  }
+  const long long per = outer_bytes_per_sample(L, S, eigen, precision);
+  const long long cb = chunk_count(batch, per);
+  OuterBufs o = outer_alloc(ws, L, cb, S, eigen, precision);
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("self-score workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  if (!accumulate) KFB_CUDA_TRY(cudaMemsetAsync(out + t_offset, 0, (size_t)batch * 4, stream));
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, eigen, qa_t, qg_t, o, precision, stream));
+    kfb_epilogue e = store_epilogue();
+    e.out_f32 = out + t_offset + b0;
+    e.out_batch_stride = 1;
+    e.mul = lambda_inv;
+    e.ldmul = di;
+    e.alpha = scale * scale;
+    e.reduce_sq = 1;
+    KFB_TRY(gemm_nt(split_batch_view(o.Lt, 0, nb), split_batch_view(o.Rt, 0, nb), e, precision, 1, stream));
+  }
+  return KFB_OK;
+}
+
 }  // namespace kfb
 
 // =================================================================================================
@@ -681,6 +772,28 @@ int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t
   KFB_CUDA_TRY(cudaMemcpyAsync(scores_host, dev_scores, (size_t)num_queries * batch * 4,
                                cudaMemcpyDeviceToHost, st));
   return KFB_OK;
+}
+
+size_t kfb_self_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  self_run(*layer, nullptr, KFB_F32, nullptr, KFB_F32, batch, seq, KFB_PRECOND_EIGEN, nullptr, nullptr, nullptr, 1.f,
+           nullptr, 0, 1, w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_self_scores(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype,
+                    int64_t batch, int64_t seq, int32_t mode, const kfb_split* qa_t,
+                    const kfb_split* qg_t, const float* lambda_inv, float scale, float* out,
+                    int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes, int precision,
+                    void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(a != nullptr && g != nullptr && out != nullptr && lambda_inv != nullptr, "self_scores: null tensor");
+  KFB_REQUIRE(mode >= KFB_PRECOND_IDENTITY && mode <= KFB_PRECOND_EIGEN, "self_scores: bad mode %d", mode);
+  if (batch <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return self_run(*layer, a, a_dtype, g, g_dtype, batch, seq, mode, qa_t, qg_t, lambda_inv, scale, out, t_offset,
+                  accumulate, w, precision, (cudaStream_t)stream);
 }
 
 int kfb_split_gather(const void* src, int src_dtype, const int64_t* desc9, const float* scale,

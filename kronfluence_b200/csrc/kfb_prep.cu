@@ -244,8 +244,11 @@ int split_im2col(const kfb_layer& L, const void* x, int x_dtype, long long batch
 // -------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void cast_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = load_as_float<T>(src, i) * scale;
+  // scale < 0 requests the SQUARE of the value times |scale|
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = load_as_float<T>(src, i);
+    dst[i] = scale < 0.f ? v * v * (-scale) : v * scale;
+  }
 }
 
 int cast_to_f32(const void* src, int src_dtype, float* dst, long long n, float scale, cudaStream_t stream) {

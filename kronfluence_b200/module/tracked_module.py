@@ -30,6 +30,7 @@ from kronfluence_b200.utils.constants import (
     NUM_LAMBDA_PROCESSED,
     PAIRWISE_SCORE_MATRIX_NAME,
     PRECONDITIONED_GRADIENT_NAME,
+    SELF_SCORE_VECTOR_NAME,
 )
 from kronfluence_b200.utils.exceptions import FactorsNotFoundError
 
@@ -42,6 +43,7 @@ class ModuleMode(str, Enum):
     LAMBDA = "lambda"
     PRECONDITION_GRADIENT = "precondition_gradient"
     PAIRWISE_SCORE = "pairwise_score"
+    SELF_SCORE = "self_score"
 
     def __str__(self) -> str:
         return self.value
@@ -339,6 +341,64 @@ class PairwiseScoreTracker(BaseTracker):
         self.module.storage[PAIRWISE_SCORE_MATRIX_NAME] = None
 
 
+class SelfScoreTracker(BaseTracker):
+    """Self-influence <P(G_t), G_t> per train example, added into the shared [T] vector
+    (tracker/self_score.py:29-120 + the module sum of score/self.py:235-260 of the reference)."""
+
+    def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
+        module = self.module
+        sink = module.storage[SELF_SCORE_VECTOR_NAME]
+        if sink is None:
+            raise RuntimeError(f"Module '{module.name}': self scoring was not set up.")
+        layer = module.layer_for(a)
+        mode = strategy_config(module.factor_args.strategy)["mode"]
+        qa = qg = None
+        if mode == ops.PRECOND_EIGEN:
+            qa, qg = module.eigen_operands(g.device)
+        lam_inv = module.storage[LAMBDA_MATRIX_NAME]
+        if lam_inv is None:  # identity strategy: P(G) = G
+            d_in, d_out = ops.factor_dims(layer)
+            lam_inv = torch.ones(d_out, d_in, dtype=torch.float32, device=g.device)
+            module.storage[LAMBDA_MATRIX_NAME] = lam_inv
+        ops.self_scores(layer, a, g, sink, module.score_offset, mode, lam_inv, qa, qg, scale=module.gradient_scale,
+                        accumulate=True, precision=precision_of(module.score_args.score_dtype))
+
+    def register_hooks(self) -> None:
+        module = self.module
+
+        @torch.no_grad()
+        def forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
+            self._cache_input(inputs)
+            self.cached_hooks.append(outputs.register_hook(backward_hook))
+
+        @torch.no_grad()
+        def backward_hook(grad: torch.Tensor) -> None:
+            if not self.cached_activations:
+                self._no_cache_error()
+            self.cached_hooks.pop().remove()
+            if module.factor_args.has_shared_parameters:
+                self.cached_gradients.append(grad.detach().clone())
+                return
+            self._update(self.cached_activations[0], grad.detach())
+            self.clear_all_cache()
+
+        self.registered_hooks.append(module.register_forward_hook(forward_hook))
+
+    @torch.no_grad()
+    def finalize_iteration(self) -> None:
+        if self.module.factor_args.has_shared_parameters and self.cached_gradients:
+            a, g = self._stacked_uses()
+            self._update(a, g)
+        self.clear_all_cache()
+
+    def exist(self) -> bool:
+        return self.module.storage[SELF_SCORE_VECTOR_NAME] is not None
+
+    def release_memory(self) -> None:
+        self.clear_all_cache()
+        self.module.storage[SELF_SCORE_VECTOR_NAME] = None
+
+
 class TrackedModule(nn.Module):
     """Wraps one nn.Linear / nn.Conv2d; behaves exactly like it in forward/backward."""
 
@@ -369,13 +429,14 @@ class TrackedModule(nn.Module):
             ModuleMode.LAMBDA: LambdaTracker(self),
             ModuleMode.PRECONDITION_GRADIENT: PreconditionTracker(self),
             ModuleMode.PAIRWISE_SCORE: PairwiseScoreTracker(self),
+            ModuleMode.SELF_SCORE: SelfScoreTracker(self),
         }
         self.attention_mask: Optional[torch.Tensor] = None
         self.gradient_scale: float = 1.0
         self.storage: Dict[str, Any] = {}
         for key in (COVARIANCE_FACTOR_NAMES + EIGENDECOMPOSITION_FACTOR_NAMES + LAMBDA_FACTOR_NAMES +
                     [PRECONDITIONED_GRADIENT_NAME, ACCUMULATED_PRECONDITIONED_GRADIENT_NAME,
-                     PAIRWISE_SCORE_MATRIX_NAME]):
+                     PAIRWISE_SCORE_MATRIX_NAME, SELF_SCORE_VECTOR_NAME]):
             self.storage[key] = None
         self.query_count = 0
         self.last_query_batch = 0

@@ -268,8 +268,26 @@ def pairwise_scores(layer: KfbLayer, store: Split, num_queries: int, a: torch.Te
 __all__ = [
     "PREC_FP32", "PREC_BF16", "PREC_STRICT", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
     "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
-    "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "layer_of", "factor_dims", "workspace",
+    "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "self_scores", "layer_of", "factor_dims", "workspace",
 ]
+
+
+def self_scores(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, out: torch.Tensor, t_offset: int, mode: int,
+                lambda_inv: torch.Tensor, qa: Optional[EigenOperands] = None, qg: Optional[EigenOperands] = None,
+                scale: float = 1.0, accumulate: bool = True, precision: int = PREC_FP32) -> None:
+    """out[t_offset + t] (+)= <P(G_t), G_t> for every example of the batch (tracker/self_score.py:32-60)."""
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    sa = qa.qt.struct() if qa is not None else None
+    sg = qg.qt.struct() if qg is not None else None
+    ws_ptr, ws_size = workspace(a.device).get(lib.kfb_self_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_self_scores(ctypes.byref(layer), a.data_ptr(), dtype_code(a.dtype), g.data_ptr(), dtype_code(g.dtype),
+                              batch, seq, mode, ctypes.byref(sa) if sa is not None else None,
+                              ctypes.byref(sg) if sg is not None else None, lambda_inv.data_ptr(), float(scale),
+                              out.data_ptr(), int(t_offset), int(accumulate), ws_ptr, ws_size, precision,
+                              stream_ptr(a.device)))
 
 
 def load_query_store(store: Split, p: torch.Tensor, q_offset: int = 0, precision: int = PREC_FP32) -> None:

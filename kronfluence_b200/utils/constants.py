@@ -41,6 +41,7 @@ LAMBDA_FACTOR_NAMES = [LAMBDA_MATRIX_NAME, NUM_LAMBDA_PROCESSED]
 PRECONDITIONED_GRADIENT_NAME = "preconditioned_gradient"
 ACCUMULATED_PRECONDITIONED_GRADIENT_NAME = "accumulated_preconditioned_gradient"
 PAIRWISE_SCORE_MATRIX_NAME = "pairwise_score_matrix"
+SELF_SCORE_VECTOR_NAME = "self_score_vector"
 
 ALL_MODULE_NAME = "all_modules"
 LAMBDA_DTYPE = torch.float64

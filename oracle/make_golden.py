@@ -224,6 +224,11 @@ def run_reference(case, dtype, strategy="ekfac", damping=None):
         out["scores"] = npy(analyzer.load_pairwise_scores("s")["all_modules"])
         for mname, tensor in analyzer.load_pairwise_scores("s_pm").items():
             out[f"scores/{mname}"] = npy(tensor)
+        if damping is None:
+            analyzer.compute_self_scores("self", factors_name="f", train_dataset=train_set,
+                                         per_device_train_batch_size=train_bs, score_args=score_args,
+                                         overwrite_output_dir=True)
+            out["self_scores"] = npy(analyzer.load_self_scores("self")["all_modules"])
         out["files_factors"] = np.array(sorted(os.listdir(os.path.join(tmp, "golden", "factors_f"))))
         out["files_scores"] = np.array(sorted(os.listdir(os.path.join(tmp, "golden", "scores_s"))))
         return out

@@ -122,8 +122,23 @@ def pairwise_scores(layer, store, num_queries, a, g, scores, t_offset=0, accumul
         view.copy_(block.to(scores.dtype))
 
 
+def self_scores(layer, a, g, out, t_offset, mode, lambda_inv, qa=None, qg=None, scale=1.0, accumulate=True,
+                precision=0):
+    grads = _per_sample(layer, a, g) * scale
+    if mode == ops.PRECOND_EIGEN:
+        pre = orc.precondition(grads, _np(lambda_inv), qa.q, qg.q)
+    else:
+        pre = orc.precondition(grads, _np(lambda_inv))
+    vals = torch.from_numpy((pre * grads).sum(axis=(1, 2))).to(out.dtype)
+    view = out[t_offset : t_offset + grads.shape[0]]
+    if accumulate:
+        view.add_(vals)
+    else:
+        view.copy_(vals)
+
+
 _PATCHED = ["layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
-            "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores"]
+            "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores", "self_scores"]
 
 
 @contextlib.contextmanager

@@ -58,7 +58,7 @@ def test_end_to_end_matches_reference(case, tmp_path):
         analyzer, scores = run_case(case, tmp_path, inject_eigen=golden)
         factors = analyzer.load_all_factors("f")
     for key, ref in golden.items():
-        if not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files"):
+        if not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files") or key.count("/") != 2:
             continue
         _, fname, mname = key.split("/", 2)
         got = factors[fname][mname].numpy()
@@ -172,3 +172,20 @@ def test_prepared_model_is_transparent():
     out_a.sum().backward()
     out_b.sum().backward()
     assert torch.allclose(x.grad, x2.grad)
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_self_scores_match_reference(case, tmp_path):
+    """Analyzer.compute_self_scores vs the reference's (tests/scores/test_self_scores.py of the reference checks
+    the same quantity against diag(pairwise))."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    tasks = fixtures.make_tasks(Task)
+    with oracle_backend():
+        analyzer, _ = run_case(case, tmp_path, inject_eigen=golden)
+        _, train_set, _ = fixtures.make_case(case)
+        scores = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=5,
+                                              score_args=ScoreArguments(damping_factor=None))
+        again = analyzer.load_self_scores("self")
+    assert rel(scores["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
+    assert torch.equal(again["all_modules"], scores["all_modules"])
+    del tasks

@@ -51,7 +51,8 @@ def test_end_to_end_with_reference_eigenbasis(case, tmp_path):
     analyzer, scores, own_eigen = run(case, tmp_path, golden, inject=True)
     factors = analyzer.load_all_factors("f")
     for key, ref in golden.items():
-        if not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files") or "eigen" in key:
+        if (not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files") or "eigen" in key
+                or key.count("/") != 2):
             continue
         _, fname, mname = key.split("/", 2)
         tol = 1e-4 if fname == "lambda_matrix" else 2e-5
@@ -117,3 +118,18 @@ def test_default_damping_parity(case, tmp_path):
     with open("gpurun_out/default_damping_parity.txt", "a", encoding="utf-8") as f:
         f.write(f"{case} ours {ours:.6e} ref_fp32 {ref_noise:.6e}\n")
     assert ours < max(1e-4, 30.0 * ref_noise)
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_self_scores(case, tmp_path):
+    """Self-influence through the CUDA path (fused ROWDOT on squared rotated operands for 2-D inputs, batched
+    GEMM with the reduce-square epilogue otherwise) vs the reference Analyzer's self scores."""
+    from kronfluence_b200.arguments import ScoreArguments
+    from tests import fixtures
+
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    analyzer, _, _ = run(case, tmp_path, golden, inject=True)
+    _, train_set, _ = fixtures.make_case(case)
+    scores = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=6,
+                                          score_args=ScoreArguments(damping_factor=None))
+    assert rel(scores["all_modules"].numpy(), golden["f32/self_scores"]) < 1e-4
