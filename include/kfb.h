@@ -190,6 +190,8 @@ int kfb_eigh_jacobi_max_dim(void);
 size_t kfb_eigh_workspace_bytes(int32_t d);
 int kfb_eigh_sym(const float* C, double count, int32_t d, float* evals, float* evecs, void* ws,
                  size_t ws_bytes, void* stream);
+/* Debug: Jacobi sweeps used by the last kfb_eigh_sym call that ran on workspace `ws` (synchronises). */
+int kfb_eigh_last_sweeps(const void* ws, int32_t d);
 /* Optional: absolute path of the libcusolver.so to dlopen for d > kfb_eigh_jacobi_max_dim().     */
 int kfb_set_cusolver_path(const char* path);
 

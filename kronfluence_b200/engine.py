@@ -71,6 +71,7 @@ SIGNATURES = {
     "kfb_eigh_jacobi_max_dim": (ctypes.c_int, []),
     "kfb_eigh_workspace_bytes": (_sz, [_i32]),
     "kfb_eigh_sym": (ctypes.c_int, [_vp, _f64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "kfb_eigh_last_sweeps": (ctypes.c_int, [_vp, _i32]),
     "kfb_set_cusolver_path": (ctypes.c_int, [ctypes.c_char_p]),
     "kfb_eigen_operands": (ctypes.c_int, [_vp, _i32, _SP, _SP, ctypes.c_int, _vp]),
     "kfb_lambda_workspace_bytes": (_sz, [_LP, _i64, _i64]),

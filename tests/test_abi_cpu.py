@@ -48,4 +48,4 @@ def test_no_cpu_path():
     layer = engine.KfbLayer(kind=0, d_in=64, d_out=32, has_bias=1)
     assert lib.kfb_pairwise_workspace_bytes(ctypes.byref(layer), 16, 1) > 0
     assert lib.kfb_eigh_workspace_bytes(128) > 2 * 128 * 128 * 8
-    assert lib.kfb_eigh_jacobi_max_dim() == 1024
+    assert lib.kfb_eigh_jacobi_max_dim() == 512

@@ -235,9 +235,9 @@ def test_ill_conditioned_preconditioning():
     assert ours < max(1e-3, 30 * ref_noise)
 
 
-@pytest.mark.parametrize("d", [257, 1024, 1500])
+@pytest.mark.parametrize("d", [257, 512, 1024, 1500])
 def test_eigh_sizes(d):
-    """Jacobi up to kfb_eigh_jacobi_max_dim() = 1024, cuSOLVER syevd (dlopen'ed) above; a rank-deficient
+    """Jacobi up to kfb_eigh_jacobi_max_dim() = 512, cuSOLVER syevd (dlopen'ed) above; a rank-deficient
     covariance (N < d) exercises the null-space handling of the Jacobi sweep."""
     import time
 
@@ -258,7 +258,8 @@ def test_eigh_sizes(d):
     resid = ((q * w) @ q.T - sym).norm() / sym.norm()
     ortho = (q.T @ q - torch.eye(d, device="cuda", dtype=torch.float64)).abs().max()
     ref = torch.linalg.eigvalsh(sym)
-    print(f"eigh d={d}: {dt * 1e3:.1f} ms, residual {resid:.2e}, orthogonality {ortho:.2e}")
+    sweeps = engine.load_library().kfb_eigh_last_sweeps(ops.workspace(cov.device).buf.data_ptr(), d)
+    print(f"eigh d={d}: {dt * 1e3:.1f} ms, residual {resid:.2e}, orthogonality {ortho:.2e}, jacobi sweeps {sweeps}")
     assert resid < 5e-6 and ortho < 5e-6
     assert (w - ref).abs().max() < 2e-6 * ref.abs().max()
     assert (w[1:] >= w[:-1] - 1e-6 * ref.abs().max()).all()
