@@ -27,7 +27,7 @@ from torch.utils import data
 
 from kronfluence_b200 import ops
 from kronfluence_b200.arguments import FactorArguments, ScoreArguments
-from kronfluence_b200.module.tracked_module import ModuleMode, TrackedModule, strategy_config
+from kronfluence_b200.module.tracked_module import ModuleMode, ScoreSink, TrackedModule, strategy_config
 from kronfluence_b200.module.utils import (
     collect_factors,
     finalize_iteration,
@@ -613,10 +613,11 @@ class Analyzer:
 
         def train_sweep(num_queries: int) -> None:
             set_mode(self.model, ModuleMode.PAIRWISE_SCORE, names, release_memory=False)
+            per_token = score_args.compute_per_token_scores
             if per_module:
-                sinks = {m.name: torch.zeros(num_queries, t_local, dtype=torch.float32, device=device) for m in modules}
+                sinks = {m.name: ScoreSink(num_queries, t_local, device, per_token) for m in modules}
             else:
-                shared = torch.zeros(num_queries, t_local, dtype=torch.float32, device=device)
+                shared = ScoreSink(num_queries, t_local, device, per_token)
                 sinks = {m.name: shared for m in modules}
             for module in modules:
                 module.storage[PAIRWISE_SCORE_MATRIX_NAME] = sinks[module.name]
@@ -635,7 +636,8 @@ class Analyzer:
                 del loss
             self.model.zero_grad(set_to_none=True)
             results = {m.name: sinks[m.name] for m in modules} if per_module else {ALL_MODULE_NAME: shared}
-            for key, local_scores in results.items():
+            for key, sink in results.items():
+                local_scores = sink.result().contiguous()
                 if self.state.use_distributed:
                     gathered = [torch.empty_like(local_scores) for _ in range(world)] if self.state.is_main_process else None
                     dist.gather(local_scores, gathered, dst=0)
@@ -695,7 +697,7 @@ class Analyzer:
                                 overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
         del target_data_partitions, target_module_partitions
         score_args = ScoreArguments() if score_args is None else score_args
-        for flag in ("compute_per_token_scores", "aggregate_query_gradients", "aggregate_train_gradients"):
+        for flag in ("aggregate_query_gradients", "aggregate_train_gradients"):
             if getattr(score_args, flag):
                 raise NotImplementedError(f"`{flag}` is not part of the B200 hot path yet (SURVEY.md §8f).")
         if score_args.query_gradient_low_rank is not None:

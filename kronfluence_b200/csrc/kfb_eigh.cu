@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(double* __restrict__ W
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int total_warps = gridDim.x * warps_per_block;
   const int lane = threadIdx.x & 31;
-  // Noise floor: columns whose squared norm is below (eps * d)^2 * ||S||_F^2 carry no information
-  // (null space of a rank-deficient covariance); rotating them never converges and never matters.
+  // Noise floor: the input covariance is an fp32 sum, so columns of W = S V whose norm is below 1e-9 ||S||_F
+  // (eigenvalues eight orders below the spectrum's scale) are rounding noise of a rank-deficient factor;
+  // rotating them never converges and never matters.
   if (blockIdx.x == 0 && threadIdx.x == 0) state[2] = 0ull;
   grid.sync();
   {
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(double* __restrict__ W
   }
   grid.sync();
   const double frob2 = *reinterpret_cast<double*>(&state[2]);
-  const double floor2 = (2.3e-16 * d) * (2.3e-16 * d) * frob2;
+  const double floor2 = 1e-18 * frob2;
   int sweep = 0;
   for (; sweep < kJacobiMaxSweeps; ++sweep) {
     if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = 0ull;

@@ -69,6 +69,34 @@ def strategy_config(name: str) -> Dict[str, Any]:
     return STRATEGIES[name]
 
 
+class ScoreSink:
+    """The device buffer pairwise scores of one train sweep accumulate into: [Q, T_local] or, with
+    `compute_per_token_scores`, [Q, T_local * S] (token-major within an example).  S is only known once the first
+    tracked module has seen an input, so the buffer is allocated lazily; modules that share a sink must agree on S."""
+
+    def __init__(self, num_queries: int, t_local: int, device: torch.device, per_token: bool) -> None:
+        self.num_queries, self.t_local, self.device, self.per_token = num_queries, t_local, device, per_token
+        self.tokens: Optional[int] = None
+        self.tensor: Optional[torch.Tensor] = None
+
+    def get(self, tokens: int) -> torch.Tensor:
+        if self.tensor is None:
+            self.tokens = tokens
+            self.tensor = torch.zeros(self.num_queries, self.t_local * tokens, dtype=torch.float32, device=self.device)
+        elif tokens != self.tokens:
+            raise RuntimeError(
+                "The pairwise scores dimension does not match. When computing per-token scores, only include modules "
+                "that see [batch, sequence, features] inputs of one sequence length (use "
+                "`Task.get_influence_tracked_modules`).")
+        return self.tensor
+
+    def result(self) -> torch.Tensor:
+        out = self.get(1) if self.tensor is None else self.tensor
+        if self.per_token:
+            return out.view(self.num_queries, self.t_local, self.tokens)
+        return out
+
+
 class BaseTracker:
     """Hook manager for one mode of one module (tracker/base.py:8-88 of the reference)."""
 
@@ -320,10 +348,21 @@ class PairwiseScoreTracker(BaseTracker):
             qa = qg = None
             if strategy_config(module.factor_args.strategy)["mode"] == ops.PRECOND_EIGEN:
                 qa, qg = module.eigen_operands(grad.device)  # the store holds eigenbasis images
+            grad = grad.detach()
+            tokens = 1
+            if sink.per_token:
+                # "qio,bti,bto->qbt" (linear.py:100-111 of the reference): every token is scored like an example
+                # with a single position, i.e. the fused ROWDOT kernel on the flattened [B*S, d] operands.
+                if module.is_conv or a.dim() != 3:
+                    sink.get(-1 if sink.tokens is None else sink.tokens + 1)  # raises the dimension error
+                    raise RuntimeError("Per-token scores need [batch, sequence, features] module inputs.")
+                tokens = a.shape[1]
+                a = a.reshape(-1, a.shape[-1])
+                grad = grad.reshape(-1, grad.shape[-1])
             # Every use of a shared module adds its own term (the mathematically correct sum; the
             # reference keeps only the last use).
-            ops.pairwise_scores(layer, store, module.query_count, a, grad.detach(), sink, module.score_offset,
-                                accumulate=True, scale=module.gradient_scale,
+            ops.pairwise_scores(layer, store, module.query_count, a, grad, sink.get(tokens),
+                                module.score_offset * tokens, accumulate=True, scale=module.gradient_scale,
                                 precision=precision_of(module.score_args.score_dtype), qa=qa, qg=qg)
             if not module.factor_args.has_shared_parameters:
                 self.clear_all_cache()

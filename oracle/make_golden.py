@@ -224,6 +224,12 @@ def run_reference(case, dtype, strategy="ekfac", damping=None):
         out["scores"] = npy(analyzer.load_pairwise_scores("s")["all_modules"])
         for mname, tensor in analyzer.load_pairwise_scores("s_pm").items():
             out[f"scores/{mname}"] = npy(tensor)
+        if damping is None and case == "seq":
+            score_args_pt = ScoreArguments(**{**score_args.__dict__, "compute_per_token_scores": True})
+            analyzer.compute_pairwise_scores("s_pt", factors_name="f", query_dataset=query_set, train_dataset=train_set,
+                                             per_device_query_batch_size=query_bs, per_device_train_batch_size=train_bs,
+                                             score_args=score_args_pt, overwrite_output_dir=True)
+            out["scores_per_token"] = npy(analyzer.load_pairwise_scores("s_pt")["all_modules"])
         if damping is None:
             analyzer.compute_self_scores("self", factors_name="f", train_dataset=train_set,
                                          per_device_train_batch_size=train_bs, score_args=score_args,

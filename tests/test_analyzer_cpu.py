@@ -189,3 +189,15 @@ def test_self_scores_match_reference(case, tmp_path):
     assert rel(scores["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
     assert torch.equal(again["all_modules"], scores["all_modules"])
     del tasks
+
+
+def test_per_token_scores(tmp_path):
+    """`compute_per_token_scores` ([Q, T, S]); summing tokens gives the per-example scores
+    (tests/scores/test_pairwise_scores.py:437-504 of the reference)."""
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_seq.npz")))
+    with oracle_backend():
+        _, per_token = run_case("seq", tmp_path, inject_eigen=golden, score_kwargs=dict(compute_per_token_scores=True))
+    got = per_token["all_modules"].numpy()
+    assert got.shape == golden["f32/scores_per_token"].shape == (5, 23, 11)
+    assert rel(got, golden["f32/scores_per_token"]) < 5e-5
+    assert rel(got.sum(-1), golden["f32/scores"]) < 5e-5

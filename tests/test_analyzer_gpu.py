@@ -133,3 +133,13 @@ def test_self_scores(case, tmp_path):
     scores = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=6,
                                           score_args=ScoreArguments(damping_factor=None))
     assert rel(scores["all_modules"].numpy(), golden["f32/self_scores"]) < 1e-4
+
+
+def test_per_token_scores(tmp_path):
+    """`compute_per_token_scores`: every token is one row of the fused ROWDOT kernel; [Q, T, S] vs the reference."""
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_seq.npz")))
+    _, scores, _ = run("seq", tmp_path, golden, inject=True, compute_per_token_scores=True)
+    got = scores["all_modules"].numpy()
+    assert got.shape == golden["f32/scores_per_token"].shape
+    assert rel(got, golden["f32/scores_per_token"]) < 1e-4
+    assert rel(got.sum(-1), golden["f32/scores"]) < 1e-4
