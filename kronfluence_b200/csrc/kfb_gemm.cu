@@ -50,6 +50,7 @@ struct GemmParams {
   int k_splits, kb_per_split;  // contraction split ACROSS CTAs (atomics)
   int k_chunks, kb_per_chunk;  // contraction passes INSIDE a unit (register accumulation)
   int inner;                   // REGACC_BATCH: batches per chunk
+  int n_splits, nb_per_split;  // ROWDOT: the n-tiles of one row block spread over several units (atomics)
   int regacc_mode;
   int max_pass_k;              // longest TMEM accumulation chain (contraction elements) of this launch
   long long num_units;
@@ -67,6 +68,8 @@ struct GemmParams {
   const float* g;
   long long ldg;
   int g_vec4;
+  int f32_vec4, mul_vec4;  // out_f32 rows / mul rows are 16-byte aligned
+  int batch_fastest;       // STORE: consecutive units share the (m, n) tile (and so the `mul` tile) across the batch
 };
 
 struct Tile {
@@ -75,7 +78,11 @@ struct Tile {
 
 template <int EPI>
 __device__ __forceinline__ int unit_inner_count(const GemmParams& p, long long unit) {
-  if (EPI == EPI_ROWDOT) return p.n_blocks * p.k_chunks;
+  if (EPI == EPI_ROWDOT) {
+    const int ns = (int)((unit / p.m_blocks) % p.n_splits);
+    const int nb0 = ns * p.nb_per_split;
+    return (min(p.n_blocks, nb0 + p.nb_per_split) - nb0) * p.k_chunks;
+  }
   if (EPI == EPI_REGACC) {
     if (p.regacc_mode == REGACC_BATCH) {
       const long long chunk = unit / ((long long)p.m_blocks * p.n_blocks);
@@ -93,12 +100,26 @@ __device__ __forceinline__ int unit_inner_count(const GemmParams& p, long long u
 template <int EPI>
 __device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit, int j) {
   Tile t;
+  if (EPI == EPI_STORE && p.batch_fastest) {
+    // the Lambda^-1 tile of an (m, n) block is read by every batch entry: schedule those units back to back so that
+    // it is fetched from HBM once and served from L2 to the rest
+    t.b = (int)(unit % p.batch);
+    long long r = unit / p.batch;
+    t.m_blk = (int)(r % p.m_blocks);
+    r /= p.m_blocks;
+    t.n_blk = (int)(r % p.n_blocks);
+    const int ks = (int)(r / p.n_blocks);
+    t.kb0 = ks * p.kb_per_split;
+    t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_split);
+    return t;
+  }
   t.m_blk = (int)(unit % p.m_blocks);
   long long r = unit / p.m_blocks;
   if (EPI == EPI_ROWDOT) {
-    t.b = (int)r;
-    t.n_blk = j / p.k_chunks;
-    const int kc = j - t.n_blk * p.k_chunks;
+    t.b = (int)(r / p.n_splits);
+    const int jn = j / p.k_chunks;
+    t.n_blk = (int)(r % p.n_splits) * p.nb_per_split + jn;
+    const int kc = j - jn * p.k_chunks;
     t.kb0 = kc * p.kb_per_chunk;
     t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_chunk);
   } else if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH) {
@@ -125,80 +146,228 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit,
   return t;
 }
 
-// Writes 8 consecutive accumulator columns of one row through every STORE option (kept to 8 values at a
-// time so that the register-accumulating epilogue does not spill).
-__device__ __forceinline__ void store8(const GemmParams& p, int b, long long row, int col0, const float (&a)[8]) {
-  float x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float val = p.alpha * a[i];
-    if (p.mul != nullptr && col0 + i < p.N) val *= __ldg(p.mul + row * p.ldmul + col0 + i);
-    if (p.square) val *= val;
-    x[i] = val;
-  }
-  const bool full = col0 + 8 <= p.N;
-  if (p.out_f32 != nullptr) {
-    float* ob = p.out_f32 + (long long)b * p.out_bs;
-    if (!p.transpose_out && full && p.vec_ok && !p.use_atomic) {
-      float4* o4 = reinterpret_cast<float4*>(ob + row * p.ldo + col0);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float4 w = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-        if (p.accumulate) {
-          const float4 old = o4[i];
-          w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-        }
-        o4[i] = w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (col0 + i < p.N) {
-          float* o = p.transpose_out ? ob + (long long)(col0 + i) * p.ldo + row : ob + row * p.ldo + col0 + i;
-          if (p.use_atomic) atomicAdd(o, x[i]);
-          else if (p.accumulate) *o += x[i];
-          else *o = x[i];
-        }
-      }
-    }
-  }
-  if (p.out_hi != nullptr) {
-    __nv_bfloat16* oh = p.out_hi + (long long)b * p.out_bs_s;
-    __nv_bfloat16* ol = p.out_lo != nullptr ? p.out_lo + (long long)b * p.out_bs_s : nullptr;
-    if (!p.transpose_out && full && p.vec_ok) {
-      __nv_bfloat16 h[8], l[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) split_bf16(x[e], h[e], l[e]);
-      *reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0) = *reinterpret_cast<uint4*>(h);
-      if (ol) *reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0) = *reinterpret_cast<uint4*>(l);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (col0 + i < p.N) {
-          const long long idx = p.transpose_out ? (long long)(col0 + i) * p.ldo_s + row : row * p.ldo_s + col0 + i;
-          __nv_bfloat16 h, l;
-          split_bf16(x[i], h, l);
-          oh[idx] = h;
-          if (ol) ol[idx] = l;
-        }
-      }
-    }
-  }
+// Store of a 32 x 32 accumulator chunk (rows = the warp's 32 lanes, columns col0..col0+31) through every STORE
+// option.  Bias layers make d_in+1 odd, so fp32 factors such as the covariance [d,d], Lambda [d_out,d_in+1] and
+// Lambda^-1 have rows that are not 16-byte aligned, and a lane that walks its own accumulator row through them
+// touches 32 different cache lines per instruction.  Three paths, chosen warp-uniformly:
+//   registers  no `mul` factor and no row-major fp32 target: every layout left is contiguous per LANE (bf16 planes
+//              as 16-byte vectors, transposed fp32 as consecutive lanes), so the values never leave registers;
+//   vector     the chunk is parked in shared memory ([32][33] floats per epilogue warp) and re-read so that a group of
+//              lanes shares a row: 4 lanes x 8 columns for bf16 planes (16-byte stores, two full sectors per row), 8
+//              lanes x 4 columns for aligned fp32 rows (float4 read-modify-write / atomics); the Lambda^-1 factor is
+//              read in the same mapping, and with HOIST all loads of the chunk are issued before the first use;
+//   rows       whatever is left (unaligned fp32 rows, reduce_sq, mixed targets): lane = column, one coalesced
+//              128-byte line per row, loads hoisted in groups of rows.
+// Must be called by all 32 lanes.  Returns the lane's share of sum((alpha D)^2 * mul) when p.reduce_sq is set.
+__device__ __forceinline__ void put_f32(const GemmParams& p, float* o, float v, float old) {
+  if (p.use_atomic) atomicAdd(o, v);
+  else *o = v + old;
 }
 
-// 32 columns starting at compile-time offset OFF of a register array.
-template <int OFF, int N>
-__device__ __forceinline__ void store_values(const GemmParams& p, int b, long long row, int col0,
-                                             const float (&acc)[N]) {
+template <int OFF, int N, bool HOIST>
+__device__ __forceinline__ float store_chunk(const GemmParams& p, int b, long long row, int col0, const float (&acc)[N],
+                                             float* st, int lane) {
+  const bool direct_f32 = p.out_f32 != nullptr && !p.transpose_out && !p.reduce_sq;
+  const bool rmw = p.accumulate && !p.use_atomic;
+  const bool full = col0 + 32 <= p.N;
+  float* ob = p.out_f32 != nullptr ? p.out_f32 + (long long)b * p.out_bs : nullptr;
+  __nv_bfloat16* oh = p.out_hi != nullptr ? p.out_hi + (long long)b * p.out_bs_s : nullptr;
+  __nv_bfloat16* ol = (oh != nullptr && p.out_lo != nullptr) ? p.out_lo + (long long)b * p.out_bs_s : nullptr;
+
+  // ---- registers ----
+  if (p.mul == nullptr && !direct_f32 && !p.reduce_sq) {
+    if (row >= p.M) return 0.f;
+    if (ob != nullptr) {  // transposed fp32: consecutive lanes = consecutive addresses
 #pragma unroll
-  for (int grp = 0; grp < 4; ++grp) {
-    if (col0 + grp * 8 < p.N) {
-      float a[8];
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i < p.N) {
+          float v = p.alpha * acc[OFF + i];
+          if (p.square) v *= v;
+          float* o = ob + (long long)(col0 + i) * p.ldo + row;
+          put_f32(p, o, v, rmw ? *o : 0.f);
+        }
+      }
+    }
+    if (oh != nullptr) {
+      if (!p.transpose_out && p.vec_ok && full) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = acc[OFF + grp * 8 + i];
-      store8(p, b, row, col0 + grp * 8, a);
+        for (int grp = 0; grp < 4; ++grp) {
+          __nv_bfloat16 h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = p.alpha * acc[OFF + grp * 8 + e];
+            if (p.square) v *= v;
+            split_bf16(v, h[e], l[e]);
+          }
+          *reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(h);
+          if (ol) *reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(l);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (col0 + i < p.N) {
+            float v = p.alpha * acc[OFF + i];
+            if (p.square) v *= v;
+            const long long idx = p.transpose_out ? (long long)(col0 + i) * p.ldo_s + row : row * p.ldo_s + col0 + i;
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            oh[idx] = h;
+            if (ol) ol[idx] = l;
+          }
+        }
+      }
+    }
+    return 0.f;
+  }
+
+  // ---- park the chunk ----
+  const long long row0 = row - lane;  // first row of this warp's 32-row slab
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) st[lane * 33 + i] = p.alpha * acc[OFF + i];
+  __syncwarp();
+
+  // ---- vector: bf16 planes, 4 lanes x 8 columns per row, 8 rows per pass ----
+  if (oh != nullptr && ob == nullptr && !p.transpose_out && p.vec_ok && full) {
+    const int qr = lane >> 2, cg = (lane & 3) * 8;
+    constexpr int PASSES = HOIST ? 4 : 1;  // passes whose factor loads are in flight together
+    for (int it0 = 0; it0 < 4; it0 += PASSES) {
+      float m[PASSES][8];
+#pragma unroll
+      for (int u = 0; u < PASSES; ++u) {
+        const long long rr = row0 + (it0 + u) * 8 + qr;
+        const float* mp = p.mul + rr * p.ldmul + col0 + cg;
+        if (rr < p.M && p.mul_vec4) {
+          const float4 m0 = __ldg(reinterpret_cast<const float4*>(mp));
+          const float4 m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+          m[u][0] = m0.x; m[u][1] = m0.y; m[u][2] = m0.z; m[u][3] = m0.w;
+          m[u][4] = m1.x; m[u][5] = m1.y; m[u][6] = m1.z; m[u][7] = m1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) m[u][e] = rr < p.M ? __ldg(mp + e) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PASSES; ++u) {
+        const int r = (it0 + u) * 8 + qr;
+        const long long rr = row0 + r;
+        if (rr >= p.M) continue;
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = st[r * 33 + cg + e] * m[u][e];
+          if (p.square) v *= v;
+          split_bf16(v, h[e], l[e]);
+        }
+        *reinterpret_cast<uint4*>(oh + rr * p.ldo_s + col0 + cg) = *reinterpret_cast<uint4*>(h);
+        if (ol) *reinterpret_cast<uint4*>(ol + rr * p.ldo_s + col0 + cg) = *reinterpret_cast<uint4*>(l);
+      }
+    }
+    __syncwarp();
+    return 0.f;
+  }
+
+  // ---- vector: aligned fp32 rows, 8 lanes x 4 columns per row, 4 rows per pass ----
+  if (direct_f32 && oh == nullptr && p.f32_vec4 && full && (p.mul == nullptr || p.mul_vec4)) {
+    const int qr = lane >> 3, cg = (lane & 7) * 4;
+    constexpr int PASSES = HOIST ? 8 : 2;
+    for (int it0 = 0; it0 < 8; it0 += PASSES) {
+      float4 m[PASSES], old[PASSES];
+#pragma unroll
+      for (int u = 0; u < PASSES; ++u) {
+        const long long rr = row0 + (it0 + u) * 4 + qr;
+        const bool ok = rr < p.M;
+        m[u] = (ok && p.mul != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.mul + rr * p.ldmul + col0 + cg))
+                                        : make_float4(1.f, 1.f, 1.f, 1.f);
+        old[u] = (ok && rmw) ? *reinterpret_cast<const float4*>(ob + rr * p.ldo + col0 + cg)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < PASSES; ++u) {
+        const int r = (it0 + u) * 4 + qr;
+        const long long rr = row0 + r;
+        if (rr >= p.M) continue;
+        float4 v = make_float4(st[r * 33 + cg] * m[u].x, st[r * 33 + cg + 1] * m[u].y, st[r * 33 + cg + 2] * m[u].z,
+                               st[r * 33 + cg + 3] * m[u].w);
+        if (p.square) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
+        float4* o = reinterpret_cast<float4*>(ob + rr * p.ldo + col0 + cg);
+        if (p.use_atomic) atomicAdd(o, v);
+        else *o = make_float4(v.x + old[u].x, v.y + old[u].y, v.z + old[u].z, v.w + old[u].w);
+      }
+    }
+    __syncwarp();
+    return 0.f;
+  }
+
+  // ---- rows: lane = column ----
+  float part = 0.f;
+  const int col = col0 + lane;
+  const bool col_ok = col < p.N;
+  constexpr int G = HOIST ? 16 : 8;
+  for (int r0 = 0; r0 < 32; r0 += G) {
+    if (row0 + r0 >= p.M) break;  // warp-uniform
+    float m[G], old[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const long long rr = row0 + r0 + j;
+      const bool ok = col_ok && rr < p.M;
+      m[j] = (ok && p.mul != nullptr) ? __ldg(p.mul + rr * p.ldmul + col) : 1.f;
+      old[j] = (ok && rmw && direct_f32) ? ob[rr * p.ldo + col] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const long long rr = row0 + r0 + j;
+      const bool ok = col_ok && rr < p.M;
+      float v = st[(r0 + j) * 33 + lane];  // alpha * D[rr][col]
+      if (p.reduce_sq) {
+        if (ok) part = fmaf(v * v, m[j], part);
+        continue;
+      }
+      v *= m[j];
+      if (p.square) v *= v;
+      st[(r0 + j) * 33 + lane] = v;
+      if (direct_f32 && ok) put_f32(p, ob + rr * p.ldo + col, v, old[j]);
     }
   }
+  __syncwarp();
+  if (p.reduce_sq) return part;
+  // lanes return to their own row for the lane-contiguous layouts
+  if (row < p.M) {
+    if (ob != nullptr && p.transpose_out) {
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i < p.N) {
+          float* o = ob + (long long)(col0 + i) * p.ldo + row;
+          put_f32(p, o, st[lane * 33 + i], rmw ? *o : 0.f);
+        }
+      }
+    }
+    if (oh != nullptr) {
+      if (!p.transpose_out && p.vec_ok && full) {
+#pragma unroll
+        for (int grp = 0; grp < 4; ++grp) {
+          __nv_bfloat16 h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_bf16(st[lane * 33 + grp * 8 + e], h[e], l[e]);
+          *reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(h);
+          if (ol) *reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(l);
+        }
+      } else {
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          if (col0 + i < p.N) {
+            const long long idx = p.transpose_out ? (long long)(col0 + i) * p.ldo_s + row : row * p.ldo_s + col0 + i;
+            __nv_bfloat16 h, l;
+            split_bf16(st[lane * 33 + i], h, l);
+            oh[idx] = h;
+            if (ol) ol[idx] = l;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  return 0.f;
 }
 
 // keep the [N, ld) padding of non-transposed split outputs finite (zero): they may be re-read as part
@@ -224,7 +393,8 @@ struct GemmCfg {
   static constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_PLANE = LOAD_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PLANE + B_PLANE);
-  static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // one [32][33] fp32 staging tile per epilogue warp
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 2048 - EPI_STAGE_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STAGES = 2;
@@ -232,7 +402,7 @@ struct GemmCfg {
   static constexpr int TMEM_COLS =
       TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                  : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K must match a 128B or 64B swizzle span");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
@@ -435,6 +605,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // ======================================= epilogue ========================================
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int lane_row = quarter * 32 + lane;  // accumulator row owned by this thread
+    float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256) + quarter * (32 * 33);
     constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N : 1;
     uint32_t it = 0;
     for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
@@ -490,24 +661,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[i]);
             }
-          } else if (p.reduce_sq) {
-            if (row_ok) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (col0 + i < p.N) {
-                  const float x = __uint_as_float(v[i]);
-                  const float w = p.mul != nullptr ? __ldg(p.mul + row * p.ldmul + col0 + i) : 1.f;
-                  rowdot = fmaf(x * x, w, rowdot);
-                }
-              }
-            }
           } else {
-            if (row_ok) {
-              float x[32];
+            float x[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-              store_values<0>(p, t.b, row, col0, x);
-            }
+            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+            rowdot += store_chunk<0, 32, true>(p, t.b, row, col0, x, st, lane);
           }
         }
         if (EPI == EPI_STORE && p.reduce_sq) {
@@ -515,7 +673,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           float part = rowdot;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-          if (lane == 0 && part != 0.f) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs, p.alpha * part);
+          // store_chunk squared alpha-scaled values: sum (alpha D)^2 mul; the contract is alpha * sum D^2 mul
+          if (lane == 0 && part != 0.f) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs, part / p.alpha);
           rowdot = 0.f;
         }
         if (EPI == EPI_STORE && p.zero_pad && !p.reduce_sq && row_ok && t.n_blk == p.n_blocks - 1) store_zero_pad(p, t.b, row);
@@ -533,20 +692,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (row < p.M) {
           float* o = p.out_f32 + (long long)t.b * p.out_bs + row;
           const float val = p.alpha * rowdot;
-          if (p.accumulate) *o += val;
+          if (p.use_atomic) atomicAdd(o, val);
+          else if (p.accumulate) *o += val;
           else *o = val;
         }
       } else if (EPI == EPI_REGACC) {
         const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
-        if (row < p.M) {
-          const int n0 = t.n_blk * BLOCK_N;
-          const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
-          if (NACC >= 32 && n0 < p.N) store_values<0>(p, ob, row, n0, racc);
-          if (NACC >= 64 && n0 + 32 < p.N) store_values<(NACC >= 64 ? 32 : 0)>(p, ob, row, n0 + 32, racc);
-          if (NACC >= 128 && n0 + 64 < p.N) store_values<(NACC >= 128 ? 64 : 0)>(p, ob, row, n0 + 64, racc);
-          if (NACC >= 128 && n0 + 96 < p.N) store_values<(NACC >= 128 ? 96 : 0)>(p, ob, row, n0 + 96, racc);
-          if (p.zero_pad && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
-        }
+        const int n0 = t.n_blk * BLOCK_N;
+        const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
+        // warp-uniform conditions: store_chunk is a warp-cooperative call
+        if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false>(p, ob, row, n0, racc, st, lane);
+        if (NACC >= 64 && n0 + 32 < p.N) store_chunk<(NACC >= 64 ? 32 : 0), NACC, false>(p, ob, row, n0 + 32, racc, st, lane);
+        if (NACC >= 128 && n0 + 64 < p.N) store_chunk<(NACC >= 128 ? 64 : 0), NACC, false>(p, ob, row, n0 + 64, racc, st, lane);
+        if (NACC >= 128 && n0 + 96 < p.N) store_chunk<(NACC >= 128 ? 96 : 0), NACC, false>(p, ob, row, n0 + 96, racc, st, lane);
+        if (row < p.M && p.zero_pad && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
       }
     }
   }
@@ -719,7 +878,19 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
     p.k_chunks = (int)ceil_div_ll(p.k_blocks, max_pass_kb);
     p.kb_per_chunk = (int)ceil_div_ll(p.k_blocks, p.k_chunks);
     p.k_chunks = (int)ceil_div_ll(p.k_blocks, p.kb_per_chunk);
-    p.num_units = (long long)p.m_blocks * p.batch;
+    // few row blocks (self-influence: one "query" per batch): spread each block's n-tiles over the idle SMs
+    const long long row_units = (long long)p.m_blocks * p.batch, groups = sm_count() / CG;
+    p.n_splits = 1;
+    if (row_units * 2 <= groups && p.n_blocks > 1 && (p.batch == 1 || p.out_bs >= p.M))
+      p.n_splits = (int)(groups / row_units < p.n_blocks ? groups / row_units : p.n_blocks);
+    p.nb_per_split = (int)ceil_div_ll(p.n_blocks, p.n_splits);
+    p.n_splits = (int)ceil_div_ll(p.n_blocks, p.nb_per_split);
+    p.use_atomic = p.n_splits > 1 ? 1 : 0;
+    if (p.use_atomic && !p.accumulate && row_units > 0) {
+      if (p.batch == 1) KFB_CUDA_TRY(cudaMemsetAsync(p.out_f32, 0, (size_t)p.M * 4, stream));
+      else KFB_CUDA_TRY(cudaMemset2DAsync(p.out_f32, (size_t)p.out_bs * 4, 0, (size_t)p.M * 4, (size_t)p.batch, stream));
+    }
+    p.num_units = row_units * p.n_splits;
   } else if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH) {
     // cut the batch into chunks so that there are enough units to fill the machine
     long long chunks = ceil_div_ll(2LL * sm_count(), tiles);
@@ -886,12 +1057,13 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   if (epi.kind == KFB_EPI_STORE) {
     KFB_REQUIRE(p.out_f32 != nullptr || p.out_hi != nullptr, "gemm_nt: STORE without an output");
     p.vec_ok = 1;
-    if (p.out_f32 && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) || p.ldo % 4 || p.out_bs % 4))
-      p.vec_ok = 0;
+    p.f32_vec4 = (p.out_f32 && !((reinterpret_cast<uintptr_t>(p.out_f32) & 15) || p.ldo % 4 || p.out_bs % 4)) ? 1 : 0;
+    p.mul_vec4 = (p.mul && !((reinterpret_cast<uintptr_t>(p.mul) & 15) || p.ldmul % 4)) ? 1 : 0;
     if (p.out_hi && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) || p.ldo_s % 8 || p.out_bs_s % 8 ||
                      (p.out_lo && (reinterpret_cast<uintptr_t>(p.out_lo) & 15))))
       p.vec_ok = 0;
     p.zero_pad = (p.out_hi != nullptr && !p.transpose_out) ? 1 : 0;
+    p.batch_fastest = (p.mul != nullptr && p.batch > 1) ? 1 : 0;
     if (p.reduce_sq) {
       KFB_REQUIRE(p.out_f32 != nullptr && p.out_hi == nullptr, "gemm_nt: reduce_sq needs out_f32 only");
       KFB_REQUIRE(p.K <= p.max_pass_k, "gemm_nt: reduce_sq needs the contraction to fit one TMEM pass (K <= %d)",

@@ -352,10 +352,28 @@ static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const v
   const long long planes = planes_of(precision);
   const bool eigen = mode == KFB_PRECOND_EIGEN;
   const bool back_rotate = eigen && (p_f32 != nullptr || ws.dry);
-  long long per = outer_bytes_per_sample(L, S, eigen, precision);
+  // One position per example: the per-sample gradient is the rank-one g a^T, so the rotated, Lambda^-1-scaled
+  // operand is a streaming outer product (no GEMM) of the rotated rows
+  const bool rank1 = L.kind == KFB_LINEAR && S == 1;
+  const int rp = rot_prec(precision);
+  const long long lda = ld8(di), ldgr = ld8(L.d_out);
+  long long per = rank1 ? (lda + ldgr) * (4 + (eigen ? 2 * planes_of(rp) : 0))
+                        : outer_bytes_per_sample(L, S, eigen, precision);
   if (back_rotate) per += di * ld8(L.d_out) * 2 * planes;
   const long long cb = chunk_count(batch, per);
-  OuterBufs o = outer_alloc(ws, L, cb, S, eigen, precision);
+  OuterBufs o{};
+  kfb_split a_sp{}, g_sp{};
+  float *ar = nullptr, *gr = nullptr;
+  if (rank1) {
+    if (eigen) {
+      a_sp = ws_split(ws, cb, di, 1, rp);
+      g_sp = ws_split(ws, cb, L.d_out, 1, rp);
+    }
+    ar = static_cast<float*>(ws.take((size_t)(cb * lda) * 4));
+    gr = static_cast<float*>(ws.take((size_t)(cb * ldgr) * 4));
+  } else {
+    o = outer_alloc(ws, L, cb, S, eigen, precision);
+  }
   kfb_split Rt2{};
   if (back_rotate) Rt2 = ws_split(ws, di, L.d_out, cb, precision);
   if (ws.dry) return KFB_OK;
@@ -375,22 +393,57 @@ static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const v
                 "precondition: eigenbasis operands do not match the layer");
   for (long long b0 = 0; b0 < batch; b0 += cb) {
     const long long nb = batch - b0 < cb ? batch - b0 : cb;
-    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, eigen, qa_t, qg_t, o, precision, stream));
-    kfb_split Lt = split_batch_view(o.Lt, 0, nb), Rt = split_batch_view(o.Rt, 0, nb);
-    kfb_split Pv = split_batch_view(*P, q_offset + b0, nb);
     float* pf = p_f32 != nullptr ? p_f32 + b0 * L.d_out * di : nullptr;
-    // Pt = scale * (Lt Rt^T) [o lambda_inv]                    [nb][d_out][d_in+bias]
-    kfb_epilogue e = store_epilogue();
-    e.out_split = Pv;
-    e.mul = mode == KFB_PRECOND_IDENTITY ? nullptr : lambda_inv;
-    e.ldmul = di;
-    e.alpha = scale;
-    if (!eigen) {
-      e.out_f32 = pf;
-      e.ldo = di;
-      e.out_batch_stride = L.d_out * di;
+    if (rank1) {
+      GatherDesc ga{};
+      ga.sr = L.d_in; ga.sc2 = 1; ga.rows = nb; ga.c1 = 1; ga.c2 = L.d_in;
+      ga.ones_mode = L.has_bias ? 1 : 0;
+      GatherDesc gg{};
+      gg.sr = L.d_out; gg.sc2 = 1; gg.rows = nb; gg.c1 = 1; gg.c2 = L.d_out;
+      const void* a0 = advance(a, a_dt, b0 * L.d_in);
+      const void* g0 = advance(g, g_dt, b0 * L.d_out);
+      if (eigen) {
+        KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
+                    "precondition: eigenbasis operands do not match the layer");
+        KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+                    "precondition: eigenbasis operands must be built with KFB_PREC_STRICT");
+        kfb_split av = a_sp, gv = g_sp;
+        av.rows = nb; gv.rows = nb;
+        KFB_TRY(split_gather(a0, a_dt, ga, av, rp, stream));
+        KFB_TRY(split_gather(g0, g_dt, gg, gv, rp, stream));
+        // a~[q, n] = sum_k a[q,k] Q_A[k,n],  g~[q, n] = sum_k g[q,k] Q_G[k,n]   (fp32 rows)
+        kfb_epilogue ea = store_epilogue();
+        ea.out_f32 = ar;
+        ea.ldo = lda;
+        KFB_TRY(gemm_nt(av, *qa_t, ea, rp, 1, stream));
+        kfb_epilogue eg = store_epilogue();
+        eg.out_f32 = gr;
+        eg.ldo = ldgr;
+        KFB_TRY(gemm_nt(gv, *qg_t, eg, rp, 1, stream));
+      } else {
+        KFB_TRY(gather_f32(a0, a_dt, ga, ar, lda, stream));
+        KFB_TRY(gather_f32(g0, g_dt, gg, gr, ldgr, stream));
+      }
+      KFB_TRY(outer_split(gr, ldgr, ar, lda, mode == KFB_PRECOND_IDENTITY ? nullptr : lambda_inv, di, scale, nb,
+                          split_batch_view(*P, q_offset + b0, nb), precision, eigen ? nullptr : pf, stream));
     }
-    KFB_TRY(gemm_nt(Lt, Rt, e, precision, 1, stream));
+    kfb_split Pv = split_batch_view(*P, q_offset + b0, nb);
+    if (!rank1) {
+      KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, eigen, qa_t, qg_t, o, precision, stream));
+      kfb_split Lt = split_batch_view(o.Lt, 0, nb), Rt = split_batch_view(o.Rt, 0, nb);
+      // Pt = scale * (Lt Rt^T) [o lambda_inv]                    [nb][d_out][d_in+bias]
+      kfb_epilogue e = store_epilogue();
+      e.out_split = Pv;
+      e.mul = mode == KFB_PRECOND_IDENTITY ? nullptr : lambda_inv;
+      e.ldmul = di;
+      e.alpha = scale;
+      if (!eigen) {
+        e.out_f32 = pf;
+        e.ldo = di;
+        e.out_batch_stride = L.d_out * di;
+      }
+      KFB_TRY(gemm_nt(Lt, Rt, e, precision, 1, stream));
+    }
     if (eigen && pf != nullptr) {
       // reference layout on request:  R^T = Q_A Pt^T  [nb][d_in+bias][d_out],  P = Q_G R  [nb][d_out][d_in+bias]
       kfb_epilogue e2 = store_epilogue();

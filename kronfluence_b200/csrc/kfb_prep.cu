@@ -31,6 +31,7 @@ struct SplitDst {
   __nv_bfloat16* lo;
   __nv_bfloat16* lo2;
   long long ld, bs;
+  float* f32;  // plain fp32 destination instead of planes (gather_f32)
 };
 
 static SplitDst make_dst(const kfb_split& dst, int precision) {
@@ -40,6 +41,7 @@ static SplitDst make_dst(const kfb_split& dst, int precision) {
   d.lo2 = precision == KFB_PREC_STRICT ? (__nv_bfloat16*)dst.lo2 : nullptr;
   d.ld = dst.ld;
   d.bs = dst.batch_stride;
+  d.f32 = nullptr;
   return d;
 }
 
@@ -65,7 +67,7 @@ __device__ __forceinline__ float gather_value(const T* src, const GatherDesc& g,
   const long long cols = g.c1 * g.c2;
   float v;
   if (r < g.rows && c < cols) {
-    const long long c1 = c / g.c2, c2 = c - c1 * g.c2;
+    const long long c1 = g.c1 == 1 ? 0 : c / g.c2, c2 = c - c1 * g.c2;
     v = load_as_float<T>(src, b * g.sb + r * g.sr + c1 * g.sc1 + c2 * g.sc2);
   } else if ((g.ones_mode == 1 && c == cols && r < g.rows) ||
              (g.ones_mode == 2 && r == g.rows && c < cols)) {
@@ -79,36 +81,92 @@ __device__ __forceinline__ float gather_value(const T* src, const GatherDesc& g,
   return v;
 }
 
-// Direct variant: thread x walks the destination's contiguous dimension; the source is contiguous
-// along the same logical dimension (sc2 == 1) or the matrix is too thin to matter.
+// 8 consecutive destination elements -> one 16-byte store per plane.
+__device__ __forceinline__ void store_split8(const SplitDst& d, long long idx, const float (&v)[8]) {
+  if (d.f32 != nullptr) {
+    reinterpret_cast<float4*>(d.f32 + idx)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(d.f32 + idx)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    return;
+  }
+  __nv_bfloat16 h[8], m[8], l[8];
+  if (d.lo2 != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16_3(v[e], h[e], m[e], l[e]);
+    *reinterpret_cast<uint4*>(d.hi + idx) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(d.lo + idx) = *reinterpret_cast<uint4*>(m);
+    *reinterpret_cast<uint4*>(d.lo2 + idx) = *reinterpret_cast<uint4*>(l);
+    return;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
+  *reinterpret_cast<uint4*>(d.hi + idx) = *reinterpret_cast<uint4*>(h);
+  if (d.lo != nullptr) *reinterpret_cast<uint4*>(d.lo + idx) = *reinterpret_cast<uint4*>(l);
+}
+
+// Direct variant: each thread produces 8 consecutive elements of a destination row (the destination ld is a
+// multiple of 8, so every plane store is one aligned 16-byte vector); the source is contiguous along the same
+// logical dimension (sc2 == 1) or the matrix is too thin to matter.
 template <typename T>
 __global__ void gather_direct_kernel(const T* __restrict__ src, GatherDesc g, SplitDst d,
                                      long long out_rows, long long batch) {
-  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (c >= d.ld) return;
+  const long long c8 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+  if (c8 >= d.ld) return;
   for (long long b = blockIdx.z; b < batch; b += gridDim.z)
     for (long long r = blockIdx.y * (long long)blockDim.y + threadIdx.y; r < out_rows;
-         r += (long long)gridDim.y * blockDim.y)
-      store_split(d, b * d.bs + r * d.ld + c, gather_value<T>(src, g, b, r, c));
+         r += (long long)gridDim.y * blockDim.y) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gather_value<T>(src, g, b, r, c8 + e);
+      store_split8(d, b * d.bs + r * d.ld + c8, v);
+    }
 }
 
-// Transposing variant: the source is contiguous along the destination's ROW index (sr == 1).
+// Transposing variant: the source is contiguous along the destination's ROW index (sr == 1).  A block turns a
+// 32 (rows) x 64 (columns) tile around through shared memory: loads walk rows (source-contiguous), stores are
+// 16-byte vectors along the columns.
 template <typename T>
 __global__ void gather_transpose_kernel(const T* __restrict__ src, GatherDesc g, SplitDst d,
                                         long long out_rows, long long batch) {
-  __shared__ float tile[32][33];
-  const long long c0 = blockIdx.x * 32LL, r0 = blockIdx.y * 32LL;
+  __shared__ float tile[64][33];
+  const long long c0 = blockIdx.x * 64LL, r0 = blockIdx.y * 32LL;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 8 warps
   for (long long b = blockIdx.z; b < batch; b += gridDim.z) {
-    // load: threadIdx.x walks rows (source-contiguous), threadIdx.y walks columns
-    for (int j = threadIdx.y; j < 32; j += blockDim.y)
-      tile[j][threadIdx.x] = gather_value<T>(src, g, b, r0 + threadIdx.x, c0 + j);
+    for (int j = wid; j < 64; j += 8) tile[j][lane] = gather_value<T>(src, g, b, r0 + lane, c0 + j);
     __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-      const long long r = r0 + j, c = c0 + threadIdx.x;
-      if (r < out_rows && c < d.ld) store_split(d, b * d.bs + r * d.ld + c, tile[threadIdx.x][j]);
+    const long long r = r0 + lane, c = c0 + wid * 8;
+    if (r < out_rows && c < d.ld) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tile[wid * 8 + e][lane];
+      store_split8(d, b * d.bs + r * d.ld + c, v);
     }
     __syncthreads();
   }
+}
+
+template <typename T>
+static int launch_gather_dst(const T* src, const GatherDesc& g, const SplitDst& d, long long batch,
+                             cudaStream_t stream) {
+  const long long out_rows = g.rows + (g.ones_mode == 2 ? 1 : 0);
+  if (out_rows == 0 || batch == 0) return KFB_OK;
+  const unsigned gz = (unsigned)(batch < 65535 ? batch : 65535);
+  const bool transpose = (g.sr == 1 && g.sc2 != 1 && g.rows > 1);
+  if (transpose) {
+    dim3 grid((unsigned)ceil_div_ll(d.ld, 64), (unsigned)ceil_div_ll(out_rows, 32), gz);
+    KFB_REQUIRE(grid.y <= 65535, "split_gather: too many rows for the transposing kernel");
+    gather_transpose_kernel<T><<<grid, 256, 0, stream>>>(src, g, d, out_rows, batch);
+  } else {
+    const long long vecs = d.ld / 8;  // 8-element vectors per destination row
+    const unsigned bx = vecs >= 64 ? 64 : (vecs >= 32 ? 32 : (vecs >= 16 ? 16 : 8));
+    dim3 block(bx, 256 / bx);
+    long long gy = ceil_div_ll(out_rows, block.y);
+    if (gy > 65535) gy = 65535;  // rows beyond that are covered by the grid-stride loop
+    dim3 grid((unsigned)ceil_div_ll(vecs, block.x), (unsigned)gy, gz);
+    gather_direct_kernel<T><<<grid, block, 0, stream>>>(src, g, d, out_rows, batch);
+  }
+  count_launch();
+  KFB_CUDA_TRY(cudaGetLastError());
+  return KFB_OK;
 }
 
 template <typename T>
@@ -124,21 +182,85 @@ static int launch_gather(const T* src, const GatherDesc& g, const kfb_split& dst
   KFB_REQUIRE(dst.hi != nullptr && (precision == KFB_PREC_BF16 || dst.lo != nullptr) &&
                   (precision != KFB_PREC_STRICT || dst.lo2 != nullptr),
               "split_gather: missing destination plane");
-  if (out_rows == 0 || dst.batch == 0) return KFB_OK;
-  SplitDst d = make_dst(dst, precision);
-  const unsigned gz = (unsigned)(dst.batch < 65535 ? dst.batch : 65535);
-  const bool transpose = (g.sr == 1 && g.sc2 != 1 && g.rows > 1);
-  if (transpose) {
-    dim3 grid((unsigned)ceil_div_ll(dst.ld, 32), (unsigned)ceil_div_ll(out_rows, 32), gz);
-    KFB_REQUIRE(grid.y <= 65535, "split_gather: too many rows for the transposing kernel");
-    gather_transpose_kernel<T><<<grid, dim3(32, 8), 0, stream>>>(src, g, d, out_rows, dst.batch);
-  } else {
-    dim3 block(128, 2);
-    long long gy = ceil_div_ll(out_rows, block.y);
-    if (gy > 65535) gy = 65535;  // rows beyond that are covered by the grid-stride loop
-    dim3 grid((unsigned)ceil_div_ll(dst.ld, block.x), (unsigned)gy, gz);
-    gather_direct_kernel<T><<<grid, block, 0, stream>>>(src, g, d, out_rows, dst.batch);
+  KFB_REQUIRE((reinterpret_cast<uintptr_t>(dst.hi) & 15) == 0 && dst.batch_stride % 8 == 0,
+              "split_gather: destination planes must be 16-byte aligned");
+  return launch_gather_dst<T>(src, g, make_dst(dst, precision), dst.batch, stream);
+}
+
+int gather_f32(const void* src, int src_dtype, const GatherDesc& g, float* dst, long long ld,
+               cudaStream_t stream) {
+  const long long out_cols = g.c1 * g.c2 + (g.ones_mode == 1 ? 1 : 0);
+  KFB_REQUIRE(dst != nullptr && ld >= out_cols && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "gather_f32: bad destination (ld %lld)", ld);
+  SplitDst d{};
+  d.f32 = dst;
+  d.ld = ld;
+  switch (src_dtype) {
+    case KFB_F32: return launch_gather_dst<float>((const float*)src, g, d, 1, stream);
+    case KFB_BF16: return launch_gather_dst<__nv_bfloat16>((const __nv_bfloat16*)src, g, d, 1, stream);
+    case KFB_F16: return launch_gather_dst<__half>((const __half*)src, g, d, 1, stream);
+    case KFB_F64: return launch_gather_dst<double>((const double*)src, g, d, 1, stream);
+    default: set_error("gather_f32: unsupported dtype %d", src_dtype); return KFB_ERR_INVALID;
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Rank-one query gradients (one position per example): P[q][o][i] = scale * gv[q][o] * av[q][i] * mul[o][i]
+// written straight as operand planes (and fp32 on request).  Pure streaming: the Lambda^-1 vector of a thread
+// stays in registers for all queries; every store is one 16-byte vector, 512 contiguous bytes per warp.
+// -------------------------------------------------------------------------------------------------
+__global__ void outer_split_kernel(const float* __restrict__ gv, long long ldgv, const float* __restrict__ av,
+                                   long long ldav, const float* __restrict__ mul, long long ldmul, float scale,
+                                   long long nq, long long d_out, long long di, SplitDst d, float* __restrict__ out_f32) {
+  const long long i8 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+  const long long o = blockIdx.y * (long long)blockDim.y + threadIdx.y;
+  if (i8 >= d.ld || o >= d_out) return;
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    m[e] = i8 + e < di ? (mul != nullptr ? scale * __ldg(mul + o * ldmul + i8 + e) : scale) : 0.f;
+  for (long long q = blockIdx.z; q < nq; q += gridDim.z) {
+    const float g = __ldg(gv + q * ldgv + o);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    if (i8 < ldav) {  // ldav is a multiple of 8
+      a0 = __ldg(reinterpret_cast<const float4*>(av + q * ldav + i8));
+      a1 = __ldg(reinterpret_cast<const float4*>(av + q * ldav + i8) + 1);
+    }
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = i8 + e < di ? (g * a[e]) * m[e] : 0.f;
+    store_split8(d, q * d.bs + o * d.ld + i8, v);
+    if (out_f32 != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (i8 + e < di) out_f32[(q * d_out + o) * di + i8 + e] = v[e];
+    }
+  }
+}
+
+int outer_split(const float* gv, long long ldgv, const float* av, long long ldav, const float* mul, long long ldmul,
+                float scale, long long nq, const kfb_split& P, int precision, float* out_f32, cudaStream_t stream) {
+  const long long d_out = P.rows, di = P.cols;
+  KFB_REQUIRE(P.hi != nullptr && P.ld % 8 == 0 && P.ld >= di && P.batch >= nq && P.batch_stride % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(P.hi) & 15) == 0,
+              "outer_split: bad destination");
+  KFB_REQUIRE(ldav % 8 == 0 && ldav >= di && (reinterpret_cast<uintptr_t>(av) & 15) == 0,
+              "outer_split: the activation rows must be padded to a multiple of 8 and 16-byte aligned");
+  KFB_REQUIRE(precision == KFB_PREC_BF16 || P.lo != nullptr, "outer_split: missing lo plane");
+  if (nq == 0 || d_out == 0) return KFB_OK;
+  SplitDst d = make_dst(P, precision == KFB_PREC_STRICT ? KFB_PREC_FP32 : precision);
+  const long long vecs = P.ld / 8;
+  const unsigned bx = vecs >= 32 ? 32 : (vecs >= 16 ? 16 : 8);
+  dim3 block(bx, 256 / bx);
+  const long long gx = ceil_div_ll(vecs, block.x), gy = ceil_div_ll(d_out, block.y);
+  KFB_REQUIRE(gy <= 65535, "outer_split: too many rows");
+  // enough blocks to fill the machine; the query loop is the rest
+  long long gz = ceil_div_ll(4LL * sm_count(), gx * gy);
+  if (gz > nq) gz = nq;
+  if (gz < 1) gz = 1;
+  outer_split_kernel<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), block, 0, stream>>>(
+      gv, ldgv, av, ldav, mul, ldmul, scale, nq, d_out, di, d, out_f32);
   count_launch();
   KFB_CUDA_TRY(cudaGetLastError());
   return KFB_OK;
@@ -159,46 +281,77 @@ int split_gather(const void* src, int src_dtype, const GatherDesc& g, const kfb_
 // Conv2d im2col (+ group mean + ones column), module/conv2d.py:15-64.  Patch feature index
 // i = (c * k_h + kh) * k_w + kw  (F.unfold ordering), position s = oh * w_out + ow.
 // -------------------------------------------------------------------------------------------------
+// One patch element, already decomposed: channel c (within a group), kernel tap (kh, kw), output position (oh, ow).
 template <typename T>
-__device__ __forceinline__ float patch_value(const T* __restrict__ x, const kfb_layer& L, long long b,
-                                             int s, int i) {
-  if (i == L.d_in) return L.has_bias ? 1.f : 0.f;
-  if (i > L.d_in) return 0.f;
-  const int kk = L.k_h * L.k_w;
-  const int c = i / kk, rem = i - c * kk;
-  const int kh = rem / L.k_w, kw = rem - kh * L.k_w;
-  const int oh = s / L.w_out, ow = s - oh * L.w_out;
+__device__ __forceinline__ float patch_at(const T* __restrict__ x, const kfb_layer& L, long long b, int oh, int ow,
+                                          int c, int kh, int kw, int cpg) {
   const int ih = oh * L.stride_h - L.pad_h + kh * L.dil_h;
   const int iw = ow * L.stride_w - L.pad_w + kw * L.dil_w;
   if (ih < 0 || ih >= L.h_in || iw < 0 || iw >= L.w_in) return 0.f;
-  const int cpg = L.c_in / L.groups;
+  if (L.groups == 1) return load_as_float<T>(x, ((b * L.c_in + c) * L.h_in + ih) * (long long)L.w_in + iw);
   float acc = 0.f;
   for (int gidx = 0; gidx < L.groups; ++gidx)
     acc += load_as_float<T>(x, ((b * L.c_in + gidx * cpg + c) * L.h_in + ih) * (long long)L.w_in + iw);
-  return L.groups > 1 ? acc / (float)L.groups : acc;
+  return acc / (float)L.groups;
 }
 
+// Each thread builds 8 consecutive elements of a destination row and stores one 16-byte vector per plane.  The
+// feature index i = (c*k_h + kh)*k_w + kw and the position s = oh*w_out + ow are decomposed ONCE per thread and then
+// advanced incrementally along the row, so the inner loop has no integer division.
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ x, kfb_layer L, long long batch, int layout,
                               SplitDst d, long long out_rows, long long out_cols) {
   const int S = L.h_out * L.w_out;
-  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cpg = L.c_in / L.groups;
+  const long long c8 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
   const long long r = blockIdx.y * (long long)blockDim.y + threadIdx.y;
-  if (c >= d.ld || r >= out_rows) return;
-  if (layout == 2) {
-    // dst[i][b*S + s]
-    float v = 0.f;
-    if (c < out_cols) {
-      const long long b = c / S;
-      v = patch_value<T>(x, L, b, (int)(c - b * S), (int)r);
+  if (c8 >= d.ld || r >= out_rows) return;
+  float v[8];
+  if (layout == 0) {
+    // dst[b][s][i]: the row fixes the position, the 8 elements walk the feature index
+    const int oh = (int)r / L.w_out, ow = (int)r - oh * L.w_out;
+    const int kk = L.k_h * L.k_w;
+    const int c0 = (int)c8 / kk, rem = (int)c8 - c0 * kk;
+    const int kh0 = rem / L.k_w, kw0 = rem - kh0 * L.k_w;
+    for (long long b = blockIdx.z; b < batch; b += gridDim.z) {
+      int c = c0, kh = kh0, kw = kw0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const long long i = c8 + e;
+        v[e] = i < L.d_in ? patch_at<T>(x, L, b, oh, ow, c, kh, kw, cpg) : (i == L.d_in && L.has_bias ? 1.f : 0.f);
+        if (++kw == L.k_w) { kw = 0; if (++kh == L.k_h) { kh = 0; ++c; } }
+      }
+      store_split8(d, b * d.bs + r * d.ld + c8, v);
     }
-    store_split(d, r * d.ld + c, v);
     return;
   }
+  // dst[b][i][s] (layout 1) or dst[i][b*S + s] (layout 2): the row fixes the feature, the elements walk positions
+  const int i = (int)r;
+  const int kk = L.k_h * L.k_w;
+  const int c = i / kk, rem = i - c * kk;
+  const int kh = rem / L.k_w, kw = rem - kh * L.k_w;
+  const float fill = (i == L.d_in && L.has_bias) ? 1.f : 0.f;  // rows at/after d_in: the ones row, then padding
+  if (layout == 2) {
+    long long b = c8 / S;
+    const int s0 = (int)(c8 - b * S);
+    int oh = s0 / L.w_out, ow = s0 - oh * L.w_out;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = c8 + e >= out_cols ? 0.f : (i < L.d_in ? patch_at<T>(x, L, b, oh, ow, c, kh, kw, cpg) : fill);
+      if (++ow == L.w_out) { ow = 0; if (++oh == L.h_out) { oh = 0; ++b; } }
+    }
+    store_split8(d, r * d.ld + c8, v);
+    return;
+  }
+  const int oh0 = (int)c8 / L.w_out, ow0 = (int)c8 - oh0 * L.w_out;
   for (long long b = blockIdx.z; b < batch; b += gridDim.z) {
-    float v = 0.f;
-    if (c < out_cols) v = layout == 0 ? patch_value<T>(x, L, b, (int)r, (int)c) : patch_value<T>(x, L, b, (int)c, (int)r);
-    store_split(d, b * d.bs + r * d.ld + c, v);
+    int oh = oh0, ow = ow0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = c8 + e >= out_cols ? 0.f : (i < L.d_in ? patch_at<T>(x, L, b, oh, ow, c, kh, kw, cpg) : fill);
+      if (++ow == L.w_out) { ow = 0; ++oh; }
+    }
+    store_split8(d, b * d.bs + r * d.ld + c8, v);
   }
 }
 
@@ -215,8 +368,12 @@ static int launch_im2col(const kfb_layer& L, const T* x, long long batch, int la
   KFB_REQUIRE(layout == 2 ? dst.batch == 1 : dst.batch == batch, "im2col: bad destination batch");
   if (batch == 0) return KFB_OK;
   SplitDst d = make_dst(dst, precision);
-  dim3 block(128, 2);
-  dim3 grid((unsigned)ceil_div_ll(dst.ld, block.x), (unsigned)ceil_div_ll(rows, block.y),
+  KFB_REQUIRE((reinterpret_cast<uintptr_t>(dst.hi) & 15) == 0 && dst.batch_stride % 8 == 0,
+              "im2col: destination planes must be 16-byte aligned");
+  const long long vecs = dst.ld / 8;
+  const unsigned bx = vecs >= 32 ? 32 : (vecs >= 16 ? 16 : 8);
+  dim3 block(bx, 256 / bx);
+  dim3 grid((unsigned)ceil_div_ll(vecs, block.x), (unsigned)ceil_div_ll(rows, block.y),
             (unsigned)(layout == 2 ? 1 : (batch < 65535 ? batch : 65535)));
   KFB_REQUIRE(grid.y <= 65535, "im2col: too many rows");
   im2col_kernel<T><<<grid, block, 0, stream>>>(x, L, batch, layout, d, rows, cols);

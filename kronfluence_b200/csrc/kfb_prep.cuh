@@ -20,6 +20,13 @@ struct GatherDesc {
 
 int split_gather(const void* src, int src_dtype, const GatherDesc& g, const kfb_split& dst,
                  int precision, cudaStream_t stream);
+// Same gather into a plain fp32 matrix (one batch entry, ld a multiple of 8).
+int gather_f32(const void* src, int src_dtype, const GatherDesc& g, float* dst, long long ld,
+               cudaStream_t stream);
+// P[q][o][i] = scale * gv[q][o] * av[q][i] * (mul ? mul[o][i] : 1) as operand planes of P (batch >= nq) and, on
+// request, as fp32 [nq][d_out][d_in] (out_f32).  av rows must be padded to P.ld (16-byte aligned).
+int outer_split(const float* gv, long long ldgv, const float* av, long long ldav, const float* mul, long long ldmul,
+                float scale, long long nq, const kfb_split& P, int precision, float* out_f32, cudaStream_t stream);
 int split_im2col(const kfb_layer& L, const void* x, int x_dtype, long long batch, int layout,
                  const kfb_split& dst, int precision, cudaStream_t stream);
 int cast_to_f32(const void* src, int src_dtype, float* dst, long long n, float scale,

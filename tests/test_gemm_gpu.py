@@ -119,6 +119,23 @@ def test_rowdot(shape):
     assert (out[:, 0] == 1).all() and (out[:, t + 1 :] == 1).all()
 
 
+@pytest.mark.parametrize("shape", [(1, 2048, 4096, 512), (3, 200, 1300, 96)])
+def test_rowdot_few_row_blocks_overwrite(shape):
+    """Few row blocks: the n-tiles of a block are spread over several units (atomics into a zeroed output)."""
+    engine = _engine()
+    q, t, n, k = shape
+    sa, sb, ref = _operands(engine, 1, q, t, n, k, 0, seed=11)
+    g = torch.randn(t, n, device="cuda")
+    out = torch.full((q, t + 5), 7.0, device="cuda")
+    epi = engine.KfbEpilogue(kind=engine.EPI_ROWDOT, out_f32=out[:, 2:].data_ptr(), out_batch_stride=t + 5,
+                             g=g.data_ptr(), ldg=n, alpha=0.5, accumulate=0)
+    engine.gemm_nt(sa, sb, epi, 0)
+    torch.cuda.synchronize()
+    want = 0.5 * (ref * g.double().unsqueeze(0)).sum(-1)
+    assert _rel(out[:, 2 : t + 2], want) < 2e-5
+    assert (out[:, :2] == 7).all() and (out[:, t + 2 :] == 7).all()
+
+
 @pytest.mark.parametrize("shape", [(9, 200, 150, 40), (300, 64, 128, 16), (2, 769, 768, 128)])
 def test_sqacc(shape):
     engine = _engine()

@@ -149,6 +149,29 @@ def test_diagonal_and_identity_modes():
     assert rel(store.to_float(), g["psg_query"]) < 2e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rank_one_precondition_modes(dtype):
+    """One position per example (Linear on 2-D inputs): the store is filled by the streaming outer-product kernel in
+    every mode, with the fp32 copy on request."""
+    ops, g, layer = setup_case("linear2d")
+    di, do = ops.factor_dims(layer)
+    xq, gq = cuda(g["x_query"], dtype), cuda(g["g_query"], dtype)
+    psg = orc.linear_per_sample_gradient(xq.double().cpu().numpy(), gq.double().cpu().numpy(), bool(layer.has_bias))
+    nq = xq.shape[0]
+    store = ops.make_query_store(do, di, nq + 1, "cuda")
+    inv = torch.rand(do, di, device="cuda") + 0.5
+    p32 = torch.zeros(nq, do, di, device="cuda")
+    ops.precondition(layer, xq, gq, store, 1, ops.PRECOND_DIAGONAL, lambda_inv=inv, scale=3.0, out_f32=p32)
+    torch.cuda.synchronize()
+    want = 3.0 * psg * inv.double().cpu().numpy()
+    assert rel(store.to_float()[1:], want) < 2e-5
+    assert rel(p32, want) < 1e-6
+    assert (store.to_float()[0] == 0).all()
+    ops.precondition(layer, xq, gq, store, 0, ops.PRECOND_IDENTITY)
+    torch.cuda.synchronize()
+    assert rel(store.to_float()[:nq], psg) < 2e-5
+
+
 LARGE = [
     # (d_in, d_out, bias, T, Q, S)
     (300, 200, True, 500, 70, 1),
