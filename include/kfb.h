@@ -109,7 +109,10 @@ typedef struct {
   int32_t square;
   int32_t accumulate; /* out_f32 += ... instead of = ...                                         */
   float alpha;
-  /* ROWDOT: out_f32[b*out_batch_stride + m] (+)= alpha * sum_n D[b][m][n] * g[m*ldg + n]        */
+  /* ROWDOT: out_f32[b*out_batch_stride + m] (+)= alpha * sum_n D[b][m][n] * g[b*g_batch_stride + m*ldg + n]
+   *         (g_batch_stride = 0: one factor matrix shared by the batch).  With row_group = R > 1 the rows of
+   *         group j = m / R (the tokens of one example) are summed: out_f32[b*out_batch_stride + j] += ...
+   *         (atomic adds; accumulate must be set).                                               */
   const float* g;
   int64_t ldg;
   /* SQACC: out_f32[m*ldo + n] += alpha * sum_b D[b][m][n]^2   (atomic adds)                     */
@@ -117,6 +120,8 @@ typedef struct {
    *   out_f32[b*out_batch_stride] += alpha * sum_{m,n} D[b][m][n]^2 * (mul ? mul[m][n] : 1)
    * (one scalar per batch entry: the self-influence contraction).                                */
   int32_t reduce_sq;
+  int32_t row_group;       /* ROWDOT, see above (0 or 1: one output per row)                     */
+  int64_t g_batch_stride;  /* ROWDOT, see above                                                   */
 } kfb_epilogue;
 
 /* ---------------------------------------------------------------------------------------------
@@ -281,6 +286,21 @@ int kfb_self_scores(const kfb_layer* layer, const void* a, int a_dtype, const vo
                     const kfb_split* qg_t, const float* lambda_inv, float scale, float* out,
                     int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes, int precision,
                     void* stream);
+
+/* Pairwise contraction against rank-r query factors P_q ~ left_t[q]^T right[q]  (module/linear.py:83-99,
+ * module/conv2d.py:188-201 "qik,qko,b...i,b...o->qb"; tracker/pairwise_score.py:26-39).  left_t[q] = [r, d_out]
+ * (U_k S_k transposed), right[q] = [r, d_in+bias] (V_k^T), both densely stacked operand batches; in KFB_PRECOND_EIGEN
+ * mode they factor the eigenbasis image kfb_precondition stores and the train operands are rotated first.
+ * scores[q*ld_scores + t_offset + t] (+)= scale * <P_q, G_t>; with per_token != 0 every position of a Linear
+ * [B, S, d] input gets its own column (t = b*S + s, linear.py:100-111).                            */
+size_t kfb_pairwise_lowrank_workspace_bytes(const kfb_layer* layer, int64_t num_queries, int64_t rank,
+                                           int64_t batch, int64_t seq);
+int kfb_pairwise_scores_lowrank(const kfb_layer* layer, const kfb_split* left_t, const kfb_split* right,
+                                int64_t num_queries, const void* a, int a_dtype, const void* g, int g_dtype,
+                                int64_t batch, int64_t seq, int32_t mode, const kfb_split* qa_t,
+                                const kfb_split* qg_t, float scale, float* scores, int64_t ld_scores,
+                                int64_t t_offset, int32_t accumulate, int32_t per_token, void* ws,
+                                size_t ws_bytes, int precision, void* stream);
 
 /* Same contraction through HOST buffers (pinned or pageable): a, g are host pointers, scores_host
  * receives [num_queries, batch] fp32.  dev_a / dev_g / dev_scores are caller-provided device

@@ -580,15 +580,22 @@ class Analyzer:
         order (tracker/precondition.py:166-201 of the reference).  rank r's j-th local query is global
         query j*world + r of the batch."""
         world = self.state.num_processes
-        for module in tracked_modules(self.model, names):
-            store = module.storage["accumulated_preconditioned_gradient"]
-            local = store.storage[:, base : base + local_batch].contiguous()
+        def gather(storage: torch.Tensor) -> None:
+            local = storage[:, base : base + local_batch].contiguous()
             flat = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
             dist.all_gather_into_tensor(flat, local)  # concatenated along dim 0 (the form gloo and nccl share)
             gathered = flat.view((world,) + tuple(local.shape))
             # [world, planes, j, rows, ld] -> [planes, j, world, rows, ld] -> [planes, j*world, rows, ld]
             inter = gathered.permute(1, 2, 0, 3, 4).reshape(local.shape[0], local_batch * world, *local.shape[2:])
-            store.storage[:, base : base + local_batch * world].copy_(inter)
+            storage[:, base : base + local_batch * world].copy_(inter)
+
+        for module in tracked_modules(self.model, names):
+            store = module.storage["accumulated_preconditioned_gradient"]
+            if hasattr(store, "left_t"):  # rank-r factors: gather both operand stores
+                gather(store.left_t.storage)
+                gather(store.right.storage)
+            else:
+                gather(store.storage)
             module.query_count = base + local_batch * world
 
     def _pairwise(self, query_dataset: data.Dataset, train_dataset: data.Dataset, query_bs: int, train_bs: int,
@@ -700,8 +707,6 @@ class Analyzer:
         for flag in ("aggregate_query_gradients", "aggregate_train_gradients"):
             if getattr(score_args, flag):
                 raise NotImplementedError(f"`{flag}` is not part of the B200 hot path yet (SURVEY.md §8f).")
-        if score_args.query_gradient_low_rank is not None:
-            raise NotImplementedError("Low-rank query batching is not part of the B200 hot path yet (SURVEY.md §8f).")
         if self.task.enable_post_process_per_sample_gradient:
             raise NotImplementedError("`post_process_per_sample_gradient` needs materialised gradients; unsupported.")
         factor_args = self._load_factor_args(factors_name)
@@ -792,8 +797,12 @@ class Analyzer:
         score_args = ScoreArguments() if score_args is None else score_args
         if score_args.use_measurement_for_self_influence:
             raise NotImplementedError("`use_measurement_for_self_influence` is not part of the B200 hot path yet.")
-        if score_args.query_gradient_low_rank is not None or score_args.compute_per_token_scores:
-            raise NotImplementedError("low-rank / per-token options do not apply to self-influence scores here.")
+        # score_computer.py:617-640 of the reference: options that do not apply to self-influence are switched off
+        for key, off in (("query_gradient_accumulation_steps", 1), ("query_gradient_low_rank", None),
+                         ("compute_per_token_scores", False)):
+            if getattr(score_args, key) != off:
+                self.logger.warning("`%s` is not supported for self-influence computation; ignoring it.", key)
+                setattr(score_args, key, off)
         factor_args = self._load_factor_args(factors_name)
         out_dir = self.scores_output_dir(scores_name)
         if self.state.is_main_process:

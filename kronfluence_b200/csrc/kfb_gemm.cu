@@ -66,8 +66,9 @@ struct GemmParams {
   int reduce_sq;  // STORE: reduce D^2 (o mul) to one scalar per batch entry instead of storing
   float alpha;
   const float* g;
-  long long ldg;
+  long long ldg, g_bs;  // ROWDOT factor rows; g_bs = offset between the factors of consecutive batch entries
   int g_vec4;
+  int row_group;        // ROWDOT: rows [j*row_group, (j+1)*row_group) are summed into out[b][j] (tokens of an example)
   int f32_vec4, mul_vec4;  // out_f32 rows / mul rows are 16-byte aligned
   int batch_fastest;       // STORE: consecutive units share the (m, n) tile (and so the `mul` tile) across the batch
 };
@@ -634,7 +635,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           tmem_ld_wait();
           if (EPI == EPI_ROWDOT) {
             if (row_ok) {
-              const float* gp = p.g + row * p.ldg + col0;
+              const float* gp = p.g + (long long)t.b * p.g_bs + row * p.ldg + col0;
               if (p.g_vec4 && col0 + 32 <= p.N) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -689,7 +690,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       // ---- per-unit finalisation ----
       if (EPI == EPI_ROWDOT) {
         const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
-        if (row < p.M) {
+        if (p.row_group > 1) {
+          // sum the rows of one example: segmented warp reduction (groups are contiguous lane ranges), then one
+          // atomic per group and warp
+          const long long grp = row < p.M ? row / p.row_group : -1;
+          const unsigned peers = __match_any_sync(0xffffffffu, grp);
+          float val = p.alpha * rowdot;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const float other = __shfl_down_sync(0xffffffffu, val, off);
+            if (lane + off < 32 && ((peers >> (lane + off)) & 1u)) val += other;
+          }
+          if (grp >= 0 && lane == __ffs(peers) - 1) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs + grp, val);
+        } else if (row < p.M) {
           float* o = p.out_f32 + (long long)t.b * p.out_bs + row;
           const float val = p.alpha * rowdot;
           if (p.use_atomic) atomicAdd(o, val);
@@ -791,7 +804,11 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
     const long long m = tid % p.M, b = tid / p.M;
     float sum = 0.f;
     for (int n = 0; n < p.N; ++n)
-      sum += simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K) * p.g[m * p.ldg + n];
+      sum += simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K) * p.g[b * p.g_bs + m * p.ldg + n];
+    if (p.row_group > 1) {
+      atomicAdd(p.out_f32 + b * p.out_bs + m / p.row_group, p.alpha * sum);
+      return;
+    }
     float* o = p.out_f32 + b * p.out_bs + m;
     if (p.accumulate) *o += p.alpha * sum;
     else *o = p.alpha * sum;
@@ -1046,6 +1063,8 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   p.alpha = epi.alpha;
   p.g = epi.g;
   p.ldg = epi.ldg;
+  p.g_bs = epi.g_batch_stride;
+  p.row_group = epi.row_group > 1 ? (int)epi.row_group : 1;
   p.reduce_sq = epi.kind == KFB_EPI_STORE ? epi.reduce_sq : 0;
   p.k_splits = 1;
   p.k_chunks = 1;
@@ -1072,7 +1091,8 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   } else if (epi.kind == KFB_EPI_ROWDOT) {
     KFB_REQUIRE(p.out_f32 != nullptr && p.g != nullptr, "gemm_nt: ROWDOT needs out_f32 and g");
     KFB_REQUIRE(A.batch == 1 || A.batch == p.batch, "gemm_nt: ROWDOT batch mismatch");
-    p.g_vec4 = ((reinterpret_cast<uintptr_t>(p.g) & 15) == 0 && p.ldg % 4 == 0) ? 1 : 0;
+    p.g_vec4 = ((reinterpret_cast<uintptr_t>(p.g) & 15) == 0 && p.ldg % 4 == 0 && p.g_bs % 4 == 0) ? 1 : 0;
+    KFB_REQUIRE(p.row_group == 1 || p.accumulate, "gemm_nt: ROWDOT row groups add into the output (accumulate = 1)");
   } else if (epi.kind == KFB_EPI_SQACC) {
     KFB_REQUIRE(p.out_f32 != nullptr, "gemm_nt: SQACC needs out_f32");
     // sum over the batch of squares: register accumulation, atomically added to the target

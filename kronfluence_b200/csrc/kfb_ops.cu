@@ -195,6 +195,27 @@ static long long outer_bytes_per_sample(const kfb_layer& L, long long S, bool ro
   return b;
 }
 
+// Token-major operands of samples [0, nb):  ta[b] = [S, d_in+bias] (ones column appended, im2col for Conv2d),
+// tg[b] = [S, d_out]; both K-major in the feature index, i.e. the A operands of the eigenbasis rotations.
+static int token_operands(const kfb_layer& L, const void* a0, int a_dt, const void* g0, int g_dt, long long nb,
+                          long long S, const kfb_split& ta, const kfb_split& tg, int prec, cudaStream_t stream) {
+  if (L.kind == KFB_LINEAR) {
+    GatherDesc ga{};
+    ga.sb = S * L.d_in; ga.sr = L.d_in; ga.sc2 = 1; ga.rows = S; ga.c1 = 1; ga.c2 = L.d_in;
+    ga.ones_mode = L.has_bias ? 1 : 0;
+    KFB_TRY(split_gather(a0, a_dt, ga, ta, prec, stream));
+    GatherDesc gg{};
+    gg.sb = S * L.d_out; gg.sr = L.d_out; gg.sc2 = 1; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
+    KFB_TRY(split_gather(g0, g_dt, gg, tg, prec, stream));
+  } else {
+    KFB_TRY(split_im2col(L, a0, a_dt, nb, 0, ta, prec, stream));
+    GatherDesc gg{};
+    gg.sb = (long long)L.d_out * S; gg.sr = 1; gg.sc2 = S; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
+    KFB_TRY(split_gather(g0, g_dt, gg, tg, prec, stream));
+  }
+  return KFB_OK;
+}
+
 static int outer_fill(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt,
                       long long b0, long long nb, long long seq, bool rotate, const kfb_split* qa_t,
                       const kfb_split* qg_t, OuterBufs& o, int precision, cudaStream_t stream) {
@@ -229,20 +250,7 @@ static int outer_fill(const kfb_layer& L, const void* a, int a_dt, const void* g
   KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
               "eigenbasis operands must be built with KFB_PREC_STRICT for the fp32-parity mode");
   kfb_split ta = split_batch_view(o.tmp_a, 0, nb), tg = split_batch_view(o.tmp_g, 0, nb);
-  if (L.kind == KFB_LINEAR) {
-    GatherDesc ga{};
-    ga.sb = S * L.d_in; ga.sr = L.d_in; ga.sc2 = 1; ga.rows = S; ga.c1 = 1; ga.c2 = L.d_in;
-    ga.ones_mode = L.has_bias ? 1 : 0;
-    KFB_TRY(split_gather(a0, a_dt, ga, ta, rp, stream));
-    GatherDesc gg{};
-    gg.sb = S * L.d_out; gg.sr = L.d_out; gg.sc2 = 1; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
-    KFB_TRY(split_gather(g0, g_dt, gg, tg, rp, stream));
-  } else {
-    KFB_TRY(split_im2col(L, a0, a_dt, nb, 0, ta, rp, stream));
-    GatherDesc gg{};
-    gg.sb = (long long)L.d_out * S; gg.sr = 1; gg.sc2 = S; gg.rows = S; gg.c1 = 1; gg.c2 = L.d_out;
-    KFB_TRY(split_gather(g0, g_dt, gg, tg, rp, stream));
-  }
+  KFB_TRY(token_operands(L, a0, a_dt, g0, g_dt, nb, S, ta, tg, rp, stream));
   // Rt[b] = Q_A^T a_b^T : M = d_in+bias (eigen index), N = S, K = d_in+bias
   kfb_epilogue e = store_epilogue();
   e.out_split = Rt;
@@ -578,6 +586,100 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
 }
 
 // =================================================================================================
+// Stage 5b: pairwise contraction against rank-r query factors  P_q ~ Lt_q^T R_q  (Lt_q = [r, d_out], R_q = [r, d_in+bias]).
+// linear.py:83-99 / conv2d.py:188-201 ("qik,qko,b...i,b...o->qb"), tracker/pairwise_score.py:26-39.
+//   Y[n, (q,k)] = sum_i a[n,i] R_q[k,i]                 one GEMM over all queries (fp32 out, N = Q*r)
+//   score[q, n] = sum_k (sum_o g[n,o] Lt_q[k,o]) Y[n,(q,k)]   fused ROWDOT, batched over q, rows n = tokens
+// and the tokens of an example are summed by the epilogue (row groups) unless per-token scores are requested.
+// 2 N Q r (d_in + d_out) flops instead of 2 Q T d_in d_out.
+// =================================================================================================
+
+static int lowrank_run(const kfb_layer& L, const kfb_split* Lt, const kfb_split* R, long long nq, long long rank,
+                       const void* a, int a_dt, const void* g, int g_dt, long long batch, long long seq, int mode,
+                       const kfb_split* qa_t, const kfb_split* qg_t, float scale, float* scores, long long ld_scores,
+                       long long t_offset, int accumulate, int per_token, Ws& ws, int precision, cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const bool eigen = mode == KFB_PRECOND_EIGEN;
+  const int rp = rot_prec(precision);
+  const int tp = eigen ? rp : precision;  // precision of the raw token operands
+  const long long ldy = round_up_ll(nq * rank, 4);
+  long long per = S * (ld8(di) + ld8(L.d_out)) * 2 * planes_of(tp) + S * ldy * 4;
+  if (eigen) per += S * (ld8(di) + ld8(L.d_out)) * 2 * planes_of(precision);
+  const long long cb = chunk_count(batch, per);
+  kfb_split ta = ws_split(ws, S, di, cb, tp), tg = ws_split(ws, S, L.d_out, cb, tp);
+  kfb_split a_rot{}, g_rot{};
+  if (eigen) {
+    a_rot = ws_split(ws, cb * S, di, 1, precision);
+    g_rot = ws_split(ws, cb * S, L.d_out, 1, precision);
+  }
+  float* Y = static_cast<float*>(ws.take((size_t)(cb * S * ldy) * 4));
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("low-rank pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  KFB_REQUIRE(Lt->rows == rank && R->rows == rank && Lt->cols == L.d_out && R->cols == di,
+              "pairwise_lowrank: factor shapes do not match the layer");
+  KFB_REQUIRE(R->batch_stride == rank * R->ld, "pairwise_lowrank: the right factors must be densely stacked");
+  if (eigen) {
+    KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
+                "pairwise_lowrank: eigenbasis operands do not match the layer");
+    KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+                "pairwise_lowrank: eigenbasis operands must be built with KFB_PREC_STRICT");
+  }
+  const long long out_cols = per_token ? batch * S : batch;
+  if (!accumulate) {
+    zero_strided_kernel<<<296, 256, 0, stream>>>(scores + t_offset, nq, out_cols, ld_scores);
+    count_launch();
+  }
+  kfb_split Rf = *R;  // all queries' right factors as one [Q*r, d_in+bias] operand
+  Rf.rows = nq * rank;
+  Rf.batch = 1;
+  Rf.batch_stride = 0;
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    const void* a0 = L.kind == KFB_LINEAR ? advance(a, a_dt, b0 * S * L.d_in)
+                                          : advance(a, a_dt, b0 * (long long)L.c_in * L.h_in * L.w_in);
+    const void* g0 = advance(g, g_dt, b0 * S * L.d_out);
+    KFB_TRY(token_operands(L, a0, a_dt, g0, g_dt, nb, S, split_batch_view(ta, 0, nb), split_batch_view(tg, 0, nb), tp,
+                           stream));
+    // the per-sample [S, d] blocks are stacked densely: view them as [nb*S, d]
+    kfb_split af = ta, gf = tg;
+    af.rows = nb * S; af.batch = 1; af.batch_stride = 0;
+    gf.rows = nb * S; gf.batch = 1; gf.batch_stride = 0;
+    if (eigen) {
+      kfb_split ar = a_rot, gr = g_rot;
+      ar.rows = nb * S; gr.rows = nb * S;
+      kfb_epilogue ea = store_epilogue();
+      ea.out_split = ar;
+      KFB_TRY(gemm_nt(af, *qa_t, ea, rp, 1, stream));
+      kfb_epilogue eg = store_epilogue();
+      eg.out_split = gr;
+      KFB_TRY(gemm_nt(gf, *qg_t, eg, rp, 1, stream));
+      af = ar;
+      gf = gr;
+    }
+    kfb_epilogue ey = store_epilogue();
+    ey.out_f32 = Y;
+    ey.ldo = ldy;
+    KFB_TRY(gemm_nt(af, Rf, ey, precision, 1, stream));
+    kfb_epilogue e{};
+    e.kind = KFB_EPI_ROWDOT;
+    e.out_f32 = scores + t_offset + (per_token ? b0 * S : b0);
+    e.out_batch_stride = ld_scores;
+    e.g = Y;
+    e.ldg = ldy;
+    e.g_batch_stride = rank;
+    e.row_group = per_token ? 1 : (int32_t)S;
+    e.alpha = scale;
+    e.accumulate = 1;
+    KFB_TRY(gemm_nt(gf, split_batch_view(*Lt, 0, nq), e, precision, 1, stream));
+  }
+  return KFB_OK;
+}
+
+// =================================================================================================
 // Self-influence (next row #3 of SURVEY.md §8f).  tracker/self_score.py:32-60.
 //   self[t] = sum_{o,i} (Q_G^T G_t Q_A)[o,i]^2 * lambda_inv[o,i]      with G_t = scale * per-sample gradient
 // =================================================================================================
@@ -801,6 +903,38 @@ int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_
   KFB_REQUIRE(mode >= KFB_PRECOND_IDENTITY && mode <= KFB_PRECOND_EIGEN, "pairwise_scores: bad mode %d", mode);
   return pairwise_run(*layer, P, num_queries, a, a_dtype, g, g_dtype, batch, seq, mode, qa_t, qg_t, scale,
                       scores, ld_scores, t_offset, accumulate, w, precision, (cudaStream_t)stream);
+}
+
+size_t kfb_pairwise_lowrank_workspace_bytes(const kfb_layer* layer, int64_t num_queries, int64_t rank, int64_t batch,
+                                           int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0 || num_queries <= 0 || rank <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  lowrank_run(*layer, nullptr, nullptr, num_queries, rank, nullptr, KFB_F32, nullptr, KFB_F32, batch, seq,
+              KFB_PRECOND_EIGEN, nullptr, nullptr, 1.f, nullptr, 0, 0, 1, 0, w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_pairwise_scores_lowrank(const kfb_layer* layer, const kfb_split* left_t, const kfb_split* right,
+                                int64_t num_queries, const void* a, int a_dtype, const void* g, int g_dtype,
+                                int64_t batch, int64_t seq, int32_t mode, const kfb_split* qa_t,
+                                const kfb_split* qg_t, float scale, float* scores, int64_t ld_scores,
+                                int64_t t_offset, int32_t accumulate, int32_t per_token, void* ws, size_t ws_bytes,
+                                int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(left_t != nullptr && right != nullptr && left_t->hi != nullptr && right->hi != nullptr && a != nullptr &&
+                  g != nullptr && scores != nullptr,
+              "pairwise_scores_lowrank: null tensor");
+  KFB_REQUIRE(num_queries >= 0 && num_queries <= left_t->batch && num_queries <= right->batch,
+              "pairwise_scores_lowrank: num_queries exceeds the factor stores");
+  KFB_REQUIRE(left_t->rows == right->rows && left_t->rows > 0, "pairwise_scores_lowrank: rank mismatch");
+  const long long cols = per_token ? batch * positions(*layer, seq) : batch;
+  KFB_REQUIRE(t_offset >= 0 && t_offset + cols <= ld_scores, "pairwise_scores_lowrank: columns out of range");
+  KFB_REQUIRE(mode >= KFB_PRECOND_IDENTITY && mode <= KFB_PRECOND_EIGEN, "pairwise_scores_lowrank: bad mode %d", mode);
+  if (batch <= 0 || num_queries == 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return lowrank_run(*layer, left_t, right, num_queries, left_t->rows, a, a_dtype, g, g_dtype, batch, seq, mode, qa_t,
+                     qg_t, scale, scores, ld_scores, t_offset, accumulate, per_token, w, precision,
+                     (cudaStream_t)stream);
 }
 
 int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,

@@ -48,7 +48,8 @@ class KfbEpilogue(ctypes.Structure):
                 ("out_batch_stride", ctypes.c_int64), ("out_split", KfbSplit), ("mul", ctypes.c_void_p),
                 ("ldmul", ctypes.c_int64), ("transpose_out", ctypes.c_int32), ("square", ctypes.c_int32),
                 ("accumulate", ctypes.c_int32), ("alpha", ctypes.c_float), ("g", ctypes.c_void_p),
-                ("ldg", ctypes.c_int64), ("reduce_sq", ctypes.c_int32)]
+                ("ldg", ctypes.c_int64), ("reduce_sq", ctypes.c_int32), ("row_group", ctypes.c_int32),
+                ("g_batch_stride", ctypes.c_int64)]
 
 
 # Every symbol include/kfb.h declares, with its ctypes signature (restype, argtypes).
@@ -83,6 +84,10 @@ SIGNATURES = {
     "kfb_pairwise_scores": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _f32, _vp, _i64, _i64, _i32, _vp, _sz, ctypes.c_int, _vp]),
     "kfb_self_workspace_bytes": (_sz, [_LP, _i64, _i64]),
     "kfb_self_scores": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _vp, _f32, _vp, _i64, _i32, _vp, _sz, ctypes.c_int, _vp]),
+    "kfb_pairwise_lowrank_workspace_bytes": (_sz, [_LP, _i64, _i64, _i64, _i64]),
+    "kfb_pairwise_scores_lowrank": (ctypes.c_int, [_LP, _SP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64,
+                                                   _i32, _SP, _SP, _f32, _vp, _i64, _i64, _i32, _i32, _vp, _sz,
+                                                   ctypes.c_int, _vp]),
     "kfb_pairwise_scores_host": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _f32, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
 }
 

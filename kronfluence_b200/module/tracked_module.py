@@ -279,8 +279,16 @@ class PreconditionTracker(BaseTracker):
         if mode == ops.PRECOND_EIGEN:
             qa, qg = module.eigen_operands(g.device)
         lam_inv = module.storage[LAMBDA_MATRIX_NAME] if mode != ops.PRECOND_IDENTITY else None
-        ops.precondition(layer, a, g, store, module.query_count, mode, qa, qg, lam_inv, module.gradient_scale,
-                         precision=precision_of(module.score_args.precondition_dtype))
+        if isinstance(store, ops.LowRankStore):
+            # tracker/precondition.py:54-71: precondition this batch densely, keep only its rank-r factors
+            dense = store.scratch_for(a.shape[0], g.device)
+            ops.precondition(layer, a, g, dense, 0, mode, qa, qg, lam_inv, module.gradient_scale,
+                             precision=precision_of(module.score_args.precondition_dtype))
+            ops.lowrank_factorize(dense, a.shape[0], store, module.query_count, module.score_args.use_full_svd,
+                                  module.score_args.query_gradient_svd_dtype)
+        else:
+            ops.precondition(layer, a, g, store, module.query_count, mode, qa, qg, lam_inv, module.gradient_scale,
+                             precision=precision_of(module.score_args.precondition_dtype))
         module.last_query_batch = a.shape[0]
         module.query_count += a.shape[0]
 
@@ -350,6 +358,20 @@ class PairwiseScoreTracker(BaseTracker):
                 qa, qg = module.eigen_operands(grad.device)  # the store holds eigenbasis images
             grad = grad.detach()
             tokens = 1
+            if isinstance(store, ops.LowRankStore):
+                # "qik,qko,b...i,b...o->qb" / "...->qbt" (linear.py:83-99, conv2d.py:188-201 of the reference)
+                if sink.per_token:
+                    if module.is_conv or a.dim() != 3:
+                        sink.get(-1 if sink.tokens is None else sink.tokens + 1)  # raises the dimension error
+                        raise RuntimeError("Per-token scores need [batch, sequence, features] module inputs.")
+                    tokens = a.shape[1]
+                ops.pairwise_scores_lowrank(layer, store, module.query_count, a, grad, sink.get(tokens),
+                                            module.score_offset * tokens, accumulate=True, scale=module.gradient_scale,
+                                            precision=precision_of(module.score_args.score_dtype), qa=qa, qg=qg,
+                                            per_token=sink.per_token)
+                if not module.factor_args.has_shared_parameters:
+                    self.clear_all_cache()
+                return
             if sink.per_token:
                 # "qio,bti,bto->qbt" (linear.py:100-111 of the reference): every token is scored like an example
                 # with a single position, i.e. the fused ROWDOT kernel on the flattened [B*S, d] operands.
@@ -557,8 +579,13 @@ class TrackedModule(nn.Module):
     # ---- score plumbing ----
     def allocate_query_store(self, capacity: int, device: torch.device) -> None:
         d_in_total, d_out = ops.module_factor_dims(self.original_module)
-        self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = ops.make_query_store(
-            d_out, d_in_total, capacity, device, precision_of(self.score_args.score_dtype))
+        rank = self.score_args.query_gradient_low_rank
+        if rank is not None and min(d_out, d_in_total) > rank:  # tracker/precondition.py:60-63 of the reference
+            self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = ops.make_lowrank_store(
+                d_out, d_in_total, rank, capacity, device, precision_of(self.score_args.score_dtype))
+        else:
+            self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = ops.make_query_store(
+                d_out, d_in_total, capacity, device, precision_of(self.score_args.score_dtype))
         self.query_count = 0
 
 

@@ -265,7 +265,96 @@ def pairwise_scores(layer: KfbLayer, store: Split, num_queries: int, a: torch.Te
                                   ws_size, precision, stream_ptr(a.device)))
 
 
+# --------------------------------------------------------------------------------------------------
+# Stage 5b: rank-r query factors (tracker/precondition.py:19-75, linear.py:83-99, tracker/pairwise_score.py:26-39)
+# --------------------------------------------------------------------------------------------------
+class LowRankStore:
+    """Rank-r factors of `capacity` preconditioned query gradients of one module, P_q ~ left_t[q]^T right[q], in
+    tensor-core operand layout: left_t [capacity][r][d_out] (= (U_k S_k)^T), right [capacity][r][d_in(+1)] (= V_k^T).
+    `scratch` is the dense store one query batch is preconditioned into before it is factorised."""
+
+    def __init__(self, d_out: int, d_in_total: int, rank: int, capacity: int, device, precision: int = PREC_FP32):
+        self.rows, self.cols, self.rank, self.batch = d_out, d_in_total, rank, capacity
+        self.precision = precision
+        self.left_t = Split(rank, d_out, capacity, device=device, precision=precision, zero=True)
+        self.right = Split(rank, d_in_total, capacity, device=device, precision=precision, zero=True)
+        self.scratch: Optional[Split] = None
+
+    def scratch_for(self, batch: int, device) -> Split:
+        if self.scratch is None or self.scratch.batch < batch:
+            self.scratch = Split(self.rows, self.cols, batch, device=device, precision=self.precision, zero=True)
+        return self.scratch
+
+    def to_float(self) -> torch.Tensor:
+        """The rank-r reconstructions [capacity, d_out, d_in(+1)] (tests)."""
+        return torch.matmul(self.left_t.to_float().transpose(1, 2), self.right.to_float())
+
+
+def make_lowrank_store(d_out: int, d_in_total: int, rank: int, capacity: int, device,
+                       precision: int = PREC_FP32) -> LowRankStore:
+    return LowRankStore(d_out, d_in_total, rank, capacity, device, precision)
+
+
+def _load_split(dst: Split, x: torch.Tensor, offset: int, precision: int) -> None:
+    lib = engine.load_library()
+    x = _contig(x)
+    q, rows, cols = x.shape
+    assert rows == dst.rows and cols == dst.cols and offset + q <= dst.batch
+    desc = (ctypes.c_int64 * 9)(rows * cols, cols, 0, 1, rows, 1, cols, 0, 0)
+    view = dst.struct(offset, q)
+    check(lib.kfb_split_gather(x.data_ptr(), dtype_code(x.dtype), desc, None, ctypes.byref(view), precision,
+                               stream_ptr(x.device)))
+
+
+def lowrank_factorize(dense: Split, count: int, store: LowRankStore, q_offset: int, use_full_svd: bool = False,
+                      svd_dtype: torch.dtype = torch.float32) -> None:
+    """Factorises the first `count` matrices of `dense` and writes the factors at q_offset
+    (PreconditionTracker._compute_low_rank_preconditioned_gradient, tracker/precondition.py:19-52).
+
+    The SVD itself is the library call the reference makes (torch.linalg.svd / torch.svd_lowrank, i.e. cuSOLVER /
+    cuBLAS): it runs once per query batch and is not one of the hot-path contractions; the factors then feed the
+    hand-written low-rank scoring kernels."""
+    p = dense.to_float()[:count].to(dtype=svd_dtype)
+    rank = store.rank
+    if use_full_svd:
+        u, sv, vh = torch.linalg.svd(p, full_matrices=False)
+        left = u[:, :, :rank] * sv[:, None, :rank]
+        right = vh[:, :rank, :]
+    else:
+        u, sv, v = torch.svd_lowrank(p, q=rank)
+        left = u * sv[:, None, :]
+        right = v.transpose(1, 2)
+    _load_split(store.left_t, left.transpose(1, 2).to(torch.float32), q_offset, store.precision)
+    _load_split(store.right, right.to(torch.float32), q_offset, store.precision)
+
+
+def pairwise_scores_lowrank(layer: KfbLayer, store: LowRankStore, num_queries: int, a: torch.Tensor, g: torch.Tensor,
+                            scores: torch.Tensor, t_offset: int = 0, accumulate: bool = False, scale: float = 1.0,
+                            precision: int = PREC_FP32, qa: Optional[EigenOperands] = None,
+                            qg: Optional[EigenOperands] = None, per_token: bool = False) -> None:
+    """scores[:num_queries, t_offset + t] (+)= sum_k (g_t^T left[q][:, k]) (right[q][k, :] a_t) summed over the
+    positions of example t (or per position with per_token)."""
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    assert scores.dtype == torch.float32 and scores.stride(-1) == 1
+    left = store.left_t.struct(0, store.batch)
+    right = store.right.struct(0, store.batch)
+    mode = PRECOND_EIGEN if qa is not None else PRECOND_IDENTITY
+    sa = qa.qt.struct() if qa is not None else None
+    sg = qg.qt.struct() if qg is not None else None
+    ws_ptr, ws_size = workspace(a.device).get(
+        lib.kfb_pairwise_lowrank_workspace_bytes(ctypes.byref(layer), int(num_queries), store.rank, batch, seq))
+    check(lib.kfb_pairwise_scores_lowrank(ctypes.byref(layer), ctypes.byref(left), ctypes.byref(right), int(num_queries),
+                                          a.data_ptr(), dtype_code(a.dtype), g.data_ptr(), dtype_code(g.dtype), batch,
+                                          seq, mode, ctypes.byref(sa) if sa is not None else None,
+                                          ctypes.byref(sg) if sg is not None else None, float(scale),
+                                          scores.data_ptr(), scores.stride(0), int(t_offset), int(accumulate),
+                                          int(per_token), ws_ptr, ws_size, precision, stream_ptr(a.device)))
+
+
 __all__ = [
+    "LowRankStore", "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank",
     "PREC_FP32", "PREC_BF16", "PREC_STRICT", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
     "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
     "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "self_scores", "layer_of", "factor_dims", "workspace",

@@ -192,6 +192,20 @@ def pairwise_scores_from_gradients(p: np.ndarray, train_gradient: np.ndarray) ->
     return np.einsum("qoi,toi->qt", p, train_gradient)
 
 
+def lowrank_factorize(p: np.ndarray, rank: int) -> Tuple[np.ndarray, np.ndarray]:
+    """PreconditionTracker._compute_low_rank_preconditioned_gradient with use_full_svd=True,
+    tracker/precondition.py:36-46: P_q = U S V^T  ->  left = U_k diag(S_k) [Q, d_out, r], right = V_k^T [Q, r, d_in(+1)].
+    (The reference only factorises modules with min(d_out, d_in+1) > rank, tracker/precondition.py:60-63.)"""
+    u, sv, vt = np.linalg.svd(np.asarray(p, np.float64), full_matrices=False)
+    return u[:, :, :rank] * sv[:, None, :rank], vt[:, :rank, :]
+
+
+def lowrank_pairwise_scores_from_gradients(left: np.ndarray, right: np.ndarray, train_gradient: np.ndarray) -> np.ndarray:
+    """einsum('qki,toi,qok->qt', right, gradient, left), tracker/pairwise_score.py:26-39 (and, contracted in a
+    different order, 'qik,qko,b...i,b...o->qb' of module/linear.py:83-99 / module/conv2d.py:188-201)."""
+    return np.einsum("qok,qki,toi->qt", left, right, train_gradient)
+
+
 def linear_pairwise_scores(p: np.ndarray, a: np.ndarray, g: np.ndarray, has_bias: bool) -> np.ndarray:
     """'qio,b...i,b...o->qb' with i = output dim, o = input(+bias) dim, module/linear.py:112-122."""
     return pairwise_scores_from_gradients(p, linear_per_sample_gradient(a, g, has_bias))

@@ -187,6 +187,9 @@ def make_stage_fixtures():
 # --------------------------------------------------------------------------------------------------
 # End-to-end fixtures through the reference Analyzer
 # --------------------------------------------------------------------------------------------------
+LOW_RANK = 3
+
+
 def run_reference(case, dtype, strategy="ekfac", damping=None):
     tasks = fixtures.make_tasks(Task)
     model, train_set, query_set = fixtures.make_case(case)
@@ -231,6 +234,15 @@ def run_reference(case, dtype, strategy="ekfac", damping=None):
                                              score_args=score_args_pt, overwrite_output_dir=True)
             out["scores_per_token"] = npy(analyzer.load_pairwise_scores("s_pt")["all_modules"])
         if damping is None:
+            # rank-3 query factors through the exact SVD (deterministic, unlike torch.svd_lowrank)
+            score_args_lr = ScoreArguments(**{**score_args.__dict__, "query_gradient_low_rank": LOW_RANK,
+                                              "use_full_svd": True,
+                                              "query_gradient_svd_dtype": torch.float64 if dtype == torch.float64
+                                              else torch.float32})
+            analyzer.compute_pairwise_scores("s_lr", factors_name="f", query_dataset=query_set, train_dataset=train_set,
+                                             per_device_query_batch_size=query_bs, per_device_train_batch_size=train_bs,
+                                             score_args=score_args_lr, overwrite_output_dir=True)
+            out["scores_lowrank"] = npy(analyzer.load_pairwise_scores("s_lr")["all_modules"])
             analyzer.compute_self_scores("self", factors_name="f", train_dataset=train_set,
                                          per_device_train_batch_size=train_bs, score_args=score_args,
                                          overwrite_output_dir=True)
@@ -257,6 +269,9 @@ def make_e2e_fixtures():
         np.savez_compressed(os.path.join(GOLDEN, f"e2e_{case}.npz"), **merged)
         rel = np.linalg.norm(d32["scores"] - d64["scores"]) / np.linalg.norm(d64["scores"])
         print("e2e", case, "scores", d32["scores"].shape, "fp32-vs-fp64 rel", rel)
+        rel_lr = np.linalg.norm(d32["scores_lowrank"] - d64["scores_lowrank"]) / np.linalg.norm(d64["scores_lowrank"])
+        rel_tr = np.linalg.norm(d64["scores_lowrank"] - d64["scores"]) / np.linalg.norm(d64["scores"])
+        print("e2e", case, "rank-3 scores: fp32-vs-fp64 rel", rel_lr, "; truncation error vs dense", rel_tr)
 
 
 if __name__ == "__main__":

@@ -90,6 +90,47 @@ def make_query_store(d_out, d_in_total, capacity, device, precision=0):
     return FakeStore(d_out, d_in_total, capacity)
 
 
+class FakeLowRankStore:
+    def __init__(self, d_out, d_in_total, rank, capacity):
+        self.rows, self.cols, self.rank, self.batch = d_out, d_in_total, rank, capacity
+        self.left_t = SimpleNamespace(storage=torch.zeros(1, capacity, rank, d_out, dtype=torch.float64))
+        self.right = SimpleNamespace(storage=torch.zeros(1, capacity, rank, d_in_total, dtype=torch.float64))
+        self.scratch = None
+
+    def scratch_for(self, batch, device):
+        if self.scratch is None or self.scratch.batch < batch:
+            self.scratch = FakeStore(self.rows, self.cols, batch)
+        return self.scratch
+
+
+def make_lowrank_store(d_out, d_in_total, rank, capacity, device, precision=0):
+    return FakeLowRankStore(d_out, d_in_total, rank, capacity)
+
+
+def lowrank_factorize(dense, count, store, q_offset, use_full_svd=False, svd_dtype=torch.float32):
+    left, right = orc.lowrank_factorize(dense.storage[0, :count].numpy(), store.rank)
+    store.left_t.storage[0, q_offset : q_offset + count] = torch.from_numpy(left).transpose(1, 2)
+    store.right.storage[0, q_offset : q_offset + count] = torch.from_numpy(right)
+
+
+def pairwise_scores_lowrank(layer, store, num_queries, a, g, scores, t_offset=0, accumulate=False, scale=1.0,
+                            precision=0, qa=None, qg=None, per_token=False):
+    left = store.left_t.storage[0, :num_queries].transpose(1, 2).numpy()
+    right = store.right.storage[0, :num_queries].numpy()
+    if per_token:
+        tokens = a.shape[1]
+        a, g = a.reshape(-1, a.shape[-1]), g.reshape(-1, g.shape[-1])
+    grads = _per_sample(layer, a, g)
+    if qa is not None:
+        grads = np.matmul(qg.q.T, np.matmul(grads, qa.q))
+    block = torch.from_numpy(orc.lowrank_pairwise_scores_from_gradients(left, right, grads) * scale)
+    view = scores[:num_queries, t_offset : t_offset + grads.shape[0]]
+    if accumulate:
+        view.add_(block.to(scores.dtype))
+    else:
+        view.copy_(block.to(scores.dtype))
+
+
 def precondition(layer, a, g, store, q_offset, mode, qa=None, qg=None, lambda_inv=None, scale=1.0, out_f32=None,
                  precision=0):
     grads = _per_sample(layer, a, g)
@@ -138,7 +179,11 @@ def self_scores(layer, a, g, out, t_offset, mode, lambda_inv, qa=None, qg=None, 
 
 
 _PATCHED = ["layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
-            "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores", "self_scores"]
+            "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores", "self_scores",
+            "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank", "LowRankStore"]
+
+
+LowRankStore = FakeLowRankStore
 
 
 @contextlib.contextmanager

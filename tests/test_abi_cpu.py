@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(engine.KfbLayer) == 18 * 4
     assert ctypes.sizeof(engine.KfbSplit) == 8 * 8
     # kfb_epilogue: int32 kind (+pad), ptr, 2x int64, kfb_split, ptr, int64, 3x int32, float, ptr, int64, int32 (+pad)
-    assert ctypes.sizeof(engine.KfbEpilogue) == 8 + 8 + 16 + 64 + 8 + 8 + 16 + 8 + 8 + 8
+    assert ctypes.sizeof(engine.KfbEpilogue) == 8 + 8 + 16 + 64 + 8 + 8 + 16 + 8 + 8 + 8 + 8
 
 
 def test_no_cpu_path():

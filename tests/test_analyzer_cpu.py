@@ -201,3 +201,20 @@ def test_per_token_scores(tmp_path):
     assert got.shape == golden["f32/scores_per_token"].shape == (5, 23, 11)
     assert rel(got, golden["f32/scores_per_token"]) < 5e-5
     assert rel(got.sum(-1), golden["f32/scores"]) < 5e-5
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_low_rank_query_gradients(case, tmp_path):
+    """`query_gradient_low_rank` with the exact SVD against the reference's scores (its own test is
+    tests/scores/test_pairwise_scores.py:906-978): modules whose smaller dimension exceeds the rank are scored from
+    rank-3 factors, the others densely; also with accumulation steps and a ragged query batch."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    kwargs = dict(query_gradient_low_rank=3, use_full_svd=True)
+    with oracle_backend():
+        _, scores = run_case(case, tmp_path / "a", inject_eigen=golden, score_kwargs=kwargs)
+        _, scores_acc = run_case(case, tmp_path / "b", inject_eigen=golden, query_bs=2,
+                                 score_kwargs=dict(query_gradient_accumulation_steps=2, **kwargs))
+    want = golden["f32/scores_lowrank"]
+    assert rel(want, golden["f32/scores"]) > 0.1  # the truncation is far from a no-op on these fixtures
+    assert rel(scores["all_modules"].numpy(), want) < 5e-5
+    assert rel(scores_acc["all_modules"].numpy(), want) < 5e-5

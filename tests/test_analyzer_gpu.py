@@ -143,3 +143,24 @@ def test_per_token_scores(tmp_path):
     assert got.shape == golden["f32/scores_per_token"].shape
     assert rel(got, golden["f32/scores_per_token"]) < 1e-4
     assert rel(got.sum(-1), golden["f32/scores"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_low_rank_query_gradients(case, tmp_path):
+    """`query_gradient_low_rank` (exact SVD) end to end: rank-3 factors of the eigenbasis images, scored by the
+    low-rank kernels (one GEMM against all right factors + the fused ROWDOT over the left factors), against the
+    reference Analyzer's scores with the same arguments."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    _, scores, _ = run(case, tmp_path, golden, inject=True, query_gradient_low_rank=3, use_full_svd=True)
+    got = scores["all_modules"].numpy()
+    assert rel(got, golden["f64/scores_lowrank"]) < 1e-4
+    assert rel(got, golden["f32/scores_lowrank"]) < 1e-4
+    if case == "seq":
+        _, per_token, _ = run(case, tmp_path / "pt", golden, inject=True, query_gradient_low_rank=3, use_full_svd=True,
+                              compute_per_token_scores=True)
+        pt = per_token["all_modules"].numpy()
+        assert pt.shape == (5, 23, 11)
+        assert rel(pt.sum(-1), golden["f64/scores_lowrank"]) < 1e-4
+    # the randomized factorisation (the reference's default) only has to be close to the exact truncation
+    _, approx, _ = run(case, tmp_path / "rnd", golden, inject=True, query_gradient_low_rank=3)
+    assert rel(approx["all_modules"].numpy(), golden["f64/scores_lowrank"]) < 0.3

@@ -56,8 +56,14 @@ def _worker(rank, world, port, case, out_dir):
                                                   per_device_train_batch_size=4,
                                                   score_args=ScoreArguments(damping_factor=None,
                                                                             query_gradient_accumulation_steps=2))
+        lowrank = analyzer.compute_pairwise_scores("s_lr", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                   per_device_train_batch_size=4,
+                                                   score_args=ScoreArguments(damping_factor=None,
+                                                                             query_gradient_low_rank=3,
+                                                                             use_full_svd=True))
     if rank == 0:
         np.save(os.path.join(out_dir, "scores.npy"), scores["all_modules"].numpy())
+        np.save(os.path.join(out_dir, "scores_lowrank.npy"), lowrank["all_modules"].numpy())
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -76,6 +82,9 @@ def test_two_ranks_match_reference(case, tmp_path):
     ref = golden["f32/scores"]
     assert scores.shape == ref.shape
     assert np.linalg.norm(scores - ref) / np.linalg.norm(ref) < 5e-5
+    # rank-3 query factors are all-gathered instead of the dense gradients
+    lowrank, ref_lr = np.load(tmp_path / "scores_lowrank.npy"), golden["f32/scores_lowrank"]
+    assert np.linalg.norm(lowrank - ref_lr) / np.linalg.norm(ref_lr) < 5e-5
 
 
 def test_samplers():

@@ -119,6 +119,29 @@ def test_rowdot(shape):
     assert (out[:, 0] == 1).all() and (out[:, t + 1 :] == 1).all()
 
 
+@pytest.mark.parametrize("shape", [(5, 330, 3, 70, 11), (2, 256, 64, 128, 32), (7, 100, 40, 33, 1)])
+def test_rowdot_batched_factor_and_row_groups(shape):
+    """The low-rank scoring epilogue: every batch entry reads its own column block of the factor matrix
+    (g_batch_stride) and the rows of a group (the tokens of an example) are summed into one output."""
+    engine = _engine()
+    q, t, n, k, group = shape
+    sa, sb, ref = _operands(engine, 1, q, t, n, k, 0, seed=5)  # A = token rows (shared), B = left factors of query q
+    ldy = (q * n + 3) // 4 * 4
+    y = torch.randn(t, ldy, device="cuda")
+    groups = (t + group - 1) // group
+    out = torch.ones(q, groups + 2, device="cuda")
+    epi = engine.KfbEpilogue(kind=engine.EPI_ROWDOT, out_f32=out[:, 1:].data_ptr(), out_batch_stride=groups + 2,
+                             g=y.data_ptr(), ldg=ldy, g_batch_stride=n, row_group=group, alpha=0.5, accumulate=1)
+    engine.gemm_nt(sa, sb, epi, 0)
+    torch.cuda.synchronize()
+    yq = y[:, : q * n].double().reshape(t, q, n).permute(1, 0, 2)  # [q, t, n]
+    per_row = 0.5 * (ref * yq).sum(-1)  # [q, t]
+    pad = groups * group - t
+    want = torch.nn.functional.pad(per_row, (0, pad)).reshape(q, groups, group).sum(-1)
+    assert _rel(out[:, 1 : groups + 1] - 1.0, want) < 2e-5
+    assert (out[:, 0] == 1).all() and (out[:, groups + 1 :] == 1).all()
+
+
 @pytest.mark.parametrize("shape", [(1, 2048, 4096, 512), (3, 200, 1300, 96)])
 def test_rowdot_few_row_blocks_overwrite(shape):
     """Few row blocks: the n-tiles of a block are spread over several units (atomics into a zeroed output)."""

@@ -172,6 +172,46 @@ def test_rank_one_precondition_modes(dtype):
     assert rel(store.to_float()[:nq], psg) < 2e-5
 
 
+@pytest.mark.parametrize("case", CASES)
+def test_low_rank_pairwise(case):
+    """Rank-r query factors: scores from the low-rank kernels equal <L_q R_q, G_t> computed by the oracle, in the
+    parameter basis (identity mode) and in the eigenbasis, per example and per token."""
+    ops, g, layer = setup_case(case)
+    di, do = ops.factor_dims(layer)
+    x, grad = cuda(g["x_train"]), cuda(g["g_train"])
+    n_train, rank = x.shape[0], 3
+    nq = g["p"].shape[0]
+    left, right = orc.lowrank_factorize(g["p"], rank)  # parameter basis
+    store = ops.make_lowrank_store(do, di, rank, nq + 1, "cuda")
+    dense = ops.make_query_store(do, di, nq, "cuda")
+    ops.load_query_store(dense, cuda(g["p"]), 0)
+    ops.lowrank_factorize(dense, nq, store, 1, use_full_svd=True)
+    torch.cuda.synchronize()
+    assert rel(store.to_float()[1:], np.matmul(left, right)) < 2e-5
+    want = orc.lowrank_pairwise_scores_from_gradients(left, right, g["psg_train"])
+    scores = torch.ones(nq + 2, n_train + 3, device="cuda")
+    ops.pairwise_scores_lowrank(layer, store, nq + 1, x, grad, scores, t_offset=2, accumulate=True, scale=2.0)
+    torch.cuda.synchronize()
+    assert rel(scores[1 : 1 + nq, 2 : 2 + n_train] - 1.0, 2.0 * want) < 1e-4
+    assert (scores[0, 2 : 2 + n_train] == 1).all() and (scores[:, :2] == 1).all() and (scores[:, 2 + n_train :] == 1).all()
+    # eigenbasis: factor Q_G^T P Q_A instead and rotate the train operands
+    qa_np, qg_np = g["activation_eigenvectors"].astype(np.float64), g["gradient_eigenvectors"].astype(np.float64)
+    p_eig = np.matmul(qg_np.T, np.matmul(g["p"].astype(np.float64), qa_np))
+    ops.load_query_store(dense, cuda(p_eig), 0)
+    ops.lowrank_factorize(dense, nq, store, 0, use_full_svd=True)
+    qa, qg = ops.make_eigen_operands(cuda(qa_np)), ops.make_eigen_operands(cuda(qg_np))
+    scores = torch.full((nq, n_train), 5.0, device="cuda")
+    ops.pairwise_scores_lowrank(layer, store, nq, x, grad, scores, qa=qa, qg=qg)
+    torch.cuda.synchronize()
+    assert rel(scores, want) < 1e-4  # the truncated SVD is rotation invariant
+    if not layer.kind and x.dim() == 3:
+        seq = x.shape[1]
+        per_token = torch.zeros(nq, n_train * seq, device="cuda")
+        ops.pairwise_scores_lowrank(layer, store, nq, x, grad, per_token, qa=qa, qg=qg, per_token=True)
+        torch.cuda.synchronize()
+        assert rel(per_token.view(nq, n_train, seq).sum(-1), want) < 1e-4
+
+
 LARGE = [
     # (d_in, d_out, bias, T, Q, S)
     (300, 200, True, 500, 70, 1),
