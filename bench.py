@@ -53,16 +53,48 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi DURING the timed region."""
+    """Samples SM clocks, power and throttle reasons DURING the timed region: NVML every 25 ms when the
+    nvidia-ml-py binding is importable (it is in this image), else `nvidia-smi` (slow: ~1 sample/s)."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index: int) -> None:
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.power, self.reasons, self.max_mhz = index, [], [], set(), None
+        self.source = None
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.replace(",", "").isdigit() else self.index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # pylint: disable=broad-exception-caught
+            return False
+        self.source = "nvml"
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                self.power.append(pynvml.nvmlDeviceGetPowerUsage(handle) / 1e3)
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # pylint: disable=broad-exception-caught
+                pass
+            self._stop.wait(0.025)
+        return True
+
     def _run(self) -> None:
+        if self._run_nvml():
+            return
+        self.source = "nvidia-smi"
         query = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
@@ -74,12 +106,14 @@ class ClockSampler:
                 for name, flag in zip(names, parts[2:6]):
                     if flag.lower().startswith("active"):
                         self.reasons.add(name)
+                self.power.append(float(parts[6]))
             except Exception:  # pylint: disable=broad-exception-caught
                 pass
             self._stop.wait(0.2)
 
     def __enter__(self):
         self._thread.start()
+        time.sleep(0.05)  # let the sampler attach before the timed region starts
         return self
 
     def __exit__(self, *exc):
@@ -89,7 +123,8 @@ class ClockSampler:
 
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w": float(np.median(self.power)) if self.power else None, "source": self.source}
 
 
 def cpu_reference(d_in, d_out, bias, steps, warmup, budget_flops=6e11):

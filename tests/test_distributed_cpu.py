@@ -71,10 +71,14 @@ def _worker(rank, world, port, case, out_dir):
 @pytest.mark.parametrize("case", ["mlp", "conv"])
 def test_two_ranks_match_reference(case, tmp_path):
     for attempt in range(3):  # a TCP rendezvous on a just-released port can occasionally fail: retry
+        out_dir = tmp_path / f"attempt{attempt}"  # a failed attempt must not leave half-written factors behind
+        out_dir.mkdir()
         try:
-            mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+            mp.spawn(_worker, args=(2, _free_port(), case, str(out_dir)), nprocs=2, join=True)
+            tmp_path = out_dir
             break
-        except Exception:  # pylint: disable=broad-exception-caught
+        except Exception as exc:  # pylint: disable=broad-exception-caught
+            print(f"attempt {attempt} failed: {exc}", file=sys.stderr)
             if attempt == 2:
                 raise
     golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
