@@ -49,8 +49,10 @@ typedef enum {
 typedef enum { KFB_F32 = 0, KFB_BF16 = 1, KFB_F16 = 2, KFB_F64 = 3 } kfb_dtype;
 /* KFB_PREC_FP32: fp32 parity.  Large contractions split operands into bf16 hi+lo (3 MMAs, ~1e-5 relative
  * to the operand norms); the small eigenbasis ROTATIONS, whose errors would be amplified by Lambda^-1, run
- * in KFB_PREC_STRICT.  KFB_PREC_BF16: one MMA on bf16-rounded operands.  KFB_PREC_STRICT: bf16 hi+mid+lo
- * (24 mantissa bits), 6 MMAs, TMEM drained into fp32 registers every 64 contraction elements (~1e-6). */
+ * in KFB_PREC_STRICT.  KFB_PREC_BF16: one MMA on bf16-rounded operands.  KFB_PREC_STRICT: FP16 hi+lo planes
+ * (22 mantissa bits) of the operand scaled by a power of two derived from its largest magnitude (`absmax`, a
+ * device word filled by the operand-preparation kernels), 3 MMAs, TMEM drained into fp32 registers every 128
+ * contraction elements (24 truncating accumulations per pass): an fp32-GEMM-grade result (below 1e-6).     */
 typedef enum { KFB_PREC_FP32 = 0, KFB_PREC_BF16 = 1, KFB_PREC_STRICT = 2 } kfb_precision;
 typedef enum { KFB_LINEAR = 0, KFB_CONV2D = 1 } kfb_layer_kind;
 
@@ -80,11 +82,13 @@ typedef struct {
 /* A batch of matrices stored as two bf16 planes (hi, lo) in tensor-core operand layout:
  * row-major, `cols` contiguous (the contraction index of an NT GEMM), row stride `ld` elements
  * (multiple of 8 so TMA can address it), `batch` matrices `batch_stride` elements apart.  With
- * KFB_PREC_BF16 the lo plane is unused and may be NULL; KFB_PREC_STRICT adds a third plane lo2.   */
+ * KFB_PREC_BF16 the lo plane is unused and may be NULL.  KFB_PREC_STRICT operands hold FP16 planes of
+ * x * 2^(13 - floor(log2(absmax))) and carry the device address of that absmax (written by kfb_split_gather /
+ * kfb_split_im2col / kfb_eigen_operands, read by the GEMM epilogue to undo the scaling).          */
 typedef struct {
   void* hi;
   void* lo;
-  void* lo2; /* third plane, KFB_PREC_STRICT operands only (else NULL) */
+  float* absmax; /* KFB_PREC_STRICT operands only (else NULL): device word holding max |x| of the operand */
   int64_t rows;
   int64_t cols;
   int64_t ld;
@@ -122,6 +126,14 @@ typedef struct {
   int32_t reduce_sq;
   int32_t row_group;       /* ROWDOT, see above (0 or 1: one output per row)                     */
   int64_t g_batch_stride;  /* ROWDOT, see above                                                   */
+  /* STORE with symmetric != 0 (SYRK): A and B are the same operand and the target is a plain accumulated fp32
+   * matrix; only the tiles on or above the diagonal are computed and the off-diagonal ones are also written
+   * transposed (tracker/factor.py:85-93, :129-131: activation.t() @ activation).                */
+  int32_t symmetric;
+  /* STORE to out_split with col_group = G > 0 (multiple of 8, out_split.ld == G): the product is flat in its column
+   * index n (tokens of all examples) and column n is stored at batch entry n / G, column n % G of out_split, i.e.
+   * one [rows, G] operand per example without ever running the GEMM per example.                 */
+  int64_t col_group;
 } kfb_epilogue;
 
 /* ---------------------------------------------------------------------------------------------
@@ -129,10 +141,14 @@ typedef struct {
  * ------------------------------------------------------------------------------------------ */
 int kfb_version(void);
 const char* kfb_last_error(void);
+/* sizeof of the three ABI structs as the library was compiled: bindings check their own layouts against these.  */
+void kfb_struct_sizes(int* layer, int* split, int* epilogue);
 /* sm count and compute capability of the current device; KFB_ERR_NO_DEVICE if there is none.    */
 int kfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* 0 = tcgen05 (default and only product path), 1 = SIMT debug kernels (tests only).             */
 int kfb_set_gemm_backend(int backend);
+/* 1 (default): plain plane outputs of the GEMM leave through TMA bulk stores; 0: per-lane vector stores (debug).  */
+int kfb_set_tma_store(int enable);
 /* 1 (default): large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles); 0: single CTAs.  */
 int kfb_set_cta_pairs(int enable);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
@@ -203,7 +219,8 @@ int kfb_set_cusolver_path(const char* path);
 /* ---------------------------------------------------------------------------------------------
  * Eigenbasis operands.  Splits Q (columns = eigenvectors, as stored by kfb_eigh_sym /
  * activation_eigenvectors) into the two tensor-core operands the later stages need:
- * q (row-major copy) and qt (its transpose).  Each kfb_split has rows=cols=d.
+ * q (row-major copy) and qt (its transpose).  Each kfb_split has rows=cols=d.  With KFB_PREC_STRICT only qt (the
+ * operand of the rotations) is strict; q takes ordinary bf16 hi/lo planes (KFB_PREC_FP32 layout).
  * Replaces the per-call `.to(device)` of factor/config.py:347-349 and tracker/factor.py:191-201.
  * ------------------------------------------------------------------------------------------ */
 int kfb_eigen_operands(const float* Q, int32_t d, const kfb_split* q, const kfb_split* qt,

@@ -34,6 +34,12 @@ int kfb_version(void) { return KFB_VERSION; }
 
 const char* kfb_last_error(void) { return kfb::g_error; }
 
+void kfb_struct_sizes(int* layer, int* split, int* epilogue) {
+  if (layer) *layer = (int)sizeof(kfb_layer);
+  if (split) *split = (int)sizeof(kfb_split);
+  if (epilogue) *epilogue = (int)sizeof(kfb_epilogue);
+}
+
 int kfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

@@ -5,6 +5,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -115,6 +116,17 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tmap, uint32_t ba
       : "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+// TMA: 3-D tiled bulk tensor store shared -> global (bulk async-group completion).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -271,11 +283,12 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16: BF16 x BF16 -> FP32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// Instruction descriptor for kind::f16: BF16 x BF16 -> FP32 (or FP16 x FP16 -> FP32 for the strict operands), both
+// operands K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool f16 = false) {
   return (1u << 4)                                  // D format  = F32
-         | (1u << 7)                                // A format  = BF16
-         | (1u << 10)                               // B format  = BF16
+         | ((f16 ? 0u : 1u) << 7)                   // A format  = BF16 (1) / F16 (0)
+         | ((f16 ? 0u : 1u) << 10)                  // B format  = BF16 (1) / F16 (0)
          | (static_cast<uint32_t>(N >> 3) << 17)    // N >> 3
          | (static_cast<uint32_t>(M >> 4) << 24);   // M >> 4
 }
@@ -286,12 +299,19 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// hi + mid + lo == x to ~2^-25 relative (three bf16 planes hold 24 mantissa bits).
-__device__ __forceinline__ void split_bf16_3(float x, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(hi);
-  mid = __float2bfloat16_rn(r1);
-  lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+// Strict operands: FP16 planes of x * strict_scale(absmax), a power of two that puts the operand's largest
+// magnitude into [2^13, 2^14) (FP16 overflows at 65504).  hi + lo then holds x to max(2^-23 |x|, 2^-39 absmax):
+// 22 mantissa bits for every element within 2^-17 of the largest one, degrading gracefully below (FP16
+// subnormals), where fp32 itself would only add ~2 bits.  The products of two such planes are exact in fp32.
+__host__ __device__ __forceinline__ float strict_scale(float absmax) {
+  if (!(absmax > 0.f) || absmax > 3.0e38f) return 1.f;
+  int e;
+  frexpf(absmax, &e);          // absmax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 14 - e);  // absmax * scale in [2^13, 2^14)
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
 }
 
 #endif  // __CUDACC__

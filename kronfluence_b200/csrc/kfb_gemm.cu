@@ -42,6 +42,8 @@ enum : int { REGACC_BATCH = 0, REGACC_KCHUNK = 1 };
 // is therefore limited to kMaxPassK contraction elements (~8e-6 relative with the 3-MMA split);
 // longer contractions are cut into passes that are summed in fp32 registers (round-to-nearest).
 static const int kMaxPassK = 2048;
+static const int kAtomicPassK = 1024;
+static const int kStrictPassK = 128;
 
 struct GemmParams {
   int M, N, K, batch;
@@ -71,6 +73,13 @@ struct GemmParams {
   int row_group;        // ROWDOT: rows [j*row_group, (j+1)*row_group) are summed into out[b][j] (tokens of an example)
   int f32_vec4, mul_vec4;  // out_f32 rows / mul rows are 16-byte aligned
   int batch_fastest;       // STORE: consecutive units share the (m, n) tile (and so the `mul` tile) across the batch
+  int tma_store;           // STORE to plain (untransposed, unfactored) planes: chunks leave through TMA bulk stores
+  int f16;                 // strict operands: FP16 planes scaled by strict_scale(*absmax); the epilogue undoes it
+  const float* a_absmax;
+  const float* b_absmax;
+  int col_group;           // STORE to planes: column n lands in batch entry n / col_group at column n % col_group
+  int symmetric;           // STORE: A == B (SYRK): only tiles with n_blk >= m_blk are computed, off-diagonal ones are
+  long long tri_tiles;     //        also written transposed; tri_tiles = m_blocks (m_blocks + 1) / 2
 };
 
 struct Tile {
@@ -110,6 +119,21 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit,
     r /= p.m_blocks;
     t.n_blk = (int)(r % p.n_blocks);
     const int ks = (int)(r / p.n_blocks);
+    t.kb0 = ks * p.kb_per_split;
+    t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_split);
+    return t;
+  }
+  if (EPI == EPI_STORE && p.symmetric) {
+    // upper-triangular tile index r = n (n + 1) / 2 + m  (m <= n), then k-split, then batch
+    const long long tri = unit % p.tri_tiles;
+    long long r = unit / p.tri_tiles;
+    int n = (int)((sqrtf(8.f * (float)tri + 1.f) - 1.f) * 0.5f);
+    while ((long long)(n + 1) * (n + 2) / 2 <= tri) ++n;
+    while ((long long)n * (n + 1) / 2 > tri) --n;
+    t.n_blk = n;
+    t.m_blk = (int)(tri - (long long)n * (n + 1) / 2);
+    const int ks = (int)(r % p.k_splits);
+    t.b = (int)(r / p.k_splits);
     t.kb0 = ks * p.kb_per_split;
     t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_split);
     return t;
@@ -165,51 +189,99 @@ __device__ __forceinline__ void put_f32(const GemmParams& p, float* o, float v, 
   else *o = v + old;
 }
 
+// Offset of element (row, col) of a non-transposed plane output; with column groups (flat token index -> per-example
+// [rows, S] matrices) the column selects the batch entry.  Groups are multiples of 8, so an aligned 8-column vector
+// never straddles two of them.
+__device__ __forceinline__ long long plane_index(const GemmParams& p, long long row, int col) {
+  if (p.col_group > 0) return (long long)(col / p.col_group) * p.out_bs_s + row * p.ldo_s + (col % p.col_group);
+  return row * p.ldo_s + col;
+}
+
 template <int OFF, int N, bool HOIST>
-__device__ __forceinline__ float store_chunk(const GemmParams& p, int b, long long row, int col0, const float (&acc)[N],
-                                             float* st, int lane) {
-  const bool direct_f32 = p.out_f32 != nullptr && !p.transpose_out && !p.reduce_sq;
+__device__ __forceinline__ float store_chunk(const GemmParams& p, const CUtensorMap* tm_o_hi, const CUtensorMap* tm_o_lo,
+                                             float alpha, int b, long long row, int col0, const float (&acc)[N],
+                                             float* st, int lane, bool mirror = false) {
+  // mirror: the transposed copy of an off-diagonal tile of a symmetric product (fp32 target, no factor)
+  const bool transpose_out = p.transpose_out != 0 || mirror;
+  const bool direct_f32 = p.out_f32 != nullptr && !transpose_out && !p.reduce_sq;
   const bool rmw = p.accumulate && !p.use_atomic;
   const bool full = col0 + 32 <= p.N;
   float* ob = p.out_f32 != nullptr ? p.out_f32 + (long long)b * p.out_bs : nullptr;
   __nv_bfloat16* oh = p.out_hi != nullptr ? p.out_hi + (long long)b * p.out_bs_s : nullptr;
   __nv_bfloat16* ol = (oh != nullptr && p.out_lo != nullptr) ? p.out_lo + (long long)b * p.out_bs_s : nullptr;
 
+  // ---- TMA: plain planes.  The lane's 32 values are split, parked as a dense [32][32] bf16 tile per plane in the
+  // warp's staging buffer and leave as two asynchronous bulk tensor stores: fully coalesced lines, no LSU work per
+  // row, rows/columns outside the matrix clipped by the tensor map (whose inner extent is the padded ld, so the
+  // zero columns of the last tile double as the operand padding).
+  if (p.tma_store && !mirror) {
+    __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(st);
+    __nv_bfloat16* sl = sh + 32 * 32;
+    if (lane == 0) tma_store_wait_read();  // the previous chunk's stores have finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = alpha * acc[OFF + grp * 8 + e];
+        if (p.square) v *= v;
+        split_bf16(v, h[e], l[e]);
+      }
+      *reinterpret_cast<uint4*>(sh + lane * 32 + grp * 8) = *reinterpret_cast<uint4*>(h);
+      if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(sl + lane * 32 + grp * 8) = *reinterpret_cast<uint4*>(l);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      const int row0 = (int)(row - lane);
+      tma_store_3d(tm_o_hi, smem_u32(sh), col0, row0, b);
+      if (p.out_lo != nullptr) tma_store_3d(tm_o_lo, smem_u32(sl), col0, row0, b);
+      tma_store_commit();
+    }
+    return 0.f;
+  }
+
   // ---- registers ----
   if (p.mul == nullptr && !direct_f32 && !p.reduce_sq) {
     if (row >= p.M) return 0.f;
     if (ob != nullptr) {  // transposed fp32: consecutive lanes = consecutive addresses
+      // accumulation goes through fire-and-forget L2 reductions (every element has exactly one writer per launch
+      // unless the contraction is split, so the result is the same as load-add-store without its round trip)
+      const bool red = p.use_atomic || p.accumulate;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         if (col0 + i < p.N) {
-          float v = p.alpha * acc[OFF + i];
+          float v = alpha * acc[OFF + i];
           if (p.square) v *= v;
           float* o = ob + (long long)(col0 + i) * p.ldo + row;
-          put_f32(p, o, v, rmw ? *o : 0.f);
+          if (red) atomicAdd(o, v);
+          else *o = v;
         }
       }
     }
     if (oh != nullptr) {
-      if (!p.transpose_out && p.vec_ok && full) {
+      if (!transpose_out && p.vec_ok && full) {
 #pragma unroll
         for (int grp = 0; grp < 4; ++grp) {
           __nv_bfloat16 h[8], l[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float v = p.alpha * acc[OFF + grp * 8 + e];
+            float v = alpha * acc[OFF + grp * 8 + e];
             if (p.square) v *= v;
             split_bf16(v, h[e], l[e]);
           }
-          *reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(h);
-          if (ol) *reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(l);
+          const long long at = plane_index(p, row, col0 + grp * 8);
+          *reinterpret_cast<uint4*>(oh + at) = *reinterpret_cast<uint4*>(h);
+          if (ol) *reinterpret_cast<uint4*>(ol + at) = *reinterpret_cast<uint4*>(l);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (col0 + i < p.N) {
-            float v = p.alpha * acc[OFF + i];
+            float v = alpha * acc[OFF + i];
             if (p.square) v *= v;
-            const long long idx = p.transpose_out ? (long long)(col0 + i) * p.ldo_s + row : row * p.ldo_s + col0 + i;
+            const long long idx = transpose_out ? (long long)(col0 + i) * p.ldo_s + row : plane_index(p, row, col0 + i);
             __nv_bfloat16 h, l;
             split_bf16(v, h, l);
             oh[idx] = h;
@@ -225,11 +297,11 @@ __device__ __forceinline__ float store_chunk(const GemmParams& p, int b, long lo
   const long long row0 = row - lane;  // first row of this warp's 32-row slab
   __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) st[lane * 33 + i] = p.alpha * acc[OFF + i];
+  for (int i = 0; i < 32; ++i) st[lane * 33 + i] = alpha * acc[OFF + i];
   __syncwarp();
 
   // ---- vector: bf16 planes, 4 lanes x 8 columns per row, 8 rows per pass ----
-  if (oh != nullptr && ob == nullptr && !p.transpose_out && p.vec_ok && full) {
+  if (oh != nullptr && ob == nullptr && !transpose_out && p.vec_ok && full) {
     const int qr = lane >> 2, cg = (lane & 3) * 8;
     constexpr int PASSES = HOIST ? 4 : 1;  // passes whose factor loads are in flight together
     for (int it0 = 0; it0 < 4; it0 += PASSES) {
@@ -260,8 +332,9 @@ __device__ __forceinline__ float store_chunk(const GemmParams& p, int b, long lo
           if (p.square) v *= v;
           split_bf16(v, h[e], l[e]);
         }
-        *reinterpret_cast<uint4*>(oh + rr * p.ldo_s + col0 + cg) = *reinterpret_cast<uint4*>(h);
-        if (ol) *reinterpret_cast<uint4*>(ol + rr * p.ldo_s + col0 + cg) = *reinterpret_cast<uint4*>(l);
+        const long long at = plane_index(p, rr, col0 + cg);
+        *reinterpret_cast<uint4*>(oh + at) = *reinterpret_cast<uint4*>(h);
+        if (ol) *reinterpret_cast<uint4*>(ol + at) = *reinterpret_cast<uint4*>(l);
       }
     }
     __syncwarp();
@@ -334,7 +407,7 @@ __device__ __forceinline__ float store_chunk(const GemmParams& p, int b, long lo
   if (p.reduce_sq) return part;
   // lanes return to their own row for the lane-contiguous layouts
   if (row < p.M) {
-    if (ob != nullptr && p.transpose_out) {
+    if (ob != nullptr && transpose_out) {
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) {
         if (col0 + i < p.N) {
@@ -344,20 +417,21 @@ __device__ __forceinline__ float store_chunk(const GemmParams& p, int b, long lo
       }
     }
     if (oh != nullptr) {
-      if (!p.transpose_out && p.vec_ok && full) {
+      if (!transpose_out && p.vec_ok && full) {
 #pragma unroll
         for (int grp = 0; grp < 4; ++grp) {
           __nv_bfloat16 h[8], l[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) split_bf16(st[lane * 33 + grp * 8 + e], h[e], l[e]);
-          *reinterpret_cast<uint4*>(oh + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(h);
-          if (ol) *reinterpret_cast<uint4*>(ol + row * p.ldo_s + col0 + grp * 8) = *reinterpret_cast<uint4*>(l);
+          const long long at = plane_index(p, row, col0 + grp * 8);
+          *reinterpret_cast<uint4*>(oh + at) = *reinterpret_cast<uint4*>(h);
+          if (ol) *reinterpret_cast<uint4*>(ol + at) = *reinterpret_cast<uint4*>(l);
         }
       } else {
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           if (col0 + i < p.N) {
-            const long long idx = p.transpose_out ? (long long)(col0 + i) * p.ldo_s + row : row * p.ldo_s + col0 + i;
+            const long long idx = transpose_out ? (long long)(col0 + i) * p.ldo_s + row : plane_index(p, row, col0 + i);
             __nv_bfloat16 h, l;
             split_bf16(st[lane * 33 + i], h, l);
             oh[idx] = h;
@@ -379,6 +453,22 @@ __device__ __forceinline__ void store_zero_pad(const GemmParams& p, int b, long 
   for (long long c = p.N; c < p.ldo_s; ++c) {
     oh[c] = __float2bfloat16_rn(0.f);
     if (ol) ol[c] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// ROWDOT: the 32 factors g[row][col0 .. col0+31] of this thread's accumulator row (zeros outside the matrix), issued
+// as independent loads so that a whole chunk is in flight at once.
+__device__ __forceinline__ void load_g_chunk(const GemmParams& p, const float* grow, int col0, bool row_ok,
+                                             float (&dst)[32]) {
+  if (row_ok && p.g_vec4 && col0 + 32 <= p.N) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(grow + col0) + i);
+      dst[4 * i + 0] = gv.x; dst[4 * i + 1] = gv.y; dst[4 * i + 2] = gv.z; dst[4 * i + 3] = gv.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dst[i] = (row_ok && col0 + i < p.N) ? __ldg(grow + col0 + i) : 0.f;
   }
 }
 
@@ -414,15 +504,14 @@ template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-               const __grid_constant__ CUtensorMap tm_a_lo2, const __grid_constant__ CUtensorMap tm_b_lo2,
+               const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG>;
-  static_assert(NSPLIT >= 1 && NSPLIT <= 3, "1 (bf16), 2 (hi/lo) or 3 (hi/mid/lo) operand planes");
-  static_assert(NSPLIT < 3 || CG == 1, "the strict 3-plane mode runs on single CTAs");
+  static_assert(NSPLIT == 1 || NSPLIT == 2, "1 (bf16) or 2 (hi/lo; bf16 or, for strict operands, fp16) operand planes");
   constexpr int BLOCK_M = Cfg::BLOCK_M;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
-  constexpr uint32_t IDESC = make_idesc_bf16(Cfg::TILE_M, BLOCK_N);
+  const uint32_t IDESC = p.f16 ? make_idesc_bf16(Cfg::TILE_M, BLOCK_N, true) : make_idesc_bf16(Cfg::TILE_M, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
@@ -458,10 +547,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (NSPLIT >= 2) {
       tma_prefetch_desc(&tm_a_lo);
       tma_prefetch_desc(&tm_b_lo);
-    }
-    if (NSPLIT == 3) {
-      tma_prefetch_desc(&tm_a_lo2);
-      tma_prefetch_desc(&tm_b_lo2);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -523,10 +608,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               tma_load_3d(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
               tma_load_3d(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
             }
-            if (NSPLIT == 3) {
-              tma_load_3d(&tm_a_lo2, full_bar(stage), smem_a(stage, 2), k0, row_a, ba);
-              tma_load_3d(&tm_b_lo2, full_bar(stage), smem_b(stage, 2), k0, row_b, bb);
-            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -556,8 +637,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           const uint64_t b_hi = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, 0));
           const uint64_t a_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, NSPLIT >= 2 ? 1 : 0));
           const uint64_t b_lo = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, NSPLIT >= 2 ? 1 : 0));
-          const uint64_t a_l2 = make_kmajor_desc<Cfg::SWIZZLE>(smem_a(stage, NSPLIT == 3 ? 2 : 0));
-          const uint64_t b_l2 = make_kmajor_desc<Cfg::SWIZZLE>(smem_b(stage, NSPLIT == 3 ? 2 : 0));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advancing 16 bf16 (32 bytes) along K inside the swizzle span: +2 in 16-byte units
@@ -571,14 +650,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               } else {
                 umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, IDESC, acc);
               }
-            } else if (NSPLIT == 3) {
-              // hi/mid/lo planes (orders 0/1/2): every cross term of total order <= 2, smallest first
-              umma_bf16(d_tmem, a_l2 + koff, b_hi + koff, IDESC, acc);
-              umma_bf16(d_tmem, a_hi + koff, b_l2 + koff, IDESC, 1u);
-              umma_bf16(d_tmem, a_lo + koff, b_lo + koff, IDESC, 1u);
-              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
-              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
-              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1u);
             } else if (NSPLIT == 2) {
               umma_bf16(d_tmem, a_lo + koff, b_hi + koff, IDESC, acc);
               umma_bf16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
@@ -608,6 +679,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int lane_row = quarter * 32 + lane;  // accumulator row owned by this thread
     float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256) + quarter * (32 * 33);
     constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N : 1;
+    // strict operands were scaled by powers of two: undo both scales together with alpha (exact)
+    const float alpha = p.f16 ? p.alpha / strict_scale(__ldg(p.a_absmax)) / strict_scale(__ldg(p.b_absmax)) : p.alpha;
     uint32_t it = 0;
     for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
       const int inner = unit_inner_count<EPI>(p, unit);
@@ -620,53 +693,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         t = decode_tile<EPI>(p, unit, j);
         const uint32_t as = it % ACC_STAGES;
         const uint32_t aphase = (it / ACC_STAGES) & 1u;
-        mbar_wait(tmem_full_bar(as), aphase);
-        tcgen05_fence_after();
         const uint32_t taddr = tmem_base + as * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
         const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
         const bool row_ok = row < p.M;
         const int n0 = t.n_blk * BLOCK_N;
+        if (EPI == EPI_ROWDOT) {
+          // software pipeline: the factors of chunk 0 are requested BEFORE waiting for the accumulator and those of
+          // chunk c+1 while chunk c is reduced, so their L2 latency never sits on the pass's critical path
+          const float* grow = p.g + (long long)t.b * p.g_bs + (row_ok ? row : 0) * p.ldg;
+          float gb[2][32];
+          load_g_chunk(p, grow, n0, row_ok, gb[0]);
+          mbar_wait(tmem_full_bar(as), aphase);
+          tcgen05_fence_after();
 #pragma unroll
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          const int col0 = n0 + c * 32;
-          if (col0 >= p.N && EPI != EPI_REGACC) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (EPI == EPI_ROWDOT) {
-            if (row_ok) {
-              const float* gp = p.g + (long long)t.b * p.g_bs + row * p.ldg + col0;
-              if (p.g_vec4 && col0 + 32 <= p.N) {
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.N) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            if (c + 1 < BLOCK_N / 32 && col0 + 32 < p.N) load_g_chunk(p, grow, col0 + 32, row_ok, gb[(c + 1) & 1]);
+            tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 gv = __ldg(reinterpret_cast<const float4*>(gp) + i);
-                  rowdot = fmaf(__uint_as_float(v[4 * i + 0]), gv.x, rowdot);
-                  rowdot = fmaf(__uint_as_float(v[4 * i + 1]), gv.y, rowdot);
-                  rowdot = fmaf(__uint_as_float(v[4 * i + 2]), gv.z, rowdot);
-                  rowdot = fmaf(__uint_as_float(v[4 * i + 3]), gv.w, rowdot);
+            for (int i = 0; i < 32; ++i) rowdot = fmaf(__uint_as_float(v[i]), gb[c & 1][i], rowdot);
+          }
+        } else {
+          mbar_wait(tmem_full_bar(as), aphase);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.N && EPI != EPI_REGACC) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (EPI == EPI_REGACC) {
+              if (p.regacc_mode == REGACC_BATCH) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float x = __uint_as_float(v[i]);
+                  racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += x * x;
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.N) rowdot = fmaf(__uint_as_float(v[i]), __ldg(gp + i), rowdot);
-              }
-            }
-          } else if (EPI == EPI_REGACC) {
-            if (p.regacc_mode == REGACC_BATCH) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float x = __uint_as_float(v[i]);
-                racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += x * x;
+                for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[i]);
               }
             } else {
+              float x[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[i]);
+              for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+              rowdot += store_chunk<0, 32, true>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st, lane);
+              if (p.symmetric && t.n_blk != t.m_blk) store_chunk<0, 32, true>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st, lane, true);
             }
-          } else {
-            float x[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-            rowdot += store_chunk<0, 32, true>(p, t.b, row, col0, x, st, lane);
           }
         }
         if (EPI == EPI_STORE && p.reduce_sq) {
@@ -675,10 +752,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
           // store_chunk squared alpha-scaled values: sum (alpha D)^2 mul; the contract is alpha * sum D^2 mul
-          if (lane == 0 && part != 0.f) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs, part / p.alpha);
+          if (lane == 0 && part != 0.f) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs, part / alpha);
           rowdot = 0.f;
         }
-        if (EPI == EPI_STORE && p.zero_pad && !p.reduce_sq && row_ok && t.n_blk == p.n_blocks - 1) store_zero_pad(p, t.b, row);
+        if (EPI == EPI_STORE && p.zero_pad && !p.tma_store && !p.reduce_sq && row_ok && t.n_blk == p.n_blocks - 1)
+          store_zero_pad(p, t.b, row);
         // hand the accumulator stage back to the (leader's) MMA thread: one arrival per warp
         tcgen05_fence_before();
         __syncwarp();
@@ -695,7 +773,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           // atomic per group and warp
           const long long grp = row < p.M ? row / p.row_group : -1;
           const unsigned peers = __match_any_sync(0xffffffffu, grp);
-          float val = p.alpha * rowdot;
+          float val = alpha * rowdot;
 #pragma unroll
           for (int off = 1; off < 32; off <<= 1) {
             const float other = __shfl_down_sync(0xffffffffu, val, off);
@@ -704,7 +782,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           if (grp >= 0 && lane == __ffs(peers) - 1) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs + grp, val);
         } else if (row < p.M) {
           float* o = p.out_f32 + (long long)t.b * p.out_bs + row;
-          const float val = p.alpha * rowdot;
+          const float val = alpha * rowdot;
           if (p.use_atomic) atomicAdd(o, val);
           else if (p.accumulate) *o += val;
           else *o = val;
@@ -714,15 +792,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int n0 = t.n_blk * BLOCK_N;
         const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
         // warp-uniform conditions: store_chunk is a warp-cooperative call
-        if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false>(p, ob, row, n0, racc, st, lane);
-        if (NACC >= 64 && n0 + 32 < p.N) store_chunk<(NACC >= 64 ? 32 : 0), NACC, false>(p, ob, row, n0 + 32, racc, st, lane);
-        if (NACC >= 128 && n0 + 64 < p.N) store_chunk<(NACC >= 128 ? 64 : 0), NACC, false>(p, ob, row, n0 + 64, racc, st, lane);
-        if (NACC >= 128 && n0 + 96 < p.N) store_chunk<(NACC >= 128 ? 96 : 0), NACC, false>(p, ob, row, n0 + 96, racc, st, lane);
-        if (row < p.M && p.zero_pad && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
+        if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0, racc, st, lane);
+        if (NACC >= 64 && n0 + 32 < p.N) store_chunk<(NACC >= 64 ? 32 : 0), NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 32, racc, st, lane);
+        if (NACC >= 128 && n0 + 64 < p.N) store_chunk<(NACC >= 128 ? 64 : 0), NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 64, racc, st, lane);
+        if (NACC >= 128 && n0 + 96 < p.N) store_chunk<(NACC >= 128 ? 96 : 0), NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 96, racc, st, lane);
+        if (row < p.M && p.zero_pad && !p.tma_store && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
       }
     }
   }
 
+  if (warp >= 4 && lane == 0 && p.tma_store) tma_store_wait_all();  // staging tiles are read / outputs written
   tcgen05_fence_before();
   if (CG == 2) cluster_sync_all();  // the peer may still be reading operands / signalling our barriers
   else __syncthreads();
@@ -739,45 +818,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 struct SimtOperand {
   const __nv_bfloat16* hi;
   const __nv_bfloat16* lo;
-  const __nv_bfloat16* lo2;
   long long ld, bs;
 };
 
+__device__ __forceinline__ float simt_plane(const __nv_bfloat16* p, long long i, int f16) {
+  return f16 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : __bfloat162float(p[i]);
+}
+
 __device__ __forceinline__ float simt_dot(const SimtOperand& A, const SimtOperand& B, long long ab,
-                                          long long bb, long long m, long long n, int K) {
+                                          long long bb, long long m, long long n, int K, int f16) {
   const __nv_bfloat16* ah = A.hi + ab * A.bs + m * A.ld;
   const __nv_bfloat16* bh = B.hi + bb * B.bs + n * B.ld;
   const __nv_bfloat16* al = A.lo ? A.lo + ab * A.bs + m * A.ld : nullptr;
   const __nv_bfloat16* bl = B.lo ? B.lo + bb * B.bs + n * B.ld : nullptr;
-  const __nv_bfloat16* al2 = A.lo2 ? A.lo2 + ab * A.bs + m * A.ld : nullptr;
-  const __nv_bfloat16* bl2 = B.lo2 ? B.lo2 + bb * B.bs + n * B.ld : nullptr;
   float acc = 0.f;
   for (int k = 0; k < K; ++k) {
-    const float a_h = __bfloat162float(ah[k]), b_h = __bfloat162float(bh[k]);
-    const float a_l = al ? __bfloat162float(al[k]) : 0.f;
-    const float b_l = bl ? __bfloat162float(bl[k]) : 0.f;
-    if (al2 != nullptr) {
-      const float a_2 = __bfloat162float(al2[k]), b_2 = __bfloat162float(bl2[k]);
-      acc += (a_h + a_l + a_2) * (b_h + b_l + b_2);
-    } else {
-      acc += a_l * b_h + a_h * b_l + a_h * b_h;
-    }
+    const float a_h = simt_plane(ah, k, f16), b_h = simt_plane(bh, k, f16);
+    const float a_l = al ? simt_plane(al, k, f16) : 0.f;
+    const float b_l = bl ? simt_plane(bl, k, f16) : 0.f;
+    acc += a_l * b_h + a_h * b_l + a_h * b_h;
   }
   return acc;
 }
 
 __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int epi) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p.f16) p.alpha = p.alpha / strict_scale(*p.a_absmax) / strict_scale(*p.b_absmax);
   if (epi == KFB_EPI_STORE) {
     const long long total = (long long)p.batch * p.M * p.N;
     if (tid >= total) return;
     const long long n = tid % p.N, m = (tid / p.N) % p.M, b = tid / ((long long)p.N * p.M);
     if (p.reduce_sq) {
-      const float d = simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K);
+      const float d = simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K, p.f16);
       atomicAdd(p.out_f32 + b * p.out_bs, p.alpha * d * d * (p.mul ? p.mul[m * p.ldmul + n] : 1.f));
       return;
     }
-    float val = p.alpha * simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K);
+    float val = p.alpha * simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K, p.f16);
     if (p.mul) val *= p.mul[m * p.ldmul + n];
     if (p.square) val *= val;
     if (p.out_f32) {
@@ -786,7 +862,8 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
       else *o = val;
     }
     if (p.out_hi) {
-      const long long idx = b * p.out_bs_s + (p.transpose_out ? n * p.ldo_s + m : m * p.ldo_s + n);
+      const long long idx = p.col_group > 0 ? (n / p.col_group) * p.out_bs_s + m * p.ldo_s + (n % p.col_group)
+                                            : b * p.out_bs_s + (p.transpose_out ? n * p.ldo_s + m : m * p.ldo_s + n);
       __nv_bfloat16 h, l;
       split_bf16(val, h, l);
       p.out_hi[idx] = h;
@@ -804,7 +881,7 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
     const long long m = tid % p.M, b = tid / p.M;
     float sum = 0.f;
     for (int n = 0; n < p.N; ++n)
-      sum += simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K) * p.g[b * p.g_bs + m * p.ldg + n];
+      sum += simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K, p.f16) * p.g[b * p.g_bs + m * p.ldg + n];
     if (p.row_group > 1) {
       atomicAdd(p.out_f32 + b * p.out_bs + m / p.row_group, p.alpha * sum);
       return;
@@ -818,7 +895,7 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
     const long long n = tid % p.N, m = tid / p.N;
     float sum = 0.f;
     for (int b = 0; b < p.batch; ++b) {
-      const float d = simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K);
+      const float d = simt_dot(A, B, p.a_batched ? b : 0, p.b_batched ? b : 0, m, n, p.K, p.f16);
       sum += d * d;
     }
     p.out_f32[m * p.ldo + n] += p.alpha * sum;
@@ -831,6 +908,7 @@ __global__ void gemm_simt_kernel(SimtOperand A, SimtOperand B, GemmParams p, int
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_backend{0};
 static std::atomic<int> g_cta_pairs{1};
+static std::atomic<int> g_tma_store{1};
 void count_launch(int n) { g_launches += n; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -853,7 +931,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long long rows,
-                     long long batch, long long ld, long long bs, int box_k, int box_rows) {
+                     long long batch, long long ld, long long bs, int box_k, int box_rows, bool swizzled = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -868,7 +946,8 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
   cuuint64_t gstride[2] = {(cuuint64_t)(ld * 2), (cuuint64_t)bs_bytes};
   cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  const CUtensorMapSwizzle sw = box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw = !swizzled ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : (box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -888,7 +967,9 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   p.k_blocks = (int)ceil_div_ll(p.K, BLOCK_K);
   const int max_pass_kb = (p.max_pass_k > 0 ? p.max_pass_k : kMaxPassK) / BLOCK_K > 0
                               ? (p.max_pass_k > 0 ? p.max_pass_k : kMaxPassK) / BLOCK_K : 1;
-  const long long tiles = (long long)p.m_blocks * p.n_blocks;
+  if (EPI != EPI_STORE || Cfg::TILE_M != BLOCK_N || p.m_blocks != p.n_blocks) p.symmetric = 0;
+  p.tri_tiles = (long long)p.m_blocks * (p.m_blocks + 1) / 2;
+  const long long tiles = p.symmetric ? p.tri_tiles : (long long)p.m_blocks * p.n_blocks;
   if (EPI == EPI_ROWDOT) {
     p.k_splits = 1;
     p.kb_per_split = p.k_blocks;
@@ -947,10 +1028,13 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
     ta_lo = ta_hi;
     tb_lo = tb_hi;
   }
-  CUtensorMap ta_lo2 = ta_hi, tb_lo2 = tb_hi;
-  if (NSPLIT == 3) {
-    KFB_TRY(make_tmap(&ta_lo2, A.lo2, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
-    KFB_TRY(make_tmap(&tb_lo2, B.lo2, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
+  // output planes through TMA bulk stores (32 x 32 boxes) when the STORE target is plain planes
+  CUtensorMap to_hi = ta_hi, to_lo = ta_hi;
+  if (EPI == EPI_ROWDOT) p.tma_store = 0;
+  if (p.tma_store) {
+    KFB_TRY(make_tmap(&to_hi, p.out_hi, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, 32, 32, false));
+    if (p.out_lo != nullptr)
+      KFB_TRY(make_tmap(&to_lo, p.out_lo, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, 32, 32, false));
   }
   auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG>;
   static bool attr_set = false;
@@ -973,7 +1057,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  KFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, ta_lo2, tb_lo2, p));
+  KFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p));
   count_launch();
   KFB_CUDA_TRY(cudaGetLastError());
   return KFB_OK;
@@ -992,18 +1076,11 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
   const int bn = pick_bn(p.N, EPI == EPI_REGACC ? 128 : 256);
   // CTA pairs (M = 256 tiles) whenever the problem has at least two full 128-row tiles to pair up
   const bool pair = g_cta_pairs.load() != 0 && bn == 256 && p.M > 128;
-  if (nsplit == 3) {
-    if (EPI == EPI_ROWDOT) {
-      set_error("gemm_nt: the strict (3-plane) mode has no ROWDOT epilogue");
-      return KFB_ERR_INVALID;
-    } else {
-      if (pick_bn(p.N, 128) == 128) return launch_tc<128, 64, 3, EPI>(A, B, p, stream);
-      return launch_tc<64, 64, 3, EPI>(A, B, p, stream);
-    }
-  }
   if (nsplit == 2) {
     if (EPI != EPI_REGACC && bn == 256 && pair) return launch_tc<256, 64, 2, EPI, 2>(A, B, p, stream);
     if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 32, 2, EPI>(A, B, p, stream);
+    // register-accumulating passes (128 accumulator columns per thread): CTA pairs halve the B-operand traffic
+    if (EPI == EPI_REGACC && bn == 128 && g_cta_pairs.load() != 0 && p.M > 128) return launch_tc<128, 64, 2, EPI, 2>(A, B, p, stream);
     if (bn == 128) return launch_tc<128, 64, 2, EPI>(A, B, p, stream);
     return launch_tc<64, 64, 2, EPI>(A, B, p, stream);
   }
@@ -1015,10 +1092,8 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
 
 static int launch_simt(const kfb_split& A, const kfb_split& B, GemmParams p, int epi, int nsplit,
                        cudaStream_t stream) {
-  SimtOperand a{(const __nv_bfloat16*)A.hi, nsplit >= 2 ? (const __nv_bfloat16*)A.lo : nullptr,
-                nsplit == 3 ? (const __nv_bfloat16*)A.lo2 : nullptr, A.ld, A.batch_stride};
-  SimtOperand b{(const __nv_bfloat16*)B.hi, nsplit >= 2 ? (const __nv_bfloat16*)B.lo : nullptr,
-                nsplit == 3 ? (const __nv_bfloat16*)B.lo2 : nullptr, B.ld, B.batch_stride};
+  SimtOperand a{(const __nv_bfloat16*)A.hi, nsplit >= 2 ? (const __nv_bfloat16*)A.lo : nullptr, A.ld, A.batch_stride};
+  SimtOperand b{(const __nv_bfloat16*)B.hi, nsplit >= 2 ? (const __nv_bfloat16*)B.lo : nullptr, B.ld, B.batch_stride};
   long long total = epi == KFB_EPI_STORE    ? (long long)p.batch * p.M * p.N
                     : epi == KFB_EPI_ROWDOT ? (long long)p.batch * p.M
                                             : (long long)p.M * p.N;
@@ -1038,10 +1113,15 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
               "gemm_nt: incompatible batch counts %lld / %lld", (long long)A.batch, (long long)B.batch);
   KFB_REQUIRE(A.rows < (1LL << 31) && B.rows < (1LL << 31) && A.cols < (1LL << 31),
               "gemm_nt: dimension too large");
-  const int nsplit = precision == KFB_PREC_FP32 ? 2 : (precision == KFB_PREC_STRICT ? 3 : 1);
+  const bool strict = precision == KFB_PREC_STRICT;
+  const int nsplit = precision == KFB_PREC_BF16 ? 1 : 2;
   KFB_REQUIRE(nsplit == 1 || (A.lo != nullptr && B.lo != nullptr), "gemm_nt: missing lo planes");
-  KFB_REQUIRE(nsplit < 3 || (A.lo2 != nullptr && B.lo2 != nullptr), "gemm_nt: KFB_PREC_STRICT needs lo2 planes");
+  KFB_REQUIRE(!strict || (A.absmax != nullptr && B.absmax != nullptr),
+              "gemm_nt: KFB_PREC_STRICT operands carry an absmax word (build them with KFB_PREC_STRICT)");
   GemmParams p{};
+  p.f16 = strict ? 1 : 0;
+  p.a_absmax = A.absmax;
+  p.b_absmax = B.absmax;
   p.M = (int)A.rows;
   p.N = (int)B.rows;
   p.K = (int)A.cols;
@@ -1066,10 +1146,11 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   p.g_bs = epi.g_batch_stride;
   p.row_group = epi.row_group > 1 ? (int)epi.row_group : 1;
   p.reduce_sq = epi.kind == KFB_EPI_STORE ? epi.reduce_sq : 0;
+  p.col_group = epi.kind == KFB_EPI_STORE ? (int)epi.col_group : 0;
   p.k_splits = 1;
   p.k_chunks = 1;
-  // strict mode: 6 truncating accumulations per k-step, so drain TMEM every 64 contraction elements
-  p.max_pass_k = nsplit == 3 ? 64 : kMaxPassK;
+  // strict mode: drain TMEM every kStrictPassK contraction elements (24 truncating accumulations per pass)
+  p.max_pass_k = strict ? kStrictPassK : kMaxPassK;
   if (p.M == 0 || p.N == 0 || p.batch == 0) return KFB_OK;
   KFB_REQUIRE(p.K > 0, "gemm_nt: empty contraction");
 
@@ -1082,6 +1163,14 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
                      (p.out_lo && (reinterpret_cast<uintptr_t>(p.out_lo) & 15))))
       p.vec_ok = 0;
     p.zero_pad = (p.out_hi != nullptr && !p.transpose_out) ? 1 : 0;
+    p.tma_store = (p.out_hi != nullptr && p.out_f32 == nullptr && p.mul == nullptr && !p.transpose_out && !p.reduce_sq &&
+                   p.col_group == 0 && p.vec_ok && p.ldo_s >= 32 && g_tma_store.load() != 0) ? 1 : 0;
+    if (p.col_group > 0) {
+      KFB_REQUIRE(p.out_hi != nullptr && p.out_f32 == nullptr && p.mul == nullptr && !p.transpose_out && p.batch == 1 &&
+                      p.col_group % 8 == 0 && p.N % p.col_group == 0 && p.ldo_s == p.col_group,
+                  "gemm_nt: col_group needs a plane-only, non-transposed target with ld == col_group (multiple of 8)");
+      p.zero_pad = 0;
+    }
     p.batch_fastest = (p.mul != nullptr && p.batch > 1) ? 1 : 0;
     if (p.reduce_sq) {
       KFB_REQUIRE(p.out_f32 != nullptr && p.out_hi == nullptr, "gemm_nt: reduce_sq needs out_f32 only");
@@ -1112,24 +1201,39 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   if (epi.kind == KFB_EPI_ROWDOT) return dispatch_tc<EPI_ROWDOT>(A, B, p, nsplit, stream);
   if (epi.kind == KFB_EPI_SQACC) return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
 
-  // STORE: one TMEM pass if the contraction is short, register-accumulated passes otherwise; the
-  // contraction is additionally split across CTAs (atomic adds into an accumulated fp32 target) when
-  // there are too few output tiles to fill the machine.
+  // STORE: one TMEM pass if the contraction is short.  A longer contraction is cut into passes of at most
+  // max_pass_k elements: when the target is a plain accumulated fp32 matrix the passes are separate units of the
+  // wide (256 x 256, CTA-pair) STORE kernel combined by fp32 atomic adds in L2 (the same mechanism that splits the
+  // contraction across CTAs when there are too few output tiles to fill the machine); otherwise they are summed in
+  // registers by the REGACC kernel (128-wide tiles).
   const bool long_k = p.K > p.max_pass_k;
-  const bool splittable = p.out_hi == nullptr && p.mul == nullptr && !p.square && p.accumulate;
+  const bool splittable = p.out_hi == nullptr && p.mul == nullptr && !p.square && p.accumulate && !p.reduce_sq;
+  if (epi.symmetric) {
+    KFB_REQUIRE(A.hi == B.hi && A.rows == B.rows && A.ld == B.ld && p.batch == 1 && splittable && !p.transpose_out,
+                "gemm_nt: symmetric needs A == B and a plain accumulated fp32 target");
+    p.symmetric = 1;
+  }
   if (splittable) {
+    // Atomically combined passes are cheap (one 256 x 256 fp32 reduction per pair and pass), so in the 3-MMA mode
+    // they are kept to kAtomicPassK elements: sums of squares (covariance diagonals) see the accumulator's
+    // truncation bias coherently, and halving the chain halves it.
+    const long long passes = ceil_div_ll(p.K, strict ? kStrictPassK : (nsplit == 2 ? kAtomicPassK : p.max_pass_k));
     if (k_splits == 0) {
-      const int bn = pick_bn(p.N, long_k ? 128 : 256);
-      const long long tiles = ceil_div_ll(p.M, 128) * ceil_div_ll(p.N, bn) * p.batch;
-      const long long passes = ceil_div_ll(p.K, nsplit == 3 ? 1024 : kMaxPassK);
+      const int bn = pick_bn(p.N, 256);
+      long long tiles = ceil_div_ll(p.M, bn == 256 && p.M > 128 ? 256 : 128) * ceil_div_ll(p.N, bn) * p.batch;
+      if (p.symmetric) tiles = (tiles + 1) / 2;
       long long want = ceil_div_ll(sm_count(), tiles);
-      if (want > passes) want = passes;  // never make a split shorter than one full pass
+      const long long max_want = strict ? ceil_div_ll(p.K, 1024) : passes;
+      if (want > max_want) want = max_want;  // never make a split shorter than one full pass
       k_splits = want < 1 ? 1 : (int)want;
     }
+    if (!strict && k_splits < passes) k_splits = (int)passes;
     p.k_splits = k_splits;
+    if (!strict) return dispatch_tc<EPI_STORE>(A, B, p, nsplit, stream);
   }
   if (long_k) {
     p.regacc_mode = REGACC_KCHUNK;
+    p.symmetric = 0;
     return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
   }
   return dispatch_tc<EPI_STORE>(A, B, p, nsplit, stream);
@@ -1161,6 +1265,11 @@ int64_t kfb_launch_count(void) { return kfb::g_launches.load(); }
 
 int kfb_set_cta_pairs(int enable) {
   kfb::g_cta_pairs.store(enable ? 1 : 0);
+  return KFB_OK;
+}
+
+int kfb_set_tma_store(int enable) {
+  kfb::g_tma_store.store(enable ? 1 : 0);
   return KFB_OK;
 }
 

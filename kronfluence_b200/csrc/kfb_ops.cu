@@ -40,10 +40,11 @@ struct Ws {
 };
 
 static inline int planes_of(int precision) {
-  return precision == KFB_PREC_BF16 ? 1 : (precision == KFB_PREC_STRICT ? 3 : 2);
+  return precision == KFB_PREC_BF16 ? 1 : 2;
 }
 // Precision of the eigenbasis rotations: their component-wise errors are what Lambda^-1 amplifies, so the
-// fp32-parity mode runs them in the strict 3-plane mode (DESIGN.md "Precision model").
+// fp32-parity mode runs them in the strict mode (scaled FP16 hi/lo planes, short TMEM passes; DESIGN.md
+// "Precision model").
 static inline int rot_prec(int precision) { return precision == KFB_PREC_FP32 ? KFB_PREC_STRICT : precision; }
 
 static kfb_split ws_split(Ws& ws, long long rows, long long cols, long long batch, int precision) {
@@ -56,7 +57,7 @@ static kfb_split ws_split(Ws& ws, long long rows, long long cols, long long batc
   const size_t plane = (size_t)(rows * s.ld * batch) * 2;
   s.hi = ws.take(plane);
   s.lo = precision != KFB_PREC_BF16 ? ws.take(plane) : nullptr;
-  s.lo2 = precision == KFB_PREC_STRICT ? ws.take(plane) : nullptr;
+  s.absmax = precision == KFB_PREC_STRICT ? static_cast<float*>(ws.take(sizeof(float))) : nullptr;
   return s;
 }
 
@@ -64,7 +65,7 @@ static kfb_split split_batch_view(const kfb_split& s, long long b0, long long nb
   kfb_split v = s;
   v.hi = static_cast<char*>(s.hi) + b0 * s.batch_stride * 2;
   v.lo = s.lo ? static_cast<char*>(s.lo) + b0 * s.batch_stride * 2 : nullptr;
-  v.lo2 = s.lo2 ? static_cast<char*>(s.lo2) + b0 * s.batch_stride * 2 : nullptr;
+  v.absmax = s.absmax;  // one scale for the whole operand
   v.batch = nb;
   return v;
 }
@@ -157,6 +158,7 @@ static int cov_run(const kfb_layer& L, bool activation, const void* x, int dt, l
     e.ldo = d;
     e.accumulate = 1;
     e.alpha = alpha;
+    e.symmetric = 1;  // SYRK: upper-triangular tiles, mirrored by the epilogue
     KFB_TRY(gemm_nt(v, v, e, precision, 0, stream));
   }
   return KFB_OK;
@@ -247,12 +249,25 @@ static int outer_fill(const kfb_layer& L, const void* a, int a_dt, const void* g
   KFB_REQUIRE(qa_t->rows == di && qa_t->cols == di && qg_t->rows == L.d_out && qg_t->cols == L.d_out,
               "eigenbasis operand shapes do not match the layer");
   const int rp = rot_prec(precision);
-  KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+  KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->absmax != nullptr && qg_t->absmax != nullptr),
               "eigenbasis operands must be built with KFB_PREC_STRICT for the fp32-parity mode");
   kfb_split ta = split_batch_view(o.tmp_a, 0, nb), tg = split_batch_view(o.tmp_g, 0, nb);
   KFB_TRY(token_operands(L, a0, a_dt, g0, g_dt, nb, S, ta, tg, rp, stream));
   // Rt[b] = Q_A^T a_b^T : M = d_in+bias (eigen index), N = S, K = d_in+bias
   kfb_epilogue e = store_epilogue();
+  if (S % 8 == 0 && nb * S < (1LL << 31)) {
+    // the rotation is the same for every example: ONE flat GEMM over all nb*S tokens (full-width tiles whatever S
+    // is), whose epilogue scatters column n to example n / S, position n % S
+    kfb_split fa = ta, fg = tg;
+    fa.rows = nb * S; fa.batch = 1; fa.batch_stride = 0;
+    fg.rows = nb * S; fg.batch = 1; fg.batch_stride = 0;
+    e.col_group = S;
+    e.out_split = Rt;
+    KFB_TRY(gemm_nt(*qa_t, fa, e, rp, 1, stream));
+    e.out_split = Lt;
+    KFB_TRY(gemm_nt(*qg_t, fg, e, rp, 1, stream));
+    return KFB_OK;
+  }
   e.out_split = Rt;
   KFB_TRY(gemm_nt(*qa_t, ta, e, rp, 1, stream));
   e.out_split = Lt;
@@ -413,7 +428,7 @@ static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const v
       if (eigen) {
         KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
                     "precondition: eigenbasis operands do not match the layer");
-        KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+        KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->absmax != nullptr && qg_t->absmax != nullptr),
                     "precondition: eigenbasis operands must be built with KFB_PREC_STRICT");
         kfb_split av = a_sp, gv = g_sp;
         av.rows = nb; gv.rows = nb;
@@ -513,7 +528,7 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
     if (eigen) {
       KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
                   "pairwise: eigenbasis operands do not match the layer");
-      KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+      KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->absmax != nullptr && qg_t->absmax != nullptr),
                   "pairwise: eigenbasis operands must be built with KFB_PREC_STRICT");
       GatherDesc gg{};
       gg.sr = L.d_out; gg.sc2 = 1; gg.rows = batch; gg.c1 = 1; gg.c2 = L.d_out;
@@ -625,7 +640,7 @@ static int lowrank_run(const kfb_layer& L, const kfb_split* Lt, const kfb_split*
   if (eigen) {
     KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
                 "pairwise_lowrank: eigenbasis operands do not match the layer");
-    KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->lo2 != nullptr && qg_t->lo2 != nullptr),
+    KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->absmax != nullptr && qg_t->absmax != nullptr),
                 "pairwise_lowrank: eigenbasis operands must be built with KFB_PREC_STRICT");
   }
   const long long out_cols = per_token ? batch * S : batch;
@@ -819,7 +834,9 @@ int kfb_eigen_operands(const float* Q, int32_t d, const kfb_split* q, const kfb_
   KFB_REQUIRE(Q != nullptr && d > 0 && q != nullptr && qt != nullptr, "eigen_operands: bad argument");
   GatherDesc gq{};
   gq.sr = d; gq.sc2 = 1; gq.rows = d; gq.c1 = 1; gq.c2 = d;
-  KFB_TRY(split_gather(Q, KFB_F32, gq, *q, precision, (cudaStream_t)stream));
+  // q (untransposed) only serves the on-request back-rotation to the reference layout, an ordinary GEMM against the
+  // bf16 planes of the query store; qt drives the rotations and takes the requested (strict) precision
+  KFB_TRY(split_gather(Q, KFB_F32, gq, *q, precision == KFB_PREC_STRICT ? KFB_PREC_FP32 : precision, (cudaStream_t)stream));
   GatherDesc gt{};
   gt.sr = 1; gt.sc2 = d; gt.rows = d; gt.c1 = 1; gt.c2 = d;
   return split_gather(Q, KFB_F32, gt, *qt, precision, (cudaStream_t)stream);

@@ -29,7 +29,7 @@ __device__ __forceinline__ float load_as_float<double>(const double* p, long lon
 struct SplitDst {
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
-  __nv_bfloat16* lo2;
+  const float* absmax;  // strict operands: FP16 planes of x * strict_scale(*absmax)
   long long ld, bs;
   float* f32;  // plain fp32 destination instead of planes (gather_f32)
 };
@@ -38,7 +38,7 @@ static SplitDst make_dst(const kfb_split& dst, int precision) {
   SplitDst d;
   d.hi = (__nv_bfloat16*)dst.hi;
   d.lo = precision != KFB_PREC_BF16 ? (__nv_bfloat16*)dst.lo : nullptr;
-  d.lo2 = precision == KFB_PREC_STRICT ? (__nv_bfloat16*)dst.lo2 : nullptr;
+  d.absmax = precision == KFB_PREC_STRICT ? dst.absmax : nullptr;
   d.ld = dst.ld;
   d.bs = dst.batch_stride;
   d.f32 = nullptr;
@@ -46,12 +46,11 @@ static SplitDst make_dst(const kfb_split& dst, int precision) {
 }
 
 __device__ __forceinline__ void store_split(const SplitDst& d, long long idx, float v) {
-  if (d.lo2 != nullptr) {
-    __nv_bfloat16 h, m, l;
-    split_bf16_3(v, h, m, l);
-    d.hi[idx] = h;
-    d.lo[idx] = m;
-    d.lo2[idx] = l;
+  if (d.absmax != nullptr) {
+    __half h, l;
+    split_f16(v * strict_scale(__ldg(d.absmax)), h, l);
+    reinterpret_cast<__half*>(d.hi)[idx] = h;
+    reinterpret_cast<__half*>(d.lo)[idx] = l;
     return;
   }
   __nv_bfloat16 h, l;
@@ -88,15 +87,16 @@ __device__ __forceinline__ void store_split8(const SplitDst& d, long long idx, c
     reinterpret_cast<float4*>(d.f32 + idx)[1] = make_float4(v[4], v[5], v[6], v[7]);
     return;
   }
-  __nv_bfloat16 h[8], m[8], l[8];
-  if (d.lo2 != nullptr) {
+  if (d.absmax != nullptr) {
+    const float sc = strict_scale(__ldg(d.absmax));
+    __half hh[8], hl[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split_bf16_3(v[e], h[e], m[e], l[e]);
-    *reinterpret_cast<uint4*>(d.hi + idx) = *reinterpret_cast<uint4*>(h);
-    *reinterpret_cast<uint4*>(d.lo + idx) = *reinterpret_cast<uint4*>(m);
-    *reinterpret_cast<uint4*>(d.lo2 + idx) = *reinterpret_cast<uint4*>(l);
+    for (int e = 0; e < 8; ++e) split_f16(v[e] * sc, hh[e], hl[e]);
+    *reinterpret_cast<uint4*>(d.hi + idx) = *reinterpret_cast<uint4*>(hh);
+    *reinterpret_cast<uint4*>(d.lo + idx) = *reinterpret_cast<uint4*>(hl);
     return;
   }
+  __nv_bfloat16 h[8], l[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
   *reinterpret_cast<uint4*>(d.hi + idx) = *reinterpret_cast<uint4*>(h);
@@ -144,6 +144,34 @@ __global__ void gather_transpose_kernel(const T* __restrict__ src, GatherDesc g,
   }
 }
 
+// Largest magnitude of the gathered matrix (ones row/column and scaling included), for the strict operands' scale.
+// Non-negative floats order like their bit patterns, so the reduction is an integer atomicMax on a zeroed word.
+template <typename T>
+__global__ void gather_absmax_kernel(const T* __restrict__ src, GatherDesc g, long long out_rows, long long out_cols,
+                                     long long batch, float* absmax) {
+  // same index space as gather_direct_kernel, flattened: one thread per 8 consecutive columns of a row
+  const long long vecs = (out_cols + 7) / 8, total = batch * out_rows * vecs;
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long c8 = (i % vecs) * 8, r = (i / vecs) % out_rows, b = i / (vecs * out_rows);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(gather_value<T>(src, g, b, r, c8 + e)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(m));
+}
+
+template <typename T>
+__global__ void contiguous_absmax_kernel(const T* __restrict__ src, long long n, float floor_value, float* absmax) {
+  float m = floor_value;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(load_as_float<T>(src, i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(m));
+}
+
 template <typename T>
 static int launch_gather_dst(const T* src, const GatherDesc& g, const SplitDst& d, long long batch,
                              cudaStream_t stream) {
@@ -180,10 +208,19 @@ static int launch_gather(const T* src, const GatherDesc& g, const kfb_split& dst
   KFB_REQUIRE(dst.ld >= out_cols && dst.ld % 8 == 0, "split_gather: bad destination ld %lld",
               (long long)dst.ld);
   KFB_REQUIRE(dst.hi != nullptr && (precision == KFB_PREC_BF16 || dst.lo != nullptr) &&
-                  (precision != KFB_PREC_STRICT || dst.lo2 != nullptr),
-              "split_gather: missing destination plane");
+                  (precision != KFB_PREC_STRICT || dst.absmax != nullptr),
+              "split_gather: missing destination plane (or absmax word of a strict operand)");
   KFB_REQUIRE((reinterpret_cast<uintptr_t>(dst.hi) & 15) == 0 && dst.batch_stride % 8 == 0,
               "split_gather: destination planes must be 16-byte aligned");
+  if (precision == KFB_PREC_STRICT && out_rows > 0 && dst.batch > 0) {
+    KFB_CUDA_TRY(cudaMemsetAsync(dst.absmax, 0, sizeof(float), stream));
+    const long long total = dst.batch * out_rows * ((out_cols + 7) / 8);
+    long long blocks = ceil_div_ll(total, 256);
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    gather_absmax_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(src, g, out_rows, out_cols, dst.batch, dst.absmax);
+    count_launch();
+    KFB_CUDA_TRY(cudaGetLastError());
+  }
   return launch_gather_dst<T>(src, g, make_dst(dst, precision), dst.batch, stream);
 }
 
@@ -370,6 +407,18 @@ static int launch_im2col(const kfb_layer& L, const T* x, long long batch, int la
   SplitDst d = make_dst(dst, precision);
   KFB_REQUIRE((reinterpret_cast<uintptr_t>(dst.hi) & 15) == 0 && dst.batch_stride % 8 == 0,
               "im2col: destination planes must be 16-byte aligned");
+  if (precision == KFB_PREC_STRICT) {
+    // patches only copy (or group-average) input values, so the input's largest magnitude bounds the operand's
+    // (1.0 joins in when a ones column is appended)
+    KFB_REQUIRE(dst.absmax != nullptr, "im2col: strict operands need an absmax word");
+    KFB_CUDA_TRY(cudaMemsetAsync(dst.absmax, 0, sizeof(float), stream));
+    const long long n = batch * (long long)L.c_in * L.h_in * L.w_in;
+    long long blocks = ceil_div_ll(n, 1024);
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    contiguous_absmax_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(x, n, L.has_bias ? 1.f : 0.f, dst.absmax);
+    count_launch();
+    KFB_CUDA_TRY(cudaGetLastError());
+  }
   const long long vecs = dst.ld / 8;
   const unsigned bx = vecs >= 32 ? 32 : (vecs >= 16 ? 16 : 8);
   dim3 block(bx, 256 / bx);

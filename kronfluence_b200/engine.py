@@ -38,7 +38,7 @@ class KfbLayer(ctypes.Structure):
 
 
 class KfbSplit(ctypes.Structure):
-    _fields_ = [("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("lo2", ctypes.c_void_p), ("rows", ctypes.c_int64),
+    _fields_ = [("hi", ctypes.c_void_p), ("lo", ctypes.c_void_p), ("absmax", ctypes.c_void_p), ("rows", ctypes.c_int64),
                 ("cols", ctypes.c_int64), ("ld", ctypes.c_int64), ("batch", ctypes.c_int64),
                 ("batch_stride", ctypes.c_int64)]
 
@@ -49,7 +49,7 @@ class KfbEpilogue(ctypes.Structure):
                 ("ldmul", ctypes.c_int64), ("transpose_out", ctypes.c_int32), ("square", ctypes.c_int32),
                 ("accumulate", ctypes.c_int32), ("alpha", ctypes.c_float), ("g", ctypes.c_void_p),
                 ("ldg", ctypes.c_int64), ("reduce_sq", ctypes.c_int32), ("row_group", ctypes.c_int32),
-                ("g_batch_stride", ctypes.c_int64)]
+                ("g_batch_stride", ctypes.c_int64), ("symmetric", ctypes.c_int32), ("col_group", ctypes.c_int64)]
 
 
 # Every symbol include/kfb.h declares, with its ctypes signature (restype, argtypes).
@@ -59,9 +59,11 @@ _LP, _SP, _EP = ctypes.POINTER(KfbLayer), ctypes.POINTER(KfbSplit), ctypes.POINT
 SIGNATURES = {
     "kfb_version": (ctypes.c_int, []),
     "kfb_last_error": (ctypes.c_char_p, []),
+    "kfb_struct_sizes": (None, [ctypes.POINTER(ctypes.c_int)] * 3),
     "kfb_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
     "kfb_set_gemm_backend": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_cta_pairs": (ctypes.c_int, [ctypes.c_int]),
+    "kfb_set_tma_store": (ctypes.c_int, [ctypes.c_int]),
     "kfb_launch_count": (_i64, []),
     "kfb_split_gather": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_i64), _vp, _SP, ctypes.c_int, _vp]),
     "kfb_split_im2col": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _i64, _i32, _SP, ctypes.c_int, _vp]),
@@ -117,6 +119,12 @@ def load_library() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the ABI and the binding drift apart
         fn.restype = restype
         fn.argtypes = argtypes
+    sizes = [ctypes.c_int() for _ in range(3)]
+    lib.kfb_struct_sizes(*[ctypes.byref(x) for x in sizes])
+    mine = (ctypes.sizeof(KfbLayer), ctypes.sizeof(KfbSplit), ctypes.sizeof(KfbEpilogue))
+    if tuple(x.value for x in sizes) != mine:
+        raise KfbError(f"ABI mismatch: libkfb structs are {[x.value for x in sizes]} bytes, the binding's {list(mine)}; "
+                       "rebuild with `python -m kronfluence_b200.build`")
     _lib = lib
     _register_cusolver(lib)
     return lib
@@ -182,8 +190,20 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def strict_scale(absmax: float) -> float:
+    """The power of two the strict operands are stored with (kfb_common.cuh strict_scale): absmax * scale in
+    [2^13, 2^14)."""
+    import math
+
+    if not absmax > 0.0 or math.isinf(absmax):
+        return 1.0
+    _, exponent = math.frexp(absmax)
+    return math.ldexp(1.0, 14 - exponent)
+
+
 class Split:
-    """Device storage for a batch of matrices in tensor-core operand layout (two bf16 planes)."""
+    """Device storage for a batch of matrices in tensor-core operand layout: two bf16 planes (one for PREC_BF16),
+    or, for PREC_STRICT, two FP16 planes of the scaled operand plus the device word holding its absmax."""
 
     def __init__(self, rows: int, cols: int, batch: int = 1, device=None, precision: int = PREC_FP32,
                  zero: bool = False):
@@ -191,20 +211,25 @@ class Split:
         self.ld = round_up(max(self.cols, 1), 8)
         self.batch_stride = self.rows * self.ld
         self.precision = precision
-        planes = {PREC_FP32: 2, PREC_BF16: 1, PREC_STRICT: 3}[precision]
+        planes = {PREC_FP32: 2, PREC_BF16: 1, PREC_STRICT: 2}[precision]
         alloc = torch.zeros if zero else torch.empty
         self.storage = alloc((planes, self.batch, self.rows, self.ld), dtype=torch.bfloat16, device=device)
+        self.absmax = torch.zeros(1, dtype=torch.float32, device=device) if precision == PREC_STRICT else None
 
     def struct(self, batch_offset: int = 0, batch: Optional[int] = None) -> KfbSplit:
         nb = self.batch - batch_offset if batch is None else batch
         off = batch_offset * self.batch_stride * 2
         hi = self.storage[0].data_ptr() + off
         lo = self.storage[1].data_ptr() + off if self.storage.shape[0] >= 2 else None
-        lo2 = self.storage[2].data_ptr() + off if self.storage.shape[0] == 3 else None
-        return KfbSplit(hi, lo, lo2, self.rows, self.cols, self.ld, nb, self.batch_stride)
+        absmax = self.absmax.data_ptr() if self.absmax is not None else None
+        return KfbSplit(hi, lo, absmax, self.rows, self.cols, self.ld, nb, self.batch_stride)
 
     def to_float(self) -> torch.Tensor:
-        """hi + lo as fp32 [batch, rows, cols] (tests / debugging)."""
+        """hi + lo as fp32 [batch, rows, cols] (tests / debugging); strict operands are unscaled in fp64 first."""
+        if self.absmax is not None:
+            planes = self.storage.view(torch.float16).double()
+            val = (planes[0] + planes[1]) / strict_scale(float(self.absmax.item()))
+            return val[:, :, : self.cols]
         val = self.storage[0].float()
         for plane in range(1, self.storage.shape[0]):
             val = val + self.storage[plane].float()

@@ -148,9 +148,9 @@ def eigh_sym(cov: torch.Tensor, count: float) -> Tuple[torch.Tensor, torch.Tenso
 class EigenOperands:
     """Q and Q^T of one Kronecker factor in tensor-core operand layout (kfb_eigen_operands).
 
-    In the fp32-parity mode the rotations run in the strict 3-plane precision (their errors are what
-    Lambda^-1 amplifies), so the operands are built with three bf16 planes; the first two double as the
-    ordinary hi/lo pair."""
+    In the fp32-parity mode the rotations run in the strict precision (their errors are what Lambda^-1
+    amplifies): qt, which drives them, holds scaled FP16 hi/lo planes; q, which only serves the on-request
+    back-rotation against the bf16 query store, keeps ordinary bf16 hi/lo planes."""
 
     def __init__(self, q: torch.Tensor, precision: int = PREC_FP32):
         lib = engine.load_library()
@@ -159,7 +159,7 @@ class EigenOperands:
         q = _contig(q.to(dtype=torch.float32))
         d = q.shape[0]
         self.d = d
-        self.q = Split(d, d, 1, device=q.device, precision=precision)
+        self.q = Split(d, d, 1, device=q.device, precision=PREC_FP32 if precision == PREC_STRICT else precision)
         self.qt = Split(d, d, 1, device=q.device, precision=precision)
         sq, sqt = self.q.struct(), self.qt.struct()
         check(lib.kfb_eigen_operands(q.data_ptr(), d, ctypes.byref(sq), ctypes.byref(sqt), precision,

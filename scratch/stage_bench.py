@@ -54,7 +54,11 @@ lin = torch.nn.Linear
 run("target 4096->4096 S=1", lin(4096, 4096), (2048, 4096), 64)
 run("mnist 1024->1024 S=1", lin(1024, 1024), (1000, 1024), 128)
 run("bert ffn 768->3072 S=128", lin(768, 3072), (64, 128, 768), 64)
+run("bert ffn 768->3072 S=128 (B=256,Q=256)", lin(768, 3072), (256, 128, 768), 256)
 run("bert attn 768->768 S=128", lin(768, 768), (64, 128, 768), 128)
+run("bert attn 768->768 S=128 (B=512,Q=512)", lin(768, 768), (512, 128, 768), 512)
 run("gpt2 768->2304 S=512", lin(768, 2304), (16, 512, 768), 32)
+run("gpt2 768->2304 S=512 (B=128,Q=256)", lin(768, 2304), (128, 512, 768), 128 if False else 128)
 run("resnet9 conv 128->128 3x3 16x16", torch.nn.Conv2d(128, 128, 3, padding=1, bias=False), (256, 128, 16, 16), 128)
+run("resnet9 conv 256->256 3x3 8x8 (B=1024,Q=1000)", torch.nn.Conv2d(256, 256, 3, padding=1, bias=False), (1024, 256, 8, 8), 1000)
 run("resnet9 conv 3->64 3x3 32x32", torch.nn.Conv2d(3, 64, 3, padding=1, bias=False), (256, 3, 32, 32), 128)

@@ -32,8 +32,14 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(engine.KfbLayer) == 18 * 4
     assert ctypes.sizeof(engine.KfbSplit) == 8 * 8
-    # kfb_epilogue: int32 kind (+pad), ptr, 2x int64, kfb_split, ptr, int64, 3x int32, float, ptr, int64, int32 (+pad)
-    assert ctypes.sizeof(engine.KfbEpilogue) == 8 + 8 + 16 + 64 + 8 + 8 + 16 + 8 + 8 + 8 + 8
+    # kfb_epilogue: int32 kind (+pad), ptr, 2x int64, kfb_split, ptr, int64, 3x int32, float, ptr, int64, 2x int32,
+    # int64, int32 (+pad), int64
+    assert ctypes.sizeof(engine.KfbEpilogue) == 8 + 8 + 16 + 64 + 8 + 8 + 16 + 8 + 8 + 8 + 8 + 8 + 8
+    # ... and the library, compiled from include/kfb.h, agrees
+    sizes = [ctypes.c_int() for _ in range(3)]
+    engine.load_library().kfb_struct_sizes(*[ctypes.byref(x) for x in sizes])
+    assert [x.value for x in sizes] == [ctypes.sizeof(engine.KfbLayer), ctypes.sizeof(engine.KfbSplit),
+                                        ctypes.sizeof(engine.KfbEpilogue)]
 
 
 def test_no_cpu_path():

@@ -21,9 +21,37 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _spawn_with_retries(worker, extra_args, tmp_path, world=2, attempts=3, deadline_s=240.0):
+    """Runs `worker(rank, world, port, *extra_args, out_dir)` on `world` processes.  A TCP rendezvous on a
+    just-released port can occasionally fail or stall: every attempt gets a fresh port, a fresh output directory
+    (a failed attempt must not leave half-written factors behind) and a deadline after which it is torn down."""
+    import time
+
+    last = None
+    for attempt in range(attempts):
+        out_dir = tmp_path / f"attempt{attempt}"
+        out_dir.mkdir()
+        ctx = mp.spawn(worker, args=(world, _free_port(), *extra_args, str(out_dir)), nprocs=world, join=False)
+        start = time.monotonic()
+        try:
+            while not ctx.join(timeout=5.0):
+                if time.monotonic() - start > deadline_s:
+                    raise TimeoutError(f"world-size-{world} run exceeded {deadline_s:.0f} s")
+            return out_dir
+        except Exception as exc:  # pylint: disable=broad-exception-caught
+            last = exc
+            print(f"attempt {attempt} failed: {exc}", file=sys.stderr)
+            for proc in ctx.processes:
+                if proc.is_alive():
+                    proc.kill()
+            for proc in ctx.processes:
+                proc.join(timeout=10)
+    raise last
+
+
 def _worker(rank, world, port, case, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
-                      WORLD_SIZE=str(world))
+                      WORLD_SIZE=str(world), GLOO_SOCKET_IFNAME="lo")
     sys.path.insert(0, ROOT)
     torch.set_num_threads(1)
     from kronfluence_b200.analyzer import Analyzer, prepare_model
@@ -70,17 +98,7 @@ def _worker(rank, world, port, case, out_dir):
 
 @pytest.mark.parametrize("case", ["mlp", "conv"])
 def test_two_ranks_match_reference(case, tmp_path):
-    for attempt in range(3):  # a TCP rendezvous on a just-released port can occasionally fail: retry
-        out_dir = tmp_path / f"attempt{attempt}"  # a failed attempt must not leave half-written factors behind
-        out_dir.mkdir()
-        try:
-            mp.spawn(_worker, args=(2, _free_port(), case, str(out_dir)), nprocs=2, join=True)
-            tmp_path = out_dir
-            break
-        except Exception as exc:  # pylint: disable=broad-exception-caught
-            print(f"attempt {attempt} failed: {exc}", file=sys.stderr)
-            if attempt == 2:
-                raise
+    tmp_path = _spawn_with_retries(_worker, (case,), tmp_path)
     golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
     scores = np.load(tmp_path / "scores.npy")
     ref = golden["f32/scores"]
