@@ -289,6 +289,29 @@ int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_
                         int32_t accumulate, void* ws, size_t ws_bytes, int precision, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Aggregated gradients.  GradientTracker  module/tracker/gradient.py:14-95 with
+ * compute_summed_gradient  module/linear.py:63-66, conv2d.py:157-162; consumers
+ * score/pairwise.py:296-393 (aggregate_query_gradients) and score/dot_product.py:156-257
+ * (aggregate_train_gradients).
+ *   acc[d_out, d_in+bias] += scale * [ Q_G^T ( sum_b sum_s g_bs a_bs^T ) Q_A ] o lambda_inv
+ * qa_t / qg_t NULL: no rotation; lambda_inv NULL: no elementwise factor.  One contraction over all
+ * batch * S positions; the sum over batches lives in the caller's fp32 accumulator.
+ * ------------------------------------------------------------------------------------------ */
+size_t kfb_aggregate_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_aggregate_gradient(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype,
+                           int64_t batch, int64_t seq, const kfb_split* qa_t, const kfb_split* qg_t,
+                           const float* lambda_inv, float scale, float* acc, void* ws, size_t ws_bytes, int precision,
+                           void* stream);
+
+/* Pairwise scores against materialised gradients [num_gradients][d_out][d_in+bias] (fp32, in the basis of the
+ * query store), e.g. the aggregated train gradient:  scores[q, t_offset + t] (+)= scale * <P_q, G_t>
+ * (tracker/pairwise_score.py:120-132 finalize_all_iterations of the reference).                   */
+size_t kfb_pairwise_explicit_workspace_bytes(const kfb_layer* layer, int64_t num_gradients);
+int kfb_pairwise_scores_explicit(const kfb_layer* layer, const kfb_split* P, int64_t num_queries, const float* gradients,
+                                 int64_t num_gradients, float scale, float* scores, int64_t ld_scores, int64_t t_offset,
+                                 int32_t accumulate, void* ws, size_t ws_bytes, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Self-influence scores.  SelfScoreTracker._compute_self_score
  * tracker/self_score.py:32-60:  out[t_offset + t] (+)= sum_{o,i} P(G_t)[o,i] * G_t[o,i], G_t = scale * per-sample
  * gradient, P = the strategy's preconditioner.  Evaluated in the eigenbasis as

@@ -27,7 +27,7 @@ from torch.utils import data
 
 from kronfluence_b200 import ops
 from kronfluence_b200.arguments import FactorArguments, ScoreArguments
-from kronfluence_b200.module.tracked_module import ModuleMode, ScoreSink, TrackedModule, strategy_config
+from kronfluence_b200.module.tracked_module import ModuleMode, ScoreSink, TrackedModule, precision_of, strategy_config
 from kronfluence_b200.module.utils import (
     collect_factors,
     finalize_iteration,
@@ -45,7 +45,9 @@ from kronfluence_b200.module.utils import (
 from kronfluence_b200.task import Task
 from kronfluence_b200.utils import save as io
 from kronfluence_b200.utils.constants import (
+    ACCUMULATED_PRECONDITIONED_GRADIENT_NAME,
     ACTIVATION_COVARIANCE_MATRIX_NAME,
+    AGGREGATED_GRADIENT_NAME,
     ACTIVATION_EIGENVALUES_NAME,
     ACTIVATION_EIGENVECTORS_NAME,
     ALL_MODULE_NAME,
@@ -598,6 +600,43 @@ class Analyzer:
                 gather(store.storage)
             module.query_count = base + local_batch * world
 
+    def _aggregate_sweep(self, loader: data.DataLoader, names: List[str], precondition: bool, query_side: bool,
+                         factor_args: FactorArguments, scaler, autocast) -> None:
+        """One pass in GRADIENT_AGGREGATION mode: every module ends with sum over the loader of its (rotated, and on
+        the query side Lambda^-1-scaled) gradients in storage[AGGREGATED_GRADIENT_NAME], summed over ranks
+        (score/pairwise.py:296-393 query side, score/dot_product.py:156-257 train side of the reference)."""
+        device = self.state.device
+        modules = tracked_modules(self.model, names)
+        set_mode(self.model, ModuleMode.GRADIENT_AGGREGATION, names, release_memory=False)
+        for module in modules:
+            module.aggregate_precondition = precondition
+            module.storage[AGGREGATED_GRADIENT_NAME] = None
+        for batch in loader:
+            batch = _send_to_device(batch, device)
+            self.model.zero_grad(set_to_none=True)
+            with autocast():
+                if query_side:
+                    value = self.task.compute_measurement(batch=batch, model=self.model)
+                else:
+                    value = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
+            scaler.scale(value).backward()
+            if factor_args.has_shared_parameters:
+                finalize_iteration(self.model, names)
+            del value
+        self.model.zero_grad(set_to_none=True)
+        if self.state.use_distributed:
+            for module in modules:
+                if module.storage[AGGREGATED_GRADIENT_NAME] is None:  # this rank saw no example
+                    d_in, d_out = ops.module_factor_dims(module.original_module)
+                    module.storage[AGGREGATED_GRADIENT_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=device)
+            flat = torch.cat([m.storage[AGGREGATED_GRADIENT_NAME].reshape(-1) for m in modules])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)  # one collective for all modules
+            offset = 0
+            for module in modules:
+                target = module.storage[AGGREGATED_GRADIENT_NAME]
+                target.copy_(flat[offset : offset + target.numel()].view_as(target))
+                offset += target.numel()
+
     def _pairwise(self, query_dataset: data.Dataset, train_dataset: data.Dataset, query_bs: int, train_bs: int,
                   query_indices: Optional[Sequence[int]], train_indices: Optional[Sequence[int]],
                   factor_args: FactorArguments, score_args: ScoreArguments, names: List[str],
@@ -655,6 +694,64 @@ class Analyzer:
                 module.storage[PAIRWISE_SCORE_MATRIX_NAME] = None
             set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
 
+        train_aggregate: Dict[str, torch.Tensor] = {}
+
+        def aggregated_train_sweep(num_queries: int) -> None:
+            """`aggregate_train_gradients`: scores[q, 0] = <P_q, sum_t G_t>.  The train set is swept once, in
+            GRADIENT_AGGREGATION mode; every query chunk is scored against the kept sum."""
+            if not train_aggregate:
+                loader = self._loader(train_dataset, train_bs, train_indices, "eval", dataloader_kwargs)
+                self._aggregate_sweep(loader, names, precondition=False, query_side=False, factor_args=factor_args,
+                                      scaler=scaler, autocast=autocast)
+                for module in modules:
+                    train_aggregate[module.name] = module.storage[AGGREGATED_GRADIENT_NAME]
+                    module.storage[AGGREGATED_GRADIENT_NAME] = None
+                set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
+            shared = None if per_module else torch.zeros(num_queries, 1, dtype=torch.float32, device=device)
+            for module in modules:
+                store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
+                if isinstance(store, ops.LowRankStore):
+                    raise NotImplementedError("`aggregate_train_gradients` is not supported with `query_gradient_low_rank`.")
+                sink = torch.zeros(num_queries, 1, dtype=torch.float32, device=device) if per_module else shared
+                layer = ops.flat_layer(module.original_module)
+                ops.pairwise_scores_explicit(layer, store, num_queries, train_aggregate[module.name].unsqueeze(0), sink, 0,
+                                             accumulate=True, precision=precision_of(score_args.score_dtype))
+                if per_module:
+                    out_chunks[module.name].append(sink.to(dtype=score_args.score_dtype, device="cpu"))
+            if not per_module:
+                out_chunks[ALL_MODULE_NAME].append(shared.to(dtype=score_args.score_dtype, device="cpu"))
+
+        if score_args.aggregate_train_gradients:
+            if score_args.compute_per_token_scores:
+                raise ValueError("`compute_per_token_scores` cannot be combined with `aggregate_train_gradients`.")
+            train_sweep = aggregated_train_sweep  # noqa: F811
+
+        if score_args.aggregate_query_gradients:
+            # one aggregated, preconditioned query gradient per module (score/pairwise.py:296-393 of the reference)
+            loader = self._loader(query_dataset, query_bs, query_indices, "eval", dataloader_kwargs)
+            self._aggregate_sweep(loader, names, precondition=True, query_side=True, factor_args=factor_args,
+                                  scaler=scaler, autocast=autocast)
+            set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
+            for module in modules:
+                module.allocate_query_store(1, device)
+                total = module.storage[AGGREGATED_GRADIENT_NAME].unsqueeze(0)
+                store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
+                precision = precision_of(score_args.score_dtype)
+                if isinstance(store, ops.LowRankStore):
+                    dense = store.scratch_for(1, device)
+                    ops.load_query_store(dense, total, 0, precision)
+                    ops.lowrank_factorize(dense, 1, store, 0, score_args.use_full_svd, score_args.query_gradient_svd_dtype)
+                else:
+                    ops.load_query_store(store, total, 0, precision)
+                module.storage[AGGREGATED_GRADIENT_NAME] = None
+                module.query_count = 1
+            train_sweep(1)
+            self.model.zero_grad(set_to_none=True)
+            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            if scaler.is_enabled():
+                set_gradient_scale(self.model, 1.0)
+            return {key: torch.cat(chunks, dim=0) for key, chunks in out_chunks.items() if chunks}
+
         set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
         for module in modules:
             module.allocate_query_store(capacity, device)
@@ -704,9 +801,6 @@ class Analyzer:
                                 overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
         del target_data_partitions, target_module_partitions
         score_args = ScoreArguments() if score_args is None else score_args
-        for flag in ("aggregate_query_gradients", "aggregate_train_gradients"):
-            if getattr(score_args, flag):
-                raise NotImplementedError(f"`{flag}` is not part of the B200 hot path yet (SURVEY.md §8f).")
         if self.task.enable_post_process_per_sample_gradient:
             raise NotImplementedError("`post_process_per_sample_gradient` needs materialised gradients; unsupported.")
         factor_args = self._load_factor_args(factors_name)
@@ -792,11 +886,10 @@ class Analyzer:
                             target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                             overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
         """self[t] = sum_modules <P(grad L(z_t)), grad L(z_t)>  (score_computer.py:558-770, score/self.py:135-290
-        of the reference; the `use_measurement_for_self_influence` variant is not built yet)."""
+        of the reference).  With `use_measurement_for_self_influence` the preconditioned side is the gradient of the
+        measurement: self[t] = sum_modules <P(grad M(z_t)), grad L(z_t)>  (score/self.py:293-443)."""
         del target_data_partitions, target_module_partitions
         score_args = ScoreArguments() if score_args is None else score_args
-        if score_args.use_measurement_for_self_influence:
-            raise NotImplementedError("`use_measurement_for_self_influence` is not part of the B200 hot path yet.")
         # score_computer.py:617-640 of the reference: options that do not apply to self-influence are switched off
         for key, off in (("query_gradient_accumulation_steps", 1), ("query_gradient_low_rank", None),
                          ("compute_per_token_scores", False)):
@@ -823,7 +916,72 @@ class Analyzer:
         modules = tracked_modules(self.model, names)
         device = self.state.device
 
+        def run_with_measurement(batch_size: int) -> Dict[str, torch.Tensor]:
+            """score/self.py:293-443 of the reference: per batch, precondition the MEASUREMENT gradients of its
+            examples (PRECONDITION_GRADIENT mode, one store slot per example), then contract them example by example
+            with the LOSS gradients.  The contraction reuses the pairwise kernels on the batch against itself and
+            keeps the diagonal of the [B, B] tile (a fused diagonal epilogue is the obvious next step)."""
+            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            self._prepare_for_scores(factors, factor_args, score_args, names)
+            loader = self._loader(train_dataset, batch_size, train_indices, "stack", dataloader_kwargs)
+            scaler, autocast = self._amp(score_args.amp_dtype, factor_args.amp_scale)
+            per_module = score_args.compute_per_module_scores
+            chunks: Dict[str, List[torch.Tensor]] = {m.name: [] for m in modules} if per_module else {ALL_MODULE_NAME: []}
+            set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
+            for module in modules:
+                module.allocate_query_store(batch_size, device)
+            for batch in loader:
+                batch = _send_to_device(batch, device)
+                count = _find_batch_size(batch)
+                set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
+                for module in modules:
+                    module.query_count = 0
+                self.model.zero_grad(set_to_none=True)
+                with autocast():
+                    measurement = self.task.compute_measurement(batch=batch, model=self.model)
+                scaler.scale(measurement).backward()
+                if factor_args.has_shared_parameters:
+                    finalize_iteration(self.model, names)
+                del measurement
+                set_mode(self.model, ModuleMode.PAIRWISE_SCORE, names, release_memory=False)
+                if per_module:
+                    sinks = {m.name: ScoreSink(count, count, device, False) for m in modules}
+                else:
+                    shared_sink = ScoreSink(count, count, device, False)
+                    sinks = {m.name: shared_sink for m in modules}
+                for module in modules:
+                    module.storage[PAIRWISE_SCORE_MATRIX_NAME] = sinks[module.name]
+                    module.score_offset = 0
+                self.model.zero_grad(set_to_none=True)
+                with autocast():
+                    loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
+                scaler.scale(loss).backward()
+                if factor_args.has_shared_parameters:
+                    finalize_iteration(self.model, names)
+                del loss
+                for key in chunks:
+                    chunks[key].append(torch.diagonal(sinks[key if per_module else modules[0].name].result()).clone())
+                for module in modules:
+                    module.storage[PAIRWISE_SCORE_MATRIX_NAME] = None
+            self.model.zero_grad(set_to_none=True)
+            out: Dict[str, torch.Tensor] = {}
+            for key, parts in chunks.items():
+                local = torch.cat(parts, dim=0) if parts else torch.zeros(0, dtype=torch.float32, device=device)
+                if self.state.use_distributed:
+                    gathered = [torch.empty_like(local) for _ in range(self.state.num_processes)] \
+                        if self.state.is_main_process else None
+                    dist.gather(local, gathered, dst=0)
+                    if self.state.is_main_process:
+                        local = torch.cat(gathered, dim=0)[:n_train]
+                out[key] = local.to(dtype=score_args.score_dtype, device="cpu")
+            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+            if scaler.is_enabled():
+                set_gradient_scale(self.model, 1.0)
+            return out
+
         def run(batch_size: int) -> Dict[str, torch.Tensor]:
+            if score_args.use_measurement_for_self_influence:
+                return run_with_measurement(batch_size)
             set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
             self._prepare_for_scores(factors, factor_args, score_args, names)
             loader = self._loader(train_dataset, batch_size, train_indices, "stack", dataloader_kwargs)

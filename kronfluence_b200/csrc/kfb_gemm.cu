@@ -1150,7 +1150,8 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   p.k_splits = 1;
   p.k_chunks = 1;
   // strict mode: drain TMEM every kStrictPassK contraction elements (24 truncating accumulations per pass)
-  p.max_pass_k = strict ? kStrictPassK : kMaxPassK;
+  // (bf16 mode: one MMA per k-step and operands that are themselves only good to 2^-9, so a pass may run 4x longer)
+  p.max_pass_k = strict ? kStrictPassK : (nsplit == 1 ? 4 * kMaxPassK : kMaxPassK);
   if (p.M == 0 || p.N == 0 || p.batch == 0) return KFB_OK;
   KFB_REQUIRE(p.K > 0, "gemm_nt: empty contraction");
 

@@ -785,6 +785,130 @@ static int self_run(const kfb_layer& L, const void* a, int a_dt, const void* g, 
   return KFB_OK;
 }
 
+// =================================================================================================
+// Aggregated gradients (tracker/gradient.py:14-95, module/linear.py:63-66 / conv2d.py:157-162 "compute_summed_gradient").
+//   acc += scale * [ sum_b sum_s g_bs a_bs^T ]            (mode != EIGEN or no eigen operands: raw sum)
+//   acc += scale * [ Q_G^T (sum g a^T) Q_A ] o lambda_inv  (EIGEN: the eigenbasis image, optionally preconditioned)
+// One contraction over ALL positions of the batch (K = batch * S); the sum over query / train batches happens in
+// the fp32 accumulator `acc` [d_out, d_in+bias].  Preconditioning is linear, so scaling every batch by Lambda^-1 is
+// the aggregated query gradient of score/pairwise.py:296-393; without it, it is the aggregated train gradient of
+// score/dot_product.py:156-257 in the basis the query store uses.
+// =================================================================================================
+static int aggregate_run(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt, long long batch,
+                         long long seq, bool rotate, const kfb_split* qa_t, const kfb_split* qg_t, const float* lambda_inv,
+                         float scale, float* acc, Ws& ws, int precision, cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const int rp = rot_prec(precision);
+  const long long planes = planes_of(precision);
+  long long per = (di + L.d_out) * S * 2 * planes;
+  if (rotate) per += S * (ld8(di) + ld8(L.d_out)) * 2 * planes_of(rp);
+  const long long cb = chunk_count(batch, per);
+  kfb_split At = ws_split(ws, di, cb * S, 1, precision);        // [d_in+bias, tokens]  (K-major in the token index)
+  kfb_split Gt = ws_split(ws, L.d_out, cb * S, 1, precision);   // [d_out, tokens]
+  kfb_split ta{}, tg{};
+  if (rotate) {
+    ta = ws_split(ws, cb * S, di, 1, rp);
+    tg = ws_split(ws, cb * S, L.d_out, 1, rp);
+  }
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("aggregate workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  if (rotate)
+    KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out &&
+                    (rp != KFB_PREC_STRICT || (qa_t->absmax != nullptr && qg_t->absmax != nullptr)),
+                "aggregate: eigenbasis operands do not match the layer");
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    const void* a0 = L.kind == KFB_LINEAR ? advance(a, a_dt, b0 * S * L.d_in)
+                                          : advance(a, a_dt, b0 * (long long)L.c_in * L.h_in * L.w_in);
+    const void* g0 = advance(g, g_dt, b0 * S * L.d_out);
+    kfb_split av = At, gv = Gt;
+    av.cols = nb * S;
+    gv.cols = nb * S;
+    if (rotate) {
+      kfb_split tav = ta, tgv = tg;
+      tav.rows = nb * S;
+      tgv.rows = nb * S;
+      // token-major operands of the whole chunk as ONE matrix, rotated by two flat GEMMs into [d, tokens]
+      kfb_split tab = tav, tgb = tgv;  // batched view for the gathers: [nb][S][d]
+      tab.rows = S; tab.batch = nb; tab.batch_stride = S * tab.ld;
+      tgb.rows = S; tgb.batch = nb; tgb.batch_stride = S * tgb.ld;
+      KFB_TRY(token_operands(L, a0, a_dt, g0, g_dt, nb, S, tab, tgb, rp, stream));
+      kfb_epilogue e = store_epilogue();
+      e.out_split = av;
+      KFB_TRY(gemm_nt(*qa_t, tav, e, rp, 1, stream));
+      e.out_split = gv;
+      KFB_TRY(gemm_nt(*qg_t, tgv, e, rp, 1, stream));
+    } else if (L.kind == KFB_LINEAR) {
+      GatherDesc ga{};
+      ga.sr = 1; ga.sc2 = L.d_in; ga.rows = L.d_in; ga.c1 = 1; ga.c2 = nb * S;
+      ga.ones_mode = L.has_bias ? 2 : 0;
+      KFB_TRY(split_gather(a0, a_dt, ga, av, precision, stream));
+      GatherDesc gg{};
+      gg.sr = 1; gg.sc2 = L.d_out; gg.rows = L.d_out; gg.c1 = 1; gg.c2 = nb * S;
+      KFB_TRY(split_gather(g0, g_dt, gg, gv, precision, stream));
+    } else {
+      KFB_TRY(split_im2col(L, a0, a_dt, nb, 2, av, precision, stream));
+      GatherDesc gg{};
+      gg.sr = S; gg.sc1 = (long long)L.d_out * S; gg.sc2 = 1; gg.rows = L.d_out; gg.c1 = nb; gg.c2 = S;
+      KFB_TRY(split_gather(g0, g_dt, gg, gv, precision, stream));
+    }
+    kfb_epilogue e = store_epilogue();
+    e.out_f32 = acc;
+    e.ldo = di;
+    e.accumulate = 1;
+    e.alpha = scale;
+    e.mul = lambda_inv;
+    e.ldmul = di;
+    KFB_TRY(gemm_nt(gv, av, e, precision, 0, stream));
+  }
+  return KFB_OK;
+}
+
+// =================================================================================================
+// Pairwise scores against MATERIALISED gradients (SURVEY.md 8b "_explicit_grad"): G = [nb][d_out][d_in+bias] fp32 in
+// the basis of the query store (eigenbasis images for KFB_PRECOND_EIGEN stores), e.g. an aggregated train gradient.
+//   scores[q, t_offset + t] (+)= scale * <P_q, G_t>
+// =================================================================================================
+static int explicit_run(const kfb_layer& L, const kfb_split* P, long long nq, const float* G32, long long nb, float scale,
+                        float* scores, long long ld_scores, long long t_offset, int accumulate, Ws& ws, int precision,
+                        cudaStream_t stream) {
+  const long long di = L.d_in + L.has_bias;
+  const long long ldp = P != nullptr ? P->ld : ld8(di);
+  kfb_split G{};
+  G.rows = L.d_out; G.cols = di; G.ld = ldp; G.batch = nb; G.batch_stride = L.d_out * ldp;
+  G.hi = ws.take((size_t)(nb * G.batch_stride) * 2);
+  G.lo = precision != KFB_PREC_BF16 ? ws.take((size_t)(nb * G.batch_stride) * 2) : nullptr;
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("explicit pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  KFB_REQUIRE(P->batch_stride >= L.d_out * ldp, "pairwise_explicit: P batch stride is smaller than one matrix");
+  GatherDesc gd{};
+  gd.sb = L.d_out * di; gd.sr = di; gd.sc2 = 1; gd.rows = L.d_out; gd.c1 = 1; gd.c2 = di;
+  KFB_TRY(split_gather(G32, KFB_F32, gd, G, precision, stream));
+  if (!accumulate) {
+    zero_strided_kernel<<<296, 256, 0, stream>>>(scores + t_offset, nq, nb, ld_scores);
+    count_launch();
+  }
+  kfb_split Pf{};
+  Pf.hi = P->hi; Pf.lo = P->lo; Pf.rows = nq; Pf.cols = L.d_out * ldp; Pf.ld = P->batch_stride;
+  Pf.batch = 1; Pf.batch_stride = 0;
+  kfb_split Gf{};
+  Gf.hi = G.hi; Gf.lo = G.lo; Gf.rows = nb; Gf.cols = L.d_out * ldp; Gf.ld = G.batch_stride;
+  Gf.batch = 1; Gf.batch_stride = 0;
+  kfb_epilogue e = store_epilogue();
+  e.out_f32 = scores + t_offset;
+  e.ldo = ld_scores;
+  e.accumulate = 1;
+  e.alpha = scale;
+  return gemm_nt(Pf, Gf, e, precision, 0, stream);
+}
+
 }  // namespace kfb
 
 // =================================================================================================
@@ -952,6 +1076,50 @@ int kfb_pairwise_scores_lowrank(const kfb_layer* layer, const kfb_split* left_t,
   return lowrank_run(*layer, left_t, right, num_queries, left_t->rows, a, a_dtype, g, g_dtype, batch, seq, mode, qa_t,
                      qg_t, scale, scores, ld_scores, t_offset, accumulate, per_token, w, precision,
                      (cudaStream_t)stream);
+}
+
+size_t kfb_aggregate_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  aggregate_run(*layer, nullptr, KFB_F32, nullptr, KFB_F32, batch, seq, true, nullptr, nullptr, nullptr, 1.f, nullptr, w,
+                KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_aggregate_gradient(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype,
+                           int64_t batch, int64_t seq, const kfb_split* qa_t, const kfb_split* qg_t,
+                           const float* lambda_inv, float scale, float* acc, void* ws, size_t ws_bytes, int precision,
+                           void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(a != nullptr && g != nullptr && acc != nullptr, "aggregate_gradient: null tensor");
+  KFB_REQUIRE((qa_t == nullptr) == (qg_t == nullptr), "aggregate_gradient: give both eigenbasis operands or neither");
+  if (batch <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return aggregate_run(*layer, a, a_dtype, g, g_dtype, batch, seq, qa_t != nullptr, qa_t, qg_t, lambda_inv, scale, acc, w,
+                       precision, (cudaStream_t)stream);
+}
+
+size_t kfb_pairwise_explicit_workspace_bytes(const kfb_layer* layer, int64_t num_gradients) {
+  if (check_layer(layer) != KFB_OK || num_gradients <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  explicit_run(*layer, nullptr, 0, nullptr, num_gradients, 1.f, nullptr, 0, 0, 1, w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_pairwise_scores_explicit(const kfb_layer* layer, const kfb_split* P, int64_t num_queries, const float* gradients,
+                                 int64_t num_gradients, float scale, float* scores, int64_t ld_scores, int64_t t_offset,
+                                 int32_t accumulate, void* ws, size_t ws_bytes, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(P != nullptr && P->hi != nullptr && gradients != nullptr && scores != nullptr,
+              "pairwise_scores_explicit: null tensor");
+  KFB_REQUIRE(P->rows == layer->d_out && P->cols == layer->d_in + layer->has_bias,
+              "pairwise_scores_explicit: P layout does not match the layer");
+  KFB_REQUIRE(num_queries >= 0 && num_queries <= P->batch, "pairwise_scores_explicit: num_queries exceeds P");
+  KFB_REQUIRE(t_offset >= 0 && t_offset + num_gradients <= ld_scores, "pairwise_scores_explicit: columns out of range");
+  if (num_gradients <= 0 || num_queries == 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return explicit_run(*layer, P, num_queries, gradients, num_gradients, scale, scores, ld_scores, t_offset, accumulate, w,
+                      precision, (cudaStream_t)stream);
 }
 
 int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t num_queries,

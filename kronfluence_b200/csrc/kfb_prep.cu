@@ -165,11 +165,34 @@ __global__ void gather_absmax_kernel(const T* __restrict__ src, GatherDesc g, lo
 template <typename T>
 __global__ void contiguous_absmax_kernel(const T* __restrict__ src, long long n, float floor_value, float* absmax) {
   float m = floor_value;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(load_as_float<T>(src, i)));
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+  if (sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // fp32 source: 16-byte loads, two in flight per thread and iteration
+    const float4* v4 = reinterpret_cast<const float4*>(src);
+    const long long n4 = n / 4;
+    for (long long i = tid; i < n4; i += 2 * nthreads) {
+      const float4 a = __ldg(v4 + i);
+      const float4 b = i + nthreads < n4 ? __ldg(v4 + i + nthreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+    }
+    for (long long i = n4 * 4 + tid; i < n; i += nthreads) m = fmaxf(m, fabsf(load_as_float<T>(src, i)));
+  } else {
+    for (long long i = tid; i < n; i += nthreads) m = fmaxf(m, fabsf(load_as_float<T>(src, i)));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(m));
+}
+
+// True when the gather reads one dense block of memory (plain or transposed view of a contiguous [batch, rows, cols]
+// array, no scaling): its absmax is then a streaming reduction over that block.
+static bool gather_is_dense(const GatherDesc& g, long long batch) {
+  if (g.scale_mode != 0 || g.square || g.c1 != 1) return false;
+  const bool plain = g.sc2 == 1 && g.sr == g.c2;
+  const bool transposed = g.sr == 1 && g.sc2 == g.rows;
+  if (!plain && !transposed) return false;
+  return batch == 1 || g.sb == g.rows * g.c2;
 }
 
 template <typename T>
@@ -214,10 +237,18 @@ static int launch_gather(const T* src, const GatherDesc& g, const kfb_split& dst
               "split_gather: destination planes must be 16-byte aligned");
   if (precision == KFB_PREC_STRICT && out_rows > 0 && dst.batch > 0) {
     KFB_CUDA_TRY(cudaMemsetAsync(dst.absmax, 0, sizeof(float), stream));
-    const long long total = dst.batch * out_rows * ((out_cols + 7) / 8);
-    long long blocks = ceil_div_ll(total, 256);
-    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-    gather_absmax_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(src, g, out_rows, out_cols, dst.batch, dst.absmax);
+    if (gather_is_dense(g, dst.batch)) {
+      const long long n = dst.batch * g.rows * g.c2;
+      long long blocks = ceil_div_ll(n, 2048);
+      if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+      if (blocks < 1) blocks = 1;
+      contiguous_absmax_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(src, n, g.ones_mode != 0 ? 1.f : 0.f, dst.absmax);
+    } else {
+      const long long total = dst.batch * out_rows * ((out_cols + 7) / 8);
+      long long blocks = ceil_div_ll(total, 256);
+      if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+      gather_absmax_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(src, g, out_rows, out_cols, dst.batch, dst.absmax);
+    }
     count_launch();
     KFB_CUDA_TRY(cudaGetLastError());
   }
@@ -413,8 +444,9 @@ static int launch_im2col(const kfb_layer& L, const T* x, long long batch, int la
     KFB_REQUIRE(dst.absmax != nullptr, "im2col: strict operands need an absmax word");
     KFB_CUDA_TRY(cudaMemsetAsync(dst.absmax, 0, sizeof(float), stream));
     const long long n = batch * (long long)L.c_in * L.h_in * L.w_in;
-    long long blocks = ceil_div_ll(n, 1024);
+    long long blocks = ceil_div_ll(n, 2048);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    if (blocks < 1) blocks = 1;
     contiguous_absmax_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(x, n, L.has_bias ? 1.f : 0.f, dst.absmax);
     count_launch();
     KFB_CUDA_TRY(cudaGetLastError());

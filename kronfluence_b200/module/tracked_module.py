@@ -19,6 +19,7 @@ from kronfluence_b200.utils.constants import (
     ACCUMULATED_PRECONDITIONED_GRADIENT_NAME,
     ACTIVATION_COVARIANCE_MATRIX_NAME,
     ACTIVATION_EIGENVECTORS_NAME,
+    AGGREGATED_GRADIENT_NAME,
     COVARIANCE_FACTOR_NAMES,
     EIGENDECOMPOSITION_FACTOR_NAMES,
     GRADIENT_COVARIANCE_MATRIX_NAME,
@@ -44,6 +45,7 @@ class ModuleMode(str, Enum):
     PRECONDITION_GRADIENT = "precondition_gradient"
     PAIRWISE_SCORE = "pairwise_score"
     SELF_SCORE = "self_score"
+    GRADIENT_AGGREGATION = "gradient_aggregation"
 
     def __str__(self) -> str:
         return self.value
@@ -330,6 +332,66 @@ class PreconditionTracker(BaseTracker):
         self.module.query_count = 0
 
 
+class GradientAggregationTracker(BaseTracker):
+    """Sums the gradients of every example seen into one fp32 matrix (tracker/gradient.py:11-95 of the reference).
+
+    The sum is kept in the basis of the query store: with an eigen strategy every batch is rotated into the
+    Kronecker factors' eigenbases before it is added, and on the QUERY side (`module.aggregate_precondition`) it is
+    also scaled by Lambda^-1 — preconditioning is linear, so the sum of preconditioned gradients is the
+    preconditioned sum the reference forms in `PreconditionTracker.finalize_all_iterations`."""
+
+    def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
+        module = self.module
+        layer = module.layer_for(a)
+        d_in, d_out = ops.factor_dims(layer)
+        if module.storage[AGGREGATED_GRADIENT_NAME] is None:
+            module.storage[AGGREGATED_GRADIENT_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
+        mode = strategy_config(module.factor_args.strategy)["mode"]
+        qa = qg = None
+        if mode == ops.PRECOND_EIGEN:
+            qa, qg = module.eigen_operands(g.device)
+        lam_inv = None
+        if module.aggregate_precondition and mode != ops.PRECOND_IDENTITY:
+            lam_inv = module.storage[LAMBDA_MATRIX_NAME]
+        ops.aggregate_gradient(layer, a, g, module.storage[AGGREGATED_GRADIENT_NAME], qa, qg, lam_inv,
+                               module.gradient_scale, precision_of(module.score_args.per_sample_gradient_dtype))
+
+    def register_hooks(self) -> None:
+        module = self.module
+
+        @torch.no_grad()
+        def forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
+            self._cache_input(inputs)
+            self.cached_hooks.append(outputs.register_hook(backward_hook))
+
+        @torch.no_grad()
+        def backward_hook(grad: torch.Tensor) -> None:
+            if not self.cached_activations:
+                self._no_cache_error()
+            self.cached_hooks.pop().remove()
+            if module.factor_args.has_shared_parameters:
+                self.cached_gradients.append(grad.detach().clone())
+                return
+            self._update(self.cached_activations[0], grad.detach())
+            self.clear_all_cache()
+
+        self.registered_hooks.append(module.register_forward_hook(forward_hook))
+
+    @torch.no_grad()
+    def finalize_iteration(self) -> None:
+        if self.module.factor_args.has_shared_parameters and self.cached_gradients:
+            a, g = self._stacked_uses()
+            self._update(a, g)
+        self.clear_all_cache()
+
+    def exist(self) -> bool:
+        return self.module.storage[AGGREGATED_GRADIENT_NAME] is not None
+
+    def release_memory(self) -> None:
+        self.clear_all_cache()
+        self.module.storage[AGGREGATED_GRADIENT_NAME] = None
+
+
 class PairwiseScoreTracker(BaseTracker):
     """Train side: adds this module's <P_q, grad_t> into the shared [Q, T] score buffer
     (tracker/pairwise_score.py:16-137 + the module sum of score/dot_product.py:105-118 of the reference)."""
@@ -491,14 +553,16 @@ class TrackedModule(nn.Module):
             ModuleMode.PRECONDITION_GRADIENT: PreconditionTracker(self),
             ModuleMode.PAIRWISE_SCORE: PairwiseScoreTracker(self),
             ModuleMode.SELF_SCORE: SelfScoreTracker(self),
+            ModuleMode.GRADIENT_AGGREGATION: GradientAggregationTracker(self),
         }
         self.attention_mask: Optional[torch.Tensor] = None
         self.gradient_scale: float = 1.0
         self.storage: Dict[str, Any] = {}
         for key in (COVARIANCE_FACTOR_NAMES + EIGENDECOMPOSITION_FACTOR_NAMES + LAMBDA_FACTOR_NAMES +
                     [PRECONDITIONED_GRADIENT_NAME, ACCUMULATED_PRECONDITIONED_GRADIENT_NAME,
-                     PAIRWISE_SCORE_MATRIX_NAME, SELF_SCORE_VECTOR_NAME]):
+                     PAIRWISE_SCORE_MATRIX_NAME, SELF_SCORE_VECTOR_NAME, AGGREGATED_GRADIENT_NAME]):
             self.storage[key] = None
+        self.aggregate_precondition = False  # GRADIENT_AGGREGATION: scale by Lambda^-1 (query side) or not (train side)
         self.query_count = 0
         self.last_query_batch = 0
         self.score_offset = 0

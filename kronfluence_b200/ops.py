@@ -210,6 +210,14 @@ def module_factor_dims(module: nn.Module) -> Tuple[int, int]:
     raise ValueError(f"unsupported module type {type(module)}")
 
 
+def flat_layer(module: nn.Module) -> KfbLayer:
+    """The module as a plain [d_out, d_in(+1)] parameter matrix (no input geometry): what the ops on materialised
+    gradients need."""
+    d_in_total, d_out = module_factor_dims(module)
+    has_bias = int(module.bias is not None)
+    return KfbLayer(kind=engine.LINEAR, d_in=d_in_total - has_bias, d_out=d_out, has_bias=has_bias)
+
+
 def make_query_store(d_out: int, d_in_total: int, capacity: int, device, precision: int = PREC_FP32) -> Split:
     """Device storage for `capacity` preconditioned query gradients [d_out, d_in(+1)] of one module."""
     return Split(d_out, d_in_total, capacity, device=device, precision=precision, zero=True)
@@ -358,6 +366,7 @@ __all__ = [
     "PREC_FP32", "PREC_BF16", "PREC_STRICT", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
     "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
     "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "self_scores", "layer_of", "factor_dims", "workspace",
+    "aggregate_gradient", "pairwise_scores_explicit", "flat_layer",
 ]
 
 
@@ -377,6 +386,41 @@ def self_scores(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, out: torch.Te
                               ctypes.byref(sg) if sg is not None else None, lambda_inv.data_ptr(), float(scale),
                               out.data_ptr(), int(t_offset), int(accumulate), ws_ptr, ws_size, precision,
                               stream_ptr(a.device)))
+
+
+def aggregate_gradient(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, acc: torch.Tensor,
+                       qa: Optional[EigenOperands] = None, qg: Optional[EigenOperands] = None,
+                       lambda_inv: Optional[torch.Tensor] = None, scale: float = 1.0,
+                       precision: int = PREC_FP32) -> None:
+    """acc[d_out, d_in(+1)] += scale * [Q_G^T (sum over the batch and its positions of g a^T) Q_A] o lambda_inv
+    (tracker/gradient.py:14-95 of the reference; rotation and factor are optional)."""
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    assert acc.dtype == torch.float32 and acc.is_contiguous()
+    sa = qa.qt.struct() if qa is not None else None
+    sg = qg.qt.struct() if qg is not None else None
+    ws_ptr, ws_size = workspace(a.device).get(lib.kfb_aggregate_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_aggregate_gradient(ctypes.byref(layer), a.data_ptr(), dtype_code(a.dtype), g.data_ptr(),
+                                     dtype_code(g.dtype), batch, seq, ctypes.byref(sa) if sa is not None else None,
+                                     ctypes.byref(sg) if sg is not None else None, ptr(lambda_inv), float(scale),
+                                     acc.data_ptr(), ws_ptr, ws_size, precision, stream_ptr(a.device)))
+
+
+def pairwise_scores_explicit(layer: KfbLayer, store: Split, num_queries: int, gradients: torch.Tensor,
+                             scores: torch.Tensor, t_offset: int = 0, accumulate: bool = False, scale: float = 1.0,
+                             precision: int = PREC_FP32) -> None:
+    """scores[:num_queries, t_offset:t_offset+n] (+)= <P_q, gradients[t]> for materialised fp32 gradients
+    [n, d_out, d_in(+1)] in the basis of the store (tracker/pairwise_score.py:120-132 of the reference)."""
+    lib = engine.load_library()
+    gradients = _contig(gradients.to(torch.float32))
+    n = gradients.shape[0]
+    assert scores.dtype == torch.float32 and scores.stride(-1) == 1
+    src = store.struct(0, store.batch)
+    ws_ptr, ws_size = workspace(gradients.device).get(lib.kfb_pairwise_explicit_workspace_bytes(ctypes.byref(layer), n))
+    check(lib.kfb_pairwise_scores_explicit(ctypes.byref(layer), ctypes.byref(src), int(num_queries), gradients.data_ptr(),
+                                           n, float(scale), scores.data_ptr(), scores.stride(0), int(t_offset),
+                                           int(accumulate), ws_ptr, ws_size, precision, stream_ptr(gradients.device)))
 
 
 def load_query_store(store: Split, p: torch.Tensor, q_offset: int = 0, precision: int = PREC_FP32) -> None:

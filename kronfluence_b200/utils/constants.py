@@ -42,6 +42,7 @@ PRECONDITIONED_GRADIENT_NAME = "preconditioned_gradient"
 ACCUMULATED_PRECONDITIONED_GRADIENT_NAME = "accumulated_preconditioned_gradient"
 PAIRWISE_SCORE_MATRIX_NAME = "pairwise_score_matrix"
 SELF_SCORE_VECTOR_NAME = "self_score_vector"
+AGGREGATED_GRADIENT_NAME = "aggregated_gradient"
 
 ALL_MODULE_NAME = "all_modules"
 LAMBDA_DTYPE = torch.float64

@@ -247,6 +247,22 @@ def run_reference(case, dtype, strategy="ekfac", damping=None):
                                          per_device_train_batch_size=train_bs, score_args=score_args,
                                          overwrite_output_dir=True)
             out["self_scores"] = npy(analyzer.load_self_scores("self")["all_modules"])
+            # aggregated gradients (score/pairwise.py:296-393, score/dot_product.py:156-257) and self-influence with
+            # the measurement on the query side (score/self.py:293-443)
+            for tag, flags in (("agg_query", {"aggregate_query_gradients": True}),
+                               ("agg_train", {"aggregate_train_gradients": True}),
+                               ("agg_both", {"aggregate_query_gradients": True, "aggregate_train_gradients": True})):
+                args_agg = ScoreArguments(**{**score_args.__dict__, **flags})
+                analyzer.compute_pairwise_scores(f"s_{tag}", factors_name="f", query_dataset=query_set,
+                                                 train_dataset=train_set, per_device_query_batch_size=query_bs,
+                                                 per_device_train_batch_size=train_bs, score_args=args_agg,
+                                                 overwrite_output_dir=True)
+                out[f"scores_{tag}"] = npy(analyzer.load_pairwise_scores(f"s_{tag}")["all_modules"])
+            args_sm = ScoreArguments(**{**score_args.__dict__, "use_measurement_for_self_influence": True})
+            analyzer.compute_self_scores("self_m", factors_name="f", train_dataset=train_set,
+                                         per_device_train_batch_size=train_bs, score_args=args_sm,
+                                         overwrite_output_dir=True)
+            out["self_scores_measurement"] = npy(analyzer.load_self_scores("self_m")["all_modules"])
         out["files_factors"] = np.array(sorted(os.listdir(os.path.join(tmp, "golden", "factors_f"))))
         out["files_scores"] = np.array(sorted(os.listdir(os.path.join(tmp, "golden", "scores_s"))))
         return out

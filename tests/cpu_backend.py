@@ -163,6 +163,35 @@ def pairwise_scores(layer, store, num_queries, a, g, scores, t_offset=0, accumul
         view.copy_(block.to(scores.dtype))
 
 
+def flat_layer(module):
+    d_in_total, d_out = ops.module_factor_dims(module)
+    has_bias = int(module.bias is not None)
+    return SimpleNamespace(kind=0, d_in=d_in_total - has_bias, d_out=d_out, has_bias=has_bias, h_out=1, w_out=1, conv=None)
+
+
+def aggregate_gradient(layer, a, g, acc, qa=None, qg=None, lambda_inv=None, scale=1.0, precision=0):
+    total = _per_sample(layer, a, g).sum(axis=0)  # compute_summed_gradient (linear.py:63-66, conv2d.py:157-162)
+    if qa is not None:
+        total = qg.q.T @ total @ qa.q
+    if lambda_inv is not None:
+        total = total * _np(lambda_inv)
+    acc.add_(torch.from_numpy(total * scale).to(acc.dtype))
+
+
+def pairwise_scores_explicit(layer, store, num_queries, gradients, scores, t_offset=0, accumulate=False, scale=1.0,
+                             precision=0):
+    block = torch.from_numpy(orc.pairwise_scores_from_gradients(store.storage[0, :num_queries].numpy(), _np(gradients)) * scale)
+    view = scores[:num_queries, t_offset : t_offset + gradients.shape[0]]
+    if accumulate:
+        view.add_(block.to(scores.dtype))
+    else:
+        view.copy_(block.to(scores.dtype))
+
+
+def load_query_store(store, p, q_offset=0, precision=0):
+    store.storage[0, q_offset : q_offset + p.shape[0]] = p.double()
+
+
 def self_scores(layer, a, g, out, t_offset, mode, lambda_inv, qa=None, qg=None, scale=1.0, accumulate=True,
                 precision=0):
     grads = _per_sample(layer, a, g) * scale
@@ -180,7 +209,8 @@ def self_scores(layer, a, g, out, t_offset, mode, lambda_inv, qa=None, qg=None, 
 
 _PATCHED = ["layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
             "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores", "self_scores",
-            "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank", "LowRankStore"]
+            "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank", "LowRankStore", "flat_layer",
+            "aggregate_gradient", "pairwise_scores_explicit", "load_query_store"]
 
 
 LowRankStore = FakeLowRankStore

@@ -218,3 +218,38 @@ def test_low_rank_query_gradients(case, tmp_path):
     assert rel(want, golden["f32/scores"]) > 0.1  # the truncation is far from a no-op on these fixtures
     assert rel(scores["all_modules"].numpy(), want) < 5e-5
     assert rel(scores_acc["all_modules"].numpy(), want) < 5e-5
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_aggregated_gradients(case, tmp_path):
+    """`aggregate_query_gradients` / `aggregate_train_gradients` against the reference Analyzer (its own test,
+    tests/scores/test_pairwise_scores.py:589-759, checks them against the row / column sums of the full matrix)."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    full = golden["f32/scores"]
+    with oracle_backend():
+        _, agg_q = run_case(case, tmp_path / "q", inject_eigen=golden, score_kwargs=dict(aggregate_query_gradients=True))
+        _, agg_t = run_case(case, tmp_path / "t", inject_eigen=golden, score_kwargs=dict(aggregate_train_gradients=True),
+                            query_bs=2)
+        _, agg_b = run_case(case, tmp_path / "b", inject_eigen=golden,
+                            score_kwargs=dict(aggregate_query_gradients=True, aggregate_train_gradients=True))
+    for got, tag, sums in ((agg_q, "agg_query", full.sum(0, keepdims=True)), (agg_t, "agg_train", full.sum(1, keepdims=True)),
+                           (agg_b, "agg_both", full.sum().reshape(1, 1))):
+        got = got["all_modules"].numpy()
+        assert got.shape == golden[f"f32/scores_{tag}"].shape == sums.shape
+        assert rel(got, golden[f"f32/scores_{tag}"]) < 5e-5
+        assert rel(got, sums) < 5e-5
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_self_scores_with_measurement(case, tmp_path):
+    """`use_measurement_for_self_influence` (score/self.py:293-443 of the reference): <P(grad measurement), grad loss>."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    with oracle_backend():
+        analyzer, _ = run_case(case, tmp_path, inject_eigen=golden)
+        _, train_set, _ = fixtures.make_case(case)
+        scores = analyzer.compute_self_scores("self_m", "f", train_set, per_device_train_batch_size=5,
+                                              score_args=ScoreArguments(damping_factor=None,
+                                                                        use_measurement_for_self_influence=True))
+    got = scores["all_modules"].numpy()
+    assert got.shape == golden["f32/self_scores_measurement"].shape
+    assert rel(got, golden["f32/self_scores_measurement"]) < 5e-5

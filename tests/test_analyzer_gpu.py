@@ -164,3 +164,36 @@ def test_low_rank_query_gradients(case, tmp_path):
     # the randomized factorisation (the reference's default) only has to be close to the exact truncation
     _, approx, _ = run(case, tmp_path / "rnd", golden, inject=True, query_gradient_low_rank=3)
     assert rel(approx["all_modules"].numpy(), golden["f64/scores_lowrank"]) < 0.3
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_aggregated_gradients(case, tmp_path):
+    """`aggregate_query_gradients` / `aggregate_train_gradients` through the CUDA path (kfb_aggregate_gradient: one
+    contraction over all positions of a batch into the fp32 sum; kfb_pairwise_scores_explicit against the summed train
+    gradient) vs the reference Analyzer and vs the row / column sums of the full score matrix."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    full = golden["f64/scores"]
+    _, agg_q, _ = run(case, tmp_path / "q", golden, inject=True, aggregate_query_gradients=True)
+    _, agg_t, _ = run(case, tmp_path / "t", golden, inject=True, aggregate_train_gradients=True)
+    _, agg_b, _ = run(case, tmp_path / "b", golden, inject=True, aggregate_query_gradients=True,
+                      aggregate_train_gradients=True)
+    for got, tag, sums in ((agg_q, "agg_query", full.sum(0, keepdims=True)), (agg_t, "agg_train", full.sum(1, keepdims=True)),
+                           (agg_b, "agg_both", full.sum().reshape(1, 1))):
+        got = got["all_modules"].numpy()
+        assert got.shape == sums.shape
+        assert rel(got, golden[f"f64/scores_{tag}"]) < 1e-4
+        assert rel(got, sums) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_self_scores_with_measurement(case, tmp_path):
+    from kronfluence_b200.arguments import ScoreArguments
+    from tests import fixtures
+
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    analyzer, _, _ = run(case, tmp_path, golden, inject=True)
+    _, train_set, _ = fixtures.make_case(case)
+    scores = analyzer.compute_self_scores("self_m", "f", train_set, per_device_train_batch_size=6,
+                                          score_args=ScoreArguments(damping_factor=None,
+                                                                    use_measurement_for_self_influence=True))
+    assert rel(scores["all_modules"].numpy(), golden["f64/self_scores_measurement"]) < 1e-4

@@ -89,9 +89,15 @@ def _worker(rank, world, port, case, out_dir):
                                                    score_args=ScoreArguments(damping_factor=None,
                                                                              query_gradient_low_rank=3,
                                                                              use_full_svd=True))
+        aggregated = analyzer.compute_pairwise_scores("s_agg", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                      per_device_train_batch_size=4,
+                                                      score_args=ScoreArguments(damping_factor=None,
+                                                                                aggregate_query_gradients=True,
+                                                                                aggregate_train_gradients=True))
     if rank == 0:
         np.save(os.path.join(out_dir, "scores.npy"), scores["all_modules"].numpy())
         np.save(os.path.join(out_dir, "scores_lowrank.npy"), lowrank["all_modules"].numpy())
+        np.save(os.path.join(out_dir, "scores_aggregated.npy"), aggregated["all_modules"].numpy())
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -107,6 +113,10 @@ def test_two_ranks_match_reference(case, tmp_path):
     # rank-3 query factors are all-gathered instead of the dense gradients
     lowrank, ref_lr = np.load(tmp_path / "scores_lowrank.npy"), golden["f32/scores_lowrank"]
     assert np.linalg.norm(lowrank - ref_lr) / np.linalg.norm(ref_lr) < 5e-5
+    # aggregated query AND train gradients: per-rank sums, one all-reduce each, a single score
+    agg, ref_agg = np.load(tmp_path / "scores_aggregated.npy"), golden["f32/scores_agg_both"]
+    assert agg.shape == ref_agg.shape == (1, 1)
+    assert abs(agg - ref_agg).max() / abs(ref_agg).max() < 5e-5
 
 
 def test_samplers():
