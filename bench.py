@@ -15,7 +15,8 @@ output gradients, random P).  Every step streams all 68.9 GB of P, i.e. the work
   value      device-resident inputs: Q * T_b * steps / time, summed over ranks (weak scaling: T_b per rank)
   e2e        the same step through kfb_pairwise_scores_host with PINNED HOST activations/gradients:
              H2D of the batch + kernels + D2H of the score tile inside the timed region
-  roofline   the dominant kernel (gemm_tc_kernel<256,64,2,ROWDOT,cta_group 2>) timed alone with CUDA events:
+  roofline   the dominant kernel (gemm_tc_kernel<256,64,2,ROWDOT,cta_group 2, B-tile multicast over 2 pairs>) timed
+             alone with CUDA events:
              algorithmic FLOPs 2*Q*T_b*d_out*(d_in+1) per launch / mean launch time, against the measured
              bf16 tensor peak in MEASURED_PEAKS.json (sustained figure; fallback 1400 TF/s).  In fp32-parity
              mode the kernel ISSUES 3x those FLOPs (bf16 hi/lo split), reported as `issued_frac`.
@@ -320,20 +321,20 @@ def main() -> None:
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     achieved_tf = alg_flops / kernel_s / 1e12
     issued = 3.0 if precision == engine.PREC_FP32 else 1.0
-    # DRAM bytes per launch from the committed ncu captures (profiles/r01b_pairwise_ncu_raw.md, Q=128: fp32-parity
-    # 19.800 GB read + 8.1 MB written, bf16 8.252 GB + 5.0 MB: 2.3x / 1.9x the P planes read once), scaled by Q; only
+    # DRAM bytes per launch from the committed ncu captures (profiles/r01c_pairwise_ncu_raw.md, Q=128: fp32-parity
+    # 13.910 GB read + 6.3 MB written, bf16 5.272 GB + 8.0 MB: 1.6x / 1.2x the P planes read once), scaled by Q; only
     # meaningful for the profiled target layer and train batch.
     traffic = None
     if args.workload == "target" and t_batch == 2048:
-        per_q128 = (19.800072e9 + 8.109568e6) if precision == engine.PREC_FP32 else (8.252431e9 + 4.959232e6)
+        per_q128 = (13.910337e9 + 6.278656e6) if precision == engine.PREC_FP32 else (5.271759e9 + 7.961856e6)
         traffic = per_q128 * n_query / 128.0
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write, profiles/r01b_pairwise_ncu_raw.md, scaled Q/128",
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write, profiles/r01c_pairwise_ncu_raw.md, scaled Q/128",
                 "algorithmic_bytes": float(n_query) * do * store.ld * 2 * (2 if precision == engine.PREC_FP32 else 1)
                 + t_batch * (di + do) * 4.0,
                 "peak_source": f"{peak_kind} bf16_tflops_sustained", "kernel_ms": kernel_s * 1e3,
-                "kernel": "gemm_tc_kernel<BLOCK_N=256,BLOCK_K=64,NSPLIT=2,ROWDOT,cta_group=2>" if precision == engine.PREC_FP32
-                else "gemm_tc_kernel<256,64,1,ROWDOT,cta_group=2>",
+                "kernel": "gemm_tc_kernel<BLOCK_N=256,BLOCK_K=64,NSPLIT=2,ROWDOT,cta_group=2,multicast=2>" if precision == engine.PREC_FP32
+                else "gemm_tc_kernel<256,64,1,ROWDOT,cta_group=2,multicast=2>",
                 "issued_tflops": achieved_tf * issued, "issued_frac": achieved_tf * issued / peak_tf,
                 "kernel_share_of_step": kernel_s / (elapsed_s / args.steps)}
 

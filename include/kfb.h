@@ -149,6 +149,8 @@ int kfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int kfb_set_gemm_backend(int backend);
 /* 1 (default): plain plane outputs of the GEMM leave through TMA bulk stores; 0: per-lane vector stores (debug).  */
 int kfb_set_tma_store(int enable);
+/* 1 (default): clusters of two CTA pairs share their B tile through TMA multicast where it pays; 0: plain pairs.  */
+int kfb_set_multicast(int enable);
 /* 1 (default): large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles); 0: single CTAs.  */
 int kfb_set_cta_pairs(int enable);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */

@@ -218,6 +218,17 @@ __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* tmap, uint32_
       : "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Same, multicast: the box lands at the same CTA-relative offset in every CTA of `mask`, and each copy credits the
+// mbarrier at the same offset in the LEADER of the destination's pair (CUTLASS SM100_TMA_2SM_LOAD_MULTICAST).
+__device__ __forceinline__ void tma_load_3d_2sm_mc(const CUtensorMap* tmap, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                   int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
                : "memory");
@@ -240,11 +251,11 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, 
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive on the same-offset mbarrier of BOTH CTAs once the pair's MMAs have retired
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+// arrive on the same-offset mbarrier of every CTA in `mask` once the pair's MMAs have retired
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"((uint16_t)3)
+      "h"(mask)
       : "memory");
 }
 

@@ -49,6 +49,7 @@ struct GemmParams {
   int M, N, K, batch;
   int a_batched, b_batched;
   int m_blocks, n_blocks, k_blocks;
+  int mc, m_units;             // CTA pairs per cluster sharing one B tile (TMA multicast); m_units = ceil(m_blocks / mc)
   int k_splits, kb_per_split;  // contraction split ACROSS CTAs (atomics)
   int k_chunks, kb_per_chunk;  // contraction passes INSIDE a unit (register accumulation)
   int inner;                   // REGACC_BATCH: batches per chunk
@@ -89,17 +90,17 @@ struct Tile {
 template <int EPI>
 __device__ __forceinline__ int unit_inner_count(const GemmParams& p, long long unit) {
   if (EPI == EPI_ROWDOT) {
-    const int ns = (int)((unit / p.m_blocks) % p.n_splits);
+    const int ns = (int)((unit / p.m_units) % p.n_splits);
     const int nb0 = ns * p.nb_per_split;
     return (min(p.n_blocks, nb0 + p.nb_per_split) - nb0) * p.k_chunks;
   }
   if (EPI == EPI_REGACC) {
     if (p.regacc_mode == REGACC_BATCH) {
-      const long long chunk = unit / ((long long)p.m_blocks * p.n_blocks);
+      const long long chunk = unit / ((long long)p.m_units * p.n_blocks);
       const long long rem = (long long)p.batch - chunk * p.inner;
       return rem < p.inner ? (int)rem : p.inner;
     }
-    const int ks = (int)((unit / ((long long)p.m_blocks * p.n_blocks)) % p.k_splits);
+    const int ks = (int)((unit / ((long long)p.m_units * p.n_blocks)) % p.k_splits);
     const int kb0 = ks * p.kb_per_split;
     const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
     return (kb1 - kb0 + p.kb_per_chunk - 1) / p.kb_per_chunk;
@@ -107,8 +108,10 @@ __device__ __forceinline__ int unit_inner_count(const GemmParams& p, long long u
   return 1;
 }
 
+// `pair` is the CTA pair's index inside its cluster: the pairs of a cluster work on adjacent m-tiles of the same unit
+// (same n-tile, batch entry and k-range, i.e. the same B operand, which they fetch once and multicast).
 template <int EPI>
-__device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit, int j) {
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit, int j, int pair = 0) {
   Tile t;
   if (EPI == EPI_STORE && p.batch_fastest) {
     // the Lambda^-1 tile of an (m, n) block is read by every batch entry: schedule those units back to back so that
@@ -138,8 +141,8 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit,
     t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_split);
     return t;
   }
-  t.m_blk = (int)(unit % p.m_blocks);
-  long long r = unit / p.m_blocks;
+  t.m_blk = (int)(unit % p.m_units) * p.mc + pair;
+  long long r = unit / p.m_units;
   if (EPI == EPI_ROWDOT) {
     t.b = (int)(r / p.n_splits);
     const int jn = j / p.k_chunks;
@@ -475,11 +478,13 @@ __device__ __forceinline__ void load_g_chunk(const GemmParams& p, const float* g
 // CG = 1: one CTA per tile (M = 128).  CG = 2: a CTA PAIR per tile (tcgen05 cta_group::2, M = 256):
 // each CTA stages its own 128 rows of A and HALF of the B tile, the pair's tensor cores read both B
 // halves, so shared-memory and L2 operand traffic per MMA drop by a third.
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int CG>
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int CG, int MC = 1>
 struct GemmCfg {
   static constexpr int BLOCK_M = 128;          // accumulator rows per CTA
   static constexpr int TILE_M = BLOCK_M * CG;  // rows of one scheduled tile
   static constexpr int LOAD_N = BLOCK_N / CG;  // B rows staged by one CTA
+  static constexpr int FETCH_N = LOAD_N / MC;  // B rows one CTA fetches itself (and multicasts to its MC - 1 siblings)
+  static_assert(MC == 1 || (CG == 2 && MC == 2), "B-tile multicast is built for clusters of two CTA pairs");
   static constexpr int SWIZZLE = BLOCK_K * 2;  // bytes per smem row == swizzle span
   static constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_PLANE = LOAD_N * BLOCK_K * 2;
@@ -500,13 +505,13 @@ struct GemmCfg {
   static_assert(CG == 1 || CG == 2, "cta_group must be 1 or 2");
 };
 
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG>
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG, int MC>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG, MC>;
   static_assert(NSPLIT == 1 || NSPLIT == 2, "1 (bf16) or 2 (hi/lo; bf16 or, for strict operands, fp16) operand planes");
   constexpr int BLOCK_M = Cfg::BLOCK_M;
   constexpr int STAGES = Cfg::STAGES;
@@ -536,9 +541,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the pair's MMAs)
-  const long long unit0 = CG == 2 ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
-  const long long unit_stride = CG == 2 ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  const uint32_t cluster_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_rank & 1u;         // rank inside the CTA pair; 0 = leader (issues the pair's MMAs)
+  const int pair_id = (int)(cluster_rank >> 1);        // which pair of the cluster (MC == 2: 0 or 1)
+  const uint32_t leader_rank = cluster_rank & ~1u;     // cluster rank of this pair's leader
+  constexpr int CLUSTER = CG * MC;
+  const long long unit0 = (long long)(blockIdx.x / CLUSTER);
+  const long long unit_stride = (long long)(gridDim.x / CLUSTER);
 
   if (CG == 2) cluster_sync_all();  // both CTAs of the pair are resident before the paired TMEM allocation
   if (warp == 0 && lane == 0) {
@@ -552,7 +561,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), CG);   // one producer arrival (+tx bytes) per CTA of the group
-      mbar_init(empty_bar(s), 1);   // one tcgen05.commit (multicast to both CTAs when CG == 2)
+      mbar_init(empty_bar(s), MC);  // one tcgen05.commit per pair of the cluster (multicast to all its CTAs)
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tmem_full_bar(s), 1);
@@ -582,9 +591,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
       const int inner = unit_inner_count<EPI>(p, unit);
       for (int j = 0; j < inner; ++j) {
-        const Tile t = decode_tile<EPI>(p, unit, j);
+        const Tile t = decode_tile<EPI>(p, unit, j, pair_id);
         const int row_a = t.m_blk * Cfg::TILE_M + (int)cta_rank * BLOCK_M;
-        const int row_b = t.n_blk * BLOCK_N + (int)cta_rank * Cfg::LOAD_N;
+        const int row_b = t.n_blk * BLOCK_N + (int)cta_rank * Cfg::LOAD_N + pair_id * Cfg::FETCH_N;
         const int ba = p.a_batched ? t.b : 0;
         const int bb = p.b_batched ? t.b : 0;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
@@ -593,12 +602,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           if (CG == 2) {
             // both CTAs credit the LEADER's full barrier: its MMA thread consumes the pair's stage
             if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            else mbar_arrive_expect_tx_cluster(full_bar(stage), 0, Cfg::STAGE_BYTES);
+            else mbar_arrive_expect_tx_cluster(full_bar(stage), leader_rank, Cfg::STAGE_BYTES);
             tma_load_3d_2sm(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
-            tma_load_3d_2sm(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
-            if (NSPLIT == 2) {
-              tma_load_3d_2sm(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
-              tma_load_3d_2sm(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
+            if (NSPLIT == 2) tma_load_3d_2sm(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
+            if (MC == 2) {
+              // this CTA fetches its quarter of the B tile and multicasts it to the same-ranked CTA of both pairs
+              const uint32_t off = (uint32_t)(pair_id * Cfg::FETCH_N * Cfg::SWIZZLE);
+              const uint16_t mask = (uint16_t)(0x5u << cta_rank);
+              tma_load_3d_2sm_mc(&tm_b_hi, full_bar(stage), smem_b(stage, 0) + off, k0, row_b, bb, mask);
+              if (NSPLIT == 2) tma_load_3d_2sm_mc(&tm_b_lo, full_bar(stage), smem_b(stage, 1) + off, k0, row_b, bb, mask);
+            } else {
+              tma_load_3d_2sm(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
+              if (NSPLIT == 2) tma_load_3d_2sm(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
             }
           } else {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -624,7 +639,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
       const int inner = unit_inner_count<EPI>(p, unit);
       for (int j = 0; j < inner; ++j, ++it) {
-        const Tile t = decode_tile<EPI>(p, unit, j);
+        const Tile t = decode_tile<EPI>(p, unit, j, pair_id);
         const uint32_t as = it % ACC_STAGES;
         const uint32_t aphase = (it / ACC_STAGES) & 1u;
         mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
@@ -660,8 +675,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           }
           // smem stage reusable (in both CTAs) once these MMAs retire; accumulator published at the end
           if (CG == 2) {
-            umma_commit_2sm(empty_bar(stage));
-            if (kb == t.kb1 - 1) umma_commit_2sm(tmem_full_bar(as));
+            // the stage is free once BOTH pairs of the cluster have consumed it (their siblings write into it)
+            umma_commit_2sm(empty_bar(stage), (uint16_t)((1u << CLUSTER) - 1u));
+            if (kb == t.kb1 - 1) umma_commit_2sm(tmem_full_bar(as), (uint16_t)(3u << leader_rank));
           } else {
             umma_commit(empty_bar(stage));
             if (kb == t.kb1 - 1) umma_commit(tmem_full_bar(as));
@@ -688,9 +704,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       float racc[NACC];
 #pragma unroll
       for (int i = 0; i < NACC; ++i) racc[i] = 0.f;
-      Tile t = decode_tile<EPI>(p, unit, 0);
+      Tile t = decode_tile<EPI>(p, unit, 0, pair_id);
       for (int j = 0; j < inner; ++j, ++it) {
-        t = decode_tile<EPI>(p, unit, j);
+        t = decode_tile<EPI>(p, unit, j, pair_id);
         const uint32_t as = it % ACC_STAGES;
         const uint32_t aphase = (it / ACC_STAGES) & 1u;
         const uint32_t taddr = tmem_base + as * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
@@ -761,7 +777,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+          if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(tmem_empty_bar(as), leader_rank);
           else mbar_arrive(tmem_empty_bar(as));
         }
       }
@@ -909,6 +925,7 @@ static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_backend{0};
 static std::atomic<int> g_cta_pairs{1};
 static std::atomic<int> g_tma_store{1};
+static std::atomic<int> g_multicast{1};
 void count_launch(int n) { g_launches += n; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -959,17 +976,19 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
   return KFB_OK;
 }
 
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG = 1>
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG = 1, int MC = 1>
 static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG, MC>;
   p.m_blocks = (int)ceil_div_ll(p.M, Cfg::TILE_M);
+  p.mc = MC;
+  p.m_units = (int)ceil_div_ll(p.m_blocks, MC);
   p.n_blocks = (int)ceil_div_ll(p.N, BLOCK_N);
   p.k_blocks = (int)ceil_div_ll(p.K, BLOCK_K);
   const int max_pass_kb = (p.max_pass_k > 0 ? p.max_pass_k : kMaxPassK) / BLOCK_K > 0
                               ? (p.max_pass_k > 0 ? p.max_pass_k : kMaxPassK) / BLOCK_K : 1;
   if (EPI != EPI_STORE || Cfg::TILE_M != BLOCK_N || p.m_blocks != p.n_blocks) p.symmetric = 0;
   p.tri_tiles = (long long)p.m_blocks * (p.m_blocks + 1) / 2;
-  const long long tiles = p.symmetric ? p.tri_tiles : (long long)p.m_blocks * p.n_blocks;
+  const long long tiles = p.symmetric ? p.tri_tiles : (long long)p.m_units * p.n_blocks;
   if (EPI == EPI_ROWDOT) {
     p.k_splits = 1;
     p.kb_per_split = p.k_blocks;
@@ -977,7 +996,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
     p.kb_per_chunk = (int)ceil_div_ll(p.k_blocks, p.k_chunks);
     p.k_chunks = (int)ceil_div_ll(p.k_blocks, p.kb_per_chunk);
     // few row blocks (self-influence: one "query" per batch): spread each block's n-tiles over the idle SMs
-    const long long row_units = (long long)p.m_blocks * p.batch, groups = sm_count() / CG;
+    const long long row_units = (long long)p.m_units * p.batch, groups = sm_count() / (CG * MC);
     p.n_splits = 1;
     if (row_units * 2 <= groups && p.n_blocks > 1 && (p.batch == 1 || p.out_bs >= p.M))
       p.n_splits = (int)(groups / row_units < p.n_blocks ? groups / row_units : p.n_blocks);
@@ -1020,10 +1039,10 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   KFB_TRY(make_tmap(&ta_hi, A.hi, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
-  KFB_TRY(make_tmap(&tb_hi, B.hi, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
+  KFB_TRY(make_tmap(&tb_hi, B.hi, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::FETCH_N));
   if (NSPLIT >= 2) {
     KFB_TRY(make_tmap(&ta_lo, A.lo, A.cols, A.rows, A.batch, A.ld, A.batch_stride, BLOCK_K, 128));
-    KFB_TRY(make_tmap(&tb_lo, B.lo, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::LOAD_N));
+    KFB_TRY(make_tmap(&tb_lo, B.lo, B.cols, B.rows, B.batch, B.ld, B.batch_stride, BLOCK_K, Cfg::FETCH_N));
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
@@ -1036,27 +1055,43 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
     if (p.out_lo != nullptr)
       KFB_TRY(make_tmap(&to_lo, p.out_lo, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, 32, 32, false));
   }
-  auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG>;
+  auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG, MC>;
   static bool attr_set = false;
   if (!attr_set) {
     KFB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const long long groups = sm_count() / CG;  // CTA (pairs) resident at once: one per SM (TPC)
-  const long long grid = (p.num_units < groups ? p.num_units : groups) * CG;
+  constexpr int CLUSTER = CG * MC;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CLUSTER;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = CG == 2 ? 1 : 0;
+  cfg.numAttrs = CLUSTER > 1 ? 1 : 0;
+  // CTA groups resident at once: one CTA per SM; clusters of 4 may not tile every GPC, so ask the runtime
+  long long groups = sm_count() / CLUSTER;
+  if (MC > 1) {
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cfg.gridDim = dim3((unsigned)(groups * CLUSTER));
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = 0;
+      }
+      max_clusters = n;
+    }
+    KFB_REQUIRE(max_clusters > 0, "gemm_nt: no cluster of %d CTAs can be resident", CLUSTER);
+    if (groups > max_clusters) groups = max_clusters;
+  }
+  const long long grid = (p.num_units < groups ? p.num_units : groups) * CLUSTER;
+  cfg.gridDim = dim3((unsigned)grid);
   KFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, p));
   count_launch();
   KFB_CUDA_TRY(cudaGetLastError());
@@ -1076,6 +1111,15 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
   const int bn = pick_bn(p.N, EPI == EPI_REGACC ? 128 : 256);
   // CTA pairs (M = 256 tiles) whenever the problem has at least two full 128-row tiles to pair up
   const bool pair = g_cta_pairs.load() != 0 && bn == 256 && p.M > 128;
+  // Clusters of two CTA pairs on adjacent m-tiles fetch their common B tile once (TMA multicast): a quarter less
+  // L2->SM operand traffic, which is what bounds the single-MMA (bf16) mode of the fused pairwise kernel.
+  const bool mcast = g_multicast.load() != 0 && g_cta_pairs.load() != 0 && p.M > 256 && !p.symmetric && !p.batch_fastest;
+  if constexpr (EPI == EPI_ROWDOT) {
+    if (mcast && bn == 256 && nsplit == 2) return launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream);
+    if (mcast && bn == 256 && nsplit == 1) return launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
+  }
+  // (measured: NOT for the register-accumulating kernels — with a TMEM drain every two k-blocks, coupling the two
+  // pairs' stage releases costs more than the saved traffic: Lambda sweep 3.09 -> 3.49 ms on the BERT FFN layer)
   if (nsplit == 2) {
     if (EPI != EPI_REGACC && bn == 256 && pair) return launch_tc<256, 64, 2, EPI, 2>(A, B, p, stream);
     if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 32, 2, EPI>(A, B, p, stream);
@@ -1266,6 +1310,11 @@ int64_t kfb_launch_count(void) { return kfb::g_launches.load(); }
 
 int kfb_set_cta_pairs(int enable) {
   kfb::g_cta_pairs.store(enable ? 1 : 0);
+  return KFB_OK;
+}
+
+int kfb_set_multicast(int enable) {
+  kfb::g_multicast.store(enable ? 1 : 0);
   return KFB_OK;
 }
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "kfb_set_gemm_backend": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_cta_pairs": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_tma_store": (ctypes.c_int, [ctypes.c_int]),
+    "kfb_set_multicast": (ctypes.c_int, [ctypes.c_int]),
     "kfb_launch_count": (_i64, []),
     "kfb_split_gather": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_i64), _vp, _SP, ctypes.c_int, _vp]),
     "kfb_split_im2col": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _i64, _i32, _SP, ctypes.c_int, _vp]),
@@ -132,6 +133,11 @@ def load_library() -> ctypes.CDLL:
         raise KfbError(f"ABI mismatch: libkfb structs are {[x.value for x in sizes]} bytes, the binding's {list(mine)}; "
                        "rebuild with `python -m kronfluence_b200.build`")
     _lib = lib
+    # debugging switches of the GEMM engine (A/B measurements): KFB_MULTICAST=0, KFB_TMA_STORE=0, KFB_CTA_PAIRS=0
+    for env, setter in (("KFB_MULTICAST", lib.kfb_set_multicast), ("KFB_TMA_STORE", lib.kfb_set_tma_store),
+                        ("KFB_CTA_PAIRS", lib.kfb_set_cta_pairs)):
+        if os.environ.get(env) == "0":
+            setter(0)
     _register_cusolver(lib)
     return lib
 
