@@ -49,6 +49,7 @@ struct GemmParams {
   int M, N, K, batch;
   int a_batched, b_batched;
   int m_blocks, n_blocks, k_blocks;
+  int kb_hint;                 // host only: k-blocks of 64 per unit (pass), to keep multicast off short passes
   int mc, m_units;             // CTA pairs per cluster sharing one B tile (TMA multicast); m_units = ceil(m_blocks / mc)
   int k_splits, kb_per_split;  // contraction split ACROSS CTAs (atomics)
   int k_chunks, kb_per_chunk;  // contraction passes INSIDE a unit (register accumulation)
@@ -1118,6 +1119,14 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
     if (mcast && bn == 256 && nsplit == 2) return launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream);
     if (mcast && bn == 256 && nsplit == 1) return launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
   }
+  if constexpr (EPI == EPI_STORE) {
+    // long passes only (the flat pairwise GEMM: 16 k-blocks per pass; measured +8 % on the ResNet-9 conv layer at
+    // Q = 1000, while the K = S per-sample-gradient GEMMs with their frequent epilogues lose a little)
+    if (mcast && bn == 256 && p.kb_hint >= 16) {
+      if (nsplit == 2) return launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream);
+      return launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
+    }
+  }
   // (measured: NOT for the register-accumulating kernels — with a TMEM drain every two k-blocks, coupling the two
   // pairs' stage releases costs more than the saved traffic: Lambda sweep 3.09 -> 3.49 ms on the BERT FFN layer)
   if (nsplit == 2) {
@@ -1274,6 +1283,7 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
     }
     if (!strict && k_splits < passes) k_splits = (int)passes;
     p.k_splits = k_splits;
+    p.kb_hint = (int)(ceil_div_ll(p.K, 64) / (k_splits > 0 ? k_splits : 1));
     if (!strict) return dispatch_tc<EPI_STORE>(A, B, p, nsplit, stream);
   }
   if (long_k) {
@@ -1281,6 +1291,7 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
     p.symmetric = 0;
     return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
   }
+  p.kb_hint = (int)ceil_div_ll(p.K, 64);
   return dispatch_tc<EPI_STORE>(A, B, p, nsplit, stream);
 }
 
@@ -1314,7 +1325,7 @@ int kfb_set_cta_pairs(int enable) {
 }
 
 int kfb_set_multicast(int enable) {
-  kfb::g_multicast.store(enable ? 1 : 0);
+  kfb::g_multicast.store(enable < 0 ? 0 : enable);
   return KFB_OK;
 }
 

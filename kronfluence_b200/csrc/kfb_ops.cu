@@ -70,14 +70,19 @@ static kfb_split split_batch_view(const kfb_split& s, long long b0, long long nb
   return v;
 }
 
-// Scratch budget per intermediate family; larger batches are processed in chunks.
-static const long long kChunkBudgetBytes = 1LL << 31;
+// Scratch budget per call; larger batches are processed in chunks of EQUAL size (multiples of 8 examples), so that no
+// ragged last chunk falls back to narrow tiles: 256 examples at 13.5 MB each used to run as 148 + 108.
+static const long long kChunkBudgetBytes = 6LL << 30;
 
 static long long chunk_count(long long batch, long long bytes_per_sample) {
   long long c = bytes_per_sample > 0 ? kChunkBudgetBytes / bytes_per_sample : batch;
   if (c < 1) c = 1;
-  if (c > batch) c = batch;
-  return c < 1 ? 1 : c;
+  if (c >= batch) return batch < 1 ? 1 : batch;
+  const long long chunks = ceil_div_ll(batch, c);
+  long long even = ceil_div_ll(batch, chunks);
+  if (even > 8) even = round_up_ll(even, 8);
+  if (even > c) even = c;
+  return even < 1 ? 1 : even;
 }
 
 static kfb_epilogue store_epilogue() {

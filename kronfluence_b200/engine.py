@@ -136,8 +136,8 @@ def load_library() -> ctypes.CDLL:
     # debugging switches of the GEMM engine (A/B measurements): KFB_MULTICAST=0, KFB_TMA_STORE=0, KFB_CTA_PAIRS=0
     for env, setter in (("KFB_MULTICAST", lib.kfb_set_multicast), ("KFB_TMA_STORE", lib.kfb_set_tma_store),
                         ("KFB_CTA_PAIRS", lib.kfb_set_cta_pairs)):
-        if os.environ.get(env) == "0":
-            setter(0)
+        if os.environ.get(env, "").isdigit():
+            setter(int(os.environ[env]))
     _register_cusolver(lib)
     return lib
 
