@@ -196,7 +196,9 @@ class Analyzer:
         (computer/computer.py:135-163 of the reference)."""
         path = out_dir / f"{name}_arguments.json"
         current = None if args is None else args.to_dict()
-        if path.exists() and not overwrite:
+        existed = path.exists()
+        self.state.wait_for_everyone()  # every rank has looked before the main process starts writing
+        if existed and not overwrite:
             if io.load_json(path) != current:
                 raise ValueError(f"Attempting to use arguments that differ from the ones saved at `{path}`. "
                                  "Use a different name or set `overwrite_output_dir=True`.")
@@ -211,7 +213,9 @@ class Analyzer:
         path = out_dir / f"{dataset_name}_dataset_metadata.json"
         meta = {"type": type(dataset).__name__, "dataset_size": len(dataset),
                 "indices": None if indices is None else list(indices)}
-        if path.exists() and not overwrite:
+        existed = path.exists()
+        self.state.wait_for_everyone()  # every rank has looked before the main process starts writing
+        if existed and not overwrite:
             if io.load_json(path) != meta:
                 raise ValueError("Attempting to use the dataset that differs from the one already saved. "
                                  f"Please set `overwrite_output_dir=True`.\nNew metadata: {meta}.")

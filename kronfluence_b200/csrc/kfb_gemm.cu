@@ -1171,6 +1171,9 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   KFB_REQUIRE(nsplit == 1 || (A.lo != nullptr && B.lo != nullptr), "gemm_nt: missing lo planes");
   KFB_REQUIRE(!strict || (A.absmax != nullptr && B.absmax != nullptr),
               "gemm_nt: KFB_PREC_STRICT operands carry an absmax word (build them with KFB_PREC_STRICT)");
+  KFB_REQUIRE(strict || (A.absmax == nullptr && B.absmax == nullptr),
+              "gemm_nt: a KFB_PREC_STRICT operand (scaled FP16 planes) was passed to a bf16-plane contraction; build the "
+              "operand with the precision of the stage that consumes it");
   GemmParams p{};
   p.f16 = strict ? 1 : 0;
   p.a_absmax = A.absmax;

@@ -223,10 +223,10 @@ class LambdaTracker(BaseTracker):
             storage[LAMBDA_MATRIX_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
             storage[NUM_LAMBDA_PROCESSED] = torch.zeros(1, dtype=torch.int64)
         qa = qg = None
+        precision = precision_of(module.factor_args.lambda_dtype)
         if strategy_config(module.factor_args.strategy)["lambda_eigen"]:
-            qa, qg = module.eigen_operands(g.device)
-        ops.lambda_accum(layer, a, g, storage[LAMBDA_MATRIX_NAME], qa, qg, module.gradient_scale,
-                         precision_of(module.factor_args.lambda_dtype))
+            qa, qg = module.eigen_operands(g.device, precision)
+        ops.lambda_accum(layer, a, g, storage[LAMBDA_MATRIX_NAME], qa, qg, module.gradient_scale, precision)
         storage[NUM_LAMBDA_PROCESSED].add_(a.shape[0])
 
     def register_hooks(self) -> None:
@@ -277,20 +277,23 @@ class PreconditionTracker(BaseTracker):
         if store is None:
             raise RuntimeError(f"Module '{module.name}': the query store has not been allocated.")
         mode = strategy_config(module.factor_args.strategy)["mode"]
+        # The query store is laid out for the contraction that reads it (`score_dtype`), and the preconditioning
+        # kernels write straight into it, so the store's precision is the one this stage computes in
+        # (`precondition_dtype` is honoured when it is at most as precise).
+        precision = max(precision_of(module.score_args.precondition_dtype), precision_of(module.score_args.score_dtype))
         qa = qg = None
         if mode == ops.PRECOND_EIGEN:
-            qa, qg = module.eigen_operands(g.device)
+            qa, qg = module.eigen_operands(g.device, precision)
         lam_inv = module.storage[LAMBDA_MATRIX_NAME] if mode != ops.PRECOND_IDENTITY else None
         if isinstance(store, ops.LowRankStore):
             # tracker/precondition.py:54-71: precondition this batch densely, keep only its rank-r factors
             dense = store.scratch_for(a.shape[0], g.device)
-            ops.precondition(layer, a, g, dense, 0, mode, qa, qg, lam_inv, module.gradient_scale,
-                             precision=precision_of(module.score_args.precondition_dtype))
+            ops.precondition(layer, a, g, dense, 0, mode, qa, qg, lam_inv, module.gradient_scale, precision=precision)
             ops.lowrank_factorize(dense, a.shape[0], store, module.query_count, module.score_args.use_full_svd,
                                   module.score_args.query_gradient_svd_dtype)
         else:
             ops.precondition(layer, a, g, store, module.query_count, mode, qa, qg, lam_inv, module.gradient_scale,
-                             precision=precision_of(module.score_args.precondition_dtype))
+                             precision=precision)
         module.last_query_batch = a.shape[0]
         module.query_count += a.shape[0]
 
@@ -347,14 +350,15 @@ class GradientAggregationTracker(BaseTracker):
         if module.storage[AGGREGATED_GRADIENT_NAME] is None:
             module.storage[AGGREGATED_GRADIENT_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
         mode = strategy_config(module.factor_args.strategy)["mode"]
+        precision = precision_of(module.score_args.per_sample_gradient_dtype)
         qa = qg = None
         if mode == ops.PRECOND_EIGEN:
-            qa, qg = module.eigen_operands(g.device)
+            qa, qg = module.eigen_operands(g.device, precision)
         lam_inv = None
         if module.aggregate_precondition and mode != ops.PRECOND_IDENTITY:
             lam_inv = module.storage[LAMBDA_MATRIX_NAME]
         ops.aggregate_gradient(layer, a, g, module.storage[AGGREGATED_GRADIENT_NAME], qa, qg, lam_inv,
-                               module.gradient_scale, precision_of(module.score_args.per_sample_gradient_dtype))
+                               module.gradient_scale, precision)
 
     def register_hooks(self) -> None:
         module = self.module
@@ -417,7 +421,8 @@ class PairwiseScoreTracker(BaseTracker):
             layer = module.layer_for(a)
             qa = qg = None
             if strategy_config(module.factor_args.strategy)["mode"] == ops.PRECOND_EIGEN:
-                qa, qg = module.eigen_operands(grad.device)  # the store holds eigenbasis images
+                # the store holds eigenbasis images
+                qa, qg = module.eigen_operands(grad.device, precision_of(module.score_args.score_dtype))
             grad = grad.detach()
             tokens = 1
             if isinstance(store, ops.LowRankStore):
@@ -477,7 +482,7 @@ class SelfScoreTracker(BaseTracker):
         mode = strategy_config(module.factor_args.strategy)["mode"]
         qa = qg = None
         if mode == ops.PRECOND_EIGEN:
-            qa, qg = module.eigen_operands(g.device)
+            qa, qg = module.eigen_operands(g.device, precision_of(module.score_args.score_dtype))
         lam_inv = module.storage[LAMBDA_MATRIX_NAME]
         if lam_inv is None:  # identity strategy: P(G) = G
             d_in, d_out = ops.factor_dims(layer)
@@ -567,7 +572,7 @@ class TrackedModule(nn.Module):
         self.last_query_batch = 0
         self.score_offset = 0
         self._layers: Dict[Tuple[int, ...], Any] = {}
-        self._eigen_ops: Optional[Tuple[Any, Any]] = None
+        self._eigen_ops: Optional[Dict[int, Tuple[Any, Any]]] = None
 
     def forward(self, inputs: torch.Tensor, *args: Any, **kwargs: Any) -> torch.Tensor:
         outputs = self.original_module(inputs, *args, **kwargs)
@@ -582,18 +587,23 @@ class TrackedModule(nn.Module):
             self._layers[key] = ops.layer_of(self.original_module, tuple(x.shape))
         return self._layers[key]
 
-    def eigen_operands(self, device: torch.device):
-        """Q_A / Q_G in tensor-core operand layout, built once per set of factors (the reference moves
-        the fp32 eigenvectors to the device on every call: factor/config.py:347-349)."""
+    def eigen_operands(self, device: torch.device, precision: int = ops.PREC_FP32):
+        """Q_A / Q_G in tensor-core operand layout, built once per set of factors and per precision (the reference
+        moves the fp32 eigenvectors to the device on every call: factor/config.py:347-349).  The layout depends on
+        the precision of the stage that consumes them: strict FP16 hi/lo planes for the fp32-parity mode, one bf16
+        plane for the bf16 mode."""
         if self._eigen_ops is None:
+            self._eigen_ops = {}
+        if precision not in self._eigen_ops:
             qa, qg = self.storage[ACTIVATION_EIGENVECTORS_NAME], self.storage[GRADIENT_EIGENVECTORS_NAME]
             if qa is None or qg is None:
                 raise FactorsNotFoundError(
                     f"The strategy {self.factor_args.strategy} requires eigendecomposition results for module "
                     f"'{self.name}', but they are not found."
                 )
-            self._eigen_ops = (ops.make_eigen_operands(qa.to(device)), ops.make_eigen_operands(qg.to(device)))
-        return self._eigen_ops
+            self._eigen_ops[precision] = (ops.make_eigen_operands(qa.to(device), precision),
+                                          ops.make_eigen_operands(qg.to(device), precision))
+        return self._eigen_ops[precision]
 
     # ---- factor plumbing (names follow tracked_module.py:170-240 of the reference) ----
     def update_factor_args(self, factor_args: FactorArguments) -> None:

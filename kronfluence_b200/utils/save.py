@@ -3,6 +3,7 @@
 consumed by the other."""
 
 import json
+import os
 from pathlib import Path
 from typing import Any, Dict, Optional
 
@@ -23,9 +24,13 @@ def load_file(path: Path) -> Dict[str, torch.Tensor]:
 
 
 def save_json(obj: Any, path: Path) -> None:
-    Path(path).parent.mkdir(parents=True, exist_ok=True)
-    with open(path, "w", encoding="utf-8") as f:
+    """Atomic (write to a sibling, then rename): another rank or process never reads a half-written file."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    tmp = path.with_name(path.name + f".tmp{os.getpid()}")
+    with open(tmp, "w", encoding="utf-8") as f:
         json.dump(obj, f, indent=4, ensure_ascii=False)
+    os.replace(tmp, path)
 
 
 def load_json(path: Path) -> Dict[str, Any]:

@@ -197,3 +197,24 @@ def test_self_scores_with_measurement(case, tmp_path):
                                           score_args=ScoreArguments(damping_factor=None,
                                                                     use_measurement_for_self_influence=True))
     assert rel(scores["all_modules"].numpy(), golden["f64/self_scores_measurement"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_bf16_configuration(case, tmp_path):
+    """The reference's low-precision configuration (examples/cifar `all_low_precision`: bf16 per-sample gradients,
+    preconditioning and scores; its AMP test tolerates rtol 1e-1, tests/gpu_tests/amp_test.py:124-125): every stage runs
+    the single-MMA bf16 mode, with eigenbasis operands laid out for that mode."""
+    import torch as th
+
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    bf = th.bfloat16
+    _, scores, _ = run(case, tmp_path, golden, inject=True, per_sample_gradient_dtype=bf, precondition_dtype=bf,
+                       score_dtype=bf)
+    got = scores["all_modules"].float().numpy()
+    assert np.isfinite(got).all()
+    assert rel(got, golden["f64/scores"]) < 3e-2
+    # mixed: fp32 preconditioning into a bf16 store, and bf16 preconditioning into an fp32 store
+    _, mixed, _ = run(case, tmp_path / "m1", golden, inject=True, score_dtype=bf)
+    assert rel(mixed["all_modules"].float().numpy(), golden["f64/scores"]) < 3e-2
+    _, mixed2, _ = run(case, tmp_path / "m2", golden, inject=True, precondition_dtype=bf)
+    assert rel(mixed2["all_modules"].float().numpy(), golden["f64/scores"]) < 3e-2

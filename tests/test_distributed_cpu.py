@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _spawn_with_retries(worker, extra_args, tmp_path, world=2, attempts=3, deadline_s=240.0):
+def _spawn_with_retries(worker, extra_args, tmp_path, world=2, attempts=3, deadline_s=180.0):
     """Runs `worker(rank, world, port, *extra_args, out_dir)` on `world` processes.  A TCP rendezvous on a
     just-released port can occasionally fail or stall: every attempt gets a fresh port, a fresh output directory
     (a failed attempt must not leave half-written factors behind) and a deadline after which it is torn down."""
@@ -50,6 +50,9 @@ def _spawn_with_retries(worker, extra_args, tmp_path, world=2, attempts=3, deadl
 
 
 def _worker(rank, world, port, case, out_dir):
+    import faulthandler
+
+    faulthandler.dump_traceback_later(150, exit=False)  # a stalled rendezvous / collective shows where it hangs
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
                       WORLD_SIZE=str(world), GLOO_SOCKET_IFNAME="lo")
     sys.path.insert(0, ROOT)
