@@ -44,6 +44,7 @@ enum : int { REGACC_BATCH = 0, REGACC_KCHUNK = 1 };
 static const int kMaxPassK = 2048;
 static const int kAtomicPassK = 1024;
 static const int kStrictPassK = 128;
+static std::atomic<int> g_strict_pass_k{kStrictPassK};  // debug knob (kfb_set_strict_pass_k): pass-length experiments
 
 struct GemmParams {
   int M, N, K, batch;
@@ -722,16 +723,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           load_g_chunk(p, grow, n0, row_ok, gb[0]);
           mbar_wait(tmem_full_bar(as), aphase);
           tcgen05_fence_after();
+          // ... and so are the accumulator chunks: chunk c+1 is on its way from TMEM while chunk c is reduced
+          uint32_t v[2][32];
+          tmem_ld32(taddr, v[0]);
 #pragma unroll
           for (int c = 0; c < BLOCK_N / 32; ++c) {
             const int col0 = n0 + c * 32;
             if (col0 >= p.N) break;  // warp-uniform
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
-            if (c + 1 < BLOCK_N / 32 && col0 + 32 < p.N) load_g_chunk(p, grow, col0 + 32, row_ok, gb[(c + 1) & 1]);
+            const bool more = c + 1 < BLOCK_N / 32 && col0 + 32 < p.N;
             tmem_ld_wait();
+            if (more) {
+              tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+              load_g_chunk(p, grow, col0 + 32, row_ok, gb[(c + 1) & 1]);
+            }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) rowdot = fmaf(__uint_as_float(v[i]), gb[c & 1][i], rowdot);
+            for (int i = 0; i < 32; ++i) rowdot = fmaf(__uint_as_float(v[c & 1][i]), gb[c & 1][i], rowdot);
+          }
+          tmem_ld_wait();
+        } else if (EPI == EPI_REGACC) {
+          // A pass is short here (strict rotations drain TMEM every 128 contraction elements), so the drain must not
+          // serialise on the TMEM latency: chunk c+1 is requested before chunk c is added.
+          mbar_wait(tmem_full_bar(as), aphase);
+          tcgen05_fence_after();
+          uint32_t v[2][32];
+          tmem_ld32(taddr, v[0]);
+#pragma unroll
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < BLOCK_N / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+            if (p.regacc_mode == REGACC_BATCH) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = __uint_as_float(v[c & 1][i]);
+                racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += x * x;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[c & 1][i]);
+            }
           }
         } else {
           mbar_wait(tmem_full_bar(as), aphase);
@@ -739,22 +768,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
           for (int c = 0; c < BLOCK_N / 32; ++c) {
             const int col0 = n0 + c * 32;
-            if (col0 >= p.N && EPI != EPI_REGACC) break;  // warp-uniform
+            if (col0 >= p.N) break;  // warp-uniform
             uint32_t v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
-            if (EPI == EPI_REGACC) {
-              if (p.regacc_mode == REGACC_BATCH) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float x = __uint_as_float(v[i]);
-                  racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += x * x;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[i]);
-              }
-            } else {
+            {
               float x[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
@@ -1207,7 +1225,7 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   p.k_chunks = 1;
   // strict mode: drain TMEM every kStrictPassK contraction elements (24 truncating accumulations per pass)
   // (bf16 mode: one MMA per k-step and operands that are themselves only good to 2^-9, so a pass may run 4x longer)
-  p.max_pass_k = strict ? kStrictPassK : (nsplit == 1 ? 4 * kMaxPassK : kMaxPassK);
+  p.max_pass_k = strict ? g_strict_pass_k.load() : (nsplit == 1 ? 4 * kMaxPassK : kMaxPassK);
   if (p.M == 0 || p.N == 0 || p.batch == 0) return KFB_OK;
   KFB_REQUIRE(p.K > 0, "gemm_nt: empty contraction");
 
@@ -1274,7 +1292,7 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
     // Atomically combined passes are cheap (one 256 x 256 fp32 reduction per pair and pass), so in the 3-MMA mode
     // they are kept to kAtomicPassK elements: sums of squares (covariance diagonals) see the accumulator's
     // truncation bias coherently, and halving the chain halves it.
-    const long long passes = ceil_div_ll(p.K, strict ? kStrictPassK : (nsplit == 2 ? kAtomicPassK : p.max_pass_k));
+    const long long passes = ceil_div_ll(p.K, strict ? g_strict_pass_k.load() : (nsplit == 2 ? kAtomicPassK : p.max_pass_k));
     if (k_splits == 0) {
       const int bn = pick_bn(p.N, 256);
       long long tiles = ceil_div_ll(p.M, bn == 256 && p.M > 128 ? 256 : 128) * ceil_div_ll(p.N, bn) * p.batch;
@@ -1329,6 +1347,15 @@ int kfb_set_cta_pairs(int enable) {
 
 int kfb_set_multicast(int enable) {
   kfb::g_multicast.store(enable < 0 ? 0 : enable);
+  return KFB_OK;
+}
+
+int kfb_set_strict_pass_k(int k) {
+  if (k < 64 || k % 64 != 0) {
+    kfb::set_error("kfb_set_strict_pass_k: the pass length must be a positive multiple of 64");
+    return KFB_ERR_INVALID;
+  }
+  kfb::g_strict_pass_k.store(k);
   return KFB_OK;
 }
 

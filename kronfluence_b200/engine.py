@@ -65,6 +65,7 @@ SIGNATURES = {
     "kfb_set_cta_pairs": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_tma_store": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_multicast": (ctypes.c_int, [ctypes.c_int]),
+    "kfb_set_strict_pass_k": (ctypes.c_int, [ctypes.c_int]),
     "kfb_launch_count": (_i64, []),
     "kfb_split_gather": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_i64), _vp, _SP, ctypes.c_int, _vp]),
     "kfb_split_im2col": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _i64, _i32, _SP, ctypes.c_int, _vp]),

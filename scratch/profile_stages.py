@@ -31,6 +31,8 @@ def run(module, x_shape, n_query):
     ops.precondition(layer, x[:n_query].contiguous(), g[:n_query].contiguous(), store, 0, ops.PRECOND_EIGEN, qa, qg, lam_inv)
     scores = torch.zeros(n_query, B, device=dev)
     ops.pairwise_scores(layer, store, n_query, x, g, scores, qa=qa, qg=qg)
+    acc = torch.zeros(do, di, device=dev)
+    ops.aggregate_gradient(layer, x, g, acc, qa, qg, lam_inv)
     self_s = torch.zeros(B, device=dev)
     ops.self_scores(layer, x, g, self_s, 0, ops.PRECOND_EIGEN, lam_inv, qa, qg)
     torch.cuda.synchronize()
@@ -40,6 +42,6 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "target"):
     run(lin(4096, 4096), (2048, 4096), 32)
 if which in ("all", "bert"):
-    run(lin(768, 3072), (64, 128, 768), 64)
+    run(lin(768, 3072), (256, 128, 768), 256)
 if which in ("all", "conv"):
     run(torch.nn.Conv2d(128, 128, 3, padding=1, bias=False), (256, 128, 16, 16), 64)

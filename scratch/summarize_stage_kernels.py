@@ -29,11 +29,11 @@ def short(n):
     n = re.sub(r"\((const|kfb|float|long|int|double|unsigned|SplitDst|GatherDesc|kfb_layer).*", "", n)
     return n.replace("void ", "").replace("kfb::", "").strip()
 
-print("# Round 1 — every kernel of the hot path under ncu (one pass of each stage op)\n")
+print("# Round 1 (end of session 2) — every kernel of the hot path under ncu (one pass of each stage op)\n")
 print("`ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active...,gpu__dram_throughput...,dram__bytes_*,"
       "l1tex__throughput...,lts__throughput... --clock-control none` over `scratch/profile_stages.py`: covariance (both sides),")
-print("eigendecomposition, Lambda sweep, Lambda inversion, query preconditioning, pairwise contraction and self-influence for")
-print("(1) the target Linear 4096->4096 (S=1, B=2048), (2) a BERT-shaped Linear 768->3072 (S=128, B=64) and (3) a ResNet-9-shaped")
+print("eigendecomposition, Lambda sweep, Lambda inversion, query preconditioning, pairwise contraction, gradient aggregation and self-influence for")
+print("(1) the target Linear 4096->4096 (S=1, B=2048), (2) a BERT-shaped Linear 768->3072 (S=128, B=256, Q=256) and (3) a ResNet-9-shaped")
 print("Conv2d 128->128 3x3 on 16x16 (S=256, B=256).  Times are single cold launches (compare shares, not absolutes).")
 print(f"HBM GB/s = DRAM bytes / time; the measured HBM peak is {hbm:.0f} GB/s (MEASURED_PEAKS.json).\n")
 print("| # | kernel | grid | time (us) | tensor pipe % | DRAM % | DRAM GB | achieved HBM GB/s | L1TEX % | L2 % |")
