@@ -151,6 +151,9 @@ int kfb_set_gemm_backend(int backend);
 int kfb_set_tma_store(int enable);
 /* 1 (default): clusters of two CTA pairs share their B tile through TMA multicast where it pays; 0: plain pairs.  */
 int kfb_set_multicast(int enable);
+/* 1 (default): register-accumulating GEMMs (strict rotations, Lambda square-accumulate) use 256-wide tiles with two
+ * epilogue warpgroups; 0: 128-wide tiles.                                                                       */
+int kfb_set_wide_regacc(int enable);
 /* Debug: contraction elements per TMEM pass of KFB_PREC_STRICT GEMMs (multiple of 64; default 128).            */
 int kfb_set_strict_pass_k(int k);
 /* 1 (default): large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles); 0: single CTAs.  */

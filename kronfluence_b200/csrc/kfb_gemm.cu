@@ -480,8 +480,9 @@ __device__ __forceinline__ void load_g_chunk(const GemmParams& p, const float* g
 // CG = 1: one CTA per tile (M = 128).  CG = 2: a CTA PAIR per tile (tcgen05 cta_group::2, M = 256):
 // each CTA stages its own 128 rows of A and HALF of the B tile, the pair's tensor cores read both B
 // halves, so shared-memory and L2 operand traffic per MMA drop by a third.
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int CG, int MC = 1>
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int CG, int MC = 1, int EW = 4>
 struct GemmCfg {
+  static constexpr int THREADS = 128 + 32 * EW;  // 4 control warps + EW epilogue warps
   static constexpr int BLOCK_M = 128;          // accumulator rows per CTA
   static constexpr int TILE_M = BLOCK_M * CG;  // rows of one scheduled tile
   static constexpr int LOAD_N = BLOCK_N / CG;  // B rows staged by one CTA
@@ -491,7 +492,8 @@ struct GemmCfg {
   static constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_PLANE = LOAD_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PLANE + B_PLANE);
-  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // one [32][33] fp32 staging tile per epilogue warp
+  static constexpr int EPI_STAGE_BYTES = EW * 32 * 33 * 4;  // one [32][33] fp32 staging tile per epilogue warp
+  static_assert(EW == 4 || EW == 8, "one or two epilogue warpgroups");
   static constexpr int SMEM_BUDGET = 227 * 1024 - 2048 - EPI_STAGE_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -507,13 +509,16 @@ struct GemmCfg {
   static_assert(CG == 1 || CG == 2, "cta_group must be 1 or 2");
 };
 
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG, int MC>
-__global__ void __launch_bounds__(256, 1)
+// EW = 8 (register-accumulating kernels with 256-wide tiles): two epilogue warpgroups, each thread of which keeps
+// 128 accumulator columns of its row; the control warps hand most of their registers over (setmaxnreg).
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG, int MC, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG, MC>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG, MC, EW>;
+  static_assert(EW == 4 || EPI == EPI_REGACC, "only the register-accumulating epilogue splits the tile's columns");
   static_assert(NSPLIT == 1 || NSPLIT == 2, "1 (bf16) or 2 (hi/lo; bf16 or, for strict operands, fp16) operand planes");
   constexpr int BLOCK_M = Cfg::BLOCK_M;
   constexpr int STAGES = Cfg::STAGES;
@@ -567,7 +572,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tmem_full_bar(s), 1);
-      mbar_init(tmem_empty_bar(s), 4 * CG);  // one arrival per epilogue warp of the group
+      mbar_init(tmem_empty_bar(s), EW * CG);  // one arrival per epilogue warp of the group
     }
     fence_barrier_init();
   }
@@ -586,6 +591,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // EW == 8: 384 threads x 168 registers = 64512 at launch, and that is the pool: the control warpgroup drops to 56
+  // here, the two epilogue warpgroups rise to 224 at the top of their branch (128 x 56 + 256 x 224 = 64512)
+  if (EW == 8 && warp < 4) setmaxnreg_dec<56>();
   if (warp == 0 && lane == 0) {
     // ===================================== TMA producer ======================================
     int stage = 0;
@@ -693,10 +701,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else if (warp >= 4) {
     // ======================================= epilogue ========================================
+    if (EW == 8) setmaxnreg_inc<224>();
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int lane_row = quarter * 32 + lane;  // accumulator row owned by this thread
-    float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256) + quarter * (32 * 33);
-    constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N : 1;
+    float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 4) * (32 * 33);
+    constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N / (EW / 4) : 1;  // accumulator columns kept per thread
+    const int col_off = EW == 8 ? ((warp - 4) >> 2) * NACC : 0;          // ... starting at this column of the tile
     // strict operands were scaled by powers of two: undo both scales together with alpha (exact)
     const float alpha = p.f16 ? p.alpha / strict_scale(__ldg(p.a_absmax)) / strict_scale(__ldg(p.b_absmax)) : p.alpha;
     uint32_t it = 0;
@@ -746,11 +756,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           mbar_wait(tmem_full_bar(as), aphase);
           tcgen05_fence_after();
           uint32_t v[2][32];
-          tmem_ld32(taddr, v[0]);
+          tmem_ld32(taddr + col_off, v[0]);
 #pragma unroll
-          for (int c = 0; c < BLOCK_N / 32; ++c) {
+          for (int c = 0; c < NACC / 32; ++c) {
             tmem_ld_wait();
-            if (c + 1 < BLOCK_N / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+            if (c + 1 < NACC / 32) tmem_ld32(taddr + col_off + (c + 1) * 32, v[(c + 1) & 1]);
             if (p.regacc_mode == REGACC_BATCH) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -824,7 +834,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
       } else if (EPI == EPI_REGACC) {
         const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
-        const int n0 = t.n_blk * BLOCK_N;
+        const int n0 = t.n_blk * BLOCK_N + col_off;
         const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
         // warp-uniform conditions: store_chunk is a warp-cooperative call
         if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0, racc, st, lane);
@@ -945,6 +955,7 @@ static std::atomic<int> g_backend{0};
 static std::atomic<int> g_cta_pairs{1};
 static std::atomic<int> g_tma_store{1};
 static std::atomic<int> g_multicast{1};
+static std::atomic<int> g_wide_regacc{1};
 void count_launch(int n) { g_launches += n; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -995,9 +1006,9 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
   return KFB_OK;
 }
 
-template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG = 1, int MC = 1>
+template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG = 1, int MC = 1, int EW = 4>
 static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG, MC>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG, MC, EW>;
   p.m_blocks = (int)ceil_div_ll(p.M, Cfg::TILE_M);
   p.mc = MC;
   p.m_units = (int)ceil_div_ll(p.m_blocks, MC);
@@ -1074,7 +1085,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
     if (p.out_lo != nullptr)
       KFB_TRY(make_tmap(&to_lo, p.out_lo, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, 32, 32, false));
   }
-  auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG, MC>;
+  auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG, MC, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     KFB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1083,7 +1094,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   }
   constexpr int CLUSTER = CG * MC;
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1127,7 +1138,9 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
                        cudaStream_t stream) {
   // Tile width: as wide as N allows (wider tiles = more reuse of the A stage per MMA), except for
   // REGACC whose per-thread register accumulators limit it to 128.
-  const int bn = pick_bn(p.N, EPI == EPI_REGACC ? 128 : 256);
+  const bool wide_regacc = EPI == EPI_REGACC && nsplit == 2 && g_cta_pairs.load() != 0 && g_wide_regacc.load() != 0 &&
+                           p.M > 128 && p.N > 128;
+  const int bn = pick_bn(p.N, EPI == EPI_REGACC && !wide_regacc ? 128 : 256);
   // CTA pairs (M = 256 tiles) whenever the problem has at least two full 128-row tiles to pair up
   const bool pair = g_cta_pairs.load() != 0 && bn == 256 && p.M > 128;
   // Clusters of two CTA pairs on adjacent m-tiles fetch their common B tile once (TMA multicast): a quarter less
@@ -1147,6 +1160,10 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
   }
   // (measured: NOT for the register-accumulating kernels — with a TMEM drain every two k-blocks, coupling the two
   // pairs' stage releases costs more than the saved traffic: Lambda sweep 3.09 -> 3.49 ms on the BERT FFN layer)
+  if constexpr (EPI == EPI_REGACC) {
+    // 256-wide register-accumulating tiles on CTA pairs: two epilogue warpgroups of 128 accumulator columns each
+    if (wide_regacc && bn == 256) return launch_tc<256, 64, 2, EPI, 2, 1, 8>(A, B, p, stream);
+  }
   if (nsplit == 2) {
     if (EPI != EPI_REGACC && bn == 256 && pair) return launch_tc<256, 64, 2, EPI, 2>(A, B, p, stream);
     if (EPI != EPI_REGACC && bn == 256) return launch_tc<256, 32, 2, EPI>(A, B, p, stream);
@@ -1347,6 +1364,11 @@ int kfb_set_cta_pairs(int enable) {
 
 int kfb_set_multicast(int enable) {
   kfb::g_multicast.store(enable < 0 ? 0 : enable);
+  return KFB_OK;
+}
+
+int kfb_set_wide_regacc(int enable) {
+  kfb::g_wide_regacc.store(enable ? 1 : 0);
   return KFB_OK;
 }
 

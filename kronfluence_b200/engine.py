@@ -66,6 +66,7 @@ SIGNATURES = {
     "kfb_set_tma_store": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_multicast": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_strict_pass_k": (ctypes.c_int, [ctypes.c_int]),
+    "kfb_set_wide_regacc": (ctypes.c_int, [ctypes.c_int]),
     "kfb_launch_count": (_i64, []),
     "kfb_split_gather": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_i64), _vp, _SP, ctypes.c_int, _vp]),
     "kfb_split_im2col": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _i64, _i32, _SP, ctypes.c_int, _vp]),
@@ -136,7 +137,7 @@ def load_library() -> ctypes.CDLL:
     _lib = lib
     # debugging switches of the GEMM engine (A/B measurements): KFB_MULTICAST=0, KFB_TMA_STORE=0, KFB_CTA_PAIRS=0
     for env, setter in (("KFB_MULTICAST", lib.kfb_set_multicast), ("KFB_TMA_STORE", lib.kfb_set_tma_store),
-                        ("KFB_CTA_PAIRS", lib.kfb_set_cta_pairs)):
+                        ("KFB_CTA_PAIRS", lib.kfb_set_cta_pairs), ("KFB_WIDE_REGACC", lib.kfb_set_wide_regacc)):
         if os.environ.get(env, "").isdigit():
             setter(int(os.environ[env]))
     _register_cusolver(lib)
