@@ -1,26 +1,27 @@
 // The tensor-core engine of libkfb: a persistent, warp-specialised, batched NT GEMM for sm_100a.
 //
-//   D[b] (128 x BLOCK_N fp32 tile in TMEM)  =  sum_k  A[b][m,k] * B[b][n,k]
+//   D[b] (128 x BLOCK_N fp32 tile per CTA in TMEM)  =  sum_k  A[b][m,k] * B[b][n,k]
 //
-//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor.3d loads of the bf16 hi/lo planes of A
-//                      and B into a ring of 128B/64B-swizzled shared-memory stages (mbarrier
-//                      complete_tx signalling)
-//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16;
-//                      with KFB_PREC_FP32 three MMAs per k-step (lo*hi + hi*lo + hi*hi) into the
-//                      same fp32 accumulator; tcgen05.commit releases smem stages / publishes the
-//                      accumulator
-//   warp 2             TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the
-//                      MMAs of tile i+1)
-//   warps 4-7          epilogue: tcgen05.ld 32x32b (thread == accumulator row), then one of
-//                        STORE   fp32 and/or bf16 hi/lo store, optional transpose / square /
-//                                elementwise factor / accumulate / split-K atomics
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor.3d loads of the hi/lo operand planes (bf16; scaled FP16 for
+//                      KFB_PREC_STRICT) into a ring of 128B/64B-swizzled shared-memory stages (mbarrier complete_tx)
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma.kind::f16, K=16; cta_group::1 (M=128) or cta_group::2 CTA pairs (M=256,
+//                      each CTA stages its own A rows and half of B); with two planes three MMAs per k-step
+//                      (lo*hi + hi*lo + hi*hi) into the same fp32 accumulator; tcgen05.commit releases smem stages /
+//                      publishes the accumulator
+//   warp 2             TMEM allocator (2 accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4-7 (4-11)   epilogue: tcgen05.ld 32x32b (thread == accumulator row), then one of
+//                        STORE   fp32 and/or bf16 hi/lo planes (TMA bulk stores for plain planes), optional
+//                                transpose / square / elementwise factor / accumulate / split-K reductions /
+//                                SYRK mirroring / per-example column groups
 //                        ROWDOT  out[b,m] = sum_n D[m,n] g[m,n]   (fused pairwise-score epilogue:
 //                                module/linear.py:112-122 "qio,bi,bo->qb" without the [T,d_out]
 //                                intermediate), looping over all n-tiles of a (b, m-tile) unit
 //                        REGACC  fp32 register accumulation across TMEM passes: either over a chunk
 //                                of the batch with squaring, out[m,n] += sum_b D[b][m,n]^2 (Lambda
 //                                sweep, tracker/factor.py:218-226), or over k-chunks of one long
-//                                contraction (see kMaxPassK), finished by the STORE options
+//                                contraction (see kMaxPassK / kStrictPassK), finished by the STORE options;
+//                                256-wide tiles take two epilogue warpgroups (setmaxnreg re-balances registers)
+//   clusters           MC = 2: two CTA pairs on adjacent m-tiles fetch their common B tile once (TMA multicast)
 //
 // A second, trivially simple SIMT implementation of the same contract exists for debugging the
 // host logic (kfb_set_gemm_backend(1)); it is never selected implicitly.

@@ -366,7 +366,7 @@ static int lambda_run(const kfb_layer& L, const void* a, int a_dt, const void* g
 // rotating Pt_q back mixes its huge (nearly-null-direction) entries into every parameter, so that the
 // final dot product with G_t relies on cancellation.  In the eigenbasis every term of the score is a plain
 // product, and the only error Lambda^-1 can amplify is that of the rotated vectors, which are computed in
-// the strict 3-plane mode.  It also saves the two back-rotation GEMMs per query.  p_f32, if requested,
+// the strict mode (scaled FP16 hi/lo planes).  It also saves the two back-rotation GEMMs per query.  p_f32, if requested,
 // still receives the reference-layout P_q (two extra GEMMs; inspection / parity tests only).
 // =================================================================================================
 static int precondition_run(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt,
