@@ -305,29 +305,58 @@ class Analyzer:
             num_processed = count.cpu()
         return num_processed
 
-    def _run_factor_partitions(self, out_dir: Path, factor_names: List[str], data_parts, module_parts,
-                               fit_part: Callable[[int, int, List[str]], FACTOR_TYPE], overwrite: bool,
-                               metadata: Dict[str, str]) -> FACTOR_TYPE:
-        """Runs every (data, module) partition, summing the results.  With more than one partition each
-        result is also saved under the reference's partition file names and an existing file is reused
-        instead of recomputed — kronfluence's preemption / resume story (factor_computer.py:57-108,263-274)."""
-        partitioned = len(data_parts) > 1 or len(module_parts) > 1
+    @staticmethod
+    def _target_partitions(targets: Optional[Union[Sequence[int], int]], count: int, what: str) -> List[int]:
+        """`target_*_partitions` of the reference (computer/computer.py:218-257): None = all, an int or a list of
+        partition indices otherwise; out-of-range indices are an error."""
+        if targets is None:
+            return list(range(count))
+        chosen = [targets] if isinstance(targets, int) else list(targets)
+        for index in chosen:
+            if not 0 <= index < count:
+                raise ValueError(f"Invalid {what} partition {index}: there are {count} {what} partitions.")
+        return chosen
+
+    def _merge_factor_partitions(self, out_dir: Path, factor_names: List[str], n_data: int, n_module: int) -> Optional[FACTOR_TYPE]:
+        """Sum over data partitions, union over module partitions, of the partition files; None if one is missing
+        (factor_computer.py:57-108 `_aggregate_factors` of the reference)."""
         merged: FACTOR_TYPE = {name: {} for name in factor_names}
-        for d_idx, (start, end) in enumerate(data_parts):
-            for m_idx, names in enumerate(module_parts):
-                partition = (d_idx, m_idx)
-                if partitioned and not overwrite and io.factors_exist(out_dir, factor_names, partition):
-                    part = io.load_factors(out_dir, factor_names, partition)
-                else:
-                    part = fit_part(start, end, names)
-                    if partitioned:
-                        if self.state.is_main_process:
-                            io.save_factors(out_dir, part, partition=partition, metadata=metadata)
-                        self.state.wait_for_everyone()
+        for d_idx in range(n_data):
+            for m_idx in range(n_module):
+                if not io.factors_exist(out_dir, factor_names, (d_idx, m_idx)):
+                    return None
+                part = io.load_factors(out_dir, factor_names, (d_idx, m_idx))
                 for fname in factor_names:
                     for mname, tensor in part[fname].items():
                         merged[fname][mname] = tensor if mname not in merged[fname] else merged[fname][mname] + tensor
         return merged
+
+    def _run_factor_partitions(self, out_dir: Path, factor_names: List[str], data_parts, module_parts,
+                               fit_part: Callable[[int, int, List[str]], FACTOR_TYPE], overwrite: bool,
+                               metadata: Dict[str, str], target_data=None, target_module=None) -> Optional[FACTOR_TYPE]:
+        """Runs the requested (data, module) partitions and returns the merged factors, or None while partitions are
+        still missing.  With more than one partition each result is saved under the reference's partition file names
+        and an existing file is reused instead of recomputed — kronfluence's preemption / resume story
+        (factor_computer.py:57-108,263-274)."""
+        partitioned = len(data_parts) > 1 or len(module_parts) > 1
+        if not partitioned and (target_data is not None or target_module is not None):
+            raise ValueError("`target_data_partitions` or `target_module_partitions` were specified, while the "
+                             "`FactorArguments` did not expect any data and module partition to compute factors.")
+        chosen_data = self._target_partitions(target_data, len(data_parts), "data")
+        chosen_module = self._target_partitions(target_module, len(module_parts), "module")
+        if not partitioned:
+            return fit_part(data_parts[0][0], data_parts[0][1], module_parts[0])
+        for d_idx in chosen_data:
+            start, end = data_parts[d_idx]
+            for m_idx in chosen_module:
+                partition = (d_idx, m_idx)
+                if not overwrite and io.factors_exist(out_dir, factor_names, partition):
+                    continue
+                part = fit_part(start, end, module_parts[m_idx])
+                if self.state.is_main_process:
+                    io.save_factors(out_dir, part, partition=partition, metadata=metadata)
+                self.state.wait_for_everyone()
+        return self._merge_factor_partitions(out_dir, factor_names, len(data_parts), len(module_parts))
 
     def _resolve_batch_size(self, run: Callable[[int], Any], per_device_batch_size: Optional[int],
                             initial_attempt: int, total: int) -> int:
@@ -349,7 +378,6 @@ class Analyzer:
                                 target_data_partitions: Optional[Union[Sequence[int], int]] = None,
                                 target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                                 overwrite_output_dir: bool = False) -> None:
-        del target_data_partitions, target_module_partitions
         factor_args = FactorArguments() if factor_args is None else factor_args
         out_dir = self.factors_output_dir(factors_name)
         if self.state.is_main_process:
@@ -393,7 +421,10 @@ class Analyzer:
 
         with self.profiler.profile("Fit Covariance"):
             merged = self._run_factor_partitions(out_dir, COVARIANCE_FACTOR_NAMES, data_parts, module_parts, fit_part,
-                                                 overwrite_output_dir, factor_args.to_str_dict())
+                                                 overwrite_output_dir, factor_args.to_str_dict(),
+                                                 target_data_partitions, target_module_partitions)
+        if merged is None:  # some partitions are still to be fitted (by another call / job)
+            return
         with self.profiler.profile("Save Covariance"):
             if self.state.is_main_process:
                 io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
@@ -465,7 +496,6 @@ class Analyzer:
                             target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                             overwrite_output_dir: bool = False,
                             load_from_factors_name: Optional[str] = None) -> None:
-        del target_data_partitions, target_module_partitions
         factor_args = FactorArguments() if factor_args is None else factor_args
         out_dir = self.factors_output_dir(factors_name)
         if self.state.is_main_process:
@@ -519,7 +549,10 @@ class Analyzer:
 
         with self.profiler.profile("Fit Lambda"):
             merged = self._run_factor_partitions(out_dir, LAMBDA_FACTOR_NAMES, data_parts, module_parts, fit_part,
-                                                 overwrite_output_dir, factor_args.to_str_dict())
+                                                 overwrite_output_dir, factor_args.to_str_dict(),
+                                                 target_data_partitions, target_module_partitions)
+        if merged is None:
+            return
         with self.profiler.profile("Save Lambda"):
             if self.state.is_main_process:
                 io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
@@ -530,6 +563,29 @@ class Analyzer:
         if not io.factors_exist(out_dir, LAMBDA_FACTOR_NAMES):
             return None
         return io.load_factors(out_dir, LAMBDA_FACTOR_NAMES)
+
+    def _aggregate_factors(self, factors_name: str, factor_names: List[str], data_key: str, module_key: str) -> None:
+        out_dir = self.factors_output_dir(factors_name)
+        factor_args = self._load_factor_args(factors_name)
+        n_data, n_module = getattr(factor_args, data_key), getattr(factor_args, module_key)
+        if n_data == 1 and n_module == 1:
+            return
+        merged = self._merge_factor_partitions(out_dir, factor_names, n_data, n_module)
+        if merged is None:
+            self.logger.warning("Some partitions of `%s` are missing at %s; nothing aggregated.", factors_name, out_dir)
+            return
+        if self.state.is_main_process:
+            io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
+        self.state.wait_for_everyone()
+
+    def aggregate_covariance_matrices(self, factors_name: str) -> None:
+        """Sums the partition files into `*_covariance.safetensors` (factor_computer.py:276-297 of the reference)."""
+        self._aggregate_factors(factors_name, COVARIANCE_FACTOR_NAMES, "covariance_data_partitions",
+                                "covariance_module_partitions")
+
+    def aggregate_lambda_matrices(self, factors_name: str) -> None:
+        """Sums the partition files into `lambda_matrix.safetensors` (factor_computer.py:715-736 of the reference)."""
+        self._aggregate_factors(factors_name, LAMBDA_FACTOR_NAMES, "lambda_data_partitions", "lambda_module_partitions")
 
     def fit_all_factors(self, factors_name: str, dataset: data.Dataset, per_device_batch_size: Optional[int] = None,
                         initial_per_device_batch_size_attempt: int = 4096,
@@ -803,7 +859,6 @@ class Analyzer:
                                 target_data_partitions: Optional[Union[Sequence[int], int]] = None,
                                 target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                                 overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
-        del target_data_partitions, target_module_partitions
         score_args = ScoreArguments() if score_args is None else score_args
         if self.task.enable_post_process_per_sample_gradient:
             raise NotImplementedError("`post_process_per_sample_gradient` needs materialised gradients; unsupported.")
@@ -830,48 +885,89 @@ class Analyzer:
         base_train = list(train_indices) if train_indices is not None else list(range(n_train))
 
         partitioned = len(data_parts) > 1 or len(module_parts) > 1
+        if not partitioned and (target_data_partitions is not None or target_module_partitions is not None):
+            raise ValueError("`target_data_partitions` or `target_module_partitions` were specified, while the "
+                             "`ScoreArguments` did not expect any data and module partition to compute pairwise scores.")
+        chosen_data = self._target_partitions(target_data_partitions, len(data_parts), "data")
+        chosen_module = self._target_partitions(target_module_partitions, len(module_parts), "module")
+        scores: Optional[Dict[str, torch.Tensor]] = None
         with self.profiler.profile("Compute Pairwise Score"):
-            column_blocks: List[Dict[str, torch.Tensor]] = []
-            for d_idx, (start, end) in enumerate(data_parts):
-                block: Dict[str, torch.Tensor] = {}
-                for m_idx, names in enumerate(module_parts):
+            for d_idx in chosen_data:
+                start, end = data_parts[d_idx]
+                for m_idx in chosen_module:
+                    names = module_parts[m_idx]
                     partition = (d_idx, m_idx)
-                    part_path = io.scores_path(out_dir, partition)
-                    if partitioned and part_path.exists() and not overwrite_output_dir:
-                        part = io.load_file(part_path)  # resume (score_computer.py:77-139 of the reference)
+                    if partitioned and io.scores_path(out_dir, partition).exists() and not overwrite_output_dir:
+                        continue  # resume (score_computer.py:362-378 of the reference)
+                    set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                    self._prepare_for_scores(factors, factor_args, score_args, names)
+
+                    def run(batch_size: int, start=start, end=end, names=names) -> Dict[str, torch.Tensor]:
+                        return self._pairwise(query_dataset, train_dataset, per_device_query_batch_size, batch_size,
+                                              query_indices, base_train[start:end], factor_args, score_args, names,
+                                              dataloader_kwargs)
+
+                    if per_device_train_batch_size is None:
+                        holder: Dict[str, Any] = {}
+
+                        def probe(batch_size: int) -> None:
+                            holder["scores"] = run(batch_size)
+
+                        self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, end - start)
+                        part = holder["scores"]
                     else:
-                        set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-                        self._prepare_for_scores(factors, factor_args, score_args, names)
-
-                        def run(batch_size: int) -> Dict[str, torch.Tensor]:
-                            return self._pairwise(query_dataset, train_dataset, per_device_query_batch_size, batch_size,
-                                                  query_indices, base_train[start:end], factor_args, score_args, names,
-                                                  dataloader_kwargs)
-
-                        if per_device_train_batch_size is None:
-                            holder: Dict[str, Any] = {}
-
-                            def probe(batch_size: int) -> None:
-                                holder["scores"] = run(batch_size)
-
-                            self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, end - start)
-                            part = holder["scores"]
-                        else:
-                            part = run(per_device_train_batch_size)
-                        if partitioned:
-                            if self.state.is_main_process:
-                                io.save_scores(out_dir, part, partition=partition, metadata=score_args.to_str_dict())
-                            self.state.wait_for_everyone()
-                    for key, value in part.items():
-                        block[key] = value if key not in block else block[key] + value
-                column_blocks.append(block)
-            scores = {key: torch.cat([blk[key] for blk in column_blocks], dim=1) for key in column_blocks[0]}
+                        part = run(per_device_train_batch_size)
+                    if partitioned:
+                        if self.state.is_main_process:
+                            io.save_scores(out_dir, part, partition=partition, metadata=score_args.to_str_dict())
+                        self.state.wait_for_everyone()
+                    else:
+                        scores = part
+        if partitioned:
+            # every partition present: concatenate the data partitions, sum the module partitions
+            scores = self._merge_score_partitions(out_dir, len(data_parts), len(module_parts))
+            if scores is None:
+                release_memory()
+                return None  # the remaining partitions belong to another call (`target_*_partitions`)
         with self.profiler.profile("Save Pairwise Score"):
             if self.state.is_main_process:
                 io.save_scores(out_dir, scores, metadata=score_args.to_str_dict())
             self.state.wait_for_everyone()
         release_memory()
         return scores
+
+    def _merge_score_partitions(self, out_dir: Path, n_data: int, n_module: int) -> Optional[Dict[str, torch.Tensor]]:
+        """score_computer.py:77-139 `_aggregate_scores` of the reference: module partitions add up, data partitions
+        are concatenated along the train axis; None if a partition file is missing."""
+        blocks: List[Dict[str, torch.Tensor]] = []
+        for d_idx in range(n_data):
+            block: Dict[str, torch.Tensor] = {}
+            for m_idx in range(n_module):
+                path = io.scores_path(out_dir, (d_idx, m_idx))
+                if not path.exists():
+                    return None
+                for key, value in io.load_file(path).items():
+                    block[key] = value if key not in block else block[key] + value
+            blocks.append(block)
+        return {key: torch.cat([blk[key] for blk in blocks], dim=1) for key in blocks[0]}
+
+    def aggregate_pairwise_scores(self, scores_name: str) -> None:
+        """Aggregates the partition files into `pairwise_scores.safetensors`; nothing happens while partitions are
+        missing (score_computer.py:467-494 of the reference)."""
+        out_dir = self.scores_output_dir(scores_name)
+        args_path = out_dir / f"{SCORE_ARGUMENTS_NAME}_arguments.json"
+        if not args_path.exists():
+            raise ValueError(f"Arguments for scores with name `{scores_name}` were not found at `{out_dir}`.")
+        score_args = ScoreArguments(**io.load_json(args_path))
+        if score_args.data_partitions == 1 and score_args.module_partitions == 1:
+            return
+        scores = self._merge_score_partitions(out_dir, score_args.data_partitions, score_args.module_partitions)
+        if scores is None:
+            self.logger.warning("Some score partitions of `%s` are missing at %s; nothing aggregated.", scores_name, out_dir)
+            return
+        if self.state.is_main_process:
+            io.save_scores(out_dir, scores, metadata=score_args.to_str_dict())
+        self.state.wait_for_everyone()
 
     def load_pairwise_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:
         path = io.scores_path(self.scores_output_dir(scores_name))

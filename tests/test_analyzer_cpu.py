@@ -253,3 +253,63 @@ def test_self_scores_with_measurement(case, tmp_path):
     got = scores["all_modules"].numpy()
     assert got.shape == golden["f32/self_scores_measurement"].shape
     assert rel(got, golden["f32/self_scores_measurement"]) < 5e-5
+
+
+def test_target_partitions_and_aggregation(tmp_path):
+    """`target_data_partitions` / `target_module_partitions` (computer/computer.py:218-257 of the reference): one call
+    per partition, e.g. from separate jobs; the aggregated file appears once the last partition is in, and equals
+    the unpartitioned result.  Also `aggregate_*` and the error paths."""
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_mlp.npz")))
+    tasks = fixtures.make_tasks(Task)
+    from kronfluence_b200.utils import save as io
+
+    with oracle_backend():
+        model, train_set, query_set = fixtures.make_case("mlp")
+        task = tasks["mlp"]()
+        model = prepare_model(model, task)
+        analyzer = Analyzer("cpu", model, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        fa = FactorArguments(strategy="ekfac", use_empirical_fisher=True, covariance_data_partitions=2,
+                             lambda_data_partitions=2, lambda_module_partitions=2)
+        with pytest.raises(ValueError, match="Invalid data partition"):
+            analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8, factor_args=fa,
+                                             target_data_partitions=[2])
+        analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8, factor_args=fa, target_data_partitions=0)
+        assert analyzer.load_covariance_matrices("f") is None          # partition 1 is still missing
+        analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8, factor_args=fa, target_data_partitions=[1])
+        cov = analyzer.load_covariance_matrices("f")
+        for key in ("activation_covariance", "gradient_covariance"):
+            for mname, tensor in cov[key].items():
+                assert rel(tensor.numpy(), golden[f"f32/{key}/{mname}"]) < 1e-5
+        analyzer.perform_eigendecomposition("f", fa)
+        eig = analyzer.load_eigendecomposition("f")
+        for fname in eig:
+            for mname in eig[fname]:
+                eig[fname][mname] = torch.from_numpy(golden[f"f32/{fname}/{mname}"])
+        io.save_factors(analyzer.factors_output_dir("f"), eig)
+        for d_idx in (1, 0):
+            for m_idx in (0, 1):
+                analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=8, factor_args=fa,
+                                             target_data_partitions=d_idx, target_module_partitions=[m_idx])
+                done = analyzer.load_lambda_matrices("f") is not None
+                assert done == (d_idx == 0 and m_idx == 1)
+        os.remove(analyzer.factors_output_dir("f") / "lambda_matrix.safetensors")
+        os.remove(analyzer.factors_output_dir("f") / "num_lambda_processed.safetensors")
+        analyzer.aggregate_lambda_matrices("f")                          # rebuilt from the partition files
+        lam = analyzer.load_lambda_matrices("f")
+        for mname, tensor in lam["lambda_matrix"].items():
+            assert rel(tensor.numpy(), golden[f"f32/lambda_matrix/{mname}"]) < 5e-5
+
+        sa = ScoreArguments(damping_factor=None, data_partitions=3, module_partitions=2)
+        kwargs = dict(per_device_query_batch_size=4, per_device_train_batch_size=8, score_args=sa)
+        with pytest.raises(ValueError, match="did not expect any data and module partition"):
+            analyzer.compute_pairwise_scores("plain", "f", query_set, train_set, per_device_query_batch_size=4,
+                                             per_device_train_batch_size=8,
+                                             score_args=ScoreArguments(damping_factor=None), target_data_partitions=[0])
+        for d_idx in range(3):
+            out = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, target_data_partitions=[d_idx], **kwargs)
+            assert (out is None) == (d_idx < 2)
+        assert rel(out["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
+        os.remove(analyzer.scores_output_dir("s") / "pairwise_scores.safetensors")
+        assert analyzer.load_pairwise_scores("s") is None
+        analyzer.aggregate_pairwise_scores("s")
+        assert rel(analyzer.load_pairwise_scores("s")["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
