@@ -988,7 +988,6 @@ class Analyzer:
         """self[t] = sum_modules <P(grad L(z_t)), grad L(z_t)>  (score_computer.py:558-770, score/self.py:135-290
         of the reference).  With `use_measurement_for_self_influence` the preconditioned side is the gradient of the
         measurement: self[t] = sum_modules <P(grad M(z_t)), grad L(z_t)>  (score/self.py:293-443)."""
-        del target_data_partitions, target_module_partitions
         score_args = ScoreArguments() if score_args is None else score_args
         # score_computer.py:617-640 of the reference: options that do not apply to self-influence are switched off
         for key, off in (("query_gradient_accumulation_steps", 1), ("query_gradient_low_rank", None),
@@ -1016,131 +1015,207 @@ class Analyzer:
         modules = tracked_modules(self.model, names)
         device = self.state.device
 
-        def run_with_measurement(batch_size: int) -> Dict[str, torch.Tensor]:
-            """score/self.py:293-443 of the reference: per batch, precondition the MEASUREMENT gradients of its
-            examples (PRECONDITION_GRADIENT mode, one store slot per example), then contract them example by example
-            with the LOSS gradients.  The contraction reuses the pairwise kernels on the batch against itself and
-            keeps the diagonal of the [B, B] tile (a fused diagonal epilogue is the obvious next step)."""
-            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-            self._prepare_for_scores(factors, factor_args, score_args, names)
-            loader = self._loader(train_dataset, batch_size, train_indices, "stack", dataloader_kwargs)
-            scaler, autocast = self._amp(score_args.amp_dtype, factor_args.amp_scale)
-            per_module = score_args.compute_per_module_scores
-            chunks: Dict[str, List[torch.Tensor]] = {m.name: [] for m in modules} if per_module else {ALL_MODULE_NAME: []}
-            set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
-            for module in modules:
-                module.allocate_query_store(batch_size, device)
-            for batch in loader:
-                batch = _send_to_device(batch, device)
-                count = _find_batch_size(batch)
+        def make_runner(names: List[str], train_indices: Optional[Sequence[int]], n_train: int):
+            """`run(batch_size)` for one (data, module) partition: the modules `names` on the examples `train_indices`."""
+            modules = tracked_modules(self.model, names)
+
+            def run_with_measurement(batch_size: int) -> Dict[str, torch.Tensor]:
+                """score/self.py:293-443 of the reference: per batch, precondition the MEASUREMENT gradients of its
+                examples (PRECONDITION_GRADIENT mode, one store slot per example), then contract them example by example
+                with the LOSS gradients.  The contraction reuses the pairwise kernels on the batch against itself and
+                keeps the diagonal of the [B, B] tile (a fused diagonal epilogue is the obvious next step)."""
+                set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                self._prepare_for_scores(factors, factor_args, score_args, names)
+                loader = self._loader(train_dataset, batch_size, train_indices, "stack", dataloader_kwargs)
+                scaler, autocast = self._amp(score_args.amp_dtype, factor_args.amp_scale)
+                per_module = score_args.compute_per_module_scores
+                chunks: Dict[str, List[torch.Tensor]] = {m.name: [] for m in modules} if per_module else {ALL_MODULE_NAME: []}
                 set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
                 for module in modules:
-                    module.query_count = 0
+                    module.allocate_query_store(batch_size, device)
+                for batch in loader:
+                    batch = _send_to_device(batch, device)
+                    count = _find_batch_size(batch)
+                    set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
+                    for module in modules:
+                        module.query_count = 0
+                    self.model.zero_grad(set_to_none=True)
+                    with autocast():
+                        measurement = self.task.compute_measurement(batch=batch, model=self.model)
+                    scaler.scale(measurement).backward()
+                    if factor_args.has_shared_parameters:
+                        finalize_iteration(self.model, names)
+                    del measurement
+                    set_mode(self.model, ModuleMode.PAIRWISE_SCORE, names, release_memory=False)
+                    if per_module:
+                        sinks = {m.name: ScoreSink(count, count, device, False) for m in modules}
+                    else:
+                        shared_sink = ScoreSink(count, count, device, False)
+                        sinks = {m.name: shared_sink for m in modules}
+                    for module in modules:
+                        module.storage[PAIRWISE_SCORE_MATRIX_NAME] = sinks[module.name]
+                        module.score_offset = 0
+                    self.model.zero_grad(set_to_none=True)
+                    with autocast():
+                        loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
+                    scaler.scale(loss).backward()
+                    if factor_args.has_shared_parameters:
+                        finalize_iteration(self.model, names)
+                    del loss
+                    for key in chunks:
+                        chunks[key].append(torch.diagonal(sinks[key if per_module else modules[0].name].result()).clone())
+                    for module in modules:
+                        module.storage[PAIRWISE_SCORE_MATRIX_NAME] = None
                 self.model.zero_grad(set_to_none=True)
-                with autocast():
-                    measurement = self.task.compute_measurement(batch=batch, model=self.model)
-                scaler.scale(measurement).backward()
-                if factor_args.has_shared_parameters:
-                    finalize_iteration(self.model, names)
-                del measurement
-                set_mode(self.model, ModuleMode.PAIRWISE_SCORE, names, release_memory=False)
-                if per_module:
-                    sinks = {m.name: ScoreSink(count, count, device, False) for m in modules}
-                else:
-                    shared_sink = ScoreSink(count, count, device, False)
-                    sinks = {m.name: shared_sink for m in modules}
-                for module in modules:
-                    module.storage[PAIRWISE_SCORE_MATRIX_NAME] = sinks[module.name]
-                    module.score_offset = 0
-                self.model.zero_grad(set_to_none=True)
-                with autocast():
-                    loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
-                scaler.scale(loss).backward()
-                if factor_args.has_shared_parameters:
-                    finalize_iteration(self.model, names)
-                del loss
-                for key in chunks:
-                    chunks[key].append(torch.diagonal(sinks[key if per_module else modules[0].name].result()).clone())
-                for module in modules:
-                    module.storage[PAIRWISE_SCORE_MATRIX_NAME] = None
-            self.model.zero_grad(set_to_none=True)
-            out: Dict[str, torch.Tensor] = {}
-            for key, parts in chunks.items():
-                local = torch.cat(parts, dim=0) if parts else torch.zeros(0, dtype=torch.float32, device=device)
-                if self.state.use_distributed:
-                    gathered = [torch.empty_like(local) for _ in range(self.state.num_processes)] \
-                        if self.state.is_main_process else None
-                    dist.gather(local, gathered, dst=0)
-                    if self.state.is_main_process:
-                        local = torch.cat(gathered, dim=0)[:n_train]
-                out[key] = local.to(dtype=score_args.score_dtype, device="cpu")
-            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-            if scaler.is_enabled():
-                set_gradient_scale(self.model, 1.0)
-            return out
+                out: Dict[str, torch.Tensor] = {}
+                for key, parts in chunks.items():
+                    local = torch.cat(parts, dim=0) if parts else torch.zeros(0, dtype=torch.float32, device=device)
+                    if self.state.use_distributed:
+                        gathered = [torch.empty_like(local) for _ in range(self.state.num_processes)] \
+                            if self.state.is_main_process else None
+                        dist.gather(local, gathered, dst=0)
+                        if self.state.is_main_process:
+                            local = torch.cat(gathered, dim=0)[:n_train]
+                    out[key] = local.to(dtype=score_args.score_dtype, device="cpu")
+                set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                if scaler.is_enabled():
+                    set_gradient_scale(self.model, 1.0)
+                return out
 
-        def run(batch_size: int) -> Dict[str, torch.Tensor]:
-            if score_args.use_measurement_for_self_influence:
-                return run_with_measurement(batch_size)
-            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-            self._prepare_for_scores(factors, factor_args, score_args, names)
-            loader = self._loader(train_dataset, batch_size, train_indices, "stack", dataloader_kwargs)
-            t_local = len(loader.sampler) if self.state.use_distributed else n_train
-            scaler, autocast = self._amp(score_args.amp_dtype, factor_args.amp_scale)
-            set_mode(self.model, ModuleMode.SELF_SCORE, names, release_memory=False)
-            per_module = score_args.compute_per_module_scores
-            shared = None if per_module else torch.zeros(t_local, dtype=torch.float32, device=device)
-            sinks = {m.name: (torch.zeros(t_local, dtype=torch.float32, device=device) if per_module else shared)
-                     for m in modules}
-            for module in modules:
-                module.storage[SELF_SCORE_VECTOR_NAME] = sinks[module.name]
-            offset = 0
-            for batch in loader:
-                batch = _send_to_device(batch, device)
+            def run(batch_size: int) -> Dict[str, torch.Tensor]:
+                if score_args.use_measurement_for_self_influence:
+                    return run_with_measurement(batch_size)
+                set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                self._prepare_for_scores(factors, factor_args, score_args, names)
+                loader = self._loader(train_dataset, batch_size, train_indices, "stack", dataloader_kwargs)
+                t_local = len(loader.sampler) if self.state.use_distributed else n_train
+                scaler, autocast = self._amp(score_args.amp_dtype, factor_args.amp_scale)
+                set_mode(self.model, ModuleMode.SELF_SCORE, names, release_memory=False)
+                per_module = score_args.compute_per_module_scores
+                shared = None if per_module else torch.zeros(t_local, dtype=torch.float32, device=device)
+                sinks = {m.name: (torch.zeros(t_local, dtype=torch.float32, device=device) if per_module else shared)
+                         for m in modules}
                 for module in modules:
-                    module.score_offset = offset
+                    module.storage[SELF_SCORE_VECTOR_NAME] = sinks[module.name]
+                offset = 0
+                for batch in loader:
+                    batch = _send_to_device(batch, device)
+                    for module in modules:
+                        module.score_offset = offset
+                    self.model.zero_grad(set_to_none=True)
+                    with autocast():
+                        loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
+                    scaler.scale(loss).backward()
+                    if factor_args.has_shared_parameters:
+                        finalize_iteration(self.model, names)
+                    offset += _find_batch_size(batch)
+                    del loss
                 self.model.zero_grad(set_to_none=True)
-                with autocast():
-                    loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
-                scaler.scale(loss).backward()
-                if factor_args.has_shared_parameters:
-                    finalize_iteration(self.model, names)
-                offset += _find_batch_size(batch)
-                del loss
-            self.model.zero_grad(set_to_none=True)
-            results = {m.name: sinks[m.name] for m in modules} if per_module else {ALL_MODULE_NAME: shared}
-            out: Dict[str, torch.Tensor] = {}
-            for key, local in results.items():
-                if self.state.use_distributed:
-                    gathered = [torch.empty_like(local) for _ in range(self.state.num_processes)] \
-                        if self.state.is_main_process else None
-                    dist.gather(local, gathered, dst=0)
-                    if self.state.is_main_process:
-                        local = torch.cat(gathered, dim=0)[:n_train]
-                out[key] = local.to(dtype=score_args.score_dtype, device="cpu")
-            set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
-            if scaler.is_enabled():
-                set_gradient_scale(self.model, 1.0)
-            return out
+                results = {m.name: sinks[m.name] for m in modules} if per_module else {ALL_MODULE_NAME: shared}
+                out: Dict[str, torch.Tensor] = {}
+                for key, local in results.items():
+                    if self.state.use_distributed:
+                        gathered = [torch.empty_like(local) for _ in range(self.state.num_processes)] \
+                            if self.state.is_main_process else None
+                        dist.gather(local, gathered, dst=0)
+                        if self.state.is_main_process:
+                            local = torch.cat(gathered, dim=0)[:n_train]
+                    out[key] = local.to(dtype=score_args.score_dtype, device="cpu")
+                set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
+                if scaler.is_enabled():
+                    set_gradient_scale(self.model, 1.0)
+                return out
 
+            return run
+
+        all_names = names
+        base_train = list(train_indices) if train_indices is not None else list(range(n_train))
+        data_parts = make_indices_partition(n_train, score_args.data_partitions)
+        module_parts = make_modules_partition(all_names, score_args.module_partitions)
+        partitioned = len(data_parts) > 1 or len(module_parts) > 1
+        if not partitioned and (target_data_partitions is not None or target_module_partitions is not None):
+            raise ValueError("`target_data_partitions` or `target_module_partitions` were specified, while the "
+                             "`ScoreArguments` did not expect any data and module partition to compute self-influence scores.")
+        chosen_data = self._target_partitions(target_data_partitions, len(data_parts), "data")
+        chosen_module = self._target_partitions(target_module_partitions, len(module_parts), "module")
+        from safetensors.torch import save_file
+
+        scores: Optional[Dict[str, torch.Tensor]] = None
         with self.profiler.profile("Compute Self-Influence Score"):
-            if per_device_train_batch_size is None:
-                holder: Dict[str, Any] = {}
+            for d_idx in chosen_data:
+                start, end = data_parts[d_idx]
+                for m_idx in chosen_module:
+                    part_path = self._self_scores_path(out_dir, (d_idx, m_idx))
+                    if partitioned and part_path.exists() and not overwrite_output_dir:
+                        continue
+                    indices = base_train[start:end] if (partitioned or train_indices is not None) else None
+                    run = make_runner(module_parts[m_idx], indices, end - start)
+                    if per_device_train_batch_size is None:
+                        holder: Dict[str, Any] = {}
 
-                def probe(batch_size: int) -> None:
-                    holder["scores"] = run(batch_size)
+                        def probe(batch_size: int, run=run, holder=holder) -> None:
+                            holder["scores"] = run(batch_size)
 
-                self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, n_train)
-                scores = holder["scores"]
-            else:
-                scores = run(per_device_train_batch_size)
+                        self._resolve_batch_size(probe, None, initial_per_device_train_batch_size_attempt, end - start)
+                        part = holder["scores"]
+                    else:
+                        part = run(per_device_train_batch_size)
+                    if partitioned:
+                        if self.state.is_main_process:
+                            save_file({k: v.contiguous() for k, v in part.items()}, str(part_path),
+                                      metadata=score_args.to_str_dict())
+                        self.state.wait_for_everyone()
+                    else:
+                        scores = part
+        if partitioned:
+            scores = self._merge_self_score_partitions(out_dir, len(data_parts), len(module_parts))
+            if scores is None:
+                return None  # the remaining partitions belong to another call
         with self.profiler.profile("Save Self-Influence Score"):
             if self.state.is_main_process:
-                from safetensors.torch import save_file
-
                 save_file({k: v.contiguous() for k, v in scores.items()}, str(path), metadata=score_args.to_str_dict())
             self.state.wait_for_everyone()
         return scores
+
+    @staticmethod
+    def _self_scores_path(out_dir: Path, partition: Optional[tuple] = None) -> Path:
+        if partition is None:
+            return out_dir / "self_scores.safetensors"
+        return out_dir / f"self_scores_data_partition{partition[0]}_module_partition{partition[1]}.safetensors"
+
+    def _merge_self_score_partitions(self, out_dir: Path, n_data: int, n_module: int) -> Optional[Dict[str, torch.Tensor]]:
+        """Module partitions add up, data partitions are concatenated (score_computer.py:77-139, dim=0)."""
+        blocks: List[Dict[str, torch.Tensor]] = []
+        for d_idx in range(n_data):
+            block: Dict[str, torch.Tensor] = {}
+            for m_idx in range(n_module):
+                part_path = self._self_scores_path(out_dir, (d_idx, m_idx))
+                if not part_path.exists():
+                    return None
+                for key, value in io.load_file(part_path).items():
+                    block[key] = value if key not in block else block[key] + value
+            blocks.append(block)
+        return {key: torch.cat([blk[key] for blk in blocks], dim=0) for key in blocks[0]}
+
+    def aggregate_self_scores(self, scores_name: str) -> None:
+        """Aggregates the partition files into `self_scores.safetensors` (score_computer.py:772-799 of the reference)."""
+        out_dir = self.scores_output_dir(scores_name)
+        args_path = out_dir / f"{SCORE_ARGUMENTS_NAME}_arguments.json"
+        if not args_path.exists():
+            raise ValueError(f"Arguments for scores with name `{scores_name}` were not found at `{out_dir}`.")
+        score_args = ScoreArguments(**io.load_json(args_path))
+        if score_args.data_partitions == 1 and score_args.module_partitions == 1:
+            return
+        scores = self._merge_self_score_partitions(out_dir, score_args.data_partitions, score_args.module_partitions)
+        if scores is None:
+            self.logger.warning("Some score partitions of `%s` are missing at %s; nothing aggregated.", scores_name, out_dir)
+            return
+        if self.state.is_main_process:
+            from safetensors.torch import save_file
+
+            save_file({k: v.contiguous() for k, v in scores.items()}, str(self._self_scores_path(out_dir)),
+                      metadata=score_args.to_str_dict())
+        self.state.wait_for_everyone()
 
     def load_self_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:
         path = self.scores_output_dir(scores_name) / "self_scores.safetensors"

@@ -313,3 +313,14 @@ def test_target_partitions_and_aggregation(tmp_path):
         assert analyzer.load_pairwise_scores("s") is None
         analyzer.aggregate_pairwise_scores("s")
         assert rel(analyzer.load_pairwise_scores("s")["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
+
+        # self-influence: data partitions concatenate, module partitions add up
+        sa_self = ScoreArguments(damping_factor=None, data_partitions=2, module_partitions=2)
+        first = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=8, score_args=sa_self,
+                                             target_data_partitions=[1])
+        assert first is None and analyzer.load_self_scores("self") is None
+        full = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=8, score_args=sa_self)
+        assert rel(full["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
+        os.remove(analyzer.scores_output_dir("self") / "self_scores.safetensors")
+        analyzer.aggregate_self_scores("self")
+        assert rel(analyzer.load_self_scores("self")["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
