@@ -120,6 +120,14 @@ class BaseTracker:
         while self.cached_hooks:
             self.cached_hooks.pop().remove()
 
+    def _drop_cached_tensors(self) -> None:
+        """End of one use's backward hook: the cached tensors go, but tensor hooks of OTHER uses of the module stay
+        registered, so that a module that is used twice without `has_shared_parameters` fails loudly in its second
+        backward hook (no cached activation) instead of silently scoring one use — tracker/base.py:41-48 of the
+        reference."""
+        self.cached_activations = []
+        self.cached_gradients = []
+
     def _no_cache_error(self) -> None:
         raise RuntimeError(
             f"Module '{self.module.name}' has no cached activations. This can occur if:\n"
@@ -246,7 +254,7 @@ class LambdaTracker(BaseTracker):
                 self.cached_gradients.append(grad.detach().clone())
                 return
             self._update(self.cached_activations[0], grad.detach())
-            self.clear_all_cache()
+            self._drop_cached_tensors()
 
         self.registered_hooks.append(module.register_forward_hook(forward_hook))
 
@@ -314,7 +322,7 @@ class PreconditionTracker(BaseTracker):
                 self.cached_gradients.append(grad.detach().clone())
                 return
             self._update(self.cached_activations[0], grad.detach())
-            self.clear_all_cache()
+            self._drop_cached_tensors()
 
         self.registered_hooks.append(module.register_forward_hook(forward_hook))
 
@@ -377,7 +385,7 @@ class GradientAggregationTracker(BaseTracker):
                 self.cached_gradients.append(grad.detach().clone())
                 return
             self._update(self.cached_activations[0], grad.detach())
-            self.clear_all_cache()
+            self._drop_cached_tensors()
 
         self.registered_hooks.append(module.register_forward_hook(forward_hook))
 
@@ -437,7 +445,7 @@ class PairwiseScoreTracker(BaseTracker):
                                             precision=precision_of(module.score_args.score_dtype), qa=qa, qg=qg,
                                             per_token=sink.per_token)
                 if not module.factor_args.has_shared_parameters:
-                    self.clear_all_cache()
+                    self._drop_cached_tensors()
                 return
             if sink.per_token:
                 # "qio,bti,bto->qbt" (linear.py:100-111 of the reference): every token is scored like an example
@@ -454,7 +462,7 @@ class PairwiseScoreTracker(BaseTracker):
                                 module.score_offset * tokens, accumulate=True, scale=module.gradient_scale,
                                 precision=precision_of(module.score_args.score_dtype), qa=qa, qg=qg)
             if not module.factor_args.has_shared_parameters:
-                self.clear_all_cache()
+                self._drop_cached_tensors()
 
         self.registered_hooks.append(module.register_forward_hook(forward_hook))
 
@@ -508,7 +516,7 @@ class SelfScoreTracker(BaseTracker):
                 self.cached_gradients.append(grad.detach().clone())
                 return
             self._update(self.cached_activations[0], grad.detach())
-            self.clear_all_cache()
+            self._drop_cached_tensors()
 
         self.registered_hooks.append(module.register_forward_hook(forward_hook))
 

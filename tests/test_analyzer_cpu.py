@@ -324,3 +324,124 @@ def test_target_partitions_and_aggregation(tmp_path):
         os.remove(analyzer.scores_output_dir("self") / "self_scores.safetensors")
         analyzer.aggregate_self_scores("self")
         assert rel(analyzer.load_self_scores("self")["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
+
+
+@pytest.mark.parametrize("case", ["mlp", "conv"])
+def test_self_scores_are_the_diagonal_of_pairwise(case, tmp_path):
+    """tests/scores/test_self_scores.py:453-511 of the reference: with the train set as the query set and the
+    measurement equal to the loss, self-influence is the diagonal of the pairwise matrix."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    tasks = fixtures.make_tasks(Task)
+
+    class LossAsMeasurement(tasks[case]):
+        def compute_measurement(self, batch, model):
+            return self.compute_train_loss(batch, model, sample=False)
+
+    with oracle_backend():
+        analyzer, _ = run_case(case, tmp_path, inject_eigen=golden)
+        analyzer.task = LossAsMeasurement()
+        _, train_set, _ = fixtures.make_case(case)
+        subset = list(range(0, len(train_set), 2))
+        pair = analyzer.compute_pairwise_scores("diag", "f", train_set, train_set, per_device_query_batch_size=3,
+                                                per_device_train_batch_size=5, query_indices=subset, train_indices=subset,
+                                                score_args=ScoreArguments(damping_factor=None))
+        own = analyzer.compute_self_scores("own", "f", train_set, per_device_train_batch_size=4, train_indices=subset,
+                                           score_args=ScoreArguments(damping_factor=None))
+    diag = torch.diagonal(pair["all_modules"]).numpy()
+    assert diag.shape == own["all_modules"].shape == (len(subset),)
+    assert rel(own["all_modules"].numpy(), diag) < 1e-5
+    assert rel(own["all_modules"].numpy(), golden["f32/self_scores"][::2]) < 5e-5
+
+
+def test_shared_parameters(tmp_path):
+    """`has_shared_parameters` (tracker/factor.py:275-302 of the reference; its test uses a `repeated_mlp`): a module used
+    twice per forward pass.  Covariances see the rows of both uses, the per-sample gradient is the sum over the uses.
+    Checked against a hand-rolled pipeline on the oracle's functions (activations and output gradients of every use
+    captured with plain hooks on an untracked copy of the model)."""
+    from oracle import ekfac_oracle as orc
+
+    torch.manual_seed(5)
+
+    class Shared(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(7, 7)
+            self.head = torch.nn.Linear(7, 3)
+
+        def forward(self, x):
+            h = torch.relu(self.lin(x))
+            h = torch.relu(self.lin(h))          # the same parameters again
+            return self.head(h)
+
+    class SharedTask(Task):
+        def compute_train_loss(self, batch, model, sample=False):
+            x, y = batch
+            return torch.nn.functional.cross_entropy(model(x), y, reduction="sum")
+
+        def compute_measurement(self, batch, model):
+            return self.compute_train_loss(batch, model)
+
+    raw = Shared().double()
+    n_train, n_query = 19, 5
+    xs = torch.randn(n_train + n_query, 7, dtype=torch.float64)
+    ys = torch.randint(0, 3, (n_train + n_query,))
+    train_set = torch.utils.data.TensorDataset(xs[:n_train], ys[:n_train])
+    query_set = torch.utils.data.TensorDataset(xs[n_train:], ys[n_train:])
+
+    # ---- reference pipeline: capture (activation, output gradient) of every use ----
+    def uses(x, y):
+        acts, grads = {"lin": [], "head": []}, {"lin": [], "head": []}
+        handles = []
+        for name, mod in (("lin", raw.lin), ("head", raw.head)):
+            def fwd(_m, inp, out, name=name):
+                acts[name].append(inp[0].detach().numpy())
+                out.register_hook(lambda g, name=name: grads[name].append(g.detach().numpy()))
+            handles.append(mod.register_forward_hook(fwd))
+        raw.zero_grad()
+        torch.nn.functional.cross_entropy(raw(x), y, reduction="sum").backward()
+        for h in handles:
+            h.remove()
+        return {k: (acts[k], list(reversed(grads[k]))) for k in acts}   # backward visits the uses in reverse order
+
+    def per_sample(captured):
+        a_list, g_list = captured
+        return sum(orc.linear_per_sample_gradient(a, g, True) for a, g in zip(a_list, g_list))
+
+    tr, qu = uses(xs[:n_train], ys[:n_train]), uses(xs[n_train:], ys[n_train:])
+    want = 0.0
+    for name in ("lin", "head"):
+        a_rows = np.concatenate([orc.linear_flatten_activation(a, True)[0] for a in tr[name][0]])
+        g_rows = np.concatenate([orc.linear_flatten_gradient(g)[0] for g in tr[name][1]])
+        _, q_a = orc.eigendecompose(orc.covariance_update(None, a_rows), len(a_rows))
+        _, q_g = orc.eigendecompose(orc.covariance_update(None, g_rows), len(g_rows))
+        g_train, g_query = per_sample(tr[name]), per_sample(qu[name])
+        lam_inv = orc.lambda_inverse(orc.lambda_update(None, g_train, q_a, q_g), n_train, None)
+        want = want + orc.pairwise_scores_from_gradients(orc.precondition(g_query, lam_inv, q_a, q_g), g_train)
+
+    # ---- the product's host logic (trackers with has_shared_parameters) on the oracle-backed ops ----
+    model = Shared().double()
+    model.load_state_dict(raw.state_dict())
+    task = SharedTask()
+    model = prepare_model(model, task)
+    with oracle_backend():
+        analyzer = Analyzer("shared", model, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        fa = FactorArguments(strategy="ekfac", use_empirical_fisher=True, has_shared_parameters=True)
+        analyzer.fit_all_factors("f", train_set, per_device_batch_size=6, factor_args=fa)
+        got = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=2,
+                                               per_device_train_batch_size=4,
+                                               score_args=ScoreArguments(damping_factor=None, score_dtype=torch.float64,
+                                                                         per_sample_gradient_dtype=torch.float64,
+                                                                         precondition_dtype=torch.float64))
+        counts = analyzer.load_covariance_matrices("f")["num_activation_covariance_processed"]
+    assert int(counts["lin"]) == 2 * n_train and int(counts["head"]) == n_train
+    assert rel(got["all_modules"].numpy(), want) < 1e-6
+
+    # without the flag the second use finds no cached activation (tracker/base.py:41-48 of the reference)
+    model2 = prepare_model(Shared().double(), task)
+    with oracle_backend():
+        analyzer2 = Analyzer("shared2", model2, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        fa2 = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+        analyzer2.fit_covariance_matrices("f", train_set, per_device_batch_size=6, factor_args=fa2)
+        analyzer2.perform_eigendecomposition("f", fa2)
+        with pytest.raises(RuntimeError):
+            analyzer2.fit_lambda_matrices("f", train_set, per_device_batch_size=6, factor_args=fa2)
