@@ -1007,6 +1007,8 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
   return KFB_OK;
 }
 
+static const int kRetryWithoutMulticast = 4242;  // internal: launch_tc<..., MC = 2> declined, use the pair kernel
+
 template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG = 1, int MC = 1, int EW = 4>
 static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K, NSPLIT, CG, MC, EW>;
@@ -1118,7 +1120,9 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
       }
       max_clusters = n;
     }
-    KFB_REQUIRE(max_clusters > 0, "gemm_nt: no cluster of %d CTAs can be resident", CLUSTER);
+    // no (or hardly any) cluster of this size can be resident on this device / partition: the caller falls back to
+    // the plain CTA-pair kernel
+    if (max_clusters * CLUSTER * 4 < sm_count() * 3) return kRetryWithoutMulticast;
     if (groups > max_clusters) groups = max_clusters;
   }
   const long long grid = (p.num_units < groups ? p.num_units : groups) * CLUSTER;
@@ -1148,15 +1152,19 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
   // L2->SM operand traffic, which is what bounds the single-MMA (bf16) mode of the fused pairwise kernel.
   const bool mcast = g_multicast.load() != 0 && g_cta_pairs.load() != 0 && p.M > 256 && !p.symmetric && !p.batch_fastest;
   if constexpr (EPI == EPI_ROWDOT) {
-    if (mcast && bn == 256 && nsplit == 2) return launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream);
-    if (mcast && bn == 256 && nsplit == 1) return launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
+    if (mcast && bn == 256) {
+      const int rc = nsplit == 2 ? launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream)
+                                 : launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
+      if (rc != kRetryWithoutMulticast) return rc;
+    }
   }
   if constexpr (EPI == EPI_STORE) {
     // long passes only (the flat pairwise GEMM: 16 k-blocks per pass; measured +8 % on the ResNet-9 conv layer at
     // Q = 1000, while the K = S per-sample-gradient GEMMs with their frequent epilogues lose a little)
     if (mcast && bn == 256 && p.kb_hint >= 16) {
-      if (nsplit == 2) return launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream);
-      return launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
+      const int rc = nsplit == 2 ? launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream)
+                                 : launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
+      if (rc != kRetryWithoutMulticast) return rc;
     }
   }
   // (measured: NOT for the register-accumulating kernels — with a TMEM drain every two k-blocks, coupling the two
