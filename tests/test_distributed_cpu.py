@@ -97,7 +97,14 @@ def _worker(rank, world, port, case, out_dir):
                                                       score_args=ScoreArguments(damping_factor=None,
                                                                                 aggregate_query_gradients=True,
                                                                                 aggregate_train_gradients=True))
+        own = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=4,
+                                           score_args=ScoreArguments(damping_factor=None))
+        own_m = analyzer.compute_self_scores("self_m", "f", train_set, per_device_train_batch_size=4,
+                                             score_args=ScoreArguments(damping_factor=None,
+                                                                       use_measurement_for_self_influence=True))
     if rank == 0:
+        np.save(os.path.join(out_dir, "self.npy"), own["all_modules"].numpy())
+        np.save(os.path.join(out_dir, "self_m.npy"), own_m["all_modules"].numpy())
         np.save(os.path.join(out_dir, "scores.npy"), scores["all_modules"].numpy())
         np.save(os.path.join(out_dir, "scores_lowrank.npy"), lowrank["all_modules"].numpy())
         np.save(os.path.join(out_dir, "scores_aggregated.npy"), aggregated["all_modules"].numpy())
@@ -116,6 +123,11 @@ def test_two_ranks_match_reference(case, tmp_path):
     # rank-3 query factors are all-gathered instead of the dense gradients
     lowrank, ref_lr = np.load(tmp_path / "scores_lowrank.npy"), golden["f32/scores_lowrank"]
     assert np.linalg.norm(lowrank - ref_lr) / np.linalg.norm(ref_lr) < 5e-5
+    # self-influence: contiguous train chunks per rank, gathered in rank order
+    for fname, key in (("self.npy", "f32/self_scores"), ("self_m.npy", "f32/self_scores_measurement")):
+        got = np.load(tmp_path / fname)
+        assert got.shape == golden[key].shape
+        assert np.linalg.norm(got - golden[key]) / np.linalg.norm(golden[key]) < 5e-5
     # aggregated query AND train gradients: per-rank sums, one all-reduce each, a single score
     agg, ref_agg = np.load(tmp_path / "scores_aggregated.npy"), golden["f32/scores_agg_both"]
     assert agg.shape == ref_agg.shape == (1, 1)
