@@ -261,7 +261,10 @@ class Analyzer:
             for name in factor_names:
                 value = module.storage[name]
                 if value is None:
-                    continue
+                    # this rank saw no example (dataset or partition smaller than the world size) or never executed the
+                    # module: contribute zeros of the right shape, or the flat buffers of the ranks differ in length
+                    value = self._zero_factor(module, name)
+                    module.storage[name] = value
                 if value.device != self.state.device:
                     value = value.to(self.state.device)
                     module.storage[name] = value
@@ -275,6 +278,14 @@ class Analyzer:
             for t in group:
                 t.copy_(flat[offset : offset + t.numel()].view_as(t))
                 offset += t.numel()
+
+    def _zero_factor(self, module: TrackedModule, name: str) -> torch.Tensor:
+        d_in, d_out = ops.module_factor_dims(module.original_module)
+        shapes = {ACTIVATION_COVARIANCE_MATRIX_NAME: (d_in, d_in), GRADIENT_COVARIANCE_MATRIX_NAME: (d_out, d_out),
+                  LAMBDA_MATRIX_NAME: (d_out, d_in)}
+        if name in shapes:
+            return torch.zeros(shapes[name], dtype=torch.float32, device=self.state.device)
+        return torch.zeros(1, dtype=torch.int64, device=self.state.device)  # the num_*_processed counters
 
     def _fit_loop(self, loader: data.DataLoader, mode: ModuleMode, module_names: List[str],
                   factor_args: FactorArguments, desc: str) -> torch.Tensor:
@@ -1138,8 +1149,6 @@ class Analyzer:
                              "`ScoreArguments` did not expect any data and module partition to compute self-influence scores.")
         chosen_data = self._target_partitions(target_data_partitions, len(data_parts), "data")
         chosen_module = self._target_partitions(target_module_partitions, len(module_parts), "module")
-        from safetensors.torch import save_file
-
         scores: Optional[Dict[str, torch.Tensor]] = None
         with self.profiler.profile("Compute Self-Influence Score"):
             for d_idx in chosen_data:
@@ -1162,8 +1171,7 @@ class Analyzer:
                         part = run(per_device_train_batch_size)
                     if partitioned:
                         if self.state.is_main_process:
-                            save_file({k: v.contiguous() for k, v in part.items()}, str(part_path),
-                                      metadata=score_args.to_str_dict())
+                            io.save_tensors(part, part_path, score_args.to_str_dict())
                         self.state.wait_for_everyone()
                     else:
                         scores = part
@@ -1173,7 +1181,7 @@ class Analyzer:
                 return None  # the remaining partitions belong to another call
         with self.profiler.profile("Save Self-Influence Score"):
             if self.state.is_main_process:
-                save_file({k: v.contiguous() for k, v in scores.items()}, str(path), metadata=score_args.to_str_dict())
+                io.save_tensors(scores, path, score_args.to_str_dict())
             self.state.wait_for_everyone()
         return scores
 
@@ -1211,10 +1219,7 @@ class Analyzer:
             self.logger.warning("Some score partitions of `%s` are missing at %s; nothing aggregated.", scores_name, out_dir)
             return
         if self.state.is_main_process:
-            from safetensors.torch import save_file
-
-            save_file({k: v.contiguous() for k, v in scores.items()}, str(self._self_scores_path(out_dir)),
-                      metadata=score_args.to_str_dict())
+            io.save_tensors(scores, self._self_scores_path(out_dir), score_args.to_str_dict())
         self.state.wait_for_everyone()
 
     def load_self_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:

@@ -32,18 +32,13 @@ class DataLoaderKwargs:
 
 
 def make_indices_partition(total_data_examples: int, partition_size: int) -> List[Tuple[int, int]]:
-    """[start, end) index ranges of `partition_size` near-equal contiguous bins; the last bin absorbs
-    the remainder (utils/dataset.py:38-63 of the reference)."""
+    """[start, end) index ranges of `partition_size` near-equal contiguous bins with np.array_split's
+    boundaries: the first `total % partition_size` bins hold one example more (utils/dataset.py:38-63 of the
+    reference), so partition files written by either engine cover the same examples."""
     if total_data_examples < partition_size:
         raise ValueError("The total data examples must be equal or greater than the partition size.")
-    bin_size = total_data_examples // partition_size
-    out = []
-    start = 0
-    for i in range(partition_size):
-        end = start + bin_size if i < partition_size - 1 else total_data_examples
-        out.append((start, end))
-        start = end
-    return out
+    div, mod = divmod(total_data_examples, partition_size)
+    return [(i * div + min(i, mod), (i + 1) * div + min(i + 1, mod)) for i in range(partition_size)]
 
 
 class DistributedEvalSampler(data.Sampler):

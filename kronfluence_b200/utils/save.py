@@ -33,6 +33,16 @@ def save_json(obj: Any, path: Path) -> None:
     os.replace(tmp, path)
 
 
+def save_tensors(tensors: Dict[str, torch.Tensor], path: Path, metadata: Optional[Dict[str, str]] = None) -> None:
+    """safetensors write that is atomic like save_json: the resume logic treats any file that exists as a finished
+    partition, so a job preempted mid-write must never leave a truncated file under the final name."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    tmp = path.with_name(path.name + f".tmp{os.getpid()}")
+    save_file(tensors={k: v.contiguous() for k, v in tensors.items()}, filename=str(tmp), metadata=metadata)
+    os.replace(tmp, path)
+
+
 def load_json(path: Path) -> Dict[str, Any]:
     if not Path(path).exists():
         raise FileNotFoundError(f"File not found: {path}.")
@@ -51,8 +61,7 @@ def save_factors(output_dir: Path, factors: FACTOR_TYPE, partition: Optional[tup
                  metadata: Optional[Dict[str, str]] = None) -> None:
     Path(output_dir).mkdir(parents=True, exist_ok=True)
     for factor_name, per_module in factors.items():
-        tensors = {k: v.contiguous() for k, v in per_module.items()}
-        save_file(tensors=tensors, filename=str(factor_path(output_dir, factor_name, partition)), metadata=metadata)
+        save_tensors(per_module, factor_path(output_dir, factor_name, partition), metadata)
 
 
 def load_factors(output_dir: Path, factor_names, partition: Optional[tuple] = None) -> FACTOR_TYPE:
@@ -73,5 +82,4 @@ def scores_path(output_dir: Path, partition: Optional[tuple] = None) -> Path:
 def save_scores(output_dir: Path, scores: Dict[str, torch.Tensor], partition: Optional[tuple] = None,
                 metadata: Optional[Dict[str, str]] = None) -> None:
     Path(output_dir).mkdir(parents=True, exist_ok=True)
-    save_file(tensors={k: v.contiguous() for k, v in scores.items()}, filename=str(scores_path(output_dir, partition)),
-              metadata=metadata)
+    save_tensors(scores, scores_path(output_dir, partition), metadata)

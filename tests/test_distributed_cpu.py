@@ -146,6 +146,18 @@ def test_samplers():
     assert chunks[0] == [0, 1, 2, 3] and chunks[1] == [4, 5, 6, 7] and chunks[2] == [8, 9, 10, 0]
     q = [list(DistributedQuerySampler(data, 3, r)) for r in range(3)]
     assert q[0] == [0, 3, 6, 9] and q[2] == [2, 5, 8, 0]  # strided, wrap-padded
-    assert make_indices_partition(10, 3) == [(0, 3), (3, 6), (6, 10)]
+    assert make_indices_partition(10, 3) == [(0, 4), (4, 7), (7, 10)]  # np.array_split boundaries
     with pytest.raises(ValueError):
         make_indices_partition(2, 3)
+
+
+def test_indices_partition_matches_array_split():
+    """utils/dataset.py:38-63 of the reference builds the bins with np.array_split: partition files written by either
+    engine must cover the same examples."""
+    import numpy as np
+
+    from kronfluence_b200.utils.dataset import make_indices_partition
+
+    for total, parts in ((41, 3), (1999, 1000), (10, 10), (7, 1), (50_000, 7), (5, 2)):
+        want = [(int(c[0]), int(c[-1]) + 1) for c in np.array_split(np.arange(total), parts)]
+        assert make_indices_partition(total, parts) == want, (total, parts)
