@@ -232,6 +232,9 @@ def run_reference(spec, device_kind: str, n_query: int, n_train: int, train_bs: 
         def compute_measurement(self, batch, model):
             return self.compute_train_loss(batch, model)
 
+    from kronfluence.utils.state import State as RefState  # pylint: disable=import-error
+
+    RefState._reset_state()  # the reference's State is a process-wide singleton: a cpu run after a cuda run would reuse cuda
     if threads is not None:
         torch.set_num_threads(threads)
     model = torch.nn.Sequential(_reference_module(spec))
@@ -524,6 +527,10 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
     else:
         achieved_tf = alg_flops / step_s / 1e12
         traffic, traffic_source = ncu_traffic(name)
+        # what the stage actually issues: the algorithmic contraction + formation, plus the rotation of the train batch
+        # into the eigenbases (2 N (d_in^2 + d_out^2), not counted as algorithmic work), each x3 in fp32-parity mode
+        rot_flops = 2.0 * t_batch * seq * (float(di) * di + float(do) * do)
+        issued_tf = issued * (alg_flops + rot_flops) / step_s / 1e12
         roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_source,
                     "algorithmic_bytes": float(n_query) * do * store.ld * 2 * planes
@@ -532,7 +539,8 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
                     "kernel_ms": step_s * 1e3,
                     "kernel": "whole stage: 2 eigenbasis rotations + per-sample-gradient formation + contraction "
                               "(gemm_tc_kernel family), timed as one step",
-                    "issued_tflops": None, "issued_frac": None, "kernel_share_of_step": 1.0}
+                    "rotation_flops": rot_flops, "issued_tflops": issued_tf, "issued_frac": issued_tf / peak_tf,
+                    "kernel_share_of_step": 1.0}
 
     out = {"workload": name, "note": spec["note"], "value": value, "unit": "scores/s", "ms_per_step": step_s * 1e3,
            "steps": steps, "dtype": "bf16x3 split operands, f32 accumulate (fp32 parity)" if precision == engine.PREC_FP32
@@ -577,6 +585,9 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
     del store, acts, grads, scores, qa_ops, qg_ops
     ops.release_workspaces()
     torch.cuda.empty_cache()
+    if ctx.rank == 0:
+        print(f"[bench] {name}: {json.dumps({k: out[k] for k in ('value', 'ms_per_step', 'parity')})} "
+              f"frac={roofline['frac']:.4f}", file=sys.stderr, flush=True)
     return out
 
 
@@ -860,16 +871,31 @@ def main() -> None:
             dist.barrier()
             dist.destroy_process_group()
         return
+    if strong is not None:
+        print(f"[bench] strong: {json.dumps(strong)}", file=sys.stderr, flush=True)
     torch_ref = None
     if not args.no_torch_ref and world == 1:
         torch_ref = {}
+        seen = set()
         for name in [args.workload] + ([s["workload"] for s in secondary] if secondary else []):
-            if WORKLOADS[name]["precision"] == "bf16" and name.replace("_bf16", "") in torch_ref:
-                continue  # same layer as its fp32 twin: the leg reports both dtypes
-            torch_ref[name] = torch_gpu_reference(name, WORKLOADS[name])
+            w = WORKLOADS[name]
+            key = tuple(sorted((k, v) for k, v in w.items() if k not in ("precision", "note", "q")))
+            if key in seen:
+                continue  # same layer as an earlier workload: the leg reports both dtypes
+            seen.add(key)
+            try:
+                torch_ref[name] = torch_gpu_reference(name, w)
+            except Exception as exc:  # pylint: disable=broad-exception-caught
+                torch_ref[name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            print(f"[bench] torch_gpu_reference {name}: {json.dumps(torch_ref[name])}", file=sys.stderr, flush=True)
         if all(v is None for v in torch_ref.values()):
             torch_ref = None
-    cpu = None if (args.skip_cpu or world > 1) else cpu_reference(spec, steps=3, warmup=1)
+    cpu = None
+    if not (args.skip_cpu or world > 1):
+        try:
+            cpu = cpu_reference(spec, steps=3, warmup=1)
+        except Exception as exc:  # pylint: disable=broad-exception-caught
+            print(f"[bench] cpu_baseline failed: {type(exc).__name__}: {exc}", file=sys.stderr, flush=True)
     line = {
         "metric": "pairwise influence scores/sec", "value": primary["value"], "unit": "scores/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": primary["ms_per_step"], "higher_is_better": True,

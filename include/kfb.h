@@ -334,6 +334,31 @@ int kfb_self_scores(const kfb_layer* layer, const void* a, int a_dtype, const vo
                     int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes, int precision,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Materialised per-sample gradients: the path behind Task.post_process_per_sample_gradient (task.py:99-116 of the
+ * reference; module/linear.py:68-77 / conv2d.py:164-177 call the callback on [B, d_out, d_in+bias] tensors, and
+ * every tracker then works on its result: tracker/factor.py:218-230, tracker/precondition.py:102-123,
+ * tracker/pairwise_score.py:19-50,95-103, tracker/self_score.py:32-60, tracker/gradient.py:46-60).
+ *   kfb_per_sample_gradient   out[b][o][i] = scale * sum_s g[b,s,o] * [a|1][b,s,i]   (fp32, parameter basis)
+ *   kfb_transform_gradient    out[b] = scale * [Q_G^T G_b Q_A] o mul   (qa_t/qg_t NULL: no rotation; mul NULL: no factor),
+ *                             written as fp32 [n][d_out][d_in+bias] and / or appended to the query store P at q_offset
+ *                             (the dense twin of kfb_precondition / of the train-side rotation of kfb_pairwise_scores;
+ *                             feed its fp32 output to kfb_pairwise_scores_explicit)
+ *   kfb_sq_accum              out[i] += alpha * sum_b x[b][i]^2          (Lambda from rotated dense gradients)
+ *   kfb_weighted_sqnorm       out[b] (+)= alpha * sum_i x[b][i]^2 * w[i]  (self-influence from rotated dense gradients)
+ * `layer` of kfb_transform_gradient only needs d_in / d_out / has_bias (a "flat" Linear descriptor).
+ * ------------------------------------------------------------------------------------------ */
+size_t kfb_per_sample_gradient_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_per_sample_gradient(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
+                            int64_t seq, float scale, float* out, void* ws, size_t ws_bytes, int precision, void* stream);
+size_t kfb_transform_gradient_workspace_bytes(const kfb_layer* layer, int64_t num_gradients);
+int kfb_transform_gradient(const kfb_layer* layer, const float* gradients, int64_t num_gradients, const kfb_split* qa_t,
+                           const kfb_split* qg_t, const float* mul, float scale, float* out_f32, const kfb_split* P,
+                           int64_t q_offset, void* ws, size_t ws_bytes, int precision, void* stream);
+int kfb_sq_accum(const float* x, int64_t n, int64_t numel, float alpha, float* out, void* stream);
+int kfb_weighted_sqnorm(const float* x, const float* w, int64_t n, int64_t numel, float alpha, float* out, int32_t accumulate,
+                        void* stream);
+
 /* Pairwise contraction against rank-r query factors P_q ~ left_t[q]^T right[q]  (module/linear.py:83-99,
  * module/conv2d.py:188-201 "qik,qko,b...i,b...o->qb"; tracker/pairwise_score.py:26-39).  left_t[q] = [r, d_out]
  * (U_k S_k transposed), right[q] = [r, d_in+bias] (V_k^T), both densely stacked operand batches; in KFB_PRECOND_EIGEN

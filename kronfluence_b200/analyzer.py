@@ -871,8 +871,6 @@ class Analyzer:
                                 target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                                 overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
         score_args = ScoreArguments() if score_args is None else score_args
-        if self.task.enable_post_process_per_sample_gradient:
-            raise NotImplementedError("`post_process_per_sample_gradient` needs materialised gradients; unsupported.")
         factor_args = self._load_factor_args(factors_name)
         out_dir = self.scores_output_dir(scores_name)
         if self.state.is_main_process:

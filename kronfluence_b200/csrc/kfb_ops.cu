@@ -914,6 +914,166 @@ static int explicit_run(const kfb_layer& L, const kfb_split* P, long long nq, co
   return gemm_nt(Pf, Gf, e, precision, 0, stream);
 }
 
+// =================================================================================================
+// Dense (materialised) per-sample gradients: the path behind Task.post_process_per_sample_gradient
+// (task.py:99-116, module/linear.py:68-77 / conv2d.py:164-177 with per_sample_gradient_process_fnc, consumers
+// tracker/factor.py:218-230, tracker/precondition.py:102-123, tracker/pairwise_score.py:19-50,95-103,
+// tracker/self_score.py:32-60, tracker/gradient.py:46-60).  The callback needs [B, d_out, d_in+bias] tensors, so the
+// gradients are formed once (fp32, parameter basis), handed to Python, and come back through the ops below.
+// =================================================================================================
+static int per_sample_gradient_run(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt, long long batch,
+                                   long long seq, float scale, float* out, Ws& ws, int precision, cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const long long per = outer_bytes_per_sample(L, S, false, precision);
+  const long long cb = chunk_count(batch, per);
+  OuterBufs o = outer_alloc(ws, L, cb, S, false, precision);
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("per-sample-gradient workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, false, nullptr, nullptr, o, precision, stream));
+    kfb_epilogue e = store_epilogue();
+    e.out_f32 = out + b0 * L.d_out * di;
+    e.ldo = di;
+    e.out_batch_stride = L.d_out * di;
+    e.alpha = scale;
+    KFB_TRY(gemm_nt(split_batch_view(o.Lt, 0, nb), split_batch_view(o.Rt, 0, nb), e, precision, 1, stream));
+  }
+  return KFB_OK;
+}
+
+__global__ void scale_mul_kernel(const float* __restrict__ x, const float* __restrict__ mul, float scale, float* __restrict__ out,
+                                 long long n, long long numel) {
+  const long long total = n * numel;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    out[i] = scale * x[i] * (mul != nullptr ? __ldg(mul + i % numel) : 1.f);
+}
+
+// out[b] = scale * [Q_G^T G_b Q_A] o mul   (rotation optional: qa_t == NULL -> out[b] = scale * G_b o mul), written as
+// fp32 [n][d_out][d_in+bias] (out_f32) and / or into the query store P at batch offset q_offset.
+static int transform_gradient_run(const kfb_layer& L, const float* G, long long n, const kfb_split* qa_t,
+                                  const kfb_split* qg_t, const float* mul, float scale, float* out_f32, const kfb_split* P,
+                                  long long q_offset, Ws& ws, int precision, cudaStream_t stream) {
+  const long long di = L.d_in + L.has_bias, d_out = L.d_out;
+  const bool rotate = qa_t != nullptr || ws.dry;
+  const int rp = rot_prec(precision);
+  const long long ldt = ld8(d_out);
+  long long per = d_out * di * 4;                                       // elementwise scratch (no rotation, store target)
+  const long long per_rot = d_out * ld8(di) * 2 * planes_of(rp)          // G_b operand planes
+                            + di * ldt * 4                               // (G_b Q_A)^T fp32
+                            + di * ldt * 2 * planes_of(rp);              // ... as operand planes
+  if (per_rot > per) per = per_rot;
+  const long long cb = chunk_count(n, per);
+  kfb_split Gs{}, Tt{};
+  float* T32 = nullptr;
+  float* tmp = nullptr;
+  if (rotate) {
+    Gs = ws_split(ws, d_out, di, cb, rp);
+    T32 = static_cast<float*>(ws.take((size_t)(cb * di * ldt) * 4));
+    Tt = ws_split(ws, di, d_out, cb, rp);
+  }
+  if (!rotate || ws.dry) tmp = static_cast<float*>(ws.take((size_t)(cb * d_out * di) * 4));
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("gradient transform workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  if (P != nullptr) {
+    KFB_REQUIRE(P->hi != nullptr && P->rows == d_out && P->cols == di && P->ld % 8 == 0,
+                "transform_gradient: destination layout does not match the layer");
+    KFB_REQUIRE(q_offset >= 0 && q_offset + n <= P->batch, "transform_gradient: gradients [%lld, %lld) exceed the store capacity %lld",
+                q_offset, q_offset + n, (long long)P->batch);
+  }
+  if (rotate) {
+    KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == d_out,
+                "transform_gradient: eigenbasis operands do not match the layer");
+    KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->absmax != nullptr && qg_t->absmax != nullptr),
+                "transform_gradient: eigenbasis operands must be built with KFB_PREC_STRICT for the fp32-parity mode");
+  }
+  for (long long b0 = 0; b0 < n; b0 += cb) {
+    const long long nb = n - b0 < cb ? n - b0 : cb;
+    const float* G0 = G + b0 * d_out * di;
+    float* of = out_f32 != nullptr ? out_f32 + b0 * d_out * di : nullptr;
+    if (!rotate) {
+      float* dst = of != nullptr ? of : tmp;
+      scale_mul_kernel<<<592, 256, 0, stream>>>(G0, mul, scale, dst, nb, d_out * di);
+      count_launch();
+      KFB_CUDA_TRY(cudaGetLastError());
+      if (P != nullptr) {
+        GatherDesc gd{};
+        gd.sb = d_out * di; gd.sr = di; gd.sc2 = 1; gd.rows = d_out; gd.c1 = 1; gd.c2 = di;
+        KFB_TRY(split_gather(dst, KFB_F32, gd, split_batch_view(*P, q_offset + b0, nb), precision, stream));
+      }
+      continue;
+    }
+    GatherDesc gd{};
+    gd.sb = d_out * di; gd.sr = di; gd.sc2 = 1; gd.rows = d_out; gd.c1 = 1; gd.c2 = di;
+    KFB_TRY(split_gather(G0, KFB_F32, gd, split_batch_view(Gs, 0, nb), rp, stream));
+    // T_b^T[j][o] = sum_i G_b[o][i] Q_A[i][j]           (M = d_out, N = d_in+bias, K = d_in+bias, transposed store)
+    kfb_epilogue e1 = store_epilogue();
+    e1.out_f32 = T32;
+    e1.ldo = ldt;
+    e1.out_batch_stride = di * ldt;
+    e1.transpose_out = 1;
+    KFB_TRY(gemm_nt(split_batch_view(Gs, 0, nb), *qa_t, e1, rp, 1, stream));
+    GatherDesc gt{};
+    gt.sb = di * ldt; gt.sr = ldt; gt.sc2 = 1; gt.rows = di; gt.c1 = 1; gt.c2 = d_out;
+    KFB_TRY(split_gather(T32, KFB_F32, gt, split_batch_view(Tt, 0, nb), rp, stream));
+    // out_b[p][j] = scale * mul[p][j] * sum_o Q_G[o][p] T_b[o][j]   (M = d_out, N = d_in+bias, K = d_out)
+    kfb_epilogue e2 = store_epilogue();
+    e2.alpha = scale;
+    e2.mul = mul;
+    e2.ldmul = di;
+    if (of != nullptr) {
+      e2.out_f32 = of;
+      e2.ldo = di;
+      e2.out_batch_stride = d_out * di;
+    }
+    if (P != nullptr) e2.out_split = split_batch_view(*P, q_offset + b0, nb);
+    KFB_TRY(gemm_nt(*qg_t, split_batch_view(Tt, 0, nb), e2, rp, 1, stream));
+  }
+  return KFB_OK;
+}
+
+// out[i] += alpha * sum_b x[b][i]^2            (Lambda from materialised, already rotated gradients: tracker/factor.py:223-230)
+__global__ void sq_accum_kernel(const float* __restrict__ x, long long n, long long numel, float alpha, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (long long b = 0; b < n; ++b) {
+      const float v = x[b * numel + i];
+      acc = fmaf(v, v, acc);
+    }
+    out[i] += alpha * acc;
+  }
+}
+
+// out[b] (+)= alpha * sum_i x[b][i]^2 * (w ? w[i] : 1)     (self-influence from materialised gradients: tracker/self_score.py:32-60)
+__global__ void weighted_sqnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, long long numel, float alpha,
+                                       float* __restrict__ out, int accumulate) {
+  const long long b = blockIdx.x;
+  const float* xb = x + b * numel;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < numel; i += blockDim.x) {
+    const float v = xb[i];
+    acc = fmaf(v * v, w != nullptr ? __ldg(w + i) : 1.f, acc);
+  }
+  __shared__ float part[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[b] = alpha * acc + (accumulate ? out[b] : 0.f);
+  }
+}
+
 }  // namespace kfb
 
 // =================================================================================================
@@ -1148,6 +1308,62 @@ int kfb_pairwise_scores_host(const kfb_layer* layer, const kfb_split* P, int64_t
                               qg_t, scale, dev_scores, batch, 0, 0, ws, ws_bytes, precision, stream));
   KFB_CUDA_TRY(cudaMemcpyAsync(scores_host, dev_scores, (size_t)num_queries * batch * 4,
                                cudaMemcpyDeviceToHost, st));
+  return KFB_OK;
+}
+
+size_t kfb_per_sample_gradient_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  per_sample_gradient_run(*layer, nullptr, KFB_F32, nullptr, KFB_F32, batch, seq, 1.f, nullptr, w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_per_sample_gradient(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
+                            int64_t seq, float scale, float* out, void* ws, size_t ws_bytes, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(a != nullptr && g != nullptr && out != nullptr, "per_sample_gradient: null tensor");
+  if (batch <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return per_sample_gradient_run(*layer, a, a_dtype, g, g_dtype, batch, seq, scale, out, w, precision, (cudaStream_t)stream);
+}
+
+size_t kfb_transform_gradient_workspace_bytes(const kfb_layer* layer, int64_t num_gradients) {
+  if (check_layer(layer) != KFB_OK || num_gradients <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  transform_gradient_run(*layer, nullptr, num_gradients, nullptr, nullptr, nullptr, 1.f, nullptr, nullptr, 0, w, KFB_PREC_FP32,
+                         nullptr);
+  return w.off + 256;
+}
+
+int kfb_transform_gradient(const kfb_layer* layer, const float* gradients, int64_t num_gradients, const kfb_split* qa_t,
+                           const kfb_split* qg_t, const float* mul, float scale, float* out_f32, const kfb_split* P,
+                           int64_t q_offset, void* ws, size_t ws_bytes, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(gradients != nullptr && (out_f32 != nullptr || P != nullptr), "transform_gradient: null tensor");
+  KFB_REQUIRE((qa_t == nullptr) == (qg_t == nullptr), "transform_gradient: give both eigenbasis operands or neither");
+  if (num_gradients <= 0) return KFB_OK;
+  KFB_WS(ws, ws_bytes, false);
+  return transform_gradient_run(*layer, gradients, num_gradients, qa_t, qg_t, mul, scale, out_f32, P, q_offset, w, precision,
+                                (cudaStream_t)stream);
+}
+
+int kfb_sq_accum(const float* x, int64_t n, int64_t numel, float alpha, float* out, void* stream) {
+  KFB_REQUIRE(x != nullptr && out != nullptr && n >= 0 && numel >= 0, "sq_accum: bad argument");
+  if (n == 0 || numel == 0) return KFB_OK;
+  const unsigned blocks = (unsigned)(ceil_div_ll(numel, 256) < 2368 ? ceil_div_ll(numel, 256) : 2368);
+  sq_accum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, numel, alpha, out);
+  count_launch();
+  KFB_CUDA_TRY(cudaGetLastError());
+  return KFB_OK;
+}
+
+int kfb_weighted_sqnorm(const float* x, const float* w, int64_t n, int64_t numel, float alpha, float* out, int32_t accumulate,
+                        void* stream) {
+  KFB_REQUIRE(x != nullptr && out != nullptr && n >= 0 && numel >= 0, "weighted_sqnorm: bad argument");
+  if (n == 0) return KFB_OK;
+  weighted_sqnorm_kernel<<<(unsigned)n, 512, 0, (cudaStream_t)stream>>>(x, w, numel, alpha, out, accumulate);
+  count_launch();
+  KFB_CUDA_TRY(cudaGetLastError());
   return KFB_OK;
 }
 

@@ -99,6 +99,13 @@ SIGNATURES = {
     "kfb_pairwise_explicit_workspace_bytes": (_sz, [_LP, _i64]),
     "kfb_pairwise_scores_explicit": (ctypes.c_int, [_LP, _SP, _i64, _vp, _i64, _f32, _vp, _i64, _i64, _i32, _vp, _sz,
                                                     ctypes.c_int, _vp]),
+    "kfb_per_sample_gradient_workspace_bytes": (_sz, [_LP, _i64, _i64]),
+    "kfb_per_sample_gradient": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _f32, _vp, _vp, _sz,
+                                               ctypes.c_int, _vp]),
+    "kfb_transform_gradient_workspace_bytes": (_sz, [_LP, _i64]),
+    "kfb_transform_gradient": (ctypes.c_int, [_LP, _vp, _i64, _SP, _SP, _vp, _f32, _vp, _SP, _i64, _vp, _sz, ctypes.c_int, _vp]),
+    "kfb_sq_accum": (ctypes.c_int, [_vp, _i64, _i64, _f32, _vp, _vp]),
+    "kfb_weighted_sqnorm": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f32, _vp, _i32, _vp]),
     "kfb_pairwise_scores_host": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _f32, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_int, _vp]),
 }
 

@@ -160,6 +160,21 @@ class BaseTracker:
         flat_g = [g.reshape(g.shape[0], -1, g.shape[-1]) for g in grads]
         return torch.cat(flat_a, dim=1), torch.cat(flat_g, dim=1)
 
+    def _processed_gradient(self, layer, a: torch.Tensor, g: torch.Tensor) -> Optional[torch.Tensor]:
+        """With `Task.enable_post_process_per_sample_gradient`: the materialised per-sample gradients
+        [B, d_out, d_in(+1)] after the task's callback (module/linear.py:68-77, conv2d.py:164-177 of the reference:
+        the callback sees them before `gradient_scale` is applied).  None when the task does not post-process, in which
+        case the fused paths never form these tensors."""
+        fnc = self.module.per_sample_gradient_process_fnc
+        if fnc is None:
+            return None
+        grads = ops.per_sample_gradient(layer, a, g)
+        processed = fnc(module_name=self.module.name, gradient=grads)
+        if processed.shape != grads.shape:
+            raise ValueError(f"`post_process_per_sample_gradient` changed the gradient shape of '{self.module.name}' "
+                             f"from {tuple(grads.shape)} to {tuple(processed.shape)}.")
+        return processed.to(dtype=torch.float32).contiguous()
+
     # --- protocol ---
     def register_hooks(self) -> None: ...
 
@@ -234,7 +249,15 @@ class LambdaTracker(BaseTracker):
         precision = precision_of(module.factor_args.lambda_dtype)
         if strategy_config(module.factor_args.strategy)["lambda_eigen"]:
             qa, qg = module.eigen_operands(g.device, precision)
-        ops.lambda_accum(layer, a, g, storage[LAMBDA_MATRIX_NAME], qa, qg, module.gradient_scale, precision)
+        dense = self._processed_gradient(layer, a, g)
+        if dense is not None:
+            # tracker/factor.py:218-230 on the callback's output: rotate the dense gradients, then square-accumulate
+            flat = ops.flat_layer(module.original_module)
+            if qa is not None:
+                dense = ops.transform_gradient(flat, dense, qa, qg, None, 1.0, precision=precision)
+            ops.sq_accum(dense, storage[LAMBDA_MATRIX_NAME], module.gradient_scale**2)
+        else:
+            ops.lambda_accum(layer, a, g, storage[LAMBDA_MATRIX_NAME], qa, qg, module.gradient_scale, precision)
         storage[NUM_LAMBDA_PROCESSED].add_(a.shape[0])
 
     def register_hooks(self) -> None:
@@ -293,6 +316,20 @@ class PreconditionTracker(BaseTracker):
         if mode == ops.PRECOND_EIGEN:
             qa, qg = module.eigen_operands(g.device, precision)
         lam_inv = module.storage[LAMBDA_MATRIX_NAME] if mode != ops.PRECOND_IDENTITY else None
+        dense_grad = self._processed_gradient(layer, a, g)
+        if dense_grad is not None:
+            # the callback's output goes through the same preconditioner, on materialised gradients
+            flat = ops.flat_layer(module.original_module)
+            target = store.scratch_for(a.shape[0], g.device) if isinstance(store, ops.LowRankStore) else store
+            offset = 0 if isinstance(store, ops.LowRankStore) else module.query_count
+            ops.transform_gradient(flat, dense_grad, qa, qg, lam_inv, module.gradient_scale, want_f32=False, store=target,
+                                   q_offset=offset, precision=precision)
+            if isinstance(store, ops.LowRankStore):
+                ops.lowrank_factorize(target, a.shape[0], store, module.query_count, module.score_args.use_full_svd,
+                                      module.score_args.query_gradient_svd_dtype)
+            module.last_query_batch = a.shape[0]
+            module.query_count += a.shape[0]
+            return
         if isinstance(store, ops.LowRankStore):
             # tracker/precondition.py:54-71: precondition this batch densely, keep only its rank-r factors
             dense = store.scratch_for(a.shape[0], g.device)
@@ -365,6 +402,14 @@ class GradientAggregationTracker(BaseTracker):
         lam_inv = None
         if module.aggregate_precondition and mode != ops.PRECOND_IDENTITY:
             lam_inv = module.storage[LAMBDA_MATRIX_NAME]
+        dense = self._processed_gradient(layer, a, g)
+        if dense is not None:
+            # tracker/gradient.py:46-60 of the reference: per-sample gradients through the callback, summed over the batch
+            total = dense.sum(dim=0, keepdim=True)
+            flat = ops.flat_layer(module.original_module)
+            module.storage[AGGREGATED_GRADIENT_NAME].add_(
+                ops.transform_gradient(flat, total, qa, qg, lam_inv, module.gradient_scale, precision=precision)[0])
+            return
         ops.aggregate_gradient(layer, a, g, module.storage[AGGREGATED_GRADIENT_NAME], qa, qg, lam_inv,
                                module.gradient_scale, precision)
 
@@ -433,6 +478,24 @@ class PairwiseScoreTracker(BaseTracker):
                 qa, qg = module.eigen_operands(grad.device, precision_of(module.score_args.score_dtype))
             grad = grad.detach()
             tokens = 1
+            dense = self._processed_gradient(layer, a, grad)
+            if dense is not None:
+                # tracker/pairwise_score.py:19-50,95-103 of the reference: "qio,tio->qt" on the callback's output,
+                # here in the basis of the query store (rotate the dense train gradients first)
+                if sink.per_token:
+                    raise ValueError("`compute_per_token_scores` cannot be combined with `post_process_per_sample_gradient`.")
+                if isinstance(store, ops.LowRankStore):
+                    raise NotImplementedError("`query_gradient_low_rank` with `post_process_per_sample_gradient` is not "
+                                              "supported; use dense query gradients.")
+                flat = ops.flat_layer(module.original_module)
+                precision = precision_of(module.score_args.score_dtype)
+                if qa is not None:
+                    dense = ops.transform_gradient(flat, dense, qa, qg, None, 1.0, precision=precision)
+                ops.pairwise_scores_explicit(flat, store, module.query_count, dense, sink.get(1), module.score_offset,
+                                             accumulate=True, scale=module.gradient_scale, precision=precision)
+                if not module.factor_args.has_shared_parameters:
+                    self._drop_cached_tensors()
+                return
             if isinstance(store, ops.LowRankStore):
                 # "qik,qko,b...i,b...o->qb" / "...->qbt" (linear.py:83-99, conv2d.py:188-201 of the reference)
                 if sink.per_token:
@@ -496,6 +559,14 @@ class SelfScoreTracker(BaseTracker):
             d_in, d_out = ops.factor_dims(layer)
             lam_inv = torch.ones(d_out, d_in, dtype=torch.float32, device=g.device)
             module.storage[LAMBDA_MATRIX_NAME] = lam_inv
+        dense = self._processed_gradient(layer, a, g)
+        if dense is not None:
+            flat = ops.flat_layer(module.original_module)
+            precision = precision_of(module.score_args.score_dtype)
+            if qa is not None:
+                dense = ops.transform_gradient(flat, dense, qa, qg, None, 1.0, precision=precision)
+            ops.weighted_sqnorm(dense, lam_inv, sink, module.score_offset, module.gradient_scale**2, accumulate=True)
+            return
         ops.self_scores(layer, a, g, sink, module.score_offset, mode, lam_inv, qa, qg, scale=module.gradient_scale,
                         accumulate=True, precision=precision_of(module.score_args.score_dtype))
 

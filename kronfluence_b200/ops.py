@@ -367,6 +367,7 @@ __all__ = [
     "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
     "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "self_scores", "layer_of", "factor_dims", "workspace",
     "aggregate_gradient", "pairwise_scores_explicit", "flat_layer",
+    "per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
 ]
 
 
@@ -433,3 +434,62 @@ def load_query_store(store: Split, p: torch.Tensor, q_offset: int = 0, precision
     dst = store.struct(q_offset, q)
     check(lib.kfb_split_gather(p.data_ptr(), dtype_code(p.dtype), desc, None, ctypes.byref(dst), precision,
                                stream_ptr(p.device)))
+
+
+# --------------------------------------------------------------------------------------------------
+# Materialised per-sample gradients: the path behind Task.post_process_per_sample_gradient (task.py:99-116,
+# module/linear.py:68-77, module/conv2d.py:164-177 of the reference)
+# --------------------------------------------------------------------------------------------------
+def per_sample_gradient(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, scale: float = 1.0,
+                        precision: int = PREC_FP32) -> torch.Tensor:
+    """[B, d_out, d_in(+1)] fp32 per-sample gradients, bias as the last input column ("b...i,b...o->bio")."""
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    d_in, d_out = factor_dims(layer)
+    out = torch.empty(batch, d_out, d_in, dtype=torch.float32, device=g.device)
+    ws_ptr, ws_size = workspace(a.device).get(lib.kfb_per_sample_gradient_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_per_sample_gradient(ctypes.byref(layer), a.data_ptr(), dtype_code(a.dtype), g.data_ptr(),
+                                      dtype_code(g.dtype), batch, seq, float(scale), out.data_ptr(), ws_ptr, ws_size,
+                                      precision, stream_ptr(a.device)))
+    return out
+
+
+def transform_gradient(layer: KfbLayer, gradients: torch.Tensor, qa: Optional[EigenOperands] = None,
+                       qg: Optional[EigenOperands] = None, mul: Optional[torch.Tensor] = None, scale: float = 1.0,
+                       want_f32: bool = True, store: Optional[Split] = None, q_offset: int = 0,
+                       precision: int = PREC_FP32) -> Optional[torch.Tensor]:
+    """scale * [Q_G^T G_b Q_A] o mul for materialised gradients [n, d_out, d_in(+1)] (rotation and factor optional):
+    returned as fp32 (want_f32) and / or appended to the query store at q_offset."""
+    lib = engine.load_library()
+    gradients = _contig(gradients.to(torch.float32))
+    n = gradients.shape[0]
+    out = torch.empty_like(gradients) if want_f32 else None
+    sa = qa.qt.struct() if qa is not None else None
+    sg = qg.qt.struct() if qg is not None else None
+    dst = store.struct(0, store.batch) if store is not None else None
+    ws_ptr, ws_size = workspace(gradients.device).get(lib.kfb_transform_gradient_workspace_bytes(ctypes.byref(layer), n))
+    check(lib.kfb_transform_gradient(ctypes.byref(layer), gradients.data_ptr(), n,
+                                     ctypes.byref(sa) if sa is not None else None,
+                                     ctypes.byref(sg) if sg is not None else None, ptr(mul), float(scale), ptr(out),
+                                     ctypes.byref(dst) if dst is not None else None, int(q_offset), ws_ptr, ws_size,
+                                     precision, stream_ptr(gradients.device)))
+    return out
+
+
+def sq_accum(x: torch.Tensor, out: torch.Tensor, alpha: float = 1.0) -> None:
+    """out += alpha * sum_b x[b]^2 (Lambda from materialised gradients, tracker/factor.py:223-230)."""
+    lib = engine.load_library()
+    x = _contig(x)
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x[0].numel()
+    check(lib.kfb_sq_accum(x.data_ptr(), x.shape[0], out.numel(), float(alpha), out.data_ptr(), stream_ptr(x.device)))
+
+
+def weighted_sqnorm(x: torch.Tensor, w: Optional[torch.Tensor], out: torch.Tensor, t_offset: int = 0, alpha: float = 1.0,
+                    accumulate: bool = True) -> None:
+    """out[t_offset + b] (+)= alpha * sum_i x[b][i]^2 * w[i] (self-influence from materialised gradients)."""
+    lib = engine.load_library()
+    x = _contig(x)
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
+    check(lib.kfb_weighted_sqnorm(x.data_ptr(), ptr(w), x.shape[0], x[0].numel(), float(alpha),
+                                  out.data_ptr() + 4 * int(t_offset), int(accumulate), stream_ptr(x.device)))

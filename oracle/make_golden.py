@@ -290,10 +290,67 @@ def make_e2e_fixtures():
         print("e2e", case, "rank-3 scores: fp32-vs-fp64 rel", rel_lr, "; truncation error vs dense", rel_tr)
 
 
+def run_reference_postprocess(case, dtype):
+    """The reference Analyzer with a Task that post-processes per-sample gradients (task.py:99-116,
+    module/linear.py:73-76, tracker/pairwise_score.py:95-103): Lambda, pairwise and self-influence scores."""
+    tasks = fixtures.make_postprocess_tasks(Task)
+    model, train_set, query_set = fixtures.make_case(case)
+    model = model.to(dtype=dtype)
+    _, _, _, _, train_bs, query_bs = fixtures.CASES[case]
+    task = tasks[case]()
+    model = prepare_model(model, task)
+    tmp = tempfile.mkdtemp(prefix="kfb_golden_pp_")
+    try:
+        analyzer = Analyzer(analysis_name="golden", model=model, task=task, cpu=True, output_dir=tmp,
+                            disable_tqdm=True, disable_model_save=True)
+        factor_args = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+        score_args = ScoreArguments(damping_factor=None)
+        if dtype == torch.float64:
+            for key in ("activation_covariance_dtype", "gradient_covariance_dtype", "per_sample_gradient_dtype",
+                        "lambda_dtype"):
+                setattr(factor_args, key, torch.float64)
+            for key in ("per_sample_gradient_dtype", "precondition_dtype", "score_dtype"):
+                setattr(score_args, key, torch.float64)
+        analyzer.fit_all_factors("f", dataset=train_set, per_device_batch_size=train_bs, factor_args=factor_args,
+                                 overwrite_output_dir=True)
+        analyzer.compute_pairwise_scores("s", factors_name="f", query_dataset=query_set, train_dataset=train_set,
+                                         per_device_query_batch_size=query_bs, per_device_train_batch_size=train_bs,
+                                         score_args=score_args, overwrite_output_dir=True)
+        analyzer.compute_self_scores("self", factors_name="f", train_dataset=train_set,
+                                     per_device_train_batch_size=train_bs, score_args=score_args, overwrite_output_dir=True)
+        out = {}
+        for fname, per_module in analyzer.load_all_factors("f").items():
+            for mname, tensor in per_module.items():
+                out[f"{fname}/{mname}"] = npy(tensor)
+        out["scores"] = npy(analyzer.load_pairwise_scores("s")["all_modules"])
+        out["self_scores"] = npy(analyzer.load_self_scores("self")["all_modules"])
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+        State._shared_state.clear()
+
+
+def make_postprocess_fixtures():
+    for case in fixtures.CASES:
+        d32 = run_reference_postprocess(case, torch.float32)
+        d64 = run_reference_postprocess(case, torch.float64)
+        merged = {f"f32/{k}": v for k, v in d32.items()}
+        merged.update({f"f64/{k}": v for k, v in d64.items()})
+        np.savez_compressed(os.path.join(GOLDEN, f"e2e_postprocess_{case}.npz"), **merged)
+        plain = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+        changed = np.linalg.norm(d64["scores"] - plain["f64/scores"]) / np.linalg.norm(plain["f64/scores"])
+        rel = np.linalg.norm(d32["scores"] - d64["scores"]) / np.linalg.norm(d64["scores"])
+        print("postprocess", case, "scores fp32-vs-fp64 rel", rel, "; change vs the task without the callback", changed)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(4)
+    if "--postprocess-only" in sys.argv:
+        make_postprocess_fixtures()
+        sys.exit(0)
     make_stage_fixtures()
     make_e2e_fixtures()
+    make_postprocess_fixtures()
     total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print(f"golden fixtures: {total / 1024:.1f} KiB")

@@ -207,7 +207,38 @@ def self_scores(layer, a, g, out, t_offset, mode, lambda_inv, qa=None, qg=None, 
         view.copy_(vals)
 
 
-_PATCHED = ["layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
+def per_sample_gradient(layer, a, g, scale=1.0, precision=0):
+    return torch.from_numpy(_per_sample(layer, a, g) * scale)
+
+
+def transform_gradient(layer, gradients, qa=None, qg=None, mul=None, scale=1.0, want_f32=True, store=None, q_offset=0,
+                       precision=0):
+    out = _np(gradients)
+    if qa is not None:
+        out = np.matmul(qg.q.T, np.matmul(out, qa.q))
+    if mul is not None:
+        out = out * _np(mul)
+    out = torch.from_numpy(out * scale)
+    if store is not None:
+        store.storage[0, q_offset : q_offset + out.shape[0]] = out
+    return out if want_f32 else None
+
+
+def sq_accum(x, out, alpha=1.0):
+    out.add_((alpha * (x.double() ** 2).sum(dim=0)).to(out.dtype))
+
+
+def weighted_sqnorm(x, w, out, t_offset=0, alpha=1.0, accumulate=True):
+    vals = (x.double() ** 2 * (1.0 if w is None else w.double())).flatten(1).sum(dim=1) * alpha
+    view = out[t_offset : t_offset + x.shape[0]]
+    if accumulate:
+        view.add_(vals.to(out.dtype))
+    else:
+        view.copy_(vals.to(out.dtype))
+
+
+_PATCHED = ["per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
+            "layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
             "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores", "self_scores",
             "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank", "LowRankStore", "flat_layer",
             "aggregate_gradient", "pairwise_scores_explicit", "load_query_store"]

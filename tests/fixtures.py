@@ -131,6 +131,26 @@ def make_tasks(task_base):
     return {"mlp": RegressionTask, "seq": SeqTask, "conv": ImageTask}
 
 
+POSTPROCESS_CLIP = 1.0
+
+
+def make_postprocess_tasks(task_base):
+    """The same three tasks with `Task.post_process_per_sample_gradient` switched on (task.py:99-116 of the reference):
+    every per-sample gradient [B, d_out, d_in(+1)] is clipped to Frobenius norm <= POSTPROCESS_CLIP — nonlinear, so the
+    result differs from the fused paths unless the callback really runs on the materialised gradients."""
+
+    def clip(self, module_name, gradient):
+        del self, module_name
+        norm = gradient.flatten(1).norm(dim=1).clamp_min(1e-12)
+        return gradient * torch.clamp(POSTPROCESS_CLIP / norm, max=1.0).view(-1, 1, 1).to(gradient.dtype)
+
+    out = {}
+    for name, cls in make_tasks(task_base).items():
+        out[name] = type(cls.__name__ + "PostProcess", (cls,), {"enable_post_process_per_sample_gradient": True,
+                                                                "post_process_per_sample_gradient": clip})
+    return out
+
+
 CASES = {
     # name: (model factory, dataset factory, n_train, n_query, train batch, query batch)
     "mlp": (make_mlp, make_regression_dataset, 41, 7, 8, 3),

@@ -445,3 +445,42 @@ def test_shared_parameters(tmp_path):
         analyzer2.perform_eigendecomposition("f", fa2)
         with pytest.raises(RuntimeError):
             analyzer2.fit_lambda_matrices("f", train_set, per_device_batch_size=6, factor_args=fa2)
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_post_process_per_sample_gradient(case, tmp_path):
+    """`Task.post_process_per_sample_gradient` (task.py:99-116 of the reference) reaches Lambda, the preconditioned
+    query gradients, pairwise and self-influence scores: the reference Analyzer run with the same clipping callback is
+    the golden (tests/golden/e2e_postprocess_*.npz)."""
+    golden = dict(np.load(os.path.join(GOLDEN, f"e2e_postprocess_{case}.npz")))
+    tasks = fixtures.make_postprocess_tasks(Task)
+    with oracle_backend():
+        from kronfluence_b200.utils import save as io
+
+        model, train_set, query_set = fixtures.make_case(case)
+        _, _, _, _, train_bs, query_bs = fixtures.CASES[case]
+        task = tasks[case]()
+        model = prepare_model(model, task)
+        analyzer = Analyzer("pp", model, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        fa = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+        analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=train_bs, factor_args=fa)
+        analyzer.perform_eigendecomposition("f", fa)
+        eig = analyzer.load_eigendecomposition("f")
+        for fname in eig:
+            for mname in eig[fname]:
+                eig[fname][mname] = torch.from_numpy(golden[f"f32/{fname}/{mname}"])
+        io.save_factors(analyzer.factors_output_dir("f"), eig)
+        analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=train_bs, factor_args=fa)
+        sa = ScoreArguments(damping_factor=None)
+        scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=query_bs,
+                                                  per_device_train_batch_size=train_bs, score_args=sa)
+        self_scores = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=train_bs,
+                                                   score_args=ScoreArguments(damping_factor=None))
+        lam = analyzer.load_lambda_matrices("f")["lambda_matrix"]
+    for mname, value in lam.items():
+        assert rel(value.numpy(), golden[f"f32/lambda_matrix/{mname}"]) < 2e-5, mname
+    assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
+    assert rel(self_scores["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
+    # and the callback really changed the answer
+    plain = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+    assert rel(scores["all_modules"].numpy(), plain["f32/scores"]) > 1e-2
