@@ -597,8 +597,9 @@ def torch_gpu_reference(name, spec):
     import torch
 
     seq = spec["seq"] if spec["kind"] == "linear" else spec["hw"] ** 2
-    q_s = min(spec["q"], 128 if seq == 1 else 64)
-    t_bs = min(spec["t_batch"], 1024 if seq == 1 else 64)
+    # large enough that the reference's per-call overheads (hooks, einsum path search, file IO) are amortised
+    q_s = min(spec["q"], 128 if seq == 1 else 256)
+    t_bs = min(spec["t_batch"], 1024 if seq == 1 else 128)
     out = {}
     for dtype_name in ("fp32", "bf16"):
         try:

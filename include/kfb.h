@@ -220,6 +220,11 @@ int kfb_eigh_sym(const float* C, double count, int32_t d, float* evals, float* e
                  size_t ws_bytes, void* stream);
 /* Debug: Jacobi sweeps used by the last kfb_eigh_sym call that ran on workspace `ws` (synchronises). */
 int kfb_eigh_last_sweeps(const void* ws, int32_t d);
+/* Outcome of the last kfb_eigh_sym call on workspace `ws` (synchronises the device): KFB_OK, or
+ * KFB_ERR_NOT_CONVERGED when the Jacobi sweep limit was hit, cuSOLVER's devInfo was non-zero, or an eigenvalue is not
+ * finite (NaN / Inf in the covariance).  kfb_eigh_sym is safe to call from several host threads at once (one stream,
+ * workspace and cuSOLVER handle per thread).                                                                        */
+int kfb_eigh_status(const void* ws);
 /* Optional: absolute path of the libcusolver.so to dlopen for d > kfb_eigh_jacobi_max_dim().     */
 int kfb_set_cusolver_path(const char* path);
 

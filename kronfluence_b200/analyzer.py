@@ -649,18 +649,19 @@ class Analyzer:
                 module.set_factor(LAMBDA_MATRIX_NAME, ops.lambda_invert(lam, count, score_args.damping_factor))
 
     def _gather_queries(self, names: List[str], base: int, local_batch: int) -> None:
-        """All-gathers this batch's preconditioned query gradients and re-interleaves them to dataset
-        order (tracker/precondition.py:166-201 of the reference).  rank r's j-th local query is global
-        query j*world + r of the batch."""
-        world = self.state.num_processes
-        def gather(storage: torch.Tensor) -> None:
-            local = storage[:, base : base + local_batch].contiguous()
-            flat = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-            dist.all_gather_into_tensor(flat, local)  # concatenated along dim 0 (the form gloo and nccl share)
-            gathered = flat.view((world,) + tuple(local.shape))
-            # [world, planes, j, rows, ld] -> [planes, j, world, rows, ld] -> [planes, j*world, rows, ld]
-            inter = gathered.permute(1, 2, 0, 3, 4).reshape(local.shape[0], local_batch * world, *local.shape[2:])
-            storage[:, base : base + local_batch * world].copy_(inter)
+        """All-gathers this batch's preconditioned query gradients IN PLACE (tracker/precondition.py:166-201 of the
+        reference): rank r has written its `local_batch` queries at store slots [base + r*local_batch, ...), which is
+        exactly its send buffer inside the receive buffer [base, base + world*local_batch) of ncclAllGather, so no
+        temporary of the size of P is needed.  The store therefore holds each batch rank-major (slot r*local_batch + j
+        = query j*world + r of the batch); `_pairwise` un-permutes the ROWS of the score matrix instead of the stores."""
+        world, rank = self.state.num_processes, self.state.process_index
+
+        def gather(storage: torch.Tensor) -> None:  # [planes, capacity, rows, ld]
+            for plane in range(storage.shape[0]):
+                full = storage[plane, base : base + world * local_batch]
+                mine = storage[plane, base + rank * local_batch : base + (rank + 1) * local_batch]
+                # NCCL supports the aliasing; gloo (CPU host-logic tests) gets a private send buffer
+                dist.all_gather_into_tensor(full, mine if storage.is_cuda else mine.clone())
 
         for module in tracked_modules(self.model, names):
             store = module.storage["accumulated_preconditioned_gradient"]
@@ -728,6 +729,17 @@ class Analyzer:
         per_module = score_args.compute_per_module_scores
         out_chunks: Dict[str, List[torch.Tensor]] = {m.name: [] for m in modules} if per_module else {ALL_MODULE_NAME: []}
 
+        # store slot -> position of its query in the current chunk (dataset order); -1 marks the wrap-padded duplicates of
+        # a ragged last batch.  Only differs from the identity when query batches were all-gathered rank-major.
+        slot_positions: List[int] = []
+
+        def select_rows(local_scores: torch.Tensor) -> torch.Tensor:
+            if not slot_positions or slot_positions == list(range(local_scores.shape[0])):
+                return local_scores
+            order = [slot for slot, _ in sorted(((s, p) for s, p in enumerate(slot_positions) if p >= 0),
+                                                key=lambda item: item[1])]
+            return local_scores.index_select(0, torch.tensor(order, dtype=torch.long, device=local_scores.device))
+
         def train_sweep(num_queries: int) -> None:
             set_mode(self.model, ModuleMode.PAIRWISE_SCORE, names, release_memory=False)
             per_token = score_args.compute_per_token_scores
@@ -754,7 +766,7 @@ class Analyzer:
             self.model.zero_grad(set_to_none=True)
             results = {m.name: sinks[m.name] for m in modules} if per_module else {ALL_MODULE_NAME: shared}
             for key, sink in results.items():
-                local_scores = sink.result().contiguous()
+                local_scores = select_rows(sink.result()).contiguous()
                 if self.state.use_distributed:
                     gathered = [torch.empty_like(local_scores) for _ in range(world)] if self.state.is_main_process else None
                     dist.gather(local_scores, gathered, dst=0)
@@ -828,9 +840,14 @@ class Analyzer:
             module.allocate_query_store(capacity, device)
         remaining = n_query
         step = 0
+        chunk_done = 0
         for batch in query_loader:
             batch = _send_to_device(batch, device)
             base = modules[0].query_count
+            local_batch = _find_batch_size(batch)
+            if self.state.use_distributed:
+                for module in modules:  # this rank's slice of the batch's slots (see _gather_queries)
+                    module.query_count = base + self.state.process_index * local_batch
             self.model.zero_grad(set_to_none=True)
             with autocast():
                 measurement = self.task.compute_measurement(batch=batch, model=self.model)
@@ -838,19 +855,24 @@ class Analyzer:
             if factor_args.has_shared_parameters:
                 finalize_iteration(self.model, names)
             del measurement
-            local_batch = _find_batch_size(batch)
             if self.state.use_distributed:
                 self._gather_queries(names, base, local_batch)
-            # drop the wrap-padded duplicates of the last, ragged batch (score/pairwise.py:244-246)
+            # the wrap-padded duplicates of the last, ragged batch are dropped (score/pairwise.py:244-246): slot
+            # r*local_batch + j holds query j*world + r of the batch, valid while that index is below `valid`
             valid = min(local_batch * world, remaining)
-            for module in modules:
-                module.query_count = base + valid
+            for slot in range(local_batch * world):
+                r, j = divmod(slot, local_batch)
+                pos = j * world + r
+                slot_positions.append(chunk_done + pos if pos < valid else -1)
+            chunk_done += valid
             remaining -= valid
             step += 1
             if step % steps == 0 or remaining == 0:
                 train_sweep(modules[0].query_count)
                 for module in modules:
                     module.query_count = 0
+                slot_positions.clear()
+                chunk_done = 0
             if remaining == 0:
                 break
         self.model.zero_grad(set_to_none=True)

@@ -45,6 +45,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 
 // state[0]: off-diagonal measure of the current sweep (max |gamma|/sqrt(alpha beta)), as uint64 bits
 // state[1]: number of sweeps executed
+// state[3]: status of the solve (0 converged, 1 sweep limit reached with columns still not orthogonal, 2 non-finite input)
 __global__ void __launch_bounds__(256) eigh_jacobi_kernel(double* __restrict__ W, double* __restrict__ V,
                                                           int d, double tol, unsigned long long* state) {
   cg::grid_group grid = cg::this_grid();
@@ -73,7 +74,15 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(double* __restrict__ W
   grid.sync();
   const double frob2 = *reinterpret_cast<double*>(&state[2]);
   const double floor2 = 1e-18 * frob2;
+  if (!(frob2 == frob2) || frob2 > 1e300) {  // NaN / Inf in the covariance: nothing to decompose
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      state[1] = 0ull;
+      state[3] = 2ull;
+    }
+    return;
+  }
   int sweep = 0;
+  double last_max = 0.0;
   for (; sweep < kJacobiMaxSweeps; ++sweep) {
     if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = 0ull;
     grid.sync();
@@ -131,13 +140,31 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(double* __restrict__ W
     if (lane == 0) atomicMax(&state[0], (unsigned long long)__double_as_longlong(local_max));
     grid.sync();
     const double sweep_max = __longlong_as_double((long long)state[0]);
+    last_max = sweep_max;
     grid.sync();
     if (sweep_max <= tol) {
       ++sweep;
       break;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) state[1] = (unsigned long long)sweep;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state[1] = (unsigned long long)sweep;
+    // delivered in fp32: columns orthogonal to 1e-7 are converged for every consumer
+    state[3] = (last_max > 1e-7) ? 1ull : 0ull;
+  }
+}
+
+// status |= 2 when an eigenvalue is not finite (NaN / Inf covariance that slipped through the solver); for the
+// cuSOLVER path also folds syevd's devInfo in (status |= 1 when info != 0).
+__global__ void eigh_check_kernel(const float* __restrict__ evals, int d, const int* __restrict__ info,
+                                  unsigned long long* __restrict__ status) {
+  unsigned long long bad = 0ull;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    const float v = evals[i];
+    if (!(v == v) || fabsf(v) > 3.0e38f) bad = 2ull;
+  }
+  if (info != nullptr && threadIdx.x == 0 && *info != 0) bad |= 1ull;
+  if (bad != 0ull) atomicOr(status, bad);
 }
 
 // eigenvalues w_j = v_j . W_j (one warp per column), then ascending rank and scatter to fp32.
@@ -185,7 +212,7 @@ typedef int (*cusolverDnDsyevd_t)(void*, int, int, int, double*, int, double*, d
 
 struct CusolverApi {
   void* lib = nullptr;
-  void* handle = nullptr;
+  cusolverDnCreate_t create = nullptr;
   cusolverDnSetStream_t set_stream = nullptr;
   cusolverDnDsyevd_bufferSize_t buffer_size = nullptr;
   cusolverDnDsyevd_t syevd = nullptr;
@@ -193,10 +220,19 @@ struct CusolverApi {
 static CusolverApi g_cusolver;
 static std::string g_cusolver_path;
 static std::mutex g_cusolver_mutex;
+// One handle per host thread: the Analyzer decomposes several factors concurrently (one thread + CUDA stream each).
+static thread_local void* t_cusolver_handle = nullptr;
 
 static int load_cusolver() {
   std::lock_guard<std::mutex> lock(g_cusolver_mutex);
-  if (g_cusolver.handle != nullptr) return KFB_OK;
+  if (g_cusolver.lib != nullptr && g_cusolver.create != nullptr) {
+    if (t_cusolver_handle == nullptr && (g_cusolver.create(&t_cusolver_handle) != 0 || t_cusolver_handle == nullptr)) {
+      set_error("cusolverDnCreate failed");
+      t_cusolver_handle = nullptr;
+      return KFB_ERR_CUDA;
+    }
+    return KFB_OK;
+  }
   const char* candidates[] = {g_cusolver_path.empty() ? nullptr : g_cusolver_path.c_str(),
                               getenv("KFB_CUSOLVER_PATH"), "libcusolver.so.11",
                               "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"};
@@ -210,7 +246,7 @@ static int load_cusolver() {
               dlerror());
     return KFB_ERR_CUDA;
   }
-  auto create = (cusolverDnCreate_t)dlsym(g_cusolver.lib, "cusolverDnCreate");
+  cusolverDnCreate_t create = (cusolverDnCreate_t)dlsym(g_cusolver.lib, "cusolverDnCreate");
   g_cusolver.set_stream = (cusolverDnSetStream_t)dlsym(g_cusolver.lib, "cusolverDnSetStream");
   g_cusolver.buffer_size = (cusolverDnDsyevd_bufferSize_t)dlsym(g_cusolver.lib, "cusolverDnDsyevd_bufferSize");
   g_cusolver.syevd = (cusolverDnDsyevd_t)dlsym(g_cusolver.lib, "cusolverDnDsyevd");
@@ -218,9 +254,10 @@ static int load_cusolver() {
     set_error("cuSOLVER symbols missing");
     return KFB_ERR_CUDA;
   }
-  if (create(&g_cusolver.handle) != 0 || g_cusolver.handle == nullptr) {
+  g_cusolver.create = create;
+  if (create(&t_cusolver_handle) != 0 || t_cusolver_handle == nullptr) {
     set_error("cusolverDnCreate failed");
-    g_cusolver.handle = nullptr;
+    t_cusolver_handle = nullptr;
     return KFB_ERR_CUDA;
   }
   return KFB_OK;
@@ -240,7 +277,7 @@ __global__ void eigh_transpose_out_kernel(const double* __restrict__ A, const do
 
 static size_t jacobi_ws_bytes(int d) {
   const size_t mat = (size_t)d * d * 8;
-  return 2 * (mat + 256) + (size_t)d * 8 + 256 + (size_t)d * 4 + 256 + 64 + 256;
+  return 256 + 2 * (mat + 256) + (size_t)d * 8 + 256 + (size_t)d * 4 + 256 + 256;
 }
 
 int eigh_sym(const float* C, double count, int d, float* evals, float* evecs, void* ws, size_t ws_bytes,
@@ -256,12 +293,15 @@ int eigh_sym(const float* C, double count, int d, float* evals, float* evecs, vo
     return p;
   };
   const unsigned egrid = (unsigned)(ceil_div_ll((long long)d * d, 256) < 148 * 8 ? ceil_div_ll((long long)d * d, 256) : 148 * 8);
+  // the first 64 bytes of the workspace hold the Jacobi state; word 3 is the status kfb_eigh_status() reports
+  unsigned long long* state = (unsigned long long*)take(64);
+  KFB_REQUIRE(ws != nullptr && ws_bytes >= 64, "eigh: workspace missing");
+  KFB_CUDA_TRY(cudaMemsetAsync(state, 0, 64, stream));
   if (d <= kJacobiMaxDim) {
     double* W = (double*)take((size_t)d * d * 8);
     double* V = (double*)take((size_t)d * d * 8);
     double* w = (double*)take((size_t)d * 8);
     int* rank = (int*)take((size_t)d * 4);
-    unsigned long long* state = (unsigned long long*)take(64);
     if (off > ws_bytes) {
       set_error("eigh workspace too small: need %zu bytes, have %zu", off, ws_bytes);
       return KFB_ERR_WORKSPACE;
@@ -287,7 +327,8 @@ int eigh_sym(const float* C, double count, int d, float* evals, float* evecs, vo
     eigh_values_kernel<<<(unsigned)ceil_div_ll((long long)d * 32, 256), 256, 0, stream>>>(W, V, d, w);
     eigh_rank_kernel<<<(unsigned)ceil_div_ll(d, 128), 128, 0, stream>>>(w, d, rank);
     eigh_scatter_kernel<<<egrid, 256, 0, stream>>>(V, w, rank, d, evals, evecs);
-    count_launch(3);
+    eigh_check_kernel<<<1, 256, 0, stream>>>(evals, d, nullptr, state + 3);
+    count_launch(4);
     KFB_CUDA_TRY(cudaGetLastError());
     return KFB_OK;
   }
@@ -295,12 +336,12 @@ int eigh_sym(const float* C, double count, int d, float* evals, float* evecs, vo
   double* A = (double*)take((size_t)d * d * 8);
   double* w = (double*)take((size_t)d * 8);
   int* info = (int*)take(64);
-  if (g_cusolver.set_stream(g_cusolver.handle, stream) != 0) {
+  if (g_cusolver.set_stream(t_cusolver_handle, stream) != 0) {
     set_error("cusolverDnSetStream failed");
     return KFB_ERR_CUDA;
   }
   int lwork = 0;
-  if (g_cusolver.buffer_size(g_cusolver.handle, /*CUSOLVER_EIG_MODE_VECTOR*/ 1, /*CUBLAS_FILL_MODE_LOWER*/ 0, d,
+  if (g_cusolver.buffer_size(t_cusolver_handle, /*CUSOLVER_EIG_MODE_VECTOR*/ 1, /*CUBLAS_FILL_MODE_LOWER*/ 0, d,
                              A, d, w, &lwork) != 0) {
     set_error("cusolverDnDsyevd_bufferSize failed");
     return KFB_ERR_CUDA;
@@ -312,13 +353,14 @@ int eigh_sym(const float* C, double count, int d, float* evals, float* evecs, vo
   }
   eigh_prepare_kernel<<<egrid, 256, 0, stream>>>(C, 1.0 / count, d, A, nullptr);
   count_launch();
-  const int rc = g_cusolver.syevd(g_cusolver.handle, 1, 0, d, A, d, w, work, lwork, info);
+  const int rc = g_cusolver.syevd(t_cusolver_handle, 1, 0, d, A, d, w, work, lwork, info);
   if (rc != 0) {
     set_error("cusolverDnDsyevd failed with status %d", rc);
     return rc == 2 /*ALLOC_FAILED*/ ? KFB_ERR_OOM : KFB_ERR_CUDA;
   }
   eigh_transpose_out_kernel<<<egrid, 256, 0, stream>>>(A, w, d, evals, evecs);
-  count_launch();
+  eigh_check_kernel<<<1, 256, 0, stream>>>(evals, d, info, state + 3);
+  count_launch(2);
   KFB_CUDA_TRY(cudaGetLastError());
   return KFB_OK;
 }
@@ -333,7 +375,7 @@ size_t kfb_eigh_workspace_bytes(int32_t d) {
   if (d <= 0) return 0;
   if (d <= kfb::kJacobiMaxDim) return kfb::jacobi_ws_bytes(d);
   // A + w + info + syevd work.  cuSOLVER 11.7 asks for ~4.1 d^2 doubles at d = 1500 (measured); leave slack.
-  return (size_t)d * d * 8 + (size_t)d * 8 + ((size_t)6 * d * d + 64 * (size_t)d + 4096) * 8 + 4096;
+  return 256 + (size_t)d * d * 8 + (size_t)d * 8 + ((size_t)6 * d * d + 64 * (size_t)d + 4096) * 8 + 4096;
 }
 
 int kfb_set_cusolver_path(const char* path) {
@@ -345,22 +387,31 @@ int kfb_set_cusolver_path(const char* path) {
 /* Debug: number of Jacobi sweeps the last kfb_eigh_sym call on this workspace used (synchronises). */
 int kfb_eigh_last_sweeps(const void* ws, int32_t d) {
   if (ws == nullptr || d <= 1 || d > kfb::kJacobiMaxDim) return -1;
-  size_t off = 0;
-  auto take = [&](size_t n) {
-    off = (off + 255) & ~static_cast<size_t>(255);
-    const size_t at = off;
-    off += n;
-    return at;
-  };
-  take((size_t)d * d * 8);
-  take((size_t)d * d * 8);
-  take((size_t)d * 8);
-  take((size_t)d * 4);
-  const size_t state_off = take(64);
-  unsigned long long state[3] = {0, 0, 0};
-  if (cudaMemcpy(state, static_cast<const char*>(ws) + state_off, sizeof(state), cudaMemcpyDeviceToHost) != cudaSuccess)
-    return -1;
+  unsigned long long state[4] = {0, 0, 0, 0};
+  if (cudaMemcpy(state, ws, sizeof(state), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int)state[1];
+}
+
+/* Outcome of the last kfb_eigh_sym call that ran on workspace `ws` (synchronises): KFB_OK, or KFB_ERR_NOT_CONVERGED if
+ * the Jacobi sweep limit was reached / cuSOLVER reported devInfo != 0 / an eigenvalue is not finite (NaN or Inf in the
+ * covariance), so that a poisoned decomposition is never written to the eigen files (factor/eigen.py:204-212 of the
+ * reference surfaces LAPACK's failure the same way). */
+int kfb_eigh_status(const void* ws) {
+  if (ws == nullptr) {
+    kfb::set_error("eigh_status: null workspace");
+    return KFB_ERR_INVALID;
+  }
+  unsigned long long state[4] = {0, 0, 0, 0};
+  if (cudaMemcpy(state, ws, sizeof(state), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    kfb::set_error("eigh_status: reading the solver state failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return KFB_ERR_CUDA;
+  }
+  if (state[3] != 0ull) {
+    kfb::set_error("eigendecomposition failed: %s%s", (state[3] & 2ull) ? "non-finite values in the covariance / eigenvalues" : "",
+                   (state[3] & 1ull) ? " solver did not converge" : "");
+    return KFB_ERR_NOT_CONVERGED;
+  }
+  return KFB_OK;
 }
 
 int kfb_eigh_sym(const float* C, double count, int32_t d, float* evals, float* evecs, void* ws,

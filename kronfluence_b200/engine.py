@@ -78,6 +78,7 @@ SIGNATURES = {
     "kfb_eigh_workspace_bytes": (_sz, [_i32]),
     "kfb_eigh_sym": (ctypes.c_int, [_vp, _f64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "kfb_eigh_last_sweeps": (ctypes.c_int, [_vp, _i32]),
+    "kfb_eigh_status": (ctypes.c_int, [_vp]),
     "kfb_set_cusolver_path": (ctypes.c_int, [ctypes.c_char_p]),
     "kfb_eigen_operands": (ctypes.c_int, [_vp, _i32, _SP, _SP, ctypes.c_int, _vp]),
     "kfb_lambda_workspace_bytes": (_sz, [_LP, _i64, _i64]),
@@ -183,6 +184,8 @@ def check(rc: int) -> None:
         raise KfbError(f"libkfb needs an sm_100 (B200) device and has no CPU path: {msg}")
     if rc == KFB_ERR_WORKSPACE:
         raise KfbError(f"libkfb workspace too small: {msg}")
+    if rc == KFB_ERR_NOT_CONVERGED:
+        raise KfbError(f"libkfb: {msg}")
     raise KfbError(f"libkfb failure ({rc}): {msg}")
 
 

@@ -132,16 +132,21 @@ def cov_accum_gradient(layer: KfbLayer, g: torch.Tensor, cov: torch.Tensor, alph
 # --------------------------------------------------------------------------------------------------
 # Stage 2: eigendecomposition (factor/eigen.py:140-224)
 # --------------------------------------------------------------------------------------------------
-def eigh_sym(cov: torch.Tensor, count: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Returns (eigenvalues ascending [d], eigenvectors as columns [d, d]) in fp32 on cov's device."""
+def eigh_sym(cov: torch.Tensor, count: float, return_sweeps: bool = False):
+    """Returns (eigenvalues ascending [d], eigenvectors as columns [d, d]) in fp32 on cov's device; with
+    `return_sweeps` also the number of Jacobi sweeps (-1 on the cuSOLVER path; debugging)."""
     lib = engine.load_library()
     cov = _contig(cov.to(dtype=torch.float32))
     d = cov.shape[0]
     evals = torch.empty(d, dtype=torch.float32, device=cov.device)
     evecs = torch.empty(d, d, dtype=torch.float32, device=cov.device)
-    ws_ptr, ws_size = workspace(cov.device).get(lib.kfb_eigh_workspace_bytes(d))
-    check(lib.kfb_eigh_sym(cov.data_ptr(), float(count), d, evals.data_ptr(), evecs.data_ptr(), ws_ptr, ws_size,
+    # a private workspace per call: the Analyzer runs several decompositions concurrently (thread + stream each)
+    ws = torch.empty(max(int(lib.kfb_eigh_workspace_bytes(d)), 256), dtype=torch.uint8, device=cov.device)
+    check(lib.kfb_eigh_sym(cov.data_ptr(), float(count), d, evals.data_ptr(), evecs.data_ptr(), ws.data_ptr(), ws.numel(),
                            stream_ptr(cov.device)))
+    check(lib.kfb_eigh_status(ws.data_ptr()))  # NaN / Inf covariances and unconverged solves must not reach the files
+    if return_sweeps:
+        return evals, evecs, int(lib.kfb_eigh_last_sweeps(ws.data_ptr(), d))
     return evals, evecs
 
 

@@ -313,7 +313,7 @@ def test_eigh_sizes(d):
     cov = x.T @ x
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    evals, evecs = ops.eigh_sym(cov, float(n))
+    evals, evecs, sweeps = ops.eigh_sym(cov, float(n), return_sweeps=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     sym = (0.5 * (cov + cov.T) / n).double()
@@ -321,8 +321,51 @@ def test_eigh_sizes(d):
     resid = ((q * w) @ q.T - sym).norm() / sym.norm()
     ortho = (q.T @ q - torch.eye(d, device="cuda", dtype=torch.float64)).abs().max()
     ref = torch.linalg.eigvalsh(sym)
-    sweeps = engine.load_library().kfb_eigh_last_sweeps(ops.workspace(cov.device).buf.data_ptr(), d)
     print(f"eigh d={d}: {dt * 1e3:.1f} ms, residual {resid:.2e}, orthogonality {ortho:.2e}, jacobi sweeps {sweeps}")
     assert resid < 5e-6 and ortho < 5e-6
     assert (w - ref).abs().max() < 2e-6 * ref.abs().max()
     assert (w[1:] >= w[:-1] - 1e-6 * ref.abs().max()).all()
+
+
+@pytest.mark.parametrize("d", [64, 700])
+def test_eigh_reports_failure(d):
+    """A covariance with NaN must raise (KFB_ERR_NOT_CONVERGED) on both the Jacobi and the cuSOLVER path instead of
+    writing a poisoned decomposition."""
+    from kronfluence_b200 import engine, ops
+
+    cov = torch.eye(d, device="cuda")
+    cov[3, 5] = float("nan")
+    with pytest.raises(engine.KfbError):
+        ops.eigh_sym(cov, 1.0)
+    evals, _ = ops.eigh_sym(torch.eye(d, device="cuda") * 2.0, 1.0)  # the next call on a clean matrix is fine
+    assert torch.allclose(evals, torch.full_like(evals, 2.0))
+
+
+def test_eigh_concurrent_threads():
+    """kfb_eigh_sym from several host threads (own stream, workspace and cuSOLVER handle each), as the Analyzer runs it."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from kronfluence_b200 import ops
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    covs = []
+    for d in (600, 300, 768, 130, 900, 768):
+        x = torch.randn(2 * d, d, device="cuda", generator=gen)
+        covs.append(x.T @ x)
+    torch.cuda.synchronize()
+
+    def work(cov):
+        torch.cuda.set_device(dev)
+        with torch.cuda.stream(torch.cuda.Stream(dev)):
+            evals, evecs = ops.eigh_sym(cov, float(2 * cov.shape[0]))
+            torch.cuda.current_stream().synchronize()
+        return evals, evecs
+
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        results = list(pool.map(work, covs))
+    for cov, (evals, evecs) in zip(covs, results):
+        d = cov.shape[0]
+        sym = (0.5 * (cov + cov.T) / (2 * d)).double()
+        q, w = evecs.double(), evals.double()
+        assert ((q * w) @ q.T - sym).norm() / sym.norm() < 5e-6
