@@ -300,6 +300,24 @@ int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_
                         float scale, float* scores, int64_t ld_scores, int64_t t_offset,
                         int32_t accumulate, void* ws, size_t ws_bytes, int precision, void* stream);
 
+/* The two halves of kfb_pairwise_scores, for callers that sweep the same train batches against several query chunks
+ * (the reference re-runs the whole train forward/backward per query chunk, score/pairwise.py:133-293).
+ *   kfb_pairwise_prepare            activations / output gradients of a batch -> tensor-core operands in `operands`
+ *                                   (rotated into the eigenbases for KFB_PRECOND_EIGEN stores); independent of the queries
+ *   kfb_pairwise_scores_prepared    operands x query store -> score columns (same result as kfb_pairwise_scores)
+ * `operands` is a caller-owned device buffer of kfb_pairwise_operand_bytes(); its layout is private to the library and
+ * depends on (layer, batch, seq, precision), which must be the same in both calls.                                */
+size_t kfb_pairwise_operand_bytes(const kfb_layer* layer, int64_t batch, int64_t seq, int precision);
+size_t kfb_pairwise_prepare_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_pairwise_prepare(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
+                         int64_t seq, int32_t mode, const kfb_split* qa_t, const kfb_split* qg_t, void* operands,
+                         size_t operand_bytes, void* ws, size_t ws_bytes, int precision, void* stream);
+size_t kfb_pairwise_prepared_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq);
+int kfb_pairwise_scores_prepared(const kfb_layer* layer, const kfb_split* P, int64_t num_queries, const void* operands,
+                                 size_t operand_bytes, int64_t batch, int64_t seq, float scale, float* scores,
+                                 int64_t ld_scores, int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes,
+                                 int precision, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Aggregated gradients.  GradientTracker  module/tracker/gradient.py:14-95 with
  * compute_summed_gradient  module/linear.py:63-66, conv2d.py:157-162; consumers

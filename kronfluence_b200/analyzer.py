@@ -27,7 +27,8 @@ from torch.utils import data
 
 from kronfluence_b200 import ops
 from kronfluence_b200.arguments import FactorArguments, ScoreArguments
-from kronfluence_b200.module.tracked_module import ModuleMode, ScoreSink, TrackedModule, precision_of, strategy_config
+from kronfluence_b200.module.tracked_module import (ModuleMode, ScoreSink, TrackedModule, TrainOperandCache, precision_of,
+                                                     strategy_config)
 from kronfluence_b200.module.utils import (
     collect_factors,
     finalize_iteration,
@@ -178,6 +179,10 @@ class Analyzer:
             self.output_dir.mkdir(parents=True, exist_ok=True)
         self.profiler = Profiler(self.state, profile)
         self._dataloader_params = DataLoaderKwargs()
+        # Fraction of the free device memory the pairwise stage may spend on keeping prepared train operands across query
+        # chunks (0 disables; see TrainOperandCache).  `last_train_operand_cache` reports what the last run did.
+        self.train_operand_cache_fraction = 0.5
+        self.last_train_operand_cache: Optional[Dict[str, Any]] = None
 
     # ------------------------------------------------------------------------------------------
     # small helpers
@@ -471,23 +476,76 @@ class Analyzer:
                                        "To perform eigendecomposition, covariance matrices need to be fitted first.")
         eigen: FACTOR_TYPE = {name: {} for name in EIGENDECOMPOSITION_FACTOR_NAMES}
         with self.profiler.profile("Perform Eigendecomposition"):
-            if self.state.is_main_process:  # factor_computer.py:449 of the reference
-                for mname in covariance[ACTIVATION_COVARIANCE_MATRIX_NAME]:
-                    for cov_name, num_name, vec_name, val_name in (
-                        (ACTIVATION_COVARIANCE_MATRIX_NAME, NUM_ACTIVATION_COVARIANCE_PROCESSED,
-                         ACTIVATION_EIGENVECTORS_NAME, ACTIVATION_EIGENVALUES_NAME),
-                        (GRADIENT_COVARIANCE_MATRIX_NAME, NUM_GRADIENT_COVARIANCE_PROCESSED,
-                         GRADIENT_EIGENVECTORS_NAME, GRADIENT_EIGENVALUES_NAME),
-                    ):
-                        cov = covariance[cov_name][mname]
-                        count = float(covariance[num_name][mname].item())
-                        evals, evecs = ops.eigh_sym(cov.to(device=self.state.device, dtype=torch.float32), count)
-                        eigen[val_name][mname] = evals.to(dtype=cov.dtype, device="cpu")
-                        eigen[vec_name][mname] = evecs.to(dtype=cov.dtype, device="cpu")
+            self._eigendecompose(covariance, eigen)
         with self.profiler.profile("Save Eigendecomposition"):
             if self.state.is_main_process:
                 io.save_factors(out_dir, eigen, metadata=factor_args.to_str_dict())
             self.state.wait_for_everyone()
+
+    def _eigendecompose(self, covariance: FACTOR_TYPE, eigen: FACTOR_TYPE) -> None:
+        """factor/eigen.py:140-224 of the reference for every module and side.  The reference decomposes one matrix at
+        a time on rank 0 (factor_computer.py:449); here the (module, side) jobs are independent, so they are (i) dealt
+        to the ranks largest-first (longest-processing-time greedy on d^3), (ii) run concurrently on each GPU, one host
+        thread + CUDA stream + solver handle per job in flight (a 768-wide syevd does not fill a B200), and (iii)
+        delivered to the main process with one broadcast per result."""
+        import os as _os
+        from concurrent.futures import ThreadPoolExecutor
+
+        device = self.state.device
+        world, rank = self.state.num_processes, self.state.process_index
+        sides = ((ACTIVATION_COVARIANCE_MATRIX_NAME, NUM_ACTIVATION_COVARIANCE_PROCESSED,
+                  ACTIVATION_EIGENVECTORS_NAME, ACTIVATION_EIGENVALUES_NAME),
+                 (GRADIENT_COVARIANCE_MATRIX_NAME, NUM_GRADIENT_COVARIANCE_PROCESSED,
+                  GRADIENT_EIGENVECTORS_NAME, GRADIENT_EIGENVALUES_NAME))
+        jobs = []
+        for mname in covariance[ACTIVATION_COVARIANCE_MATRIX_NAME]:
+            for side, (cov_name, _, _, _) in enumerate(sides):
+                jobs.append((int(covariance[cov_name][mname].shape[0]), mname, side))
+        jobs.sort(key=lambda job: (-job[0], job[1], job[2]))  # deterministic on every rank
+        loads = [0.0] * world
+        owners = []
+        for d, _, _ in jobs:
+            target = min(range(world), key=lambda r: (loads[r], r))
+            owners.append(target)
+            loads[target] += float(d) ** 3
+
+        def solve(job):
+            d, mname, side = job
+            cov_name, num_name, _, _ = sides[side]
+            cov = covariance[cov_name][mname]
+            count = float(covariance[num_name][mname].item())
+            if device.type != "cuda":
+                return ops.eigh_sym(cov.to(dtype=torch.float32), count)
+            torch.cuda.set_device(device)  # the current device is per host thread
+            with torch.cuda.stream(torch.cuda.Stream(device)):
+                evals, evecs = ops.eigh_sym(cov.to(device=device, dtype=torch.float32), count)
+                torch.cuda.current_stream(device).synchronize()
+            return evals, evecs
+
+        mine = [job for job, owner in zip(jobs, owners) if owner == rank]
+        threads = max(1, min(int(_os.environ.get("KFB_EIGH_THREADS", "4")), len(mine)))
+        if threads > 1:
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                solved = dict(zip(mine, pool.map(solve, mine)))
+        else:
+            solved = {job: solve(job) for job in mine}
+        for job, owner in zip(jobs, owners):
+            d, mname, side = job
+            cov_name, _, vec_name, val_name = sides[side]
+            dtype = covariance[cov_name][mname].dtype
+            if world > 1:
+                if owner == rank:
+                    evals, evecs = (t.to(device) for t in solved.pop(job))
+                else:
+                    evals = torch.empty(d, dtype=torch.float32, device=device)
+                    evecs = torch.empty(d, d, dtype=torch.float32, device=device)
+                dist.broadcast(evals, src=owner)
+                dist.broadcast(evecs, src=owner)
+            else:
+                evals, evecs = solved.pop(job)
+            if self.state.is_main_process:
+                eigen[val_name][mname] = evals.to(dtype=dtype, device="cpu")
+                eigen[vec_name][mname] = evecs.to(dtype=dtype, device="cpu")
 
     def load_eigendecomposition(self, factors_name: str) -> Optional[FACTOR_TYPE]:
         out_dir = self.factors_output_dir(factors_name)
@@ -740,6 +798,24 @@ class Analyzer:
                                                 key=lambda item: item[1])]
             return local_scores.index_select(0, torch.tensor(order, dtype=torch.long, device=local_scores.device))
 
+        # Several query chunks sweep the same train batches: keep their prepared (rotated) operands on the device if they
+        # fit, and replay them for the later chunks instead of running the model again.
+        n_chunks = math.ceil(math.ceil(n_query / (query_bs * world)) / steps)
+        cache: Optional[TrainOperandCache] = None
+        if (n_chunks > 1 and self.train_operand_cache_fraction > 0 and score_args.query_gradient_low_rank is None
+                and not self.task.enable_post_process_per_sample_gradient):
+            free_bytes = torch.cuda.mem_get_info(device)[0] if device.type == "cuda" else 1 << 40
+            cache = TrainOperandCache(int(free_bytes * self.train_operand_cache_fraction))
+        for module in modules:
+            module.train_operand_cache = cache
+
+        def replay_sweep(num_queries: int, sinks: Dict[str, ScoreSink]) -> None:
+            for module in modules:
+                store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
+                for prepared, column, scale, tokens in cache.entries.get(module.name, []):
+                    ops.pairwise_scores_prepared(store, num_queries, prepared, sinks[module.name].get(tokens), column,
+                                                 accumulate=True, scale=scale)
+
         def train_sweep(num_queries: int) -> None:
             set_mode(self.model, ModuleMode.PAIRWISE_SCORE, names, release_memory=False)
             per_token = score_args.compute_per_token_scores
@@ -751,18 +827,23 @@ class Analyzer:
             for module in modules:
                 module.storage[PAIRWISE_SCORE_MATRIX_NAME] = sinks[module.name]
             offset = 0
-            for batch in train_loader:
-                batch = _send_to_device(batch, device)
-                for module in modules:
-                    module.score_offset = offset
-                self.model.zero_grad(set_to_none=True)
-                with autocast():
-                    loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
-                scaler.scale(loss).backward()
-                if factor_args.has_shared_parameters:
-                    finalize_iteration(self.model, names)
-                offset += _find_batch_size(batch)
-                del loss
+            if cache is not None and cache.complete:
+                replay_sweep(num_queries, sinks)
+            else:
+                for batch in train_loader:
+                    batch = _send_to_device(batch, device)
+                    for module in modules:
+                        module.score_offset = offset
+                    self.model.zero_grad(set_to_none=True)
+                    with autocast():
+                        loss = self.task.compute_train_loss(batch=batch, model=self.model, sample=False)
+                    scaler.scale(loss).backward()
+                    if factor_args.has_shared_parameters:
+                        finalize_iteration(self.model, names)
+                    offset += _find_batch_size(batch)
+                    del loss
+                if cache is not None and cache.recording:
+                    cache.finish_recording()
             self.model.zero_grad(set_to_none=True)
             results = {m.name: sinks[m.name] for m in modules} if per_module else {ALL_MODULE_NAME: shared}
             for key, sink in results.items():
@@ -876,6 +957,11 @@ class Analyzer:
             if remaining == 0:
                 break
         self.model.zero_grad(set_to_none=True)
+        if cache is not None:
+            self.last_train_operand_cache = {"complete": cache.complete, "bytes": cache.bytes, "budget": cache.budget}
+            cache.clear()
+        for module in modules:
+            module.train_operand_cache = None
         set_mode(self.model, ModuleMode.DEFAULT, release_memory=True)
         if scaler.is_enabled():
             set_gradient_scale(self.model, 1.0)

@@ -496,79 +496,155 @@ __global__ void zero_strided_kernel(float* p, long long rows, long long cols, lo
     p[(i / cols) * ld + (i % cols)] = 0.f;
 }
 
-static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, const void* a, int a_dt,
-                        const void* g, int g_dt, long long batch, long long seq, int mode,
-                        const kfb_split* qa_t, const kfb_split* qg_t, float scale, float* scores,
-                        long long ld_scores, long long t_offset, int accumulate, Ws& ws, int precision,
-                        cudaStream_t stream) {
+// The train side of the contraction depends only on the train batch, not on the queries, so it is split in two:
+//   prepare   raw activations / output gradients -> tensor-core operands (rotated into the eigenbases when the store
+//             holds eigenbasis images):  S = 1: a~ as operand planes + g~ as fp32 rows;  S > 1 / Conv2d: the per-example
+//             outer-product operands Lt[b] = [d_out, S], Rt[b] = [d_in+bias, S]
+//   contract  operands x query store -> score columns
+// kfb_pairwise_scores runs both back to back on workspace memory; kfb_pairwise_prepare / kfb_pairwise_scores_prepared
+// expose the halves so that a caller can keep the operands of its train batches (they are small next to P) and sweep
+// them against several query chunks without re-running the model or the rotations.
+struct PairOperands {
+  kfb_split a_op;  // S == 1: [batch, d_in+bias] planes
+  float* g32;      // S == 1: [batch, d_out] fp32
+  kfb_split Lt, Rt;  // S > 1: [batch][d_out][S], [batch][d_in+bias][S] planes
+};
+
+static inline bool pair_rank1(const kfb_layer& L, long long S) { return L.kind == KFB_LINEAR && S == 1; }
+
+static PairOperands pair_operands_alloc(Ws& ws, const kfb_layer& L, long long batch, long long S, int precision) {
+  PairOperands o{};
+  const long long di = L.d_in + L.has_bias;
+  if (pair_rank1(L, S)) {
+    o.a_op = ws_split(ws, batch, di, 1, precision);
+    o.g32 = static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
+  } else {
+    o.Lt = ws_split(ws, L.d_out, S, batch, precision);
+    o.Rt = ws_split(ws, di, S, batch, precision);
+  }
+  return o;
+}
+
+static PairOperands pair_operands_view(const PairOperands& o, const kfb_layer& L, long long b0, long long nb) {
+  PairOperands v = o;
+  if (o.g32 != nullptr) {
+    v.a_op.hi = static_cast<char*>(o.a_op.hi) + b0 * o.a_op.ld * 2;
+    v.a_op.lo = o.a_op.lo ? static_cast<char*>(o.a_op.lo) + b0 * o.a_op.ld * 2 : nullptr;
+    v.a_op.rows = nb;
+    v.g32 = o.g32 + b0 * L.d_out;
+  } else {
+    v.Lt = split_batch_view(o.Lt, b0, nb);
+    v.Rt = split_batch_view(o.Rt, b0, nb);
+  }
+  return v;
+}
+
+// scratch bytes per train example of pairwise_prepare
+static long long pair_prepare_bytes_per_sample(const kfb_layer& L, long long S, bool eigen, int precision) {
+  const long long di = L.d_in + L.has_bias;
+  if (!eigen) return 0;
+  return S * (ld8(di) + ld8(L.d_out)) * 2 * planes_of(rot_prec(precision));
+}
+
+static int pairwise_prepare(const kfb_layer& L, const void* a, int a_dt, const void* g, int g_dt, long long batch,
+                            long long seq, bool eigen, const kfb_split* qa_t, const kfb_split* qg_t, const PairOperands& o,
+                            Ws& ws, int precision, cudaStream_t stream) {
   const long long S = positions(L, seq);
   const long long di = L.d_in + L.has_bias;
-  const long long planes = planes_of(precision);
-  const bool eigen = mode == KFB_PRECOND_EIGEN;  // P is stored in the eigenbasis: rotate the train operands
   const int rp = rot_prec(precision);
-  if (L.kind == KFB_LINEAR && S == 1) {
-    // Fused path: scores[q, t] = sum_o g[t,o] * (sum_i a[t,i] P[q,o,i]); the inner GEMM is the
-    // tensor-core tile (M = t, N = o, K = i, batched over q), the outer sum is the ROWDOT epilogue.
-    kfb_split a_sp = ws_split(ws, batch, di, 1, eigen ? rp : precision);
-    kfb_split g_sp{}, a_rot{};
-    float* g32 = nullptr;
+  const long long cb = chunk_count(batch, pair_prepare_bytes_per_sample(L, S, eigen, precision));
+  if (pair_rank1(L, S)) {
+    kfb_split a_sp{}, g_sp{};
     if (eigen) {
-      g_sp = ws_split(ws, batch, L.d_out, 1, rp);
-      a_rot = ws_split(ws, batch, di, 1, precision);
-      g32 = static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
-    } else if (g_dt != KFB_F32) {
-      g32 = static_cast<float*>(ws.take((size_t)(batch * L.d_out) * 4));
+      a_sp = ws_split(ws, cb, di, 1, rp);
+      g_sp = ws_split(ws, cb, L.d_out, 1, rp);
     }
     if (ws.dry) return KFB_OK;
     if (!ws.fits()) {
       set_error("pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
       return KFB_ERR_WORKSPACE;
     }
-    GatherDesc ga{};
-    ga.sr = L.d_in; ga.sc2 = 1; ga.rows = batch; ga.c1 = 1; ga.c2 = L.d_in;
-    ga.ones_mode = L.has_bias ? 1 : 0;
-    KFB_TRY(split_gather(a, a_dt, ga, a_sp, eigen ? rp : precision, stream));
-    const float* gp = static_cast<const float*>(g);
-    const kfb_split* a_operand = &a_sp;
     if (eigen) {
       KFB_REQUIRE(qa_t != nullptr && qg_t != nullptr && qa_t->rows == di && qg_t->rows == L.d_out,
                   "pairwise: eigenbasis operands do not match the layer");
       KFB_REQUIRE(rp != KFB_PREC_STRICT || (qa_t->absmax != nullptr && qg_t->absmax != nullptr),
                   "pairwise: eigenbasis operands must be built with KFB_PREC_STRICT");
+    }
+    for (long long b0 = 0; b0 < batch; b0 += cb) {
+      const long long nb = batch - b0 < cb ? batch - b0 : cb;
+      const PairOperands v = pair_operands_view(o, L, b0, nb);
+      GatherDesc ga{};
+      ga.sr = L.d_in; ga.sc2 = 1; ga.rows = nb; ga.c1 = 1; ga.c2 = L.d_in;
+      ga.ones_mode = L.has_bias ? 1 : 0;
+      const void* a0 = advance(a, a_dt, b0 * L.d_in);
+      const void* g0 = advance(g, g_dt, b0 * L.d_out);
+      if (!eigen) {
+        KFB_TRY(split_gather(a0, a_dt, ga, v.a_op, precision, stream));
+        KFB_TRY(cast_to_f32(g0, g_dt, v.g32, nb * L.d_out, 1.f, stream));
+        continue;
+      }
+      kfb_split av = a_sp, gv = g_sp;
+      av.rows = nb; gv.rows = nb;
+      KFB_TRY(split_gather(a0, a_dt, ga, av, rp, stream));
       GatherDesc gg{};
-      gg.sr = L.d_out; gg.sc2 = 1; gg.rows = batch; gg.c1 = 1; gg.c2 = L.d_out;
-      KFB_TRY(split_gather(g, g_dt, gg, g_sp, rp, stream));
+      gg.sr = L.d_out; gg.sc2 = 1; gg.rows = nb; gg.c1 = 1; gg.c2 = L.d_out;
+      KFB_TRY(split_gather(g0, g_dt, gg, gv, rp, stream));
       // a~[t, n] = sum_k a[t,k] Q_A[k,n]  (operand planes for the fused kernel);  g~[t, n] likewise (fp32)
       kfb_epilogue ea = store_epilogue();
-      ea.out_split = a_rot;
-      KFB_TRY(gemm_nt(a_sp, *qa_t, ea, rp, 1, stream));
+      ea.out_split = v.a_op;
+      KFB_TRY(gemm_nt(av, *qa_t, ea, rp, 1, stream));
       kfb_epilogue eg = store_epilogue();
-      eg.out_f32 = g32;
+      eg.out_f32 = v.g32;
       eg.ldo = L.d_out;
-      KFB_TRY(gemm_nt(g_sp, *qg_t, eg, rp, 1, stream));
-      a_operand = &a_rot;
-      gp = g32;
-    } else if (g32 != nullptr) {
-      KFB_TRY(cast_to_f32(g, g_dt, g32, batch * L.d_out, 1.f, stream));
-      gp = g32;
+      KFB_TRY(gemm_nt(gv, *qg_t, eg, rp, 1, stream));
     }
+    return KFB_OK;
+  }
+  // sequences / Conv2d: outer-product operands, rotated first when the store is in the eigenbasis
+  OuterBufs ob{};
+  if (eigen) {
+    ob.tmp_a = ws_split(ws, S, di, cb, rp);
+    ob.tmp_g = ws_split(ws, S, L.d_out, cb, rp);
+  }
+  if (ws.dry) return KFB_OK;
+  if (!ws.fits()) {
+    set_error("pairwise workspace too small: need %zu bytes, have %zu", ws.off, ws.cap);
+    return KFB_ERR_WORKSPACE;
+  }
+  for (long long b0 = 0; b0 < batch; b0 += cb) {
+    const long long nb = batch - b0 < cb ? batch - b0 : cb;
+    const PairOperands v = pair_operands_view(o, L, b0, nb);
+    ob.Lt = v.Lt;
+    ob.Rt = v.Rt;
+    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, eigen, qa_t, qg_t, ob, precision, stream));
+  }
+  return KFB_OK;
+}
+
+static int pairwise_contract(const kfb_layer& L, const kfb_split* P, long long nq, const PairOperands& o, long long batch,
+                             long long seq, float scale, float* scores, long long ld_scores, long long t_offset,
+                             int accumulate, Ws& ws, int precision, cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const long long planes = planes_of(precision);
+  if (pair_rank1(L, S)) {
+    // Fused path: scores[q, t] = sum_o g[t,o] * (sum_i a[t,i] P[q,o,i]); the inner GEMM is the
+    // tensor-core tile (M = t, N = o, K = i, batched over q), the outer sum is the ROWDOT epilogue.
+    if (ws.dry) return KFB_OK;
     kfb_epilogue e{};
     e.kind = KFB_EPI_ROWDOT;
     e.out_f32 = scores + t_offset;
     e.out_batch_stride = ld_scores;
-    e.g = gp;
+    e.g = o.g32;
     e.ldg = L.d_out;
     e.alpha = scale;
     e.accumulate = accumulate;
-    return gemm_nt(*a_operand, split_batch_view(*P, 0, nq), e, precision, 1, stream);
+    return gemm_nt(o.a_op, split_batch_view(*P, 0, nq), e, precision, 1, stream);
   }
-  // General path (sequences, Conv2d): per-sample gradients G_t = g_t^T a_t (rotated into the eigenbasis
-  // first when P is) via a batched GEMM (K = S) written straight in P's operand layout, then
-  // scores = P_flat G_flat^T (K = d_out*ld).
+  // General path (sequences, Conv2d): per-sample gradients G_t = Lt[t] Rt[t]^T via a batched GEMM (K = S) written
+  // straight in P's operand layout, then scores = P_flat G_flat^T (K = d_out*ld).
   const long long ldp = P != nullptr ? P->ld : ld8(di);
-  const long long per = outer_bytes_per_sample(L, S, eigen, precision) + L.d_out * ldp * 2 * planes;
-  const long long cb = chunk_count(batch, per);
-  OuterBufs o = outer_alloc(ws, L, cb, S, eigen, precision);
+  const long long cb = chunk_count(batch, L.d_out * ldp * 2 * planes);
   kfb_split G{};
   G.rows = L.d_out; G.cols = di; G.ld = ldp; G.batch = cb; G.batch_stride = L.d_out * ldp;
   G.hi = ws.take((size_t)(cb * G.batch_stride) * 2);
@@ -585,10 +661,9 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
   }
   for (long long b0 = 0; b0 < batch; b0 += cb) {
     const long long nb = batch - b0 < cb ? batch - b0 : cb;
-    KFB_TRY(outer_fill(L, a, a_dt, g, g_dt, b0, nb, seq, eigen, qa_t, qg_t, o, precision, stream));
     kfb_epilogue e1 = store_epilogue();
     e1.out_split = split_batch_view(G, 0, nb);
-    KFB_TRY(gemm_nt(split_batch_view(o.Lt, 0, nb), split_batch_view(o.Rt, 0, nb), e1, precision, 1, stream));
+    KFB_TRY(gemm_nt(split_batch_view(o.Lt, b0, nb), split_batch_view(o.Rt, b0, nb), e1, precision, 1, stream));
     kfb_split Pf{};
     Pf.hi = P->hi; Pf.lo = P->lo; Pf.rows = nq; Pf.cols = L.d_out * ldp; Pf.ld = P->batch_stride;
     Pf.batch = 1; Pf.batch_stride = 0;
@@ -602,6 +677,42 @@ static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, co
     e2.alpha = scale;
     KFB_TRY(gemm_nt(Pf, Gf, e2, precision, 0, stream));
   }
+  return KFB_OK;
+}
+
+static int pairwise_run(const kfb_layer& L, const kfb_split* P, long long nq, const void* a, int a_dt,
+                        const void* g, int g_dt, long long batch, long long seq, int mode,
+                        const kfb_split* qa_t, const kfb_split* qg_t, float scale, float* scores,
+                        long long ld_scores, long long t_offset, int accumulate, Ws& ws, int precision,
+                        cudaStream_t stream) {
+  const long long S = positions(L, seq);
+  const long long di = L.d_in + L.has_bias;
+  const long long planes = planes_of(precision);
+  const bool eigen = mode == KFB_PRECOND_EIGEN;  // P is stored in the eigenbasis: rotate the train operands
+  // chunks of the batch whose operands + scratch stay within the budget (one chunk for S = 1 and ordinary batches)
+  const long long ldp = P != nullptr ? P->ld : ld8(di);
+  const long long per = pair_rank1(L, S) ? 0 : outer_bytes_per_sample(L, S, eigen, precision) + L.d_out * ldp * 2 * planes;
+  const long long cb = chunk_count(batch, per);
+  const PairOperands o = pair_operands_alloc(ws, L, cb, S, precision);
+  // the preparation scratch and the per-sample-gradient buffer of the contraction are never live together
+  const size_t mark = ws.off;
+  size_t peak = mark;
+  for (long long b0 = 0; b0 < batch || ws.dry; b0 += cb) {
+    const long long nb = ws.dry ? cb : (batch - b0 < cb ? batch - b0 : cb);
+    const void* a0 = L.kind == KFB_LINEAR ? advance(a, a_dt, b0 * S * L.d_in)
+                                          : advance(a, a_dt, b0 * (long long)L.c_in * L.h_in * L.w_in);
+    const void* g0 = advance(g, g_dt, b0 * S * L.d_out);
+    const PairOperands v = pair_operands_view(o, L, 0, nb);
+    ws.off = mark;
+    KFB_TRY(pairwise_prepare(L, a0, a_dt, g0, g_dt, nb, seq, eigen, qa_t, qg_t, v, ws, precision, stream));
+    if (ws.off > peak) peak = ws.off;
+    ws.off = mark;
+    KFB_TRY(pairwise_contract(L, P, nq, v, nb, seq, scale, scores, ld_scores, t_offset + b0, accumulate, ws, precision,
+                              stream));
+    if (ws.off > peak) peak = ws.off;
+    if (ws.dry) break;
+  }
+  ws.off = peak;
   return KFB_OK;
 }
 
@@ -1209,6 +1320,64 @@ int kfb_pairwise_scores(const kfb_layer* layer, const kfb_split* P, int64_t num_
   KFB_REQUIRE(mode >= KFB_PRECOND_IDENTITY && mode <= KFB_PRECOND_EIGEN, "pairwise_scores: bad mode %d", mode);
   return pairwise_run(*layer, P, num_queries, a, a_dtype, g, g_dtype, batch, seq, mode, qa_t, qg_t, scale,
                       scores, ld_scores, t_offset, accumulate, w, precision, (cudaStream_t)stream);
+}
+
+size_t kfb_pairwise_operand_bytes(const kfb_layer* layer, int64_t batch, int64_t seq, int precision) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  pair_operands_alloc(w, *layer, batch, positions(*layer, seq), precision);
+  return w.off + 256;
+}
+
+size_t kfb_pairwise_prepare_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  PairOperands o{};
+  pairwise_prepare(*layer, nullptr, KFB_F32, nullptr, KFB_F32, batch, seq, true, nullptr, nullptr, o, w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_pairwise_prepare(const kfb_layer* layer, const void* a, int a_dtype, const void* g, int g_dtype, int64_t batch,
+                         int64_t seq, int32_t mode, const kfb_split* qa_t, const kfb_split* qg_t, void* operands,
+                         size_t operand_bytes, void* ws, size_t ws_bytes, int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(a != nullptr && g != nullptr && operands != nullptr, "pairwise_prepare: null tensor");
+  KFB_REQUIRE(mode >= KFB_PRECOND_IDENTITY && mode <= KFB_PRECOND_EIGEN, "pairwise_prepare: bad mode %d", mode);
+  if (batch <= 0) return KFB_OK;
+  Ws ow{static_cast<char*>(operands), operand_bytes, 0, false};
+  const PairOperands o = pair_operands_alloc(ow, *layer, batch, positions(*layer, seq), precision);
+  KFB_REQUIRE(ow.fits(), "pairwise_prepare: operand buffer too small: need %zu bytes, have %zu", ow.off, operand_bytes);
+  KFB_WS(ws, ws_bytes, false);
+  return pairwise_prepare(*layer, a, a_dtype, g, g_dtype, batch, seq, mode == KFB_PRECOND_EIGEN, qa_t, qg_t, o, w, precision,
+                          (cudaStream_t)stream);
+}
+
+size_t kfb_pairwise_prepared_workspace_bytes(const kfb_layer* layer, int64_t batch, int64_t seq) {
+  if (check_layer(layer) != KFB_OK || batch <= 0) return 0;
+  KFB_WS(nullptr, 0, true);
+  PairOperands o{};
+  pairwise_contract(*layer, nullptr, 0, o, batch, seq, 1.f, nullptr, 0, 0, 1, w, KFB_PREC_FP32, nullptr);
+  return w.off + 256;
+}
+
+int kfb_pairwise_scores_prepared(const kfb_layer* layer, const kfb_split* P, int64_t num_queries, const void* operands,
+                                 size_t operand_bytes, int64_t batch, int64_t seq, float scale, float* scores,
+                                 int64_t ld_scores, int64_t t_offset, int32_t accumulate, void* ws, size_t ws_bytes,
+                                 int precision, void* stream) {
+  KFB_TRY(check_layer(layer));
+  KFB_REQUIRE(P != nullptr && P->hi != nullptr && operands != nullptr && scores != nullptr,
+              "pairwise_scores_prepared: null tensor");
+  KFB_REQUIRE(P->rows == layer->d_out && P->cols == layer->d_in + layer->has_bias,
+              "pairwise_scores_prepared: P layout does not match the layer");
+  KFB_REQUIRE(num_queries >= 0 && num_queries <= P->batch, "pairwise_scores_prepared: num_queries exceeds P");
+  KFB_REQUIRE(t_offset >= 0 && t_offset + batch <= ld_scores, "pairwise_scores_prepared: columns out of range");
+  if (batch <= 0 || num_queries == 0) return KFB_OK;
+  Ws ow{static_cast<char*>(const_cast<void*>(operands)), operand_bytes, 0, false};
+  const PairOperands o = pair_operands_alloc(ow, *layer, batch, positions(*layer, seq), precision);
+  KFB_REQUIRE(ow.fits(), "pairwise_scores_prepared: operand buffer too small: need %zu bytes, have %zu", ow.off, operand_bytes);
+  KFB_WS(ws, ws_bytes, false);
+  return pairwise_contract(*layer, P, num_queries, o, batch, seq, scale, scores, ld_scores, t_offset, accumulate, w, precision,
+                           (cudaStream_t)stream);
 }
 
 size_t kfb_pairwise_lowrank_workspace_bytes(const kfb_layer* layer, int64_t num_queries, int64_t rank, int64_t batch,

@@ -88,6 +88,13 @@ SIGNATURES = {
     "kfb_precondition": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _SP, _SP, _vp, _f32, _SP, _i64, _vp, _vp, _sz, ctypes.c_int, _vp]),
     "kfb_pairwise_workspace_bytes": (_sz, [_LP, _i64, _i64]),
     "kfb_pairwise_scores": (ctypes.c_int, [_LP, _SP, _i64, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _f32, _vp, _i64, _i64, _i32, _vp, _sz, ctypes.c_int, _vp]),
+    "kfb_pairwise_operand_bytes": (_sz, [_LP, _i64, _i64, ctypes.c_int]),
+    "kfb_pairwise_prepare_workspace_bytes": (_sz, [_LP, _i64, _i64]),
+    "kfb_pairwise_prepare": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _vp, _sz,
+                                            _vp, _sz, ctypes.c_int, _vp]),
+    "kfb_pairwise_prepared_workspace_bytes": (_sz, [_LP, _i64, _i64]),
+    "kfb_pairwise_scores_prepared": (ctypes.c_int, [_LP, _SP, _i64, _vp, _sz, _i64, _i64, _f32, _vp, _i64, _i64, _i32, _vp,
+                                                    _sz, ctypes.c_int, _vp]),
     "kfb_self_workspace_bytes": (_sz, [_LP, _i64, _i64]),
     "kfb_self_scores": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _i64, _i32, _SP, _SP, _vp, _f32, _vp, _i64, _i32, _vp, _sz, ctypes.c_int, _vp]),
     "kfb_pairwise_lowrank_workspace_bytes": (_sz, [_LP, _i64, _i64, _i64, _i64]),

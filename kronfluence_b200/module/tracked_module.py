@@ -99,6 +99,34 @@ class ScoreSink:
         return out
 
 
+class TrainOperandCache:
+    """Prepared train operands of every (module, train batch) of one train sweep, kept on the device while they fit a
+    byte budget (the reference re-runs the entire train forward/backward once per query chunk,
+    score/pairwise.py:133-293).  All-or-nothing: if the budget overflows during the recording sweep the cache is dropped
+    and later chunks run the model again."""
+
+    def __init__(self, budget_bytes: int) -> None:
+        self.budget, self.bytes = int(budget_bytes), 0
+        self.recording, self.complete = True, False
+        self.entries: Dict[str, List[Tuple[Any, int, float, int]]] = {}
+
+    def add(self, module_name: str, prepared: Any, column: int, scale: float, tokens: int) -> None:
+        self.bytes += prepared.nbytes()
+        if self.bytes > self.budget:
+            self.recording = False
+            self.entries.clear()
+            return
+        self.entries.setdefault(module_name, []).append((prepared, column, scale, tokens))
+
+    def finish_recording(self) -> None:
+        self.complete = self.recording
+        self.recording = False
+
+    def clear(self) -> None:
+        self.entries.clear()
+        self.recording = self.complete = False
+
+
 class BaseTracker:
     """Hook manager for one mode of one module (tracker/base.py:8-88 of the reference)."""
 
@@ -521,9 +549,18 @@ class PairwiseScoreTracker(BaseTracker):
                 grad = grad.reshape(-1, grad.shape[-1])
             # Every use of a shared module adds its own term (the mathematically correct sum; the
             # reference keeps only the last use).
-            ops.pairwise_scores(layer, store, module.query_count, a, grad, sink.get(tokens),
-                                module.score_offset * tokens, accumulate=True, scale=module.gradient_scale,
-                                precision=precision_of(module.score_args.score_dtype), qa=qa, qg=qg)
+            cache = module.train_operand_cache
+            if cache is not None and cache.recording:
+                # first sweep of a multi-chunk run: keep the query-independent half of the work (operand preparation and
+                # the rotation into the eigenbases) so that later query chunks replay it without the model
+                prepared = ops.pairwise_prepare(layer, a, grad, precision_of(module.score_args.score_dtype), qa, qg)
+                ops.pairwise_scores_prepared(store, module.query_count, prepared, sink.get(tokens),
+                                             module.score_offset * tokens, accumulate=True, scale=module.gradient_scale)
+                cache.add(module.name, prepared, module.score_offset * tokens, module.gradient_scale, tokens)
+            else:
+                ops.pairwise_scores(layer, store, module.query_count, a, grad, sink.get(tokens),
+                                    module.score_offset * tokens, accumulate=True, scale=module.gradient_scale,
+                                    precision=precision_of(module.score_args.score_dtype), qa=qa, qg=qg)
             if not module.factor_args.has_shared_parameters:
                 self._drop_cached_tensors()
 
@@ -646,6 +683,7 @@ class TrackedModule(nn.Module):
                     [PRECONDITIONED_GRADIENT_NAME, ACCUMULATED_PRECONDITIONED_GRADIENT_NAME,
                      PAIRWISE_SCORE_MATRIX_NAME, SELF_SCORE_VECTOR_NAME, AGGREGATED_GRADIENT_NAME]):
             self.storage[key] = None
+        self.train_operand_cache: Optional["TrainOperandCache"] = None  # PAIRWISE_SCORE: see TrainOperandCache
         self.aggregate_precondition = False  # GRADIENT_AGGREGATION: scale by Lambda^-1 (query side) or not (train side)
         self.query_count = 0
         self.last_query_batch = 0

@@ -278,6 +278,52 @@ def pairwise_scores(layer: KfbLayer, store: Split, num_queries: int, a: torch.Te
                                   ws_size, precision, stream_ptr(a.device)))
 
 
+class PreparedBatch:
+    """Tensor-core operands of one train batch of one module (kfb_pairwise_prepare): rotated into the factors' eigenbases,
+    independent of the queries, small next to the query store.  Kept by the Analyzer to sweep the same train batches
+    against several query chunks without re-running the model or the rotations."""
+
+    def __init__(self, layer: KfbLayer, buffer: torch.Tensor, batch: int, seq: int, precision: int):
+        self.layer, self.buffer, self.batch, self.seq, self.precision = layer, buffer, batch, seq, precision
+
+    def nbytes(self) -> int:
+        return self.buffer.numel()
+
+
+def pairwise_prepare(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, precision: int = PREC_FP32,
+                     qa: Optional[EigenOperands] = None, qg: Optional[EigenOperands] = None) -> PreparedBatch:
+    lib = engine.load_library()
+    a, g = _contig(a), _contig(g)
+    batch, seq = _batch_seq(layer, a)
+    mode = PRECOND_EIGEN if qa is not None else PRECOND_IDENTITY
+    sa = qa.qt.struct() if qa is not None else None
+    sg = qg.qt.struct() if qg is not None else None
+    buf = torch.empty(int(lib.kfb_pairwise_operand_bytes(ctypes.byref(layer), batch, seq, precision)), dtype=torch.uint8,
+                      device=a.device)
+    ws_ptr, ws_size = workspace(a.device).get(lib.kfb_pairwise_prepare_workspace_bytes(ctypes.byref(layer), batch, seq))
+    check(lib.kfb_pairwise_prepare(ctypes.byref(layer), a.data_ptr(), dtype_code(a.dtype), g.data_ptr(), dtype_code(g.dtype),
+                                   batch, seq, mode, ctypes.byref(sa) if sa is not None else None,
+                                   ctypes.byref(sg) if sg is not None else None, buf.data_ptr(), buf.numel(), ws_ptr, ws_size,
+                                   precision, stream_ptr(a.device)))
+    return PreparedBatch(layer, buf, batch, seq, precision)
+
+
+def pairwise_scores_prepared(store: Split, num_queries: int, prepared: PreparedBatch, scores: torch.Tensor,
+                             t_offset: int = 0, accumulate: bool = False, scale: float = 1.0) -> None:
+    """The contraction half of `pairwise_scores` on operands made by `pairwise_prepare`."""
+    lib = engine.load_library()
+    assert scores.dtype == torch.float32 and scores.stride(-1) == 1
+    layer = prepared.layer
+    src = store.struct(0, store.batch)
+    device = prepared.buffer.device
+    ws_ptr, ws_size = workspace(device).get(
+        lib.kfb_pairwise_prepared_workspace_bytes(ctypes.byref(layer), prepared.batch, prepared.seq))
+    check(lib.kfb_pairwise_scores_prepared(ctypes.byref(layer), ctypes.byref(src), int(num_queries),
+                                           prepared.buffer.data_ptr(), prepared.buffer.numel(), prepared.batch, prepared.seq,
+                                           float(scale), scores.data_ptr(), scores.stride(0), int(t_offset),
+                                           int(accumulate), ws_ptr, ws_size, prepared.precision, stream_ptr(device)))
+
+
 # --------------------------------------------------------------------------------------------------
 # Stage 5b: rank-r query factors (tracker/precondition.py:19-75, linear.py:83-99, tracker/pairwise_score.py:26-39)
 # --------------------------------------------------------------------------------------------------
@@ -373,6 +419,7 @@ __all__ = [
     "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "self_scores", "layer_of", "factor_dims", "workspace",
     "aggregate_gradient", "pairwise_scores_explicit", "flat_layer",
     "per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
+    "PreparedBatch", "pairwise_prepare", "pairwise_scores_prepared",
 ]
 
 

@@ -237,7 +237,17 @@ def weighted_sqnorm(x, w, out, t_offset=0, alpha=1.0, accumulate=True):
         view.copy_(vals.to(out.dtype))
 
 
-_PATCHED = ["per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
+def pairwise_prepare(layer, a, g, precision=0, qa=None, qg=None):
+    return SimpleNamespace(layer=layer, a=a.clone(), g=g.clone(), qa=qa, qg=qg, precision=precision,
+                           nbytes=lambda: a.numel() * 4 + g.numel() * 4)
+
+
+def pairwise_scores_prepared(store, num_queries, prepared, scores, t_offset=0, accumulate=False, scale=1.0):
+    pairwise_scores(prepared.layer, store, num_queries, prepared.a, prepared.g, scores, t_offset, accumulate, scale,
+                    prepared.precision, prepared.qa, prepared.qg)
+
+
+_PATCHED = ["pairwise_prepare", "pairwise_scores_prepared", "per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
             "layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
             "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores", "self_scores",
             "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank", "LowRankStore", "flat_layer",

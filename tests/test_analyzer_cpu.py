@@ -3,6 +3,7 @@ double (tests/cpu_backend.py); everything else — prepare_model, trackers, Anal
 layout — is the product code.  Results are compared with the reference's own Analyzer outputs
 (tests/golden/e2e_*.npz)."""
 
+import math
 import os
 
 import numpy as np
@@ -484,3 +485,48 @@ def test_post_process_per_sample_gradient(case, tmp_path):
     # and the callback really changed the answer
     plain = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
     assert rel(scores["all_modules"].numpy(), plain["f32/scores"]) > 1e-2
+
+
+def test_train_operand_cache_across_query_chunks(tmp_path):
+    """Several query chunks: the train operands prepared during the first sweep are replayed for the later chunks, so
+    the model's train forward/backward runs once per train batch instead of once per (chunk, batch) as in the reference
+    (score/pairwise.py:133-293); the scores do not change."""
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_seq.npz")))
+    calls = {"train": 0}
+    tasks = fixtures.make_tasks(Task)
+
+    class Counting(tasks["seq"]):
+        def compute_train_loss(self, batch, model, sample=False):
+            calls["train"] += 1
+            return super().compute_train_loss(batch, model, sample)
+
+        def compute_measurement(self, batch, model):
+            return tasks["seq"].compute_train_loss(self, batch, model, sample=False)
+
+    with oracle_backend():
+        from kronfluence_b200.utils import save as io
+
+        model, train_set, query_set = fixtures.make_case("seq")
+        task = Counting()
+        model = prepare_model(model, task)
+        analyzer = Analyzer("cache", model, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        fa = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+        analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=6, factor_args=fa)
+        analyzer.perform_eigendecomposition("f", fa)
+        eig = analyzer.load_eigendecomposition("f")
+        eig = {f: {m: torch.from_numpy(golden[f"f32/{f}/{m}"]) for m in eig[f]} for f in eig}
+        io.save_factors(analyzer.factors_output_dir("f"), eig)
+        analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=6, factor_args=fa)
+        n_batches = math.ceil(len(train_set) / 6)
+        calls["train"] = 0
+        scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                  per_device_train_batch_size=6, score_args=ScoreArguments(damping_factor=None))
+        assert analyzer.last_train_operand_cache["complete"]
+        assert calls["train"] == n_batches  # 3 query chunks, one train sweep through the model
+        analyzer.train_operand_cache_fraction = 0.0
+        calls["train"] = 0
+        plain = analyzer.compute_pairwise_scores("s2", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                 per_device_train_batch_size=6, score_args=ScoreArguments(damping_factor=None))
+        assert calls["train"] == 3 * n_batches
+    assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
+    assert rel(scores["all_modules"].numpy(), plain["all_modules"].numpy()) < 1e-6

@@ -218,3 +218,55 @@ def test_bf16_configuration(case, tmp_path):
     assert rel(mixed["all_modules"].float().numpy(), golden["f64/scores"]) < 3e-2
     _, mixed2, _ = run(case, tmp_path / "m2", golden, inject=True, precondition_dtype=bf)
     assert rel(mixed2["all_modules"].float().numpy(), golden["f64/scores"]) < 3e-2
+
+
+def test_train_operand_cache_across_query_chunks(tmp_path):
+    """kfb_pairwise_prepare / kfb_pairwise_scores_prepared behind the Analyzer: with several query chunks the prepared
+    (rotated) train operands of the first sweep are replayed, the train forward/backward runs once per batch, and the
+    scores equal both the reference's and the uncached run's (S = 1, S > 1 and Conv2d layers)."""
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+    from kronfluence_b200.utils import save as io
+    from tests import fixtures
+
+    for case in ("seq", "conv", "mlp"):
+        golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
+        calls = {"train": 0}
+        base = fixtures.make_tasks(Task)[case]
+
+        class Counting(base):
+            def compute_train_loss(self, batch, model, sample=False):
+                calls["train"] += 1
+                return super().compute_train_loss(batch, model, sample)
+
+            def compute_measurement(self, batch, model):
+                return base.compute_measurement(self, batch, model)
+
+        if case != "conv":  # their measurement is the train loss: do not count those calls
+            Counting.compute_measurement = lambda self, batch, model: base.compute_train_loss(self, batch, model, False)
+        model, train_set, query_set = fixtures.make_case(case)
+        _, _, n_train, _, train_bs, _ = fixtures.CASES[case]
+        task = Counting()
+        model = prepare_model(model, task)
+        analyzer = Analyzer(f"cache_{case}", model, task, output_dir=str(tmp_path), disable_tqdm=True)
+        fa = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+        analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=train_bs, factor_args=fa)
+        analyzer.perform_eigendecomposition("f", fa)
+        eig = analyzer.load_eigendecomposition("f")
+        eig = {f: {m: torch.from_numpy(golden[f"f32/{f}/{m}"]) for m in eig[f]} for f in eig}
+        io.save_factors(analyzer.factors_output_dir("f"), eig)
+        analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=train_bs, factor_args=fa)
+        n_batches = -(-n_train // train_bs)
+        calls["train"] = 0
+        scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                  per_device_train_batch_size=train_bs,
+                                                  score_args=ScoreArguments(damping_factor=None))
+        assert analyzer.last_train_operand_cache["complete"], case
+        assert calls["train"] == n_batches, case
+        analyzer.train_operand_cache_fraction = 0.0
+        plain = analyzer.compute_pairwise_scores("s2", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                 per_device_train_batch_size=train_bs,
+                                                 score_args=ScoreArguments(damping_factor=None))
+        assert rel(scores["all_modules"].numpy(), golden["f64/scores"]) < 1e-4, case
+        assert rel(scores["all_modules"].numpy(), plain["all_modules"].numpy()) < 1e-6, case
