@@ -621,11 +621,13 @@ def torch_gpu_reference(name, spec):
 # Strong scaling: the whole north_star job, fixed size, sharded over the ranks
 # --------------------------------------------------------------------------------------------------
 def strong_job(ctx, n_query=1024, t_total=50_000, t_batch=2048, d=4096):
-    """Q preconditioned query gradients of the target layer are produced by kfb_precondition on a query shard per rank
-    and all-gathered IN PLACE over NCCL (tracker/precondition.py:166-201); every rank then sweeps its contiguous
-    ceil(T/W) train examples (utils/dataset.py:148-199) in batches of t_batch, ragged tail included, and rank 0 gathers
-    the [Q, T/W] tiles (score/dot_product.py:139-150).  Data depend only on global indices, so the result is the same
-    at every world size; a block of it is checked against fp64 torch."""
+    """The whole north_star job at fixed size.  Q preconditioned query gradients of the target layer are produced by
+    kfb_precondition on a query shard per rank and all-gathered IN PLACE over NCCL (tracker/precondition.py:166-201);
+    every rank prepares (rotates) its contiguous ceil(T/W) train examples once (utils/dataset.py:148-199; batches of
+    t_batch, ragged tail included) and sweeps them against the queries group by group, so that the all-gather of query
+    group k+1 runs under the contraction of group k; rank 0 gathers the [Q, T/W] tiles (score/dot_product.py:139-150).
+    Data depend only on global indices, so the result is the same at every world size; a block of it is checked against
+    fp64 torch."""
     import torch
     import torch.distributed as dist
 
@@ -662,47 +664,76 @@ def strong_job(ctx, n_query=1024, t_total=50_000, t_batch=2048, d=4096):
     g_loc = torch.cat(g_parts) if g_parts else torch.zeros(0, do, device=device)
     del a_parts, g_parts
 
-    q_per = -(-n_query // world)
+    q_per = n_query // world
     assert q_per * world == n_query, "Q must divide over the ranks"
+    groups = 1 if world == 1 else max(1, min(4, q_per // 8))
+    q_sub = q_per // groups
+    assert q_sub * groups == q_per
+    group_slots = world * q_sub
+    # slot g*group_slots + r*q_sub + j holds query r*q_per + g*q_sub + j: every group is one in-place all-gather
+    slot_query = torch.empty(n_query, dtype=torch.long)
+    for g in range(groups):
+        for r in range(world):
+            base = g * group_slots + r * q_sub
+            slot_query[base : base + q_sub] = torch.arange(r * q_per + g * q_sub, r * q_per + (g + 1) * q_sub)
     store = ops.make_query_store(do, di, n_query, device, precision)
     scores = torch.zeros(n_query, per_rank, dtype=torch.float32, device=device)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    gathered = [torch.empty_like(scores) for _ in range(world)] if (world > 1 and rank == 0) else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+
+    def gather_group(g: int, async_op: bool):
+        works = []
+        for plane in range(store.storage.shape[0]):
+            full = store.storage[plane, g * group_slots : (g + 1) * group_slots]
+            mine = full[rank * q_sub : (rank + 1) * q_sub]
+            works.append(dist.all_gather_into_tensor(full, mine, async_op=async_op))  # in place
+        return works
 
     def job():
         ev[0].record()
-        q0 = rank * q_per
-        for c0 in range(0, q_per, 64):  # bounded scratch per call
-            c1 = min(q_per, c0 + 64)
-            ops.precondition(layer, a_q[q0 + c0 : q0 + c1], g_q[q0 + c0 : q0 + c1], store, q0 + c0, ops.PRECOND_EIGEN,
-                             qa_ops, qg_ops, lam_inv, precision=precision)
+        for g in range(groups):
+            q0 = rank * q_per + g * q_sub
+            slot0 = g * group_slots + rank * q_sub
+            for c0 in range(0, q_sub, 64):  # bounded scratch per call
+                c1 = min(q_sub, c0 + 64)
+                ops.precondition(layer, a_q[q0 + c0 : q0 + c1], g_q[q0 + c0 : q0 + c1], store, slot0 + c0,
+                                 ops.PRECOND_EIGEN, qa_ops, qg_ops, lam_inv, precision=precision)
         ev[1].record()
         if world > 1:
-            for plane in range(store.storage.shape[0]):
-                full = store.storage[plane]
-                dist.all_gather_into_tensor(full, full[q0 : q0 + q_per])  # in place: rank r's slice is its input
+            gather_group(0, async_op=False)
         ev[2].record()
+        prepared = []
         for b0 in range(0, n_local, t_batch):
             b1 = min(n_local, b0 + t_batch)
-            ops.pairwise_scores(layer, store, n_query, a_loc[b0:b1], g_loc[b0:b1], scores, t_offset=b0,
-                                accumulate=False, precision=precision, qa=qa_ops, qg=qg_ops)
+            prepared.append((b0, ops.pairwise_prepare(layer, a_loc[b0:b1], g_loc[b0:b1], precision, qa_ops, qg_ops)))
         ev[3].record()
-        gathered = None
-        if world > 1:
-            gathered = [torch.empty_like(scores) for _ in range(world)] if rank == 0 else None
-            dist.gather(scores, gathered, dst=0)
+        pending = None
+        for g in range(groups):
+            if pending is not None:
+                for work in pending:
+                    work.wait()
+            pending = gather_group(g + 1, async_op=True) if (world > 1 and g + 1 < groups) else None
+            rows = scores[g * group_slots : (g + 1) * group_slots]
+            for b0, prep in prepared:
+                ops.pairwise_scores_prepared(store, group_slots, prep, rows, t_offset=b0, accumulate=False,
+                                             q_offset=g * group_slots)
         ev[4].record()
-        return gathered
+        if world > 1:
+            dist.gather(scores, gathered, dst=0)
+        ev[5].record()
 
     job()  # warm-up: NCCL connection setup, workspace growth
     ctx.barrier()
-    gathered = job()
+    job()
     ctx.barrier()
-    phases = [ctx.max_over_ranks(ev[i].elapsed_time(ev[i + 1])) for i in range(4)]
-    wall_ms = ctx.max_over_ranks(ev[0].elapsed_time(ev[4]))
-    sweep_wall_ms = ctx.max_over_ranks(ev[2].elapsed_time(ev[4]))
+    phases = [ctx.max_over_ranks(ev[i].elapsed_time(ev[i + 1])) for i in range(5)]
+    wall_ms = ctx.max_over_ranks(ev[0].elapsed_time(ev[5]))
     out = None
     if rank == 0:
         full = torch.cat(gathered, dim=1)[:, :t_total] if world > 1 else scores[:, :t_total]
+        order = torch.empty_like(slot_query)
+        order[slot_query] = torch.arange(n_query)  # order[q] = slot of query q
+        full = full.index_select(0, order.to(device))
         # parity block: queries 0..15 and the last 16, train columns 0..63 and the ragged tail
         qs = list(range(16)) + list(range(n_query - 16, n_query))
         ts = list(range(64)) + list(range(t_total - 64, t_total))
@@ -720,20 +751,22 @@ def strong_job(ctx, n_query=1024, t_total=50_000, t_batch=2048, d=4096):
         got = full[qs][:, ts].double()
         parity = float((got - ref).norm() / ref.norm())
         p_bytes = float(store.storage.numel()) * 2
+        exposed = phases[1]
         out = {"q": n_query, "t_total": t_total, "t_batch": t_batch, "n_gpus": world, "wall_s": wall_ms / 1e3,
-               "scores_per_s": n_query * t_total / (wall_ms / 1e3),
-               "sweep_scores_per_s": n_query * t_total / (sweep_wall_ms / 1e3),
-               "phases_ms": {"precondition_shard": phases[0], "allgather_P": phases[1], "train_sweep": phases[2],
-                             "gather_scores": phases[3]},
+               "scores_per_s": n_query * t_total / (wall_ms / 1e3), "query_groups": groups,
+               "phases_ms": {"precondition_shard": phases[0], "allgather_P_first_group": phases[1],
+                             "prepare_train_operands": phases[2], "train_sweep_with_overlapped_allgather": phases[3],
+                             "gather_scores": phases[4]},
                "allgather": None if world == 1 else {
                    "bytes_total": p_bytes, "bytes_received_per_rank": p_bytes * (world - 1) / world,
-                   "gbs_per_rank": p_bytes * (world - 1) / world / (phases[1] / 1e3) / 1e9,
-                   "collective": "ncclAllGather in place, one call per operand plane"},
+                   "first_group_gbs_per_rank": p_bytes / groups * (world - 1) / world / (exposed / 1e3) / 1e9,
+                   "collective": f"ncclAllGather in place, one call per operand plane and query group ({groups} groups); "
+                                 "groups 1.. run under the contraction of the previous group"},
                "parity": {"rel_frobenius": parity, "bar": 1e-4, "ok": parity < 1e-4,
                           "block": "32 queries x 128 train examples (first / last of each axis) vs fp64 torch"},
-               "note": "wall = precondition of the query shard + all-gather of P + train sweep (ragged tail) + gather "
-                       "of score tiles, max over ranks; sweep_scores_per_s excludes the query-side setup"}
-    del store, scores, a_loc, g_loc
+               "note": "wall = precondition of the query shard + all-gather of P + preparation of the local train shard "
+                       "+ sweep (ragged tail) + gather of score tiles, max over ranks, CUDA events"}
+    del store, scores, a_loc, g_loc, gathered
     ops.release_workspaces()
     torch.cuda.empty_cache()
     return out

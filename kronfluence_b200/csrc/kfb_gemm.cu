@@ -203,7 +203,7 @@ __device__ __forceinline__ long long plane_index(const GemmParams& p, long long 
   return row * p.ldo_s + col;
 }
 
-template <int OFF, int N, bool HOIST>
+template <int OFF, int N, bool HOIST, bool TMA2 = false>
 __device__ __forceinline__ float store_chunk(const GemmParams& p, const CUtensorMap* tm_o_hi, const CUtensorMap* tm_o_lo,
                                              float alpha, int b, long long row, int col0, const float (&acc)[N],
                                              float* st, int lane, bool mirror = false) {
@@ -223,7 +223,12 @@ __device__ __forceinline__ float store_chunk(const GemmParams& p, const CUtensor
   if (p.tma_store && !mirror) {
     __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(st);
     __nv_bfloat16* sl = sh + 32 * 32;
-    if (lane == 0) tma_store_wait_read();  // the previous chunk's stores have finished reading the staging tile
+    // TMA2: the caller alternates between two staging tiles, so only the stores of the chunk BEFORE the previous one
+    // must have finished reading shared memory (bulk groups retire in order); otherwise the previous chunk's.
+    if (lane == 0) {
+      if (TMA2) tma_store_wait_read1();
+      else tma_store_wait_read();
+    }
     __syncwarp();
 #pragma unroll
     for (int grp = 0; grp < 4; ++grp) {
@@ -451,6 +456,20 @@ __device__ __forceinline__ float store_chunk(const GemmParams& p, const CUtensor
   return 0.f;
 }
 
+// Width of the MMA issued for tile `t`: the last n-tile of a ragged N (every bias layer: d_in + 1 = 769, 4097, ...) only
+// needs its valid columns, rounded up to whole 32-column epilogue chunks (so that every column of a chunk that is read
+// back was written by this tile: zeros from the zero-filled operand rows, never stale TMEM).  A 32-wide MMA costs about a
+// quarter of a 256-wide one (it is bound by the shared-memory read of A).  Not with B-tile multicast (fixed quarters).
+template <int BLOCK_N, int MC>
+__device__ __forceinline__ int tile_n_mma(const GemmParams& p, const Tile& t) {
+  if (MC != 1) return BLOCK_N;
+  const int valid = p.N - t.n_blk * BLOCK_N;
+  if (valid >= BLOCK_N) return BLOCK_N;
+  if (BLOCK_N > 128 && valid > 64) return valid > 128 ? BLOCK_N : 128;
+  if (BLOCK_N > 64 && valid > 32) return valid > 64 ? BLOCK_N : 64;
+  return BLOCK_N > 32 ? (valid > 32 ? BLOCK_N : 32) : BLOCK_N;
+}
+
 // keep the [N, ld) padding of non-transposed split outputs finite (zero): they may be re-read as part
 // of a flattened contraction dimension.
 __device__ __forceinline__ void store_zero_pad(const GemmParams& p, int b, long long row) {
@@ -493,7 +512,10 @@ struct GemmCfg {
   static constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_PLANE = LOAD_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PLANE + B_PLANE);
-  static constexpr int EPI_STAGE_BYTES = EW * 32 * 33 * 4;  // one [32][33] fp32 staging tile per epilogue warp
+  // per epilogue warp: one [32][33] fp32 staging tile; with one epilogue warpgroup twice 4 KB, so that the TMA plane
+  // stores of consecutive chunks alternate between two staging tiles instead of waiting for each other
+  static constexpr int EPI_WARP_BYTES = EW == 4 ? 8192 : 32 * 33 * 4;
+  static constexpr int EPI_STAGE_BYTES = EW * EPI_WARP_BYTES;
   static_assert(EW == 4 || EW == 8, "one or two epilogue warpgroups");
   static constexpr int SMEM_BUDGET = 227 * 1024 - 2048 - EPI_STAGE_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
@@ -604,7 +626,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int j = 0; j < inner; ++j) {
         const Tile t = decode_tile<EPI>(p, unit, j, pair_id);
         const int row_a = t.m_blk * Cfg::TILE_M + (int)cta_rank * BLOCK_M;
-        const int row_b = t.n_blk * BLOCK_N + (int)cta_rank * Cfg::LOAD_N + pair_id * Cfg::FETCH_N;
+        // each CTA of a pair stages ITS half of the B rows the MMA reads (a narrower MMA on a ragged last n-tile reads
+        // fewer rows: the second CTA's half starts right behind the first one's)
+        const int row_b = t.n_blk * BLOCK_N + (int)cta_rank * (tile_n_mma<BLOCK_N, MC>(p, t) / CG) + pair_id * Cfg::FETCH_N;
         const int ba = p.a_batched ? t.b : 0;
         const int bb = p.b_batched ? t.b : 0;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
@@ -656,6 +680,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        const int n_mma = tile_n_mma<BLOCK_N, MC>(p, t);
+        const uint32_t idesc = n_mma == BLOCK_N ? IDESC : make_idesc_bf16(Cfg::TILE_M, n_mma, p.f16 != 0);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -670,18 +696,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const uint32_t acc = (kb > t.kb0 || k > 0) ? 1u : 0u;
             if (CG == 2) {
               if (NSPLIT == 2) {
-                umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, IDESC, acc);
-                umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
-                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1u);
+                umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, acc);
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
               } else {
-                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, IDESC, acc);
+                umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, acc);
               }
             } else if (NSPLIT == 2) {
-              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, IDESC, acc);
-              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
-              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, 1u);
+              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, acc);
+              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
             } else {
-              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, IDESC, acc);
+              umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, acc);
             }
           }
           // smem stage reusable (in both CTAs) once these MMAs retire; accumulator published at the end
@@ -705,7 +731,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (EW == 8) setmaxnreg_inc<224>();
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int lane_row = quarter * 32 + lane;  // accumulator row owned by this thread
-    float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 4) * (32 * 33);
+    float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 4) * (Cfg::EPI_WARP_BYTES / 4);
+    constexpr bool TMA2 = EW == 4;  // two staging tiles per warp for TMA plane stores
+    uint32_t tma_sel = 0;
+    auto st_next = [&]() { return (TMA2 && p.tma_store) ? st + (tma_sel++ & 1u) * 1024 : st; };
     constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N / (EW / 4) : 1;  // accumulator columns kept per thread
     const int col_off = EW == 8 ? ((warp - 4) >> 2) * NACC : 0;          // ... starting at this column of the tile
     // strict operands were scaled by powers of two: undo both scales together with alpha (exact)
@@ -787,7 +816,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               float x[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-              rowdot += store_chunk<0, 32, true>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st, lane);
+              rowdot += store_chunk<0, 32, true, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st_next(), lane);
               if (p.symmetric && t.n_blk != t.m_blk) store_chunk<0, 32, true>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st, lane, true);
             }
           }
@@ -838,10 +867,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int n0 = t.n_blk * BLOCK_N + col_off;
         const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
         // warp-uniform conditions: store_chunk is a warp-cooperative call
-        if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0, racc, st, lane);
-        if (NACC >= 64 && n0 + 32 < p.N) store_chunk<(NACC >= 64 ? 32 : 0), NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 32, racc, st, lane);
-        if (NACC >= 128 && n0 + 64 < p.N) store_chunk<(NACC >= 128 ? 64 : 0), NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 64, racc, st, lane);
-        if (NACC >= 128 && n0 + 96 < p.N) store_chunk<(NACC >= 128 ? 96 : 0), NACC, false>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 96, racc, st, lane);
+        if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0, racc, st_next(), lane);
+        if (NACC >= 64 && n0 + 32 < p.N) store_chunk<(NACC >= 64 ? 32 : 0), NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 32, racc, st_next(), lane);
+        if (NACC >= 128 && n0 + 64 < p.N) store_chunk<(NACC >= 128 ? 64 : 0), NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 64, racc, st_next(), lane);
+        if (NACC >= 128 && n0 + 96 < p.N) store_chunk<(NACC >= 128 ? 96 : 0), NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 96, racc, st_next(), lane);
         if (row < p.M && p.zero_pad && !p.tma_store && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
       }
     }

@@ -309,12 +309,13 @@ def pairwise_prepare(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, precisio
 
 
 def pairwise_scores_prepared(store: Split, num_queries: int, prepared: PreparedBatch, scores: torch.Tensor,
-                             t_offset: int = 0, accumulate: bool = False, scale: float = 1.0) -> None:
-    """The contraction half of `pairwise_scores` on operands made by `pairwise_prepare`."""
+                             t_offset: int = 0, accumulate: bool = False, scale: float = 1.0, q_offset: int = 0) -> None:
+    """The contraction half of `pairwise_scores` on operands made by `pairwise_prepare`; with `q_offset` against the
+    store slots [q_offset, q_offset + num_queries) (row i of `scores` is slot q_offset + i)."""
     lib = engine.load_library()
     assert scores.dtype == torch.float32 and scores.stride(-1) == 1
     layer = prepared.layer
-    src = store.struct(0, store.batch)
+    src = store.struct(q_offset, store.batch - q_offset)
     device = prepared.buffer.device
     ws_ptr, ws_size = workspace(device).get(
         lib.kfb_pairwise_prepared_workspace_bytes(ctypes.byref(layer), prepared.batch, prepared.seq))

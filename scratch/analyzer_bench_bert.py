@@ -18,6 +18,8 @@ ap.add_argument("--query-batch", type=int, default=64)
 ap.add_argument("--factor-examples", type=int, default=4096)
 ap.add_argument("--layers", type=int, default=12)
 ap.add_argument("--bf16", action="store_true")
+ap.add_argument("--chunks", type=int, default=1, help="query chunks (each sweeps the whole train set)")
+ap.add_argument("--no-cache", action="store_true", help="re-run the train forward/backward for every query chunk")
 args = ap.parse_args()
 SEQ = 128
 
@@ -67,6 +69,8 @@ n_params = sum(m.original_module.weight.numel() + (m.original_module.bias.numel(
                for m in tracked)
 train, query = Glue(args.train, 0), Glue(args.queries, 1)
 analyzer = Analyzer("bench", model, task, output_dir=tempfile.mkdtemp(), disable_tqdm=True, profile=True)
+if args.no_cache:
+    analyzer.train_operand_cache_fraction = 0.0
 
 
 def timed(fn):
@@ -74,13 +78,13 @@ def timed(fn):
 
 
 fa = FactorArguments(strategy="ekfac", covariance_max_examples=args.factor_examples, lambda_max_examples=args.factor_examples)
-sa = ScoreArguments(query_gradient_accumulation_steps=max(1, args.queries // args.query_batch))
+sa = ScoreArguments(query_gradient_accumulation_steps=max(1, args.queries // args.query_batch // args.chunks))
 if args.bf16:
     bf = torch.bfloat16
     fa = FactorArguments(strategy="ekfac", covariance_max_examples=args.factor_examples, lambda_max_examples=args.factor_examples,
                          amp_dtype=bf, activation_covariance_dtype=bf, gradient_covariance_dtype=bf,
                          per_sample_gradient_dtype=bf, lambda_dtype=bf)
-    sa = ScoreArguments(query_gradient_accumulation_steps=max(1, args.queries // args.query_batch), amp_dtype=bf,
+    sa = ScoreArguments(query_gradient_accumulation_steps=max(1, args.queries // args.query_batch // args.chunks), amp_dtype=bf,
                         per_sample_gradient_dtype=bf, precondition_dtype=bf, score_dtype=bf)
 t_f, _ = timed(lambda: analyzer.fit_all_factors("f", train, per_device_batch_size=args.train_batch, factor_args=fa,
                                                 overwrite_output_dir=True))
@@ -94,6 +98,7 @@ out = {"precision": "bf16" if args.bf16 else "fp32 parity",
        "fit_all_factors_s": round(t_f, 2), "factor_examples_per_s": round(2 * args.factor_examples / t_f),
        "pairwise_s": round(t_s, 2), "pairwise_scores_per_s": round(args.queries * args.train / t_s),
        "algorithmic_TFLOPs": round(2.0 * args.queries * args.train * n_params / t_s / 1e12, 1),
+       "query_chunks": args.chunks, "train_operand_cache": analyzer.last_train_operand_cache,
        "shape": list(s.shape), "finite": bool(torch.isfinite(s).all()), "max_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
 print(analyzer.profiler.summary())
 print(json.dumps(out))
