@@ -203,10 +203,15 @@ __device__ __forceinline__ long long plane_index(const GemmParams& p, long long 
   return row * p.ldo_s + col;
 }
 
-template <int OFF, int N, bool HOIST, bool TMA2 = false>
+// TMA64 (one epilogue warpgroup): plain plane outputs leave as [32 rows x 64 columns] boxes, i.e. whole 128-byte lines
+// per row — two consecutive 32-column chunks share one 128B-swizzled staging tile per plane (`half` says which half this
+// chunk fills, `flush` that the box is complete or has no second chunk inside the matrix).  A B200 SM retires TMA store
+// requests at a fixed rate per box ROW, so 64-byte rows (32-column boxes) capped the per-sample-gradient formation at
+// ~2.5 TB/s of plane writes; full lines double the bytes per request.
+template <int OFF, int N, bool HOIST, bool TMA64 = false>
 __device__ __forceinline__ float store_chunk(const GemmParams& p, const CUtensorMap* tm_o_hi, const CUtensorMap* tm_o_lo,
                                              float alpha, int b, long long row, int col0, const float (&acc)[N],
-                                             float* st, int lane, bool mirror = false) {
+                                             float* st, int lane, bool mirror = false, int half = 0, bool flush = true) {
   // mirror: the transposed copy of an off-diagonal tile of a symmetric product (fp32 target, no factor)
   const bool transpose_out = p.transpose_out != 0 || mirror;
   const bool direct_f32 = p.out_f32 != nullptr && !transpose_out && !p.reduce_sq;
@@ -220,15 +225,50 @@ __device__ __forceinline__ float store_chunk(const GemmParams& p, const CUtensor
   // warp's staging buffer and leave as two asynchronous bulk tensor stores: fully coalesced lines, no LSU work per
   // row, rows/columns outside the matrix clipped by the tensor map (whose inner extent is the padded ld, so the
   // zero columns of the last tile double as the operand padding).
+  if (p.tma_store && !mirror && TMA64) {
+    uint8_t* sh = reinterpret_cast<uint8_t*>(st);  // [32 rows][128 bytes], 16-byte chunks XOR-swizzled by (row & 7)
+    uint8_t* sl = sh + 4096;
+    if (half == 0) {
+      if (lane == 0) tma_store_wait_read();  // the previous box's stores have finished reading the staging tiles
+      __syncwarp();
+    }
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = alpha * acc[OFF + grp * 8 + e];
+        if (p.square) v *= v;
+        split_bf16(v, h[e], l[e]);
+      }
+      const int at = lane * 128 + (((half * 4 + grp) ^ (lane & 7)) << 4);
+      *reinterpret_cast<uint4*>(sh + at) = *reinterpret_cast<uint4*>(h);
+      if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(sl + at) = *reinterpret_cast<uint4*>(l);
+    }
+    if (flush) {
+      if (half == 0) {  // no second chunk inside the matrix: the right half of the box is operand padding (zeros)
+#pragma unroll
+        for (int grp = 4; grp < 8; ++grp) {
+          const int at = lane * 128 + ((grp ^ (lane & 7)) << 4);
+          *reinterpret_cast<uint4*>(sh + at) = make_uint4(0u, 0u, 0u, 0u);
+          if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(sl + at) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = (int)(row - lane);
+        tma_store_3d(tm_o_hi, smem_u32(sh), col0 - half * 32, row0, b);
+        if (p.out_lo != nullptr) tma_store_3d(tm_o_lo, smem_u32(sl), col0 - half * 32, row0, b);
+        tma_store_commit();
+      }
+    }
+    return 0.f;
+  }
   if (p.tma_store && !mirror) {
     __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(st);
     __nv_bfloat16* sl = sh + 32 * 32;
-    // TMA2: the caller alternates between two staging tiles, so only the stores of the chunk BEFORE the previous one
-    // must have finished reading shared memory (bulk groups retire in order); otherwise the previous chunk's.
-    if (lane == 0) {
-      if (TMA2) tma_store_wait_read1();
-      else tma_store_wait_read();
-    }
+    if (lane == 0) tma_store_wait_read();  // the previous chunk's stores have finished reading the staging tile
     __syncwarp();
 #pragma unroll
     for (int grp = 0; grp < 4; ++grp) {
@@ -512,10 +552,11 @@ struct GemmCfg {
   static constexpr int A_PLANE = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_PLANE = LOAD_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PLANE + B_PLANE);
-  // per epilogue warp: one [32][33] fp32 staging tile; with one epilogue warpgroup twice 4 KB, so that the TMA plane
-  // stores of consecutive chunks alternate between two staging tiles instead of waiting for each other
+  // per epilogue warp: one [32][33] fp32 staging tile; with one epilogue warpgroup 8 KB (1024-byte aligned): two
+  // 128B-swizzled [32 rows][64 columns] bf16 tiles (hi, lo) for the 64-column TMA plane stores
   static constexpr int EPI_WARP_BYTES = EW == 4 ? 8192 : 32 * 33 * 4;
   static constexpr int EPI_STAGE_BYTES = EW * EPI_WARP_BYTES;
+  static constexpr int BARRIER_BYTES = 1024;  // keeps the staging tiles behind it 1024-byte aligned
   static_assert(EW == 4 || EW == 8, "one or two epilogue warpgroups");
   static constexpr int SMEM_BUDGET = 227 * 1024 - 2048 - EPI_STAGE_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
@@ -525,7 +566,8 @@ struct GemmCfg {
   static constexpr int TMEM_COLS =
       TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                  : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + BARRIER_BYTES + EPI_STAGE_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K must match a 128B or 64B swizzle span");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
@@ -731,10 +773,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (EW == 8) setmaxnreg_inc<224>();
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int lane_row = quarter * 32 + lane;  // accumulator row owned by this thread
-    float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 4) * (Cfg::EPI_WARP_BYTES / 4);
-    constexpr bool TMA2 = EW == 4;  // two staging tiles per warp for TMA plane stores
-    uint32_t tma_sel = 0;
-    auto st_next = [&]() { return (TMA2 && p.tma_store) ? st + (tma_sel++ & 1u) * 1024 : st; };
+    float* st = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::BARRIER_BYTES) + (warp - 4) * (Cfg::EPI_WARP_BYTES / 4);
+    constexpr bool TMA64 = EW == 4;  // 64-column TMA plane stores (see store_chunk)
     constexpr int NACC = EPI == EPI_REGACC ? BLOCK_N / (EW / 4) : 1;  // accumulator columns kept per thread
     const int col_off = EW == 8 ? ((warp - 4) >> 2) * NACC : 0;          // ... starting at this column of the tile
     // strict operands were scaled by powers of two: undo both scales together with alpha (exact)
@@ -816,7 +856,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               float x[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-              rowdot += store_chunk<0, 32, true, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st_next(), lane);
+              const bool last_of_box = (c & 1) || c + 1 == BLOCK_N / 32 || col0 + 32 >= p.N;
+              rowdot += store_chunk<0, 32, true, TMA64>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st, lane, false, c & 1, last_of_box);
               if (p.symmetric && t.n_blk != t.m_blk) store_chunk<0, 32, true>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st, lane, true);
             }
           }
@@ -867,10 +908,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int n0 = t.n_blk * BLOCK_N + col_off;
         const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
         // warp-uniform conditions: store_chunk is a warp-cooperative call
-        if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0, racc, st_next(), lane);
-        if (NACC >= 64 && n0 + 32 < p.N) store_chunk<(NACC >= 64 ? 32 : 0), NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 32, racc, st_next(), lane);
-        if (NACC >= 128 && n0 + 64 < p.N) store_chunk<(NACC >= 128 ? 64 : 0), NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 64, racc, st_next(), lane);
-        if (NACC >= 128 && n0 + 96 < p.N) store_chunk<(NACC >= 128 ? 96 : 0), NACC, false, TMA2>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 96, racc, st_next(), lane);
+        if (NACC >= 32 && n0 < p.N) store_chunk<0, NACC, false, TMA64>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0, racc, st, lane, false, 0, NACC < 64 || n0 + 32 >= p.N);
+        if (NACC >= 64 && n0 + 32 < p.N) store_chunk<(NACC >= 64 ? 32 : 0), NACC, false, TMA64>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 32, racc, st, lane, false, 1, true);
+        if (NACC >= 128 && n0 + 64 < p.N) store_chunk<(NACC >= 128 ? 64 : 0), NACC, false, TMA64>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 64, racc, st, lane, false, 0, n0 + 96 >= p.N);
+        if (NACC >= 128 && n0 + 96 < p.N) store_chunk<(NACC >= 128 ? 96 : 0), NACC, false, TMA64>(p, &tm_o_hi, &tm_o_lo, alpha, ob, row, n0 + 96, racc, st, lane, false, 1, true);
         if (row < p.M && p.zero_pad && !p.tma_store && t.n_blk == p.n_blocks - 1) store_zero_pad(p, ob, row);
       }
     }
@@ -1113,9 +1154,11 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   CUtensorMap to_hi = ta_hi, to_lo = ta_hi;
   if (EPI == EPI_ROWDOT) p.tma_store = 0;
   if (p.tma_store) {
-    KFB_TRY(make_tmap(&to_hi, p.out_hi, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, 32, 32, false));
+    // one epilogue warpgroup: [32 rows x 64 columns] boxes out of 128B-swizzled staging tiles; two: plain 32 x 32 boxes
+    const int box_cols = EW == 4 ? 64 : 32;
+    KFB_TRY(make_tmap(&to_hi, p.out_hi, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, box_cols, 32, EW == 4));
     if (p.out_lo != nullptr)
-      KFB_TRY(make_tmap(&to_lo, p.out_lo, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, 32, 32, false));
+      KFB_TRY(make_tmap(&to_lo, p.out_lo, p.ldo_s, p.M, p.batch, p.ldo_s, p.out_bs_s, box_cols, 32, EW == 4));
   }
   auto kernel = gemm_tc_kernel<BLOCK_N, BLOCK_K, NSPLIT, EPI, CG, MC, EW>;
   static bool attr_set = false;
@@ -1294,7 +1337,7 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
       p.vec_ok = 0;
     p.zero_pad = (p.out_hi != nullptr && !p.transpose_out) ? 1 : 0;
     p.tma_store = (p.out_hi != nullptr && p.out_f32 == nullptr && p.mul == nullptr && !p.transpose_out && !p.reduce_sq &&
-                   p.col_group == 0 && p.vec_ok && p.ldo_s >= 32 && g_tma_store.load() != 0) ? 1 : 0;
+                   p.col_group == 0 && p.vec_ok && p.ldo_s >= 64 && g_tma_store.load() != 0) ? 1 : 0;
     if (p.col_group > 0) {
       KFB_REQUIRE(p.out_hi != nullptr && p.out_f32 == nullptr && p.mul == nullptr && !p.transpose_out && p.batch == 1 &&
                       p.col_group % 8 == 0 && p.N % p.col_group == 0 && p.ldo_s == p.col_group,
