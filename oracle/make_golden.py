@@ -220,20 +220,20 @@ def run_reference(case, dtype, strategy="ekfac", damping=None):
                                          score_args=score_args_pm, overwrite_output_dir=True)
         out = {}
         factors = analyzer.load_all_factors("f")
-        factors.update(analyzer.load_covariance_matrices("f"))
+        factors.update(analyzer.load_covariance_matrices("f") or {})  # identity / diagonal fit no covariances
         for fname, per_module in factors.items():
             for mname, tensor in per_module.items():
                 out[f"{fname}/{mname}"] = npy(tensor)
         out["scores"] = npy(analyzer.load_pairwise_scores("s")["all_modules"])
         for mname, tensor in analyzer.load_pairwise_scores("s_pm").items():
             out[f"scores/{mname}"] = npy(tensor)
-        if damping is None and case == "seq":
+        if damping is None and case == "seq" and strategy == "ekfac":
             score_args_pt = ScoreArguments(**{**score_args.__dict__, "compute_per_token_scores": True})
             analyzer.compute_pairwise_scores("s_pt", factors_name="f", query_dataset=query_set, train_dataset=train_set,
                                              per_device_query_batch_size=query_bs, per_device_train_batch_size=train_bs,
                                              score_args=score_args_pt, overwrite_output_dir=True)
             out["scores_per_token"] = npy(analyzer.load_pairwise_scores("s_pt")["all_modules"])
-        if damping is None:
+        if damping is None and strategy == "ekfac":
             # rank-3 query factors through the exact SVD (deterministic, unlike torch.svd_lowrank)
             score_args_lr = ScoreArguments(**{**score_args.__dict__, "query_gradient_low_rank": LOW_RANK,
                                               "use_full_svd": True,
@@ -343,14 +343,36 @@ def make_postprocess_fixtures():
         print("postprocess", case, "scores fp32-vs-fp64 rel", rel, "; change vs the task without the callback", changed)
 
 
+def make_strategy_fixtures():
+    """The other factor strategies of factor/config.py:127-285 (identity, diagonal, kfac) through the reference Analyzer:
+    pairwise scores in fp32 / fp64 plus the eigendecomposition kfac needs injected (eigenvalues included)."""
+    merged = {}
+    for case in ("mlp", "conv"):
+        for strategy in ("identity", "diagonal", "kfac"):
+            for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+                out = run_reference(case, dtype, strategy=strategy, damping=None if strategy != "identity" else 1e-8)
+                merged[f"{case}/{strategy}/{tag}/scores"] = out["scores"]
+                for key, value in out.items():
+                    if "eigen" in key or key.startswith("lambda_matrix") or key.startswith("num_lambda"):
+                        merged[f"{case}/{strategy}/{tag}/{key}"] = value
+            rel = np.linalg.norm(merged[f"{case}/{strategy}/f32/scores"] - merged[f"{case}/{strategy}/f64/scores"]) / \
+                np.linalg.norm(merged[f"{case}/{strategy}/f64/scores"])
+            print("strategy", case, strategy, "scores fp32-vs-fp64 rel", rel)
+    np.savez_compressed(os.path.join(GOLDEN, "e2e_strategies.npz"), **merged)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(4)
     if "--postprocess-only" in sys.argv:
         make_postprocess_fixtures()
         sys.exit(0)
+    if "--strategies-only" in sys.argv:
+        make_strategy_fixtures()
+        sys.exit(0)
     make_stage_fixtures()
     make_e2e_fixtures()
     make_postprocess_fixtures()
+    make_strategy_fixtures()
     total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print(f"golden fixtures: {total / 1024:.1f} KiB")
