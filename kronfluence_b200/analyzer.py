@@ -285,7 +285,7 @@ class Analyzer:
                 offset += t.numel()
 
     def _zero_factor(self, module: TrackedModule, name: str) -> torch.Tensor:
-        d_in, d_out = ops.module_factor_dims(module.original_module)
+        d_in, d_out = module.factor_dims()
         shapes = {ACTIVATION_COVARIANCE_MATRIX_NAME: (d_in, d_in), GRADIENT_COVARIANCE_MATRIX_NAME: (d_out, d_out),
                   LAMBDA_MATRIX_NAME: (d_out, d_in)}
         if name in shapes:
@@ -692,6 +692,26 @@ class Analyzer:
         ({Diagonal,Kfac,Ekfac}.prepare, factor/config.py:193-203,252-271,322-339 of the reference)."""
         config = strategy_config(factor_args.strategy)
         device = self.state.device
+        if config["mode"] is None:
+            # a user FactorConfig registered over a strategy name (factor/config.py:30-125 of the reference): load what its
+            # requires_*_for_precondition properties ask for as plain device tensors under the reference's storage keys
+            # and let its own `prepare` run (module/utils.py:201-235 `load_factors` + `prepare_modules` of the reference)
+            user = config["config"]
+            wanted: List[str] = []
+            if user.requires_covariance_matrices_for_precondition:
+                wanted += COVARIANCE_FACTOR_NAMES
+            if user.requires_eigendecomposition_for_precondition:
+                wanted += EIGENDECOMPOSITION_FACTOR_NAMES
+            if user.requires_lambda_matrices_for_precondition:
+                wanted += LAMBDA_FACTOR_NAMES
+            for module in tracked_modules(self.model, names):
+                for fname in wanted:
+                    if fname not in factors or module.name not in factors[fname]:
+                        raise FactorsNotFoundError(f"The strategy {factor_args.strategy} requires `{fname}` for module "
+                                                   f"'{module.name}', but it is not found.")
+                    module.set_factor(fname, factors[fname][module.name].to(device))
+                user.prepare(storage=module.storage, score_args=score_args, device=device)
+            return
         for module in tracked_modules(self.model, names):
             mname = module.name
             if config["eigen"]:
@@ -757,7 +777,7 @@ class Analyzer:
         if self.state.use_distributed:
             for module in modules:
                 if module.storage[AGGREGATED_GRADIENT_NAME] is None:  # this rank saw no example
-                    d_in, d_out = ops.module_factor_dims(module.original_module)
+                    d_in, d_out = module.factor_dims()
                     module.storage[AGGREGATED_GRADIENT_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=device)
             flat = torch.cat([m.storage[AGGREGATED_GRADIENT_NAME].reshape(-1) for m in modules])
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)  # one collective for all modules
@@ -877,7 +897,7 @@ class Analyzer:
                 if isinstance(store, ops.LowRankStore):
                     raise NotImplementedError("`aggregate_train_gradients` is not supported with `query_gradient_low_rank`.")
                 sink = torch.zeros(num_queries, 1, dtype=torch.float32, device=device) if per_module else shared
-                layer = ops.flat_layer(module.original_module)
+                layer = module.flat_layer()
                 ops.pairwise_scores_explicit(layer, store, num_queries, train_aggregate[module.name].unsqueeze(0), sink, 0,
                                              accumulate=True, precision=precision_of(score_args.score_dtype))
                 if per_module:

@@ -58,7 +58,7 @@ class FactorArguments(Arguments):
     lambda_data_partitions: int = 1
     lambda_module_partitions: int = 1
     use_iterative_lambda_aggregation: bool = False  # no-op here: Lambda never materialises [B, d_out, d_in]
-    offload_activations_to_cpu: bool = False  # no-op here: cached activations stay in HBM
+    offload_activations_to_cpu: bool = False  # cached activations wait for their backward hook in host memory
     per_sample_gradient_dtype: torch.dtype = torch.float32
     lambda_dtype: torch.dtype = torch.float32
 
@@ -79,7 +79,7 @@ class FactorArguments(Arguments):
 class ScoreArguments(Arguments):
     damping_factor: Optional[float] = 1e-08
     amp_dtype: Optional[torch.dtype] = None
-    offload_activations_to_cpu: bool = False  # no-op here
+    offload_activations_to_cpu: bool = False  # cached activations wait for their backward hook in host memory
 
     data_partitions: int = 1
     module_partitions: int = 1

@@ -56,19 +56,19 @@ def precision_of(dtype: torch.dtype) -> int:
     return ops.PREC_BF16 if dtype in (torch.bfloat16, torch.float16) else ops.PREC_FP32
 
 
-# Which statistics each strategy needs (factor/config.py:127-353 of the reference, as a table).
-STRATEGIES: Dict[str, Dict[str, Any]] = {
-    "identity": dict(covariance=False, eigen=False, lambda_=False, lambda_eigen=False, mode=ops.PRECOND_IDENTITY),
-    "diagonal": dict(covariance=False, eigen=False, lambda_=True, lambda_eigen=False, mode=ops.PRECOND_DIAGONAL),
-    "kfac": dict(covariance=True, eigen=True, lambda_=False, lambda_eigen=False, mode=ops.PRECOND_EIGEN),
-    "ekfac": dict(covariance=True, eigen=True, lambda_=True, lambda_eigen=True, mode=ops.PRECOND_EIGEN),
-}
-
-
 def strategy_config(name: str) -> Dict[str, Any]:
-    if name not in STRATEGIES:
-        raise ValueError(f"Unknown factor strategy {name!r}; expected one of {sorted(STRATEGIES)}.")
-    return STRATEGIES[name]
+    """Which statistics a strategy needs and how its preconditioner runs, read from the `FactorConfig` registered under
+    `name` (factor/config.py:30-125 of the reference).  `mode` is the libkfb preconditioning mode of the four built-in
+    strategies, or None for a user subclass: its own `precondition_gradient` then runs on materialised gradients."""
+    from kronfluence_b200.factor.config import FactorConfig
+
+    name = str(getattr(name, "value", name))
+    if name not in FactorConfig.CONFIGS:
+        raise ValueError(f"Unknown factor strategy {name!r}; expected one of {sorted(FactorConfig.CONFIGS)}.")
+    config = FactorConfig.CONFIGS[name]
+    return dict(covariance=bool(config.requires_covariance_matrices), eigen=bool(config.requires_eigendecomposition),
+                lambda_=bool(config.requires_lambda_matrices), lambda_eigen=bool(config.requires_eigendecomposition_for_lambda),
+                mode=config.native_mode, config=config)
 
 
 class ScoreSink:
@@ -117,6 +117,12 @@ class TrainOperandCache:
             self.entries.clear()
             return
         self.entries.setdefault(module_name, []).append((prepared, column, scale, tokens))
+
+    def abandon(self) -> None:
+        """A module scored a batch on a path that keeps no operands (materialised or rank-r gradients): replaying the cache
+        would miss its contribution, so later chunks run the model again."""
+        self.recording = False
+        self.entries.clear()
 
     def finish_recording(self) -> None:
         self.complete = self.recording
@@ -168,6 +174,14 @@ class BaseTracker:
         # A private copy, like the reference's `.to(copy=True)`: later in-place ops on the activation
         # (residual adds, in-place ReLU on a shared buffer) must not change what backward sees.
         cached = inputs[0].detach().clone()
+        if self.module.score_args.offload_activations_to_cpu and self.module.current_mode in (
+                ModuleMode.PRECONDITION_GRADIENT, ModuleMode.PAIRWISE_SCORE, ModuleMode.SELF_SCORE,
+                ModuleMode.GRADIENT_AGGREGATION):
+            # ScoreArguments.offload_activations_to_cpu (tracker/pairwise_score.py:60-64 of the reference): the cached
+            # copy waits for its backward hook in host memory
+            cached = cached.to("cpu")
+        elif self.module.factor_args.offload_activations_to_cpu and self.module.current_mode == ModuleMode.LAMBDA:
+            cached = cached.to("cpu")  # FactorArguments.offload_activations_to_cpu (tracker/factor.py:243-249)
         if self.module.factor_args.has_shared_parameters:
             self.cached_activations.append(cached)
         else:
@@ -181,25 +195,37 @@ class BaseTracker:
         if len(acts) != len(grads) or not acts:
             self._no_cache_error()
         if len(acts) == 1:
-            return acts[0], grads[0]
+            return acts[0].to(grads[0].device), grads[0]
         if self.module.is_conv:
             raise NotImplementedError("has_shared_parameters is not supported for shared Conv2d modules.")
+        acts = [a.to(grads[0].device) for a in acts]
         flat_a = [a.reshape(a.shape[0], -1, a.shape[-1]) for a in acts]
         flat_g = [g.reshape(g.shape[0], -1, g.shape[-1]) for g in grads]
         return torch.cat(flat_a, dim=1), torch.cat(flat_g, dim=1)
 
-    def _processed_gradient(self, layer, a: torch.Tensor, g: torch.Tensor) -> Optional[torch.Tensor]:
-        """With `Task.enable_post_process_per_sample_gradient`: the materialised per-sample gradients
-        [B, d_out, d_in(+1)] after the task's callback (module/linear.py:68-77, conv2d.py:164-177 of the reference:
-        the callback sees them before `gradient_scale` is applied).  None when the task does not post-process, in which
-        case the fused paths never form these tensors."""
-        fnc = self.module.per_sample_gradient_process_fnc
-        if fnc is None:
+    def _processed_gradient(self, layer, a: torch.Tensor, g: torch.Tensor, force: bool = False) -> Optional[torch.Tensor]:
+        """Materialised per-sample gradients [B, d_out, d_in(+1)] (fp32, parameter basis) when something needs them:
+          * `Task.enable_post_process_per_sample_gradient`: the task's callback runs on them (module/linear.py:68-77,
+            conv2d.py:164-177 of the reference: before `gradient_scale` is applied);
+          * a third-party layer plugin (a `TrackedModule` subclass for another module type): its own
+            `compute_per_sample_gradient`, which like the reference's applies the callback itself;
+          * `force`: a user `FactorConfig` whose `precondition_gradient` takes them.
+        None otherwise: the fused paths never form these tensors."""
+        module = self.module
+        if not module.native:
+            grads = module.compute_per_sample_gradient(input_activation=a, output_gradient=g)
+            grads = grads.to(dtype=torch.float32).contiguous()
+            module.plugin_dims = (int(grads.shape[1]), int(grads.shape[2]))
+            return grads
+        fnc = module.per_sample_gradient_process_fnc
+        if fnc is None and not force:
             return None
         grads = ops.per_sample_gradient(layer, a, g)
-        processed = fnc(module_name=self.module.name, gradient=grads)
+        if fnc is None:
+            return grads
+        processed = fnc(module_name=module.name, gradient=grads)
         if processed.shape != grads.shape:
-            raise ValueError(f"`post_process_per_sample_gradient` changed the gradient shape of '{self.module.name}' "
+            raise ValueError(f"`post_process_per_sample_gradient` changed the gradient shape of '{module.name}' "
                              f"from {tuple(grads.shape)} to {tuple(processed.shape)}.")
         return processed.to(dtype=torch.float32).contiguous()
 
@@ -219,6 +245,37 @@ class CovarianceTracker(BaseTracker):
 
     def register_hooks(self) -> None:
         module = self.module
+
+        @torch.no_grad()
+        def plugin_forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
+            # a third-party layer plugin flattens its own activations / gradients (tracked_module.py:321-350 of the
+            # reference: [N, d] matrices, ones column and mask already applied); the SYRK kernels take it from there
+            flat, count = module.get_flattened_activation(inputs[0].detach().clone())
+            flat = flat.contiguous()
+            storage = module.storage
+            if storage[ACTIVATION_COVARIANCE_MATRIX_NAME] is None:
+                storage[ACTIVATION_COVARIANCE_MATRIX_NAME] = torch.zeros(flat.shape[1], flat.shape[1], dtype=torch.float32,
+                                                                         device=flat.device)
+                storage[NUM_ACTIVATION_COVARIANCE_PROCESSED] = torch.zeros(1, dtype=torch.int64, device=flat.device)
+            ops.cov_accum_activation(ops.flat_dims_layer(flat.shape[1], 1), flat, storage[ACTIVATION_COVARIANCE_MATRIX_NAME],
+                                     None, precision_of(module.factor_args.activation_covariance_dtype))
+            storage[NUM_ACTIVATION_COVARIANCE_PROCESSED].add_(count if not torch.is_tensor(count) else count.to(torch.int64))
+            self.cached_hooks.append(outputs.register_hook(plugin_backward_hook))
+
+        @torch.no_grad()
+        def plugin_backward_hook(grad: torch.Tensor) -> None:
+            self.cached_hooks.pop().remove()
+            flat, count = module.get_flattened_gradient(grad.detach())
+            flat = flat.contiguous()
+            storage = module.storage
+            if storage[GRADIENT_COVARIANCE_MATRIX_NAME] is None:
+                storage[GRADIENT_COVARIANCE_MATRIX_NAME] = torch.zeros(flat.shape[1], flat.shape[1], dtype=torch.float32,
+                                                                       device=flat.device)
+                storage[NUM_GRADIENT_COVARIANCE_PROCESSED] = torch.zeros(1, dtype=torch.int64, device=flat.device)
+            alpha = module.gradient_scale**2.0 if module.gradient_scale != 1.0 else 1.0
+            ops.cov_accum_gradient(ops.flat_dims_layer(1, flat.shape[1]), flat, storage[GRADIENT_COVARIANCE_MATRIX_NAME], alpha,
+                                   precision_of(module.factor_args.gradient_covariance_dtype))
+            storage[NUM_GRADIENT_COVARIANCE_PROCESSED].add_(count if not torch.is_tensor(count) else count.to(torch.int64))
 
         @torch.no_grad()
         def forward_hook(_mod: nn.Module, inputs: Tuple[torch.Tensor, ...], outputs: torch.Tensor) -> None:
@@ -252,7 +309,7 @@ class CovarianceTracker(BaseTracker):
                                    precision_of(module.factor_args.gradient_covariance_dtype))
             storage[NUM_GRADIENT_COVARIANCE_PROCESSED].add_(rows if mask is None else mask.sum().to(torch.int64))
 
-        self.registered_hooks.append(module.register_forward_hook(forward_hook))
+        self.registered_hooks.append(module.register_forward_hook(forward_hook if module.native else plugin_forward_hook))
 
     def exist(self) -> bool:
         return all(self.module.storage[name] is not None for name in COVARIANCE_FACTOR_NAMES)
@@ -267,22 +324,22 @@ class LambdaTracker(BaseTracker):
 
     def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
         module = self.module
+        a = a.to(g.device, non_blocking=True)  # no-op unless the activation was offloaded to the host
         layer = module.layer_for(a)
-        d_in, d_out = ops.factor_dims(layer)
         storage = module.storage
-        if storage[LAMBDA_MATRIX_NAME] is None:
-            storage[LAMBDA_MATRIX_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
-            storage[NUM_LAMBDA_PROCESSED] = torch.zeros(1, dtype=torch.int64)
         qa = qg = None
         precision = precision_of(module.factor_args.lambda_dtype)
         if strategy_config(module.factor_args.strategy)["lambda_eigen"]:
             qa, qg = module.eigen_operands(g.device, precision)
         dense = self._processed_gradient(layer, a, g)
+        d_in, d_out = module.factor_dims()
+        if storage[LAMBDA_MATRIX_NAME] is None:
+            storage[LAMBDA_MATRIX_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
+            storage[NUM_LAMBDA_PROCESSED] = torch.zeros(1, dtype=torch.int64)
         if dense is not None:
-            # tracker/factor.py:218-230 on the callback's output: rotate the dense gradients, then square-accumulate
-            flat = ops.flat_layer(module.original_module)
+            # tracker/factor.py:218-230 on materialised gradients: rotate them, then square-accumulate
             if qa is not None:
-                dense = ops.transform_gradient(flat, dense, qa, qg, None, 1.0, precision=precision)
+                dense = ops.transform_gradient(module.flat_layer(), dense, qa, qg, None, 1.0, precision=precision)
             ops.sq_accum(dense, storage[LAMBDA_MATRIX_NAME], module.gradient_scale**2)
         else:
             ops.lambda_accum(layer, a, g, storage[LAMBDA_MATRIX_NAME], qa, qg, module.gradient_scale, precision)
@@ -331,11 +388,10 @@ class PreconditionTracker(BaseTracker):
 
     def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
         module = self.module
+        a = a.to(g.device, non_blocking=True)  # no-op unless the activation was offloaded to the host
         layer = module.layer_for(a)
-        store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
-        if store is None:
-            raise RuntimeError(f"Module '{module.name}': the query store has not been allocated.")
-        mode = strategy_config(module.factor_args.strategy)["mode"]
+        strategy = strategy_config(module.factor_args.strategy)
+        mode = strategy["mode"]
         # The query store is laid out for the contraction that reads it (`score_dtype`), and the preconditioning
         # kernels write straight into it, so the store's precision is the one this stage computes in
         # (`precondition_dtype` is honoured when it is at most as precise).
@@ -343,15 +399,23 @@ class PreconditionTracker(BaseTracker):
         qa = qg = None
         if mode == ops.PRECOND_EIGEN:
             qa, qg = module.eigen_operands(g.device, precision)
-        lam_inv = module.storage[LAMBDA_MATRIX_NAME] if mode != ops.PRECOND_IDENTITY else None
-        dense_grad = self._processed_gradient(layer, a, g)
+        lam_inv = module.storage[LAMBDA_MATRIX_NAME] if mode not in (None, ops.PRECOND_IDENTITY) else None
+        dense_grad = self._processed_gradient(layer, a, g, force=mode is None)
+        store = module.ensure_query_store(g.device)
         if dense_grad is not None:
-            # the callback's output goes through the same preconditioner, on materialised gradients
-            flat = ops.flat_layer(module.original_module)
+            flat = module.flat_layer()
             target = store.scratch_for(a.shape[0], g.device) if isinstance(store, ops.LowRankStore) else store
             offset = 0 if isinstance(store, ops.LowRankStore) else module.query_count
-            ops.transform_gradient(flat, dense_grad, qa, qg, lam_inv, module.gradient_scale, want_f32=False, store=target,
-                                   q_offset=offset, precision=precision)
+            if mode is None:
+                # a user FactorConfig (factor/config.py:104-125 of the reference): its preconditioner runs on the
+                # materialised gradients; the result is kept in the PARAMETER basis
+                pre = strategy["config"].precondition_gradient(gradient=dense_grad, storage=module.storage)
+                ops.transform_gradient(flat, pre, None, None, None, module.gradient_scale, want_f32=False, store=target,
+                                       q_offset=offset, precision=precision)
+            else:
+                # the callback's / plugin's output goes through the native preconditioner, on materialised gradients
+                ops.transform_gradient(flat, dense_grad, qa, qg, lam_inv, module.gradient_scale, want_f32=False,
+                                       store=target, q_offset=offset, precision=precision)
             if isinstance(store, ops.LowRankStore):
                 ops.lowrank_factorize(target, a.shape[0], store, module.query_count, module.score_args.use_full_svd,
                                       module.score_args.query_gradient_svd_dtype)
@@ -418,25 +482,28 @@ class GradientAggregationTracker(BaseTracker):
 
     def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
         module = self.module
+        a = a.to(g.device, non_blocking=True)  # no-op unless the activation was offloaded to the host
         layer = module.layer_for(a)
-        d_in, d_out = ops.factor_dims(layer)
-        if module.storage[AGGREGATED_GRADIENT_NAME] is None:
-            module.storage[AGGREGATED_GRADIENT_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
-        mode = strategy_config(module.factor_args.strategy)["mode"]
+        strategy = strategy_config(module.factor_args.strategy)
+        mode = strategy["mode"]
         precision = precision_of(module.score_args.per_sample_gradient_dtype)
         qa = qg = None
         if mode == ops.PRECOND_EIGEN:
             qa, qg = module.eigen_operands(g.device, precision)
         lam_inv = None
-        if module.aggregate_precondition and mode != ops.PRECOND_IDENTITY:
+        if module.aggregate_precondition and mode not in (None, ops.PRECOND_IDENTITY):
             lam_inv = module.storage[LAMBDA_MATRIX_NAME]
-        dense = self._processed_gradient(layer, a, g)
+        dense = self._processed_gradient(layer, a, g, force=mode is None and module.aggregate_precondition)
+        d_in, d_out = module.factor_dims()
+        if module.storage[AGGREGATED_GRADIENT_NAME] is None:
+            module.storage[AGGREGATED_GRADIENT_NAME] = torch.zeros(d_out, d_in, dtype=torch.float32, device=g.device)
         if dense is not None:
-            # tracker/gradient.py:46-60 of the reference: per-sample gradients through the callback, summed over the batch
+            # tracker/gradient.py:46-60 of the reference: per-sample gradients (callback applied), summed over the batch
             total = dense.sum(dim=0, keepdim=True)
-            flat = ops.flat_layer(module.original_module)
+            if mode is None and module.aggregate_precondition:
+                total = strategy["config"].precondition_gradient(gradient=total, storage=module.storage)
             module.storage[AGGREGATED_GRADIENT_NAME].add_(
-                ops.transform_gradient(flat, total, qa, qg, lam_inv, module.gradient_scale, precision=precision)[0])
+                ops.transform_gradient(module.flat_layer(), total, qa, qg, lam_inv, module.gradient_scale, precision=precision)[0])
             return
         ops.aggregate_gradient(layer, a, g, module.storage[AGGREGATED_GRADIENT_NAME], qa, qg, lam_inv,
                                module.gradient_scale, precision)
@@ -495,6 +562,7 @@ class PairwiseScoreTracker(BaseTracker):
                 self._no_cache_error()
             self.cached_hooks.pop().remove()
             a = self.cached_activations.pop() if module.factor_args.has_shared_parameters else self.cached_activations[0]
+            a = a.to(grad.device, non_blocking=True)  # no-op unless the activation was offloaded to the host
             sink = module.storage[PAIRWISE_SCORE_MATRIX_NAME]
             store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
             if sink is None or store is None:
@@ -507,6 +575,8 @@ class PairwiseScoreTracker(BaseTracker):
             grad = grad.detach()
             tokens = 1
             dense = self._processed_gradient(layer, a, grad)
+            if (dense is not None or isinstance(store, ops.LowRankStore)) and module.train_operand_cache is not None:
+                module.train_operand_cache.abandon()
             if dense is not None:
                 # tracker/pairwise_score.py:19-50,95-103 of the reference: "qio,tio->qt" on the callback's output,
                 # here in the basis of the query store (rotate the dense train gradients first)
@@ -515,7 +585,7 @@ class PairwiseScoreTracker(BaseTracker):
                 if isinstance(store, ops.LowRankStore):
                     raise NotImplementedError("`query_gradient_low_rank` with `post_process_per_sample_gradient` is not "
                                               "supported; use dense query gradients.")
-                flat = ops.flat_layer(module.original_module)
+                flat = module.flat_layer()
                 precision = precision_of(module.score_args.score_dtype)
                 if qa is not None:
                     dense = ops.transform_gradient(flat, dense, qa, qg, None, 1.0, precision=precision)
@@ -583,25 +653,32 @@ class SelfScoreTracker(BaseTracker):
 
     def _update(self, a: torch.Tensor, g: torch.Tensor) -> None:
         module = self.module
+        a = a.to(g.device, non_blocking=True)  # no-op unless the activation was offloaded to the host
         sink = module.storage[SELF_SCORE_VECTOR_NAME]
         if sink is None:
             raise RuntimeError(f"Module '{module.name}': self scoring was not set up.")
         layer = module.layer_for(a)
-        mode = strategy_config(module.factor_args.strategy)["mode"]
+        strategy = strategy_config(module.factor_args.strategy)
+        mode = strategy["mode"]
         qa = qg = None
         if mode == ops.PRECOND_EIGEN:
             qa, qg = module.eigen_operands(g.device, precision_of(module.score_args.score_dtype))
+        dense = self._processed_gradient(layer, a, g, force=mode is None)
+        if mode is None:
+            # a user FactorConfig: <P(G_t), G_t> with its own preconditioner on the materialised gradients
+            pre = strategy["config"].precondition_gradient(gradient=dense, storage=module.storage)
+            vals = (pre.to(torch.float32) * dense).flatten(1).sum(dim=1) * module.gradient_scale**2
+            sink[module.score_offset : module.score_offset + dense.shape[0]].add_(vals)
+            return
         lam_inv = module.storage[LAMBDA_MATRIX_NAME]
         if lam_inv is None:  # identity strategy: P(G) = G
-            d_in, d_out = ops.factor_dims(layer)
+            d_in, d_out = module.factor_dims()
             lam_inv = torch.ones(d_out, d_in, dtype=torch.float32, device=g.device)
             module.storage[LAMBDA_MATRIX_NAME] = lam_inv
-        dense = self._processed_gradient(layer, a, g)
         if dense is not None:
-            flat = ops.flat_layer(module.original_module)
             precision = precision_of(module.score_args.score_dtype)
             if qa is not None:
-                dense = ops.transform_gradient(flat, dense, qa, qg, None, 1.0, precision=precision)
+                dense = ops.transform_gradient(module.flat_layer(), dense, qa, qg, None, 1.0, precision=precision)
             ops.weighted_sqnorm(dense, lam_inv, sink, module.score_offset, module.gradient_scale**2, accumulate=True)
             return
         ops.self_scores(layer, a, g, sink, module.score_offset, mode, lam_inv, qa, qg, scale=module.gradient_scale,
@@ -648,6 +725,11 @@ class TrackedModule(nn.Module):
 
     SUPPORTED_MODULES: Dict[Type[nn.Module], Any] = {}
     is_conv = False
+    # True for the layer types libkfb implements itself (nn.Linear, nn.Conv2d): the trackers hand raw activations and
+    # output gradients to the fused kernels.  A third-party subclass (`class TrackedX(TrackedModule, module_type=X)`,
+    # tracked_module.py:58-69 of the reference) is False: the trackers then call its get_flattened_* /
+    # compute_per_sample_gradient methods and continue on libkfb's dense-gradient ops.
+    native = False
 
     def __init_subclass__(cls, module_type: Optional[Type[nn.Module]] = None, **kwargs: Any) -> None:
         super().__init_subclass__(**kwargs)
@@ -662,7 +744,9 @@ class TrackedModule(nn.Module):
         self.original_module = original_module
         # Frozen models still need a gradient path to this module's output so that the tensor hook on
         # `outputs` fires (tracked_module.py:97-103,165-168 of the reference).
-        self._constant = nn.Parameter(torch.zeros(1, dtype=original_module.weight.dtype, requires_grad=True))
+        first_param = next(original_module.parameters(), None)
+        self._constant = nn.Parameter(torch.zeros(1, dtype=first_param.dtype if first_param is not None else torch.float32,
+                                                  requires_grad=True))
         self.current_mode = ModuleMode.DEFAULT
         self.factor_args = FactorArguments() if factor_args is None else factor_args
         self.score_args = ScoreArguments() if score_args is None else score_args
@@ -690,6 +774,8 @@ class TrackedModule(nn.Module):
         self.score_offset = 0
         self._layers: Dict[Tuple[int, ...], Any] = {}
         self._eigen_ops: Optional[Dict[int, Tuple[Any, Any]]] = None
+        self.plugin_dims: Optional[Tuple[int, int]] = None  # (d_out, d_in_total) of a third-party layer, once seen
+        self.query_capacity = 0
 
     def forward(self, inputs: torch.Tensor, *args: Any, **kwargs: Any) -> torch.Tensor:
         outputs = self.original_module(inputs, *args, **kwargs)
@@ -699,10 +785,28 @@ class TrackedModule(nn.Module):
 
     # ---- geometry / operands ----
     def layer_for(self, x: torch.Tensor):
+        if not self.native:
+            return None  # a third-party layer has no kfb_layer descriptor: it goes through the dense-gradient ops
         key = tuple(x.shape[-2:]) if self.is_conv else ()
         if key not in self._layers:
             self._layers[key] = ops.layer_of(self.original_module, tuple(x.shape))
         return self._layers[key]
+
+    def factor_dims(self) -> Tuple[int, int]:
+        """(activation factor dimension incl. the bias column, gradient factor dimension)."""
+        if self.native:
+            return ops.module_factor_dims(self.original_module)
+        if self.plugin_dims is None:
+            raise RuntimeError(f"Module '{self.name}': the parameter shape of a third-party layer is only known after its "
+                               "first per-sample gradient.")
+        return self.plugin_dims[1], self.plugin_dims[0]
+
+    def flat_layer(self):
+        """The module as a plain [d_out, d_in(+1)] parameter matrix: what the ops on materialised gradients need."""
+        if self.native:
+            return ops.flat_layer(self.original_module)
+        d_in_total, d_out = self.factor_dims()
+        return ops.flat_dims_layer(d_in_total, d_out)
 
     def eigen_operands(self, device: torch.device, precision: int = ops.PREC_FP32):
         """Q_A / Q_G in tensor-core operand layout, built once per set of factors and per precision (the reference
@@ -769,22 +873,133 @@ class TrackedModule(nn.Module):
 
     # ---- score plumbing ----
     def allocate_query_store(self, capacity: int, device: torch.device) -> None:
-        d_in_total, d_out = ops.module_factor_dims(self.original_module)
+        self.query_capacity = capacity
+        self.query_count = 0
+        self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = None
+        if self.native or self.plugin_dims is not None:
+            self.ensure_query_store(device)
+
+    def ensure_query_store(self, device: torch.device):
+        """The module's query store; a third-party layer's is allocated at its first gradient (when its shape is known)."""
+        store = self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
+        if store is not None:
+            return store
+        if self.query_capacity <= 0:
+            raise RuntimeError(f"Module '{self.name}': the query store has not been allocated.")
+        d_in_total, d_out = self.factor_dims()
         rank = self.score_args.query_gradient_low_rank
         if rank is not None and min(d_out, d_in_total) > rank:  # tracker/precondition.py:60-63 of the reference
-            self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = ops.make_lowrank_store(
-                d_out, d_in_total, rank, capacity, device, precision_of(self.score_args.score_dtype))
+            store = ops.make_lowrank_store(d_out, d_in_total, rank, self.query_capacity, device,
+                                           precision_of(self.score_args.score_dtype))
         else:
-            self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = ops.make_query_store(
-                d_out, d_in_total, capacity, device, precision_of(self.score_args.score_dtype))
-        self.query_count = 0
+            store = ops.make_query_store(d_out, d_in_total, self.query_capacity, device,
+                                         precision_of(self.score_args.score_dtype))
+        self.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME] = store
+        return store
+
+    # ---- the per-layer methods of the reference's plugin surface (tracked_module.py:321-416) ----
+    # The engine itself only calls them on third-party subclasses (`native = False`); on the built-in layers they exist
+    # for code written against kronfluence's API and run on libkfb where there is arithmetic to do.
+    def get_flattened_activation(self, input_activation: torch.Tensor):
+        raise NotImplementedError("Subclasses must implement the `get_flattened_activation` method.")
+
+    def get_flattened_gradient(self, output_gradient: torch.Tensor):
+        raise NotImplementedError("Subclasses must implement the `get_flattened_gradient` method.")
+
+    def compute_summed_gradient(self, input_activation: torch.Tensor, output_gradient: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("Subclasses must implement the `compute_summed_gradient` method.")
+
+    def compute_per_sample_gradient(self, input_activation: torch.Tensor, output_gradient: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("Subclasses must implement the `compute_per_sample_gradient` method.")
+
+    def compute_pairwise_score(self, preconditioned_gradient: torch.Tensor, input_activation: torch.Tensor,
+                               output_gradient: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("Subclasses must implement the `compute_pairwise_score` method.")
+
+    def compute_self_measurement_score(self, preconditioned_gradient: torch.Tensor, input_activation: torch.Tensor,
+                                       output_gradient: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("Subclasses must implement the `compute_self_measurement_score` method.")
 
 
-class TrackedLinear(TrackedModule, module_type=nn.Linear):
+class _NativeLayerMethods:
+    """The reference's per-layer methods for the layer types libkfb implements (module/linear.py:30-122,
+    module/conv2d.py:106-209), on the CUDA ops; flattening is pure data movement and stays in torch."""
+
+    native = True
+
+    def compute_per_sample_gradient(self, input_activation: torch.Tensor, output_gradient: torch.Tensor) -> torch.Tensor:
+        grads = ops.per_sample_gradient(self.layer_for(input_activation), input_activation, output_gradient)
+        if self.per_sample_gradient_process_fnc is not None:  # linear.py:73-76 / conv2d.py:173-176
+            grads = self.per_sample_gradient_process_fnc(module_name=self.name, gradient=grads)
+        return grads
+
+    def compute_summed_gradient(self, input_activation: torch.Tensor, output_gradient: torch.Tensor) -> torch.Tensor:
+        d_in, d_out = self.factor_dims()
+        total = torch.zeros(d_out, d_in, dtype=torch.float32, device=output_gradient.device)
+        ops.aggregate_gradient(self.layer_for(input_activation), input_activation, output_gradient, total)
+        return total.unsqueeze(0)
+
+    def compute_pairwise_score(self, preconditioned_gradient: torch.Tensor, input_activation: torch.Tensor,
+                               output_gradient: torch.Tensor) -> torch.Tensor:
+        """"qio,b...i,b...o->qb" for a dense [Q, d_out, d_in(+1)] preconditioned gradient in the parameter basis."""
+        precision = precision_of(self.score_args.score_dtype)
+        n_query = preconditioned_gradient.shape[0]
+        store = ops.make_query_store(preconditioned_gradient.shape[1], preconditioned_gradient.shape[2], n_query,
+                                     preconditioned_gradient.device, precision)
+        ops.load_query_store(store, preconditioned_gradient.to(torch.float32), 0, precision)
+        scores = torch.zeros(n_query, input_activation.shape[0], dtype=torch.float32, device=output_gradient.device)
+        ops.pairwise_scores(self.layer_for(input_activation), store, n_query, input_activation, output_gradient, scores,
+                            precision=precision)
+        return scores
+
+    def compute_self_measurement_score(self, preconditioned_gradient: torch.Tensor, input_activation: torch.Tensor,
+                                       output_gradient: torch.Tensor) -> torch.Tensor:
+        grads = ops.per_sample_gradient(self.layer_for(input_activation), input_activation, output_gradient)
+        return (preconditioned_gradient.to(torch.float32) * grads).flatten(1).sum(dim=1)
+
+
+class TrackedLinear(_NativeLayerMethods, TrackedModule, module_type=nn.Linear):
     """nn.Linear: factors are [in_features (+1 bias column)]^2 and [out_features]^2."""
 
+    def get_flattened_activation(self, input_activation: torch.Tensor):
+        """module/linear.py:30-46 of the reference: [N, d_in(+1)] with masked rows and ones column, and the row count."""
+        flat = input_activation.reshape(-1, input_activation.shape[-1])
+        mask = None
+        if self.attention_mask is not None and flat.shape[0] == self.attention_mask.numel():
+            mask = self.attention_mask.reshape(-1, 1).to(flat.dtype)
+            flat = flat * mask
+        if self.original_module.bias is not None:
+            ones = flat.new_ones(flat.shape[0], 1) if mask is None else mask
+            flat = torch.cat([flat, ones], dim=-1)
+        return flat, (flat.shape[0] if mask is None else mask.sum())
 
-class TrackedConv2d(TrackedModule, module_type=nn.Conv2d):
+    def get_flattened_gradient(self, output_gradient: torch.Tensor):
+        flat = output_gradient.reshape(-1, output_gradient.shape[-1])
+        if self.attention_mask is not None and flat.shape[0] == self.attention_mask.numel():
+            return flat, self.attention_mask.sum()
+        return flat, flat.shape[0]
+
+
+class TrackedConv2d(_NativeLayerMethods, TrackedModule, module_type=nn.Conv2d):
     """nn.Conv2d: the activation factor is over unfolded patches C_in/groups * k_h * k_w (+1)."""
 
     is_conv = True
+
+    def get_flattened_activation(self, input_activation: torch.Tensor):
+        """module/conv2d.py:15-64,106-128 of the reference: group mean, unfold to [B*O1*O2, C_in/g*k1*k2 (+1)]."""
+        conv = self.original_module
+        layer = self.layer_for(input_activation)
+        x = input_activation
+        if conv.groups > 1:
+            b, c, h, w = x.shape
+            x = x.reshape(b, conv.groups, c // conv.groups, h, w).mean(dim=1)
+        patches = torch.nn.functional.unfold(x, kernel_size=conv.kernel_size, dilation=conv.dilation,
+                                             padding=(layer.pad_h, layer.pad_w), stride=conv.stride)
+        flat = patches.transpose(1, 2).reshape(-1, patches.shape[1])
+        if conv.bias is not None:
+            flat = torch.cat([flat, flat.new_ones(flat.shape[0], 1)], dim=-1)
+        return flat, flat.shape[0]
+
+    def get_flattened_gradient(self, output_gradient: torch.Tensor):
+        flat = output_gradient.permute(0, 2, 3, 1).reshape(-1, output_gradient.shape[1])
+        return flat, flat.shape[0]

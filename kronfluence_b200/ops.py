@@ -223,6 +223,12 @@ def flat_layer(module: nn.Module) -> KfbLayer:
     return KfbLayer(kind=engine.LINEAR, d_in=d_in_total - has_bias, d_out=d_out, has_bias=has_bias)
 
 
+def flat_dims_layer(d_in_total: int, d_out: int) -> KfbLayer:
+    """A plain [d_out, d_in_total] parameter matrix without bias column handling (third-party layer plugins hand over
+    activations with their ones column already appended)."""
+    return KfbLayer(kind=engine.LINEAR, d_in=int(d_in_total), d_out=int(d_out), has_bias=0)
+
+
 def make_query_store(d_out: int, d_in_total: int, capacity: int, device, precision: int = PREC_FP32) -> Split:
     """Device storage for `capacity` preconditioned query gradients [d_out, d_in(+1)] of one module."""
     return Split(d_out, d_in_total, capacity, device=device, precision=precision, zero=True)
@@ -420,7 +426,7 @@ __all__ = [
     "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "self_scores", "layer_of", "factor_dims", "workspace",
     "aggregate_gradient", "pairwise_scores_explicit", "flat_layer",
     "per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
-    "PreparedBatch", "pairwise_prepare", "pairwise_scores_prepared",
+    "PreparedBatch", "pairwise_prepare", "pairwise_scores_prepared", "flat_dims_layer",
 ]
 
 

@@ -163,6 +163,10 @@ def pairwise_scores(layer, store, num_queries, a, g, scores, t_offset=0, accumul
         view.copy_(block.to(scores.dtype))
 
 
+def flat_dims_layer(d_in_total, d_out):
+    return SimpleNamespace(kind=0, d_in=int(d_in_total), d_out=int(d_out), has_bias=0, h_out=1, w_out=1, conv=None)
+
+
 def flat_layer(module):
     d_in_total, d_out = ops.module_factor_dims(module)
     has_bias = int(module.bias is not None)
@@ -247,7 +251,7 @@ def pairwise_scores_prepared(store, num_queries, prepared, scores, t_offset=0, a
                     prepared.precision, prepared.qa, prepared.qg)
 
 
-_PATCHED = ["pairwise_prepare", "pairwise_scores_prepared", "per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
+_PATCHED = ["flat_dims_layer", "pairwise_prepare", "pairwise_scores_prepared", "per_sample_gradient", "transform_gradient", "sq_accum", "weighted_sqnorm",
             "layer_of", "factor_dims", "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "make_eigen_operands",
             "lambda_accum", "lambda_invert", "make_query_store", "precondition", "pairwise_scores", "self_scores",
             "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank", "LowRankStore", "flat_layer",

@@ -530,3 +530,57 @@ def test_train_operand_cache_across_query_chunks(tmp_path):
         assert calls["train"] == 3 * n_batches
     assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
     assert rel(scores["all_modules"].numpy(), plain["all_modules"].numpy()) < 1e-6
+
+
+def _inject(analyzer, golden):
+    from kronfluence_b200.utils import save as io
+
+    eig = analyzer.load_eigendecomposition("f")
+    eig = {f: {m: torch.from_numpy(golden[f"f32/{f}/{m}"]) for m in eig[f]} for f in eig}
+    io.save_factors(analyzer.factors_output_dir("f"), eig)
+
+
+def test_third_party_layer_plugin(tmp_path):
+    """A `TrackedModule` subclass for an unknown module type (tracked_module.py:58-69,321-416 of the reference): its
+    flatten / per-sample-gradient methods feed the same factors and scores as the built-in nn.Linear path."""
+    from kronfluence_b200.module.tracked_module import TrackedModule
+    from tests import plugins
+
+    plugins.make_tracked_my_linear(TrackedModule)
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_mlp.npz")))
+    reference_mlp, train_set, query_set = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    model = prepare_model(plugins.make_plugin_mlp(reference_mlp), task)
+    assert all(type(m).__name__ == "TrackedMyLinear" for m in model if hasattr(m, "original_module"))
+    with oracle_backend():
+        analyzer = Analyzer("plugin", model, task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        fa = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+        analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8, factor_args=fa)
+        cov = analyzer.load_covariance_matrices("f")
+        _ = analyzer.perform_eigendecomposition("f", fa)
+        _inject(analyzer, golden)
+        analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=8, factor_args=fa)
+        scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=3,
+                                                  per_device_train_batch_size=8, score_args=ScoreArguments(damping_factor=None))
+        own = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=8,
+                                           score_args=ScoreArguments(damping_factor=None))
+    for name, value in cov["activation_covariance"].items():
+        assert rel(value.numpy(), golden[f"f32/activation_covariance/{name}"]) < 2e-5
+    assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
+    assert rel(own["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
+
+
+def test_user_factor_strategy(tmp_path):
+    """A user `FactorConfig` registered over a strategy name (factor/config.py:30-125 of the reference): its own
+    `prepare` / `precondition_gradient` run on materialised gradients, the store is kept in the parameter basis."""
+    from kronfluence_b200.factor.config import FactorConfig
+    from tests import plugins
+
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_conv.npz")))
+    registry, previous = plugins.make_user_ekfac(FactorConfig)
+    try:
+        with oracle_backend():
+            _, scores = run_case("conv", tmp_path, inject_eigen=golden)
+    finally:
+        registry["ekfac"] = previous
+    assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5

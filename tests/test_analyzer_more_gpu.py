@@ -176,3 +176,113 @@ def test_shared_parameters(tmp_path):
     analyzer2.perform_eigendecomposition("f", fa2)
     with pytest.raises(RuntimeError):
         analyzer2.fit_lambda_matrices("f", train_set, per_device_batch_size=6, factor_args=fa2)
+
+
+def _inject(analyzer, golden):
+    from kronfluence_b200.utils import save as io
+
+    eig = analyzer.load_eigendecomposition("f")
+    eig = {f: {m: torch.from_numpy(golden[f"f32/{f}/{m}"]) for m in eig[f]} for f in eig}
+    io.save_factors(analyzer.factors_output_dir("f"), eig)
+
+
+def test_third_party_layer_plugin(tmp_path):
+    """tracked_module.py:58-69,321-416 of the reference: a user `TrackedModule` subclass for an unknown module type runs
+    on libkfb's covariance and dense-gradient kernels and reproduces the reference's scores for the equivalent MLP."""
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.module.tracked_module import TrackedModule
+    from kronfluence_b200.task import Task
+    from tests import fixtures, plugins
+
+    plugins.make_tracked_my_linear(TrackedModule)
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_mlp.npz")))
+    reference_mlp, train_set, query_set = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    model = prepare_model(plugins.make_plugin_mlp(reference_mlp), task)
+    analyzer = Analyzer("plugin", model, task, output_dir=str(tmp_path), disable_tqdm=True)
+    fa = FactorArguments(strategy="ekfac", use_empirical_fisher=True)
+    analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8, factor_args=fa)
+    for name, value in analyzer.load_covariance_matrices("f")["gradient_covariance"].items():
+        assert rel(value.numpy(), golden[f"f32/gradient_covariance/{name}"]) < 2e-5
+    analyzer.perform_eigendecomposition("f", fa)
+    _inject(analyzer, golden)
+    analyzer.fit_lambda_matrices("f", train_set, per_device_batch_size=8, factor_args=fa)
+    for name, value in analyzer.load_lambda_matrices("f")["lambda_matrix"].items():
+        assert rel(value.numpy(), golden[f"f32/lambda_matrix/{name}"]) < 1e-4
+    scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=3,
+                                              per_device_train_batch_size=8, score_args=ScoreArguments(damping_factor=None))
+    assert rel(scores["all_modules"].numpy(), golden["f64/scores"]) < 1e-4
+    own = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=8,
+                                       score_args=ScoreArguments(damping_factor=None))
+    assert rel(own["all_modules"].numpy(), golden["f64/self_scores"]) < 1e-4
+
+
+def test_user_factor_strategy(tmp_path):
+    """factor/config.py:30-125 of the reference: a user `FactorConfig` registered over "ekfac" (own prepare /
+    precondition_gradient in torch) — materialised gradients in, parameter-basis store, same contraction kernels."""
+    from kronfluence_b200.factor.config import FactorConfig
+    from tests import plugins
+
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_conv.npz")))
+    registry, previous = plugins.make_user_ekfac(FactorConfig)
+    try:
+        _, scores = _run("conv", tmp_path, golden_eigen=golden)
+    finally:
+        registry["ekfac"] = previous
+    assert rel(scores["all_modules"].numpy(), golden["f64/scores"]) < 1e-4
+
+
+def test_offload_activations_to_cpu(tmp_path):
+    golden = dict(np.load(os.path.join(GOLDEN, "e2e_seq.npz")))
+    _, scores = _run("seq", tmp_path, golden_eigen=golden, factor_kwargs=dict(offload_activations_to_cpu=True),
+                     score_kwargs=dict(offload_activations_to_cpu=True))
+    assert rel(scores["all_modules"].numpy(), golden["f64/scores"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["linear3d_mask", "conv_stride_groups"])
+def test_native_layer_methods_and_strategy_methods(case):
+    """The reference's per-layer methods on the built-in layers (module/linear.py:30-122, module/conv2d.py:106-209) and
+    `Ekfac.prepare` / `precondition_gradient` (factor/config.py:322-353), against the stage goldens."""
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.factor.config import FactorConfig
+    from kronfluence_b200.module.tracked_module import TrackedModule
+
+    g = dict(np.load(os.path.join(GOLDEN, f"stage_{case}.npz")))
+    dev = torch.device("cuda")
+    if "conv_geometry" in g:
+        c_in, c_out, k1, k2, s1, s2, p1, p2, d1, d2, groups, bias = [int(v) for v in g["conv_geometry"]]
+        mod = torch.nn.Conv2d(c_in, c_out, (k1, k2), stride=(s1, s2), padding=(p1, p2), dilation=(d1, d2), groups=groups,
+                              bias=bool(bias))
+    else:
+        d_in, d_out, bias = [int(v) for v in g["linear_geometry"]]
+        mod = torch.nn.Linear(d_in, d_out, bias=bool(bias))
+    tracked = TrackedModule.SUPPORTED_MODULES[type(mod)](name="layer", original_module=mod.to(dev),
+                                                         factor_args=FactorArguments(), score_args=ScoreArguments(damping_factor=None))
+    x, gr = torch.from_numpy(g["x_train"]).float().to(dev), torch.from_numpy(g["g_train"]).float().to(dev)
+    if "mask" in g:
+        tracked.set_attention_mask(torch.from_numpy(g["mask"]).to(dev))
+    flat_a, count_a = tracked.get_flattened_activation(x.clone())
+    assert rel(flat_a.cpu().numpy(), g["flat_a"]) < 1e-6 and float(count_a) == float(g["count_a"])
+    flat_g, count_g = tracked.get_flattened_gradient(gr)
+    assert rel(flat_g.cpu().numpy(), g["flat_g"]) < 1e-6 and float(count_g) == float(g["count_g"])
+    tracked.set_attention_mask(None)
+    psg = tracked.compute_per_sample_gradient(x, gr)
+    assert rel(psg.cpu().numpy(), g["psg_train"]) < 2e-5
+    assert rel(tracked.compute_summed_gradient(x, gr).cpu().numpy(), g["psg_train"].sum(0, keepdims=True)) < 2e-5
+    p = torch.from_numpy(g["p"]).float().to(dev)
+    assert rel(tracked.compute_pairwise_score(p, x, gr).cpu().numpy(), g["scores"]) < 1e-4
+    n = min(p.shape[0], x.shape[0])
+    want = (g["p"][:n] * g["psg_train"][:n]).sum(axis=(1, 2))
+    assert rel(tracked.compute_self_measurement_score(p[:n], x[:n], gr[:n]).cpu().numpy(), want) < 1e-4
+    # Ekfac.prepare + precondition_gradient on the reference's own factors
+    storage = {"activation_eigenvectors": torch.from_numpy(g["activation_eigenvectors"]).float().to(dev),
+               "gradient_eigenvectors": torch.from_numpy(g["gradient_eigenvectors"]).float().to(dev),
+               "lambda_matrix": torch.from_numpy(g["lambda"]).float().to(dev),
+               "num_lambda_processed": torch.tensor([g["num_lambda"]]), "activation_eigenvalues": None,
+               "gradient_eigenvalues": None}
+    config = FactorConfig.CONFIGS["ekfac"]
+    config.prepare(storage=storage, score_args=ScoreArguments(damping_factor=None), device=dev)
+    assert rel(storage["lambda_matrix"].cpu().numpy(), g["lambda_inv"]) < 1e-5
+    psg_q = torch.from_numpy(g["psg_query"]).float().to(dev)
+    assert rel(config.precondition_gradient(psg_q, storage).cpu().numpy(), g["p"]) < 1e-4
