@@ -279,7 +279,7 @@ def test_native_layer_methods_and_strategy_methods(case):
     storage = {"activation_eigenvectors": torch.from_numpy(g["activation_eigenvectors"]).float().to(dev),
                "gradient_eigenvectors": torch.from_numpy(g["gradient_eigenvectors"]).float().to(dev),
                "lambda_matrix": torch.from_numpy(g["lambda"]).float().to(dev),
-               "num_lambda_processed": torch.tensor([g["num_lambda"]]), "activation_eigenvalues": None,
+               "num_lambda_processed": torch.tensor([float(g["num_lambda"])]), "activation_eigenvalues": None,
                "gradient_eigenvalues": None}
     config = FactorConfig.CONFIGS["ekfac"]
     config.prepare(storage=storage, score_args=ScoreArguments(damping_factor=None), device=dev)
