@@ -82,6 +82,7 @@ struct GemmParams {
   const float* a_absmax;
   const float* b_absmax;
   int col_group;           // STORE to planes: column n lands in batch entry n / col_group at column n % col_group
+  int max_groups;          // host only: cap on resident CTA groups (the idle-SM side launch of the fused pairwise kernel)
   int symmetric;           // STORE: A == B (SYRK): only tiles with n_blk >= m_blk are computed, off-diagonal ones are
   long long tri_tiles;     //        also written transposed; tri_tiles = m_blocks (m_blocks + 1) / 2
 };
@@ -1077,7 +1078,41 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
   return KFB_OK;
 }
 
-static const int kRetryWithoutMulticast = 4242;  // internal: launch_tc<..., MC = 2> declined, use the pair kernel
+static const int kRetryWithoutMulticast = 4242;
+static std::atomic<int> g_resident_clusters{0};  // 4-CTA clusters of the fused pairwise kernel the device holds at once
+static std::atomic<int> g_idle_fill{-1};         // percent of the queries for the idle-SM side launch; -1 = automatic
+
+// Fork / join helper for the idle-SM side launch: one non-blocking stream and two events per device.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int side_stream(SideStream** out) {
+  static SideStream table[16];
+  static std::mutex mutex;
+  int dev = 0;
+  KFB_CUDA_TRY(cudaGetDevice(&dev));
+  KFB_REQUIRE(dev >= 0 && dev < 16, "side_stream: device index out of range");
+  std::lock_guard<std::mutex> lock(mutex);
+  SideStream& s = table[dev];
+  if (s.stream == nullptr) {
+    KFB_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    KFB_CUDA_TRY(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    KFB_CUDA_TRY(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return KFB_OK;
+}
+
+static inline kfb_split batch_slice(const kfb_split& s, long long b0, long long nb) {
+  kfb_split v = s;
+  if (s.batch > 1) {
+    v.hi = static_cast<char*>(s.hi) + b0 * s.batch_stride * 2;
+    v.lo = s.lo ? static_cast<char*>(s.lo) + b0 * s.batch_stride * 2 : nullptr;
+    v.batch = nb;
+  }
+  return v;
+}  // internal: launch_tc<..., MC = 2> declined, use the pair kernel
 
 template <int BLOCK_N, int BLOCK_K, int NSPLIT, int EPI, int CG = 1, int MC = 1, int EW = 4>
 static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaStream_t stream) {
@@ -1181,6 +1216,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
   cfg.numAttrs = CLUSTER > 1 ? 1 : 0;
   // CTA groups resident at once: one CTA per SM; clusters of 4 may not tile every GPC, so ask the runtime
   long long groups = sm_count() / CLUSTER;
+  if (p.max_groups > 0 && groups > p.max_groups) groups = p.max_groups;
   if (MC > 1) {
     static int max_clusters = -1;
     if (max_clusters < 0) {
@@ -1196,6 +1232,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
     // the plain CTA-pair kernel
     if (max_clusters * CLUSTER * 4 < sm_count() * 3) return kRetryWithoutMulticast;
     if (groups > max_clusters) groups = max_clusters;
+    g_resident_clusters.store(max_clusters);
   }
   const long long grid = (p.num_units < groups ? p.num_units : groups) * CLUSTER;
   cfg.gridDim = dim3((unsigned)grid);
@@ -1225,9 +1262,56 @@ static int dispatch_tc(const kfb_split& A, const kfb_split& B, const GemmParams&
   const bool mcast = g_multicast.load() != 0 && g_cta_pairs.load() != 0 && p.M > 256 && !p.symmetric && !p.batch_fastest;
   if constexpr (EPI == EPI_ROWDOT) {
     if (mcast && bn == 256) {
-      const int rc = nsplit == 2 ? launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream)
-                                 : launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
-      if (rc != kRetryWithoutMulticast) return rc;
+      // Clusters of four CTAs do not tile the GPCs: 33 of them are resident on a B200, 132 of 148 SMs.  When there are
+      // many queries, the last few percent of them go to a concurrent launch of the plain CTA-pair kernel on a side
+      // stream, capped at the idle SMs (launched second, so the cluster kernel is placed first).
+      const int resident = g_resident_clusters.load();
+      const int idle_pairs = resident > 0 ? (sm_count() - 4 * resident) / 2 : 0;
+      long long side_q = 0;
+      // Measured (target layer, Q = 1024): single-MMA (bf16) mode +2.4 % at 8-9 % of the queries; the 3-MMA mode runs
+      // against the 1 kW power cap, where more active SMs only lower the clock (+-1 %), so it stays off there unless
+      // kfb_set_idle_fill() asks for it.
+      const int pct = g_idle_fill.load();
+      if (idle_pairs >= 2 && p.batch >= 128 && p.row_group <= 1 && (long long)p.batch * ((p.M + 511) / 512) >= 4LL * resident &&
+          (nsplit == 1 || pct > 0)) {
+        // a pair of the side launch retires m-tiles at ~0.8 of the rate of a cluster's pair (no multicast: more
+        // L2 -> SM operand traffic per tile), and both launches share the L2
+        const double rate = 0.8;
+        const double frac = pct >= 0 ? pct / 100.0 : idle_pairs * rate / (2.0 * resident + idle_pairs * rate);
+        side_q = (long long)(p.batch * frac + 0.5);
+        if (side_q < 8 || side_q * 2 > p.batch) side_q = 0;
+      }
+      if (side_q > 0) {
+        const long long main_q = p.batch - side_q;
+        GemmParams pm = p;
+        pm.batch = (int)main_q;
+        const kfb_split Am = batch_slice(A, 0, main_q), Bm = batch_slice(B, 0, main_q);
+        SideStream* side = nullptr;
+        KFB_TRY(side_stream(&side));
+        KFB_CUDA_TRY(cudaEventRecord(side->fork, stream));
+        KFB_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        const int rc = nsplit == 2 ? launch_tc<256, 64, 2, EPI, 2, 2>(Am, Bm, pm, stream)
+                                   : launch_tc<256, 64, 1, EPI, 2, 2>(Am, Bm, pm, stream);
+        if (rc != KFB_OK && rc != kRetryWithoutMulticast) return rc;
+        if (rc == KFB_OK) {
+          GemmParams ps = p;
+          ps.batch = (int)side_q;
+          ps.out_f32 = p.out_f32 + main_q * p.out_bs;
+          ps.g = p.g + main_q * p.g_bs;
+          ps.max_groups = idle_pairs;
+          const kfb_split As = batch_slice(A, main_q, side_q), Bs = batch_slice(B, main_q, side_q);
+          KFB_TRY(nsplit == 2 ? (launch_tc<256, 64, 2, EPI, 2>(As, Bs, ps, side->stream))
+                              : (launch_tc<256, 64, 1, EPI, 2>(As, Bs, ps, side->stream)));
+          KFB_CUDA_TRY(cudaEventRecord(side->join, side->stream));
+          KFB_CUDA_TRY(cudaStreamWaitEvent(stream, side->join, 0));
+          return KFB_OK;
+        }
+        // no cluster launch on this device: everything goes to the pair kernel below
+      } else {
+        const int rc = nsplit == 2 ? launch_tc<256, 64, 2, EPI, 2, 2>(A, B, p, stream)
+                                   : launch_tc<256, 64, 1, EPI, 2, 2>(A, B, p, stream);
+        if (rc != kRetryWithoutMulticast) return rc;
+      }
     }
   }
   if constexpr (EPI == EPI_STORE) {
@@ -1445,6 +1529,11 @@ int kfb_set_cta_pairs(int enable) {
 
 int kfb_set_multicast(int enable) {
   kfb::g_multicast.store(enable < 0 ? 0 : enable);
+  return KFB_OK;
+}
+
+int kfb_set_idle_fill(int percent) {
+  kfb::g_idle_fill.store(percent < 0 ? -1 : (percent > 50 ? 50 : percent));
   return KFB_OK;
 }
 
