@@ -157,6 +157,9 @@ int kfb_set_wide_regacc(int enable);
 /* Share (percent, 0..50) of the queries the fused pairwise kernel hands to a concurrent CTA-pair launch on the SMs its
  * 4-CTA clusters cannot occupy (16 of 148 on a B200); -1 (default): derived from the idle SM count; 0: off.        */
 int kfb_set_idle_fill(int percent);
+/* 1 (default): the clusters of the fused pairwise kernel that stream the same query's P tiles start every unit together
+ * (a rendezvous in global memory), so that P is fetched from HBM once instead of once per cluster; 0: free-running.  */
+int kfb_set_group_sync(int enable);
 /* Debug: contraction elements per TMEM pass of KFB_PREC_STRICT GEMMs (multiple of 64; default 128).            */
 int kfb_set_strict_pass_k(int k);
 /* 1 (default): large GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles); 0: single CTAs.  */

@@ -239,6 +239,36 @@ __device__ __forceinline__ void tma_load_3d_2sm_mc(const CUtensorMap* tmap, uint
       : "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
       : "memory");
 }
+// L2 eviction policies for TMA loads: a streamed operand (used once) must not push a reused one out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_3d_2sm_hint(const CUtensorMap* tmap, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                     int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm_mc_hint(const CUtensorMap* tmap, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                        int c2, uint16_t mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6, %7;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "h"(mask),
+        "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
                : "memory");

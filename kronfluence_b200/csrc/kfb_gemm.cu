@@ -82,10 +82,15 @@ struct GemmParams {
   const float* a_absmax;
   const float* b_absmax;
   int col_group;           // STORE to planes: column n lands in batch entry n / col_group at column n % col_group
+  unsigned int* sync_ctr;  // ROWDOT on clusters: one counter per group of `sync_group` clusters that stream the same
+  int sync_group;          //   query's P tiles (adjacent m-units): they start every unit together (see the producer)
   int max_groups;          // host only: cap on resident CTA groups (the idle-SM side launch of the fused pairwise kernel)
   int symmetric;           // STORE: A == B (SYRK): only tiles with n_blk >= m_blk are computed, off-diagonal ones are
   long long tri_tiles;     //        also written transposed; tri_tiles = m_blocks (m_blocks + 1) / 2
 };
+
+// Counters of the cluster-group rendezvous of the fused pairwise kernel (zeroed before every launch that uses them).
+__device__ unsigned int g_rowdot_sync[64];
 
 struct Tile {
   int b, m_blk, n_blk, kb0, kb1;
@@ -664,9 +669,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // ===================================== TMA producer ======================================
     int stage = 0;
     uint32_t phase = 0;
+    uint32_t sync_step = 0;
+    // ROWDOT streams B (the query store: every byte used once per launch) past a small A (the train batch, re-read for
+    // every query): without hints the stream evicts A from L2 and A comes back from HBM once per query (measured: +50 %
+    // DRAM traffic on the target layer)
+    const bool hint = EPI == EPI_ROWDOT && CG == 2;
+    const uint64_t pol_a = hint ? l2_policy_evict_last() : 0ull;
+    const uint64_t pol_b = hint ? l2_policy_evict_first() : 0ull;
     for (long long unit = unit0; unit < p.num_units; unit += unit_stride) {
       const int inner = unit_inner_count<EPI>(p, unit);
       for (int j = 0; j < inner; ++j) {
+        if (EPI == EPI_ROWDOT && p.sync_group > 0 && j % p.k_chunks == 0) {
+          // The `sync_group` clusters that work on the m-units of one query stream the SAME P tiles.  They only share
+          // them through L2 while they run within its retention window (~100 us of stream) of each other, and nothing
+          // keeps them there over thousands of units: measured at Q = 1024, every cluster ended up fetching its own copy
+          // from HBM (4.2x the algorithmic traffic).  A rendezvous of the group's producers at every n-tile restores the
+          // lock-step; the grid is a whole number of groups, so the members of a group always hold the same query.
+          const unsigned grp = (unsigned)(blockIdx.x / CLUSTER) / (unsigned)p.sync_group;
+          const unsigned target = (unsigned)(CLUSTER * p.sync_group) * (++sync_step);
+          atomicAdd(p.sync_ctr + grp, 1u);
+          const long long t0 = clock64();
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_ctr + grp) : "memory");
+            if (seen >= target) break;
+            __nanosleep(32);
+            if (clock64() - t0 > KFB_WATCHDOG_CYCLES) __trap();
+          } while (true);
+        }
         const Tile t = decode_tile<EPI>(p, unit, j, pair_id);
         const int row_a = t.m_blk * Cfg::TILE_M + (int)cta_rank * BLOCK_M;
         // each CTA of a pair stages ITS half of the B rows the MMA reads (a narrower MMA on a ragged last n-tile reads
@@ -681,14 +711,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             // both CTAs credit the LEADER's full barrier: its MMA thread consumes the pair's stage
             if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             else mbar_arrive_expect_tx_cluster(full_bar(stage), leader_rank, Cfg::STAGE_BYTES);
-            tma_load_3d_2sm(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
-            if (NSPLIT == 2) tma_load_3d_2sm(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
+            if (hint) {
+              tma_load_3d_2sm_hint(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba, pol_a);
+              if (NSPLIT == 2) tma_load_3d_2sm_hint(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba, pol_a);
+            } else {
+              tma_load_3d_2sm(&tm_a_hi, full_bar(stage), smem_a(stage, 0), k0, row_a, ba);
+              if (NSPLIT == 2) tma_load_3d_2sm(&tm_a_lo, full_bar(stage), smem_a(stage, 1), k0, row_a, ba);
+            }
             if (MC == 2) {
               // this CTA fetches its quarter of the B tile and multicasts it to the same-ranked CTA of both pairs
               const uint32_t off = (uint32_t)(pair_id * Cfg::FETCH_N * Cfg::SWIZZLE);
               const uint16_t mask = (uint16_t)(0x5u << cta_rank);
-              tma_load_3d_2sm_mc(&tm_b_hi, full_bar(stage), smem_b(stage, 0) + off, k0, row_b, bb, mask);
-              if (NSPLIT == 2) tma_load_3d_2sm_mc(&tm_b_lo, full_bar(stage), smem_b(stage, 1) + off, k0, row_b, bb, mask);
+              if (hint) {
+                tma_load_3d_2sm_mc_hint(&tm_b_hi, full_bar(stage), smem_b(stage, 0) + off, k0, row_b, bb, mask, pol_b);
+                if (NSPLIT == 2) tma_load_3d_2sm_mc_hint(&tm_b_lo, full_bar(stage), smem_b(stage, 1) + off, k0, row_b, bb, mask, pol_b);
+              } else {
+                tma_load_3d_2sm_mc(&tm_b_hi, full_bar(stage), smem_b(stage, 0) + off, k0, row_b, bb, mask);
+                if (NSPLIT == 2) tma_load_3d_2sm_mc(&tm_b_lo, full_bar(stage), smem_b(stage, 1) + off, k0, row_b, bb, mask);
+              }
+            } else if (hint) {
+              tma_load_3d_2sm_hint(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb, pol_b);
+              if (NSPLIT == 2) tma_load_3d_2sm_hint(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb, pol_b);
             } else {
               tma_load_3d_2sm(&tm_b_hi, full_bar(stage), smem_b(stage, 0), k0, row_b, bb);
               if (NSPLIT == 2) tma_load_3d_2sm(&tm_b_lo, full_bar(stage), smem_b(stage, 1), k0, row_b, bb);
@@ -1080,7 +1123,8 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long cols, long lon
 
 static const int kRetryWithoutMulticast = 4242;
 static std::atomic<int> g_resident_clusters{0};  // 4-CTA clusters of the fused pairwise kernel the device holds at once
-static std::atomic<int> g_idle_fill{-1};         // percent of the queries for the idle-SM side launch; -1 = automatic
+static std::atomic<int> g_idle_fill{-1};
+static std::atomic<int> g_group_sync{1};         // cluster-group rendezvous of the fused pairwise kernel
 
 // Fork / join helper for the idle-SM side launch: one non-blocking stream and two events per device.
 struct SideStream {
@@ -1233,6 +1277,21 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
     if (max_clusters * CLUSTER * 4 < sm_count() * 3) return kRetryWithoutMulticast;
     if (groups > max_clusters) groups = max_clusters;
     g_resident_clusters.store(max_clusters);
+    // cluster-group rendezvous of the fused pairwise kernel (see the producer): the grid becomes a whole number of
+    // groups of m_units clusters, if that idles at most one cluster and every cluster gets several units
+    p.sync_group = 0;
+    if (EPI == EPI_ROWDOT && g_group_sync.load() != 0 && p.n_splits == 1 && p.m_units >= 2 && p.m_units <= 8 &&
+        p.max_groups == 0) {
+      const long long whole = (groups / p.m_units) * p.m_units;
+      if (whole >= p.m_units && groups - whole <= 1 && whole / p.m_units <= 64 && p.num_units >= 4 * whole) {
+        static unsigned int* ctr = nullptr;
+        if (ctr == nullptr) KFB_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_rowdot_sync));
+        KFB_CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * 64, stream));
+        p.sync_ctr = ctr;
+        p.sync_group = p.m_units;
+        groups = whole;
+      }
+    }
   }
   const long long grid = (p.num_units < groups ? p.num_units : groups) * CLUSTER;
   cfg.gridDim = dim3((unsigned)grid);
@@ -1529,6 +1588,11 @@ int kfb_set_cta_pairs(int enable) {
 
 int kfb_set_multicast(int enable) {
   kfb::g_multicast.store(enable < 0 ? 0 : enable);
+  return KFB_OK;
+}
+
+int kfb_set_group_sync(int enable) {
+  kfb::g_group_sync.store(enable ? 1 : 0);
   return KFB_OK;
 }
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "kfb_set_strict_pass_k": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_wide_regacc": (ctypes.c_int, [ctypes.c_int]),
     "kfb_set_idle_fill": (ctypes.c_int, [ctypes.c_int]),
+    "kfb_set_group_sync": (ctypes.c_int, [ctypes.c_int]),
     "kfb_launch_count": (_i64, []),
     "kfb_split_gather": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_i64), _vp, _SP, ctypes.c_int, _vp]),
     "kfb_split_im2col": (ctypes.c_int, [_LP, _vp, ctypes.c_int, _i64, _i32, _SP, ctypes.c_int, _vp]),
@@ -155,7 +156,8 @@ def load_library() -> ctypes.CDLL:
     if os.environ.get("KFB_IDLE_FILL", "").lstrip("-").isdigit():
         lib.kfb_set_idle_fill(int(os.environ["KFB_IDLE_FILL"]))
     for env, setter in (("KFB_MULTICAST", lib.kfb_set_multicast), ("KFB_TMA_STORE", lib.kfb_set_tma_store),
-                        ("KFB_CTA_PAIRS", lib.kfb_set_cta_pairs), ("KFB_WIDE_REGACC", lib.kfb_set_wide_regacc)):
+                        ("KFB_CTA_PAIRS", lib.kfb_set_cta_pairs), ("KFB_WIDE_REGACC", lib.kfb_set_wide_regacc),
+                        ("KFB_GROUP_SYNC", lib.kfb_set_group_sync)):
         if os.environ.get(env, "").isdigit():
             setter(int(os.environ[env]))
     _register_cusolver(lib)
