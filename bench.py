@@ -506,6 +506,24 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
     parity = float((got - ref).norm() / ref.norm())
     del ref, got
 
+    # ---- the contraction alone on prepared (cached) train operands: what a later query chunk costs once the Analyzer's
+    # train-operand cache holds the rotated operands of the batch (kfb_pairwise_prepare / kfb_pairwise_scores_prepared)
+    replay_ms = None
+    if seq > 1 or spec["kind"] == "conv":
+        prepared = ops.pairwise_prepare(layer, acts[0], grads[0], precision, qa_ops, qg_ops)
+        for _ in range(2):
+            ops.pairwise_scores_prepared(store, n_query, prepared, scores, t_offset=0, accumulate=False)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(steps, 6))
+        r0.record()
+        for _ in range(reps):
+            ops.pairwise_scores_prepared(store, n_query, prepared, scores, t_offset=0, accumulate=False)
+        r1.record()
+        torch.cuda.synchronize()
+        replay_ms = r0.elapsed_time(r1) / reps
+        del prepared
+
     d_total = float(do) * di
     alg_flops = 2.0 * n_query * t_batch * d_total + (2.0 * t_batch * seq * d_total if seq > 1 else 0.0)
     peaks, peak_kind = measured_peaks()
@@ -549,6 +567,12 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
                                             "block": f"{p_block.shape[0]} queries x {nt} train examples vs fp64 torch",
                                             "ok": parity < PARITY_BAR[spec["precision"]]},
            "gpu_launches": int(launches), "clocks": clocks.summary()}
+    if replay_ms is not None:
+        out["cached_operands"] = {"ms_per_step": replay_ms, "value": n_query * t_batch / (replay_ms / 1e3), "unit": "scores/s",
+                                  "algorithmic_tflops": alg_flops / (replay_ms / 1e3) / 1e12,
+                                  "frac": alg_flops / (replay_ms / 1e3) / 1e12 / peak_tf,
+                                  "what": "formation + contraction on prepared (rotated) train operands: the cost of the "
+                                          "batch for every query chunk after the first (train-operand cache)"}
 
     # ---- end to end through the C ABI with pinned host buffers ----
     if with_e2e:
