@@ -61,10 +61,14 @@ WORKLOADS = {
                           precision="fp32", note="BERT-base FFN 769->3072, S=128, fp32 parity"),
     "gpt2_attn": dict(kind="linear", d_in=768, d_out=2304, bias=True, seq=512, q=256, t_total=100_000, t_batch=64,
                       precision="fp32", note="BASELINE configs[3]: GPT-2 c_attn 769->2304, S=512"),
+    "llama_mlp_lowrank": dict(kind="linear", d_in=4096, d_out=14336, bias=False, seq=512, q=64, t_total=1_000_000, t_batch=16,
+                              precision="bf16", lowrank=64,
+                              note="BASELINE configs[4]: Llama-3-8B MLP up-projection 4096->14336, S=512, bf16, rank-64 query "
+                                   "gradients as in examples/openwebtext"),
     "mlp": dict(kind="linear", d_in=1024, d_out=1024, bias=True, seq=1, q=128, t_total=1_000, t_batch=1000,
                 precision="fp32", note="BASELINE configs[0] layer shape (parity-test sized)"),
 }
-DEFAULT_SECONDARY = ["target_bf16", "resnet_conv", "bert_ffn", "bert_ffn_fp32", "gpt2_attn"]
+DEFAULT_SECONDARY = ["target_bf16", "resnet_conv", "bert_ffn", "bert_ffn_fp32", "gpt2_attn", "llama_mlp_lowrank"]
 PARITY_BAR = {"fp32": 1e-4, "bf16": 3e-2}
 
 
@@ -429,17 +433,28 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
     di, do = ops.factor_dims(layer)
 
     # ---- state: Q preconditioned query gradients in operand layout (random values; filled in chunks) ----
-    store = ops.make_query_store(do, di, n_query, device, precision)
     gen = torch.Generator(device=device).manual_seed(1)
-    chunk = max(1, min(n_query, (1 << 28) // (do * di)))
+    rank = spec.get("lowrank")
     p_block = None
-    for q0 in range(0, n_query, chunk):
-        nq = min(chunk, n_query - q0)
-        p = torch.randn(nq, do, di, device=device, generator=gen)
-        if q0 == 0:
-            p_block = p[: min(8, nq)].clone()  # the unrounded values the parity block is checked against
-        ops.load_query_store(store, p, q0, precision)
-        del p
+    if rank:
+        # rank-r query factors (tracker/precondition.py:19-52 of the reference): left_t [Q][r][d_out], right [Q][r][d_in]
+        store = ops.make_lowrank_store(do, di, rank, n_query, device, precision)
+        left_t = torch.randn(n_query, rank, do, device=device, generator=gen) / rank**0.5
+        right = torch.randn(n_query, rank, di, device=device, generator=gen)
+        ops._load_split(store.left_t, left_t, 0, precision)  # pylint: disable=protected-access
+        ops._load_split(store.right, right, 0, precision)  # pylint: disable=protected-access
+        lr_block = (left_t[:4].clone(), right[:4].clone())
+        del left_t, right
+    else:
+        store = ops.make_query_store(do, di, n_query, device, precision)
+        chunk = max(1, min(n_query, (1 << 28) // (do * di)))
+        for q0 in range(0, n_query, chunk):
+            nq = min(chunk, n_query - q0)
+            p = torch.randn(nq, do, di, device=device, generator=gen)
+            if q0 == 0:
+                p_block = p[: min(8, nq)].clone()  # the unrounded values the parity block is checked against
+            ops.load_query_store(store, p, q0, precision)
+            del p
     # eigenbases of the two Kronecker factors (random orthogonal): the store holds eigenbasis images, every step
     # rotates its train batch before the contraction
     q_a = torch.linalg.qr(torch.randn(di, di, device=device, generator=gen))[0]
@@ -456,8 +471,12 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
     scores = torch.zeros(n_query, t_batch * min(total_steps, 8), dtype=torch.float32, device=device)
 
     def step(i: int) -> None:
-        ops.pairwise_scores(layer, store, n_query, acts[i % n_buf], grads[i % n_buf], scores,
-                            t_offset=(i % 8) * t_batch, accumulate=False, precision=precision, qa=qa_ops, qg=qg_ops)
+        if rank:
+            ops.pairwise_scores_lowrank(layer, store, n_query, acts[i % n_buf], grads[i % n_buf], scores,
+                                        t_offset=(i % 8) * t_batch, accumulate=False, precision=precision, qa=qa_ops, qg=qg_ops)
+        else:
+            ops.pairwise_scores(layer, store, n_query, acts[i % n_buf], grads[i % n_buf], scores,
+                                t_offset=(i % 8) * t_batch, accumulate=False, precision=precision, qa=qa_ops, qg=qg_ops)
 
     for i in range(warmup):
         step(i)
@@ -500,16 +519,26 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
 
     # ---- parity of the last step's tile against fp64 torch on the same inputs ----
     last = warmup + steps - 1
-    nt = min(t_batch, 64)
-    ref = fp64_block(spec, module, p_block, q_a, q_g, acts[last % n_buf][:nt], grads[last % n_buf][:nt])
-    got = scores[: p_block.shape[0], (last % 8) * t_batch : (last % 8) * t_batch + nt].double()
+    nt = min(t_batch, 64 if not rank else 4)
+    if rank:
+        # "qik,qko,b...i,b...o->qb" (module/linear.py:83-99 of the reference) in fp64, in the eigenbasis of the store
+        a64 = acts[last % n_buf][:nt].double() @ q_a.double()
+        g64 = grads[last % n_buf][:nt].double() @ q_g.double()
+        ref = torch.einsum("qbsr,qbsr->qb", torch.einsum("bso,qro->qbsr", g64, lr_block[0].double()),
+                           torch.einsum("bsi,qri->qbsr", a64, lr_block[1].double()))
+        p_rows = lr_block[0].shape[0]
+        del a64, g64
+    else:
+        ref = fp64_block(spec, module, p_block, q_a, q_g, acts[last % n_buf][:nt], grads[last % n_buf][:nt])
+        p_rows = p_block.shape[0]
+    got = scores[:p_rows, (last % 8) * t_batch : (last % 8) * t_batch + nt].double()
     parity = float((got - ref).norm() / ref.norm())
     del ref, got
 
     # ---- the contraction alone on prepared (cached) train operands: what a later query chunk costs once the Analyzer's
     # train-operand cache holds the rotated operands of the batch (kfb_pairwise_prepare / kfb_pairwise_scores_prepared)
     replay_ms = None
-    if seq > 1 or spec["kind"] == "conv":
+    if (seq > 1 or spec["kind"] == "conv") and not rank:
         prepared = ops.pairwise_prepare(layer, acts[0], grads[0], precision, qa_ops, qg_ops)
         for _ in range(2):
             ops.pairwise_scores_prepared(store, n_query, prepared, scores, t_offset=0, accumulate=False)
@@ -526,6 +555,8 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
 
     d_total = float(do) * di
     alg_flops = 2.0 * n_query * t_batch * d_total + (2.0 * t_batch * seq * d_total if seq > 1 else 0.0)
+    if rank:  # 2 N Q r (d_in + d_out) for rank-r query factors
+        alg_flops = 2.0 * t_batch * seq * n_query * rank * (di + do)
     peaks, peak_kind = measured_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     issued = 3.0 if precision == engine.PREC_FP32 else 1.0
@@ -551,12 +582,15 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
         issued_tf = issued * (alg_flops + rot_flops) / step_s / 1e12
         roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_source,
-                    "algorithmic_bytes": float(n_query) * do * store.ld * 2 * planes
+                    "algorithmic_bytes": (float(n_query) * rank * (store.left_t.ld + store.right.ld) * 2 * planes if rank
+                                          else float(n_query) * do * store.ld * 2 * planes)
                     + float(acts[0].numel() + grads[0].numel()) * 4.0,
                     "algorithmic_flops": alg_flops, "peak_source": f"{peak_kind} bf16_tflops_sustained",
                     "kernel_ms": step_s * 1e3,
-                    "kernel": "whole stage: 2 eigenbasis rotations + per-sample-gradient formation + contraction "
-                              "(gemm_tc_kernel family), timed as one step",
+                    "kernel": ("whole stage: 2 eigenbasis rotations + a~ x R^T for all queries + fused ROWDOT with g~ x L "
+                               "(gemm_tc_kernel family), timed as one step" if rank else
+                               "whole stage: 2 eigenbasis rotations + per-sample-gradient formation + contraction "
+                               "(gemm_tc_kernel family), timed as one step"),
                     "rotation_flops": rot_flops, "issued_tflops": issued_tf, "issued_frac": issued_tf / peak_tf,
                     "kernel_share_of_step": 1.0}
 
@@ -564,7 +598,7 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
            "steps": steps, "dtype": "bf16x3 split operands, f32 accumulate (fp32 parity)" if precision == engine.PREC_FP32
            else "bf16, f32 accumulate", "q": n_query, "t_batch": t_batch, "seq": seq, "d_in_total": di, "d_out": do,
            "roofline": roofline, "parity": {"rel_frobenius": parity, "bar": PARITY_BAR[spec["precision"]],
-                                            "block": f"{p_block.shape[0]} queries x {nt} train examples vs fp64 torch",
+                                            "block": f"{p_rows} queries x {nt} train examples vs fp64 torch",
                                             "ok": parity < PARITY_BAR[spec["precision"]]},
            "gpu_launches": int(launches), "clocks": clocks.summary()}
     if replay_ms is not None:
@@ -575,7 +609,7 @@ def run_workload(name, spec, ctx, steps, warmup, with_e2e=False, queries=None):
                                           "batch for every query chunk after the first (train-operand cache)"}
 
     # ---- end to end through the C ABI with pinned host buffers ----
-    if with_e2e:
+    if with_e2e and not rank:
         host_a = [a.cpu().pin_memory() for a in acts]
         host_g = [g.cpu().pin_memory() for g in grads]
         host_scores = torch.empty(n_query, t_batch, dtype=torch.float32).pin_memory()
@@ -958,7 +992,7 @@ def main() -> None:
         "metric": "pairwise influence scores/sec", "value": primary["value"], "unit": "scores/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": primary["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": primary["dtype"], "data": "synthetic", "config": config,
-        "clocks": primary["clocks"], "e2e": primary["e2e"], "gpu_launches": primary["gpu_launches"],
+        "clocks": primary["clocks"], "e2e": primary.get("e2e"), "gpu_launches": primary["gpu_launches"],
         "roofline": primary["roofline"], "parity": primary["parity"],
         "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "secondary": secondary, "strong": strong, "parity_nccl": parity_nccl, "torch_gpu_reference": torch_ref,
