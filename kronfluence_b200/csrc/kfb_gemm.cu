@@ -36,7 +36,10 @@ namespace kfb {
 // fits one TMEM accumulation pass and to EPI_REGACC (k-chunk mode) when it does not; KFB_EPI_SQACC
 // maps to EPI_REGACC (batch mode).
 enum : int { EPI_STORE = 0, EPI_ROWDOT = 1, EPI_REGACC = 2 };
-enum : int { REGACC_BATCH = 0, REGACC_KCHUNK = 1 };
+// REGACC_BATCH_DOT: the registers hold an elementwise FACTOR instead of sums: out[b] += alpha * sum_{m,n} D_b[m,n]^2 factor[m,n]
+// for every batch entry of the chunk (the self-influence contraction: the factor tile is read once per unit, not once
+// per example and chunk, whose L2 latency used to be 16 serial round trips per tile)
+enum : int { REGACC_BATCH = 0, REGACC_KCHUNK = 1, REGACC_BATCH_DOT = 2 };
 
 // The tensor core adds each MMA's partial products into the fp32 TMEM accumulator with truncation,
 // so a long accumulation chain acquires a relative bias of ~(K/16)*nsplit_mmas*2^-25.  One TMEM pass
@@ -104,7 +107,7 @@ __device__ __forceinline__ int unit_inner_count(const GemmParams& p, long long u
     return (min(p.n_blocks, nb0 + p.nb_per_split) - nb0) * p.k_chunks;
   }
   if (EPI == EPI_REGACC) {
-    if (p.regacc_mode == REGACC_BATCH) {
+    if (p.regacc_mode != REGACC_KCHUNK) {
       const long long chunk = unit / ((long long)p.m_units * p.n_blocks);
       const long long rem = (long long)p.batch - chunk * p.inner;
       return rem < p.inner ? (int)rem : p.inner;
@@ -159,7 +162,7 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, long long unit,
     const int kc = j - jn * p.k_chunks;
     t.kb0 = kc * p.kb_per_chunk;
     t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_chunk);
-  } else if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH) {
+  } else if (EPI == EPI_REGACC && p.regacc_mode != REGACC_KCHUNK) {
     t.n_blk = (int)(r % p.n_blocks);
     const long long chunk = r / p.n_blocks;
     t.b = (int)(chunk * p.inner + j);
@@ -831,6 +834,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
       for (int i = 0; i < NACC; ++i) racc[i] = 0.f;
       Tile t = decode_tile<EPI>(p, unit, 0, pair_id);
+      if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH_DOT) {
+        // this thread's slice of the factor row (all batch entries of the unit share the (m, n) tile)
+        const long long frow = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
+        const int fcol0 = t.n_blk * BLOCK_N + col_off;
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+          const bool ok = frow < p.M && fcol0 + i < p.N;
+          racc[i] = !ok ? 0.f : (p.mul != nullptr ? __ldg(p.mul + frow * p.ldmul + fcol0 + i) : 1.f);
+        }
+      }
       for (int j = 0; j < inner; ++j, ++it) {
         t = decode_tile<EPI>(p, unit, j, pair_id);
         const uint32_t as = it % ACC_STAGES;
@@ -881,6 +894,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const float x = __uint_as_float(v[c & 1][i]);
                 racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += x * x;
               }
+            } else if (p.regacc_mode == REGACC_BATCH_DOT) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = __uint_as_float(v[c & 1][i]);
+                rowdot = fmaf(x * x, racc[(EPI == EPI_REGACC ? c * 32 + i : 0)], rowdot);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[c & 1][i]);
@@ -905,6 +924,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               if (p.symmetric && t.n_blk != t.m_blk) store_chunk<0, 32, true>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, x, st, lane, true);
             }
           }
+        }
+        if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH_DOT) {
+          float part = rowdot;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (lane == 0 && part != 0.f) atomicAdd(p.out_f32 + (long long)t.b * p.out_bs, alpha * part);
+          rowdot = 0.f;
         }
         if (EPI == EPI_STORE && p.reduce_sq) {
           // one scalar per batch entry: warp-reduce, then one atomic per warp
@@ -947,7 +973,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           else if (p.accumulate) *o += val;
           else *o = val;
         }
-      } else if (EPI == EPI_REGACC) {
+      } else if (EPI == EPI_REGACC && p.regacc_mode != REGACC_BATCH_DOT) {
         const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
         const int n0 = t.n_blk * BLOCK_N + col_off;
         const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
@@ -1190,7 +1216,7 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
       else KFB_CUDA_TRY(cudaMemset2DAsync(p.out_f32, (size_t)p.out_bs * 4, 0, (size_t)p.M * 4, (size_t)p.batch, stream));
     }
     p.num_units = row_units * p.n_splits;
-  } else if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH) {
+  } else if (EPI == EPI_REGACC && p.regacc_mode != REGACC_KCHUNK) {
     // cut the batch into chunks so that there are enough units to fill the machine
     long long chunks = ceil_div_ll(2LL * sm_count(), tiles);
     if (chunks > p.batch) chunks = p.batch;
@@ -1514,6 +1540,15 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
   }
 
   if (g_backend.load() == 1) return launch_simt(A, B, p, epi.kind, nsplit, stream);
+  if (epi.kind == KFB_EPI_STORE && p.reduce_sq && p.batch > 1) {
+    // self-influence: one scalar per batch entry.  The factor tile lives in registers across the batch entries of a
+    // unit (register-accumulating kernel, batch mode) instead of being re-read from L2 for every example and chunk.
+    p.regacc_mode = REGACC_BATCH_DOT;
+    p.tma_store = 0;
+    p.zero_pad = 0;
+    p.batch_fastest = 0;
+    return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
+  }
   if (epi.kind == KFB_EPI_ROWDOT) return dispatch_tc<EPI_ROWDOT>(A, B, p, nsplit, stream);
   if (epi.kind == KFB_EPI_SQACC) return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
 

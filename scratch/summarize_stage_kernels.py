@@ -29,7 +29,7 @@ def short(n):
     n = re.sub(r"\((const|kfb|float|long|int|double|unsigned|SplitDst|GatherDesc|kfb_layer).*", "", n)
     return n.replace("void ", "").replace("kfb::", "").strip()
 
-print("# Round 1 (end of session 2) — every kernel of the hot path under ncu (one pass of each stage op)\n")
+print("# Every kernel of the hot path under ncu (one pass of each stage op); see the file name for the round\n")
 print("`ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active...,gpu__dram_throughput...,dram__bytes_*,"
       "l1tex__throughput...,lts__throughput... --clock-control none` over `scratch/profile_stages.py`: covariance (both sides),")
 print("eigendecomposition, Lambda sweep, Lambda inversion, query preconditioning, pairwise contraction, gradient aggregation and self-influence for")
