@@ -39,7 +39,9 @@ enum : int { EPI_STORE = 0, EPI_ROWDOT = 1, EPI_REGACC = 2 };
 // REGACC_BATCH_DOT: the registers hold an elementwise FACTOR instead of sums: out[b] += alpha * sum_{m,n} D_b[m,n]^2 factor[m,n]
 // for every batch entry of the chunk (the self-influence contraction: the factor tile is read once per unit, not once
 // per example and chunk, whose L2 latency used to be 16 serial round trips per tile)
-enum : int { REGACC_BATCH = 0, REGACC_KCHUNK = 1, REGACC_BATCH_DOT = 2 };
+// REGACC_BATCH_MUL: the same resident factor, but every batch entry is STORED: out[b][m,n] = alpha * D_b[m,n] factor[m,n]
+// as operand planes (query preconditioning of S > 1 layers: P~_q = scale (G~_q) o Lambda^-1 straight into the store)
+enum : int { REGACC_BATCH = 0, REGACC_KCHUNK = 1, REGACC_BATCH_DOT = 2, REGACC_BATCH_MUL = 3 };
 
 // The tensor core adds each MMA's partial products into the fp32 TMEM accumulator with truncation,
 // so a long accumulation chain acquires a relative bias of ~(K/16)*nsplit_mmas*2^-25.  One TMEM pass
@@ -71,6 +73,8 @@ struct GemmParams {
   long long ldo_s, out_bs_s;
   const float* mul;
   long long ldmul;
+  const float* factor;     // REGACC_BATCH_DOT / _MUL: the [M, N] factor kept in registers across the batch entries of a unit
+  long long ldfactor;
   int transpose_out, square, accumulate, use_atomic, vec_ok, zero_pad;
   int reduce_sq;  // STORE: reduce D^2 (o mul) to one scalar per batch entry instead of storing
   float alpha;
@@ -834,14 +838,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
       for (int i = 0; i < NACC; ++i) racc[i] = 0.f;
       Tile t = decode_tile<EPI>(p, unit, 0, pair_id);
-      if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH_DOT) {
+      if (EPI == EPI_REGACC && p.regacc_mode >= REGACC_BATCH_DOT) {
         // this thread's slice of the factor row (all batch entries of the unit share the (m, n) tile)
         const long long frow = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
         const int fcol0 = t.n_blk * BLOCK_N + col_off;
 #pragma unroll
         for (int i = 0; i < NACC; ++i) {
           const bool ok = frow < p.M && fcol0 + i < p.N;
-          racc[i] = !ok ? 0.f : (p.mul != nullptr ? __ldg(p.mul + frow * p.ldmul + fcol0 + i) : 1.f);
+          racc[i] = !ok ? 0.f : (p.factor != nullptr ? __ldg(p.factor + frow * p.ldfactor + fcol0 + i) : 1.f);
         }
       }
       for (int j = 0; j < inner; ++j, ++it) {
@@ -900,6 +904,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const float x = __uint_as_float(v[c & 1][i]);
                 rowdot = fmaf(x * x, racc[(EPI == EPI_REGACC ? c * 32 + i : 0)], rowdot);
               }
+            } else if (p.regacc_mode == REGACC_BATCH_MUL) {
+              const int col0 = n0 + col_off + c * 32;
+              if (col0 < p.N) {  // warp-uniform
+                float y[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[c & 1][i]) * racc[(EPI == EPI_REGACC ? c * 32 + i : 0)];
+                const bool last_of_box = (c & 1) || c + 1 == NACC / 32 || col0 + 32 >= p.N;
+                store_chunk<0, 32, false, TMA64>(p, &tm_o_hi, &tm_o_lo, alpha, t.b, row, col0, y, st, lane, false, c & 1, last_of_box);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) racc[(EPI == EPI_REGACC ? c * 32 + i : 0)] += __uint_as_float(v[c & 1][i]);
@@ -925,6 +938,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
           }
         }
+        if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH_MUL && row_ok && p.zero_pad && !p.tma_store && col_off == 0 &&
+            t.n_blk == p.n_blocks - 1)
+          store_zero_pad(p, t.b, row);
         if (EPI == EPI_REGACC && p.regacc_mode == REGACC_BATCH_DOT) {
           float part = rowdot;
 #pragma unroll
@@ -973,7 +989,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           else if (p.accumulate) *o += val;
           else *o = val;
         }
-      } else if (EPI == EPI_REGACC && p.regacc_mode != REGACC_BATCH_DOT) {
+      } else if (EPI == EPI_REGACC && p.regacc_mode < REGACC_BATCH_DOT) {
         const long long row = (long long)t.m_blk * Cfg::TILE_M + (long long)cta_rank * BLOCK_M + lane_row;
         const int n0 = t.n_blk * BLOCK_N + col_off;
         const int ob = p.regacc_mode == REGACC_BATCH ? 0 : t.b;
@@ -1544,9 +1560,25 @@ int gemm_nt(const kfb_split& A, const kfb_split& B, const kfb_epilogue& epi, int
     // self-influence: one scalar per batch entry.  The factor tile lives in registers across the batch entries of a
     // unit (register-accumulating kernel, batch mode) instead of being re-read from L2 for every example and chunk.
     p.regacc_mode = REGACC_BATCH_DOT;
+    p.factor = p.mul;
+    p.ldfactor = p.ldmul;
     p.tma_store = 0;
     p.zero_pad = 0;
     p.batch_fastest = 0;
+    return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
+  }
+  if (epi.kind == KFB_EPI_STORE && p.mul != nullptr && p.batch > 1 && p.out_hi != nullptr && p.out_f32 == nullptr &&
+      !p.transpose_out && !p.square && p.col_group == 0 && p.K <= p.max_pass_k && !strict) {
+    // an elementwise factor shared by a batch of short products stored as planes (query preconditioning of S > 1
+    // layers): the factor tile stays in registers across the batch entries of a unit and the planes leave through TMA
+    // stores, instead of one L2 round trip per 16 rows of every chunk and 16-byte scattered stores
+    p.regacc_mode = REGACC_BATCH_MUL;
+    p.factor = p.mul;
+    p.ldfactor = p.ldmul;
+    p.mul = nullptr;
+    p.mul_vec4 = 0;
+    p.batch_fastest = 0;
+    p.tma_store = (p.vec_ok && p.ldo_s >= 64 && g_tma_store.load() != 0) ? 1 : 0;
     return dispatch_tc<EPI_REGACC>(A, B, p, nsplit, stream);
   }
   if (epi.kind == KFB_EPI_ROWDOT) return dispatch_tc<EPI_ROWDOT>(A, B, p, nsplit, stream);
