@@ -18,7 +18,11 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 def main() -> None:
     report, name = sys.argv[1], sys.argv[2]
     index = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if report.endswith(".csv"):  # already exported on the GPU box with `ncu -i ... --page raw --csv`
+        with open(report, "r", encoding="utf-8") as f:
+            raw = f.read()
+    else:
+        raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, row = rows[0], rows[1], rows[2 + index]
     col = {h: i for i, h in enumerate(hdr)}
