@@ -1326,8 +1326,8 @@ static int launch_tc(const kfb_split& A, const kfb_split& B, GemmParams p, cudaS
         p.max_groups == 0) {
       const long long whole = (groups / p.m_units) * p.m_units;
       if (whole >= p.m_units && groups - whole <= 1 && whole / p.m_units <= 64 && p.num_units >= 4 * whole) {
-        static unsigned int* ctr = nullptr;
-        if (ctr == nullptr) KFB_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_rowdot_sync));
+        unsigned int* ctr = nullptr;  // per device: not cached (a process may drive several GPUs)
+        KFB_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_rowdot_sync));
         KFB_CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * 64, stream));
         p.sync_ctr = ctr;
         p.sync_group = p.m_units;
