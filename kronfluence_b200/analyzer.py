@@ -234,6 +234,21 @@ class Analyzer:
             raise FactorsNotFoundError(f"Factors with name `{factors_name}` not found at `{path.parent}`.")
         return FactorArguments(**io.load_json(path))
 
+    def load_factor_args(self, factors_name: str) -> Optional[FactorArguments]:
+        """The `FactorArguments` factors `factors_name` were fitted with, or None (computer/computer.py:336-342)."""
+        path = self.factors_output_dir(factors_name) / f"{FACTOR_ARGUMENTS_NAME}_arguments.json"
+        return FactorArguments(**io.load_json(path)) if path.exists() else None
+
+    def load_score_args(self, scores_name: str) -> Optional[ScoreArguments]:
+        """The `ScoreArguments` scores `scores_name` were computed with, or None (computer/computer.py:365-371)."""
+        path = self.scores_output_dir(scores_name) / f"{SCORE_ARGUMENTS_NAME}_arguments.json"
+        return ScoreArguments(**io.load_json(path)) if path.exists() else None
+
+    @staticmethod
+    def load_file(path: Union[str, Path]) -> Dict[str, torch.Tensor]:
+        """Loads any safetensors file written by either engine (analyzer.py:197-220 of the reference)."""
+        return io.load_file(Path(path))
+
     def _loader(self, dataset: data.Dataset, batch_size: int, indices: Optional[Sequence[int]], kind: str,
                 dataloader_kwargs: Optional[DataLoaderKwargs]) -> data.DataLoader:
         """kind: 'eval' (strided, unpadded), 'stack' (contiguous chunks, padded), 'query' (strided, padded)."""

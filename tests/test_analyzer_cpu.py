@@ -584,3 +584,18 @@ def test_user_factor_strategy(tmp_path):
     finally:
         registry["ekfac"] = previous
     assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
+
+
+def test_argument_and_file_loaders(tmp_path):
+    """`load_factor_args` / `load_score_args` / `Analyzer.load_file` (computer/computer.py:336-371, analyzer.py:197-220)."""
+    with oracle_backend():
+        analyzer, scores = run_case("mlp", tmp_path, score_kwargs=dict(query_gradient_accumulation_steps=2))
+    assert analyzer.load_factor_args("missing") is None and analyzer.load_score_args("missing") is None
+    fa = analyzer.load_factor_args("f")
+    assert fa.strategy == "ekfac" and fa.use_empirical_fisher and fa.lambda_dtype == torch.float32
+    sa = analyzer.load_score_args("s")
+    assert sa.damping_factor is None and sa.query_gradient_accumulation_steps == 2
+    loaded = Analyzer.load_file(analyzer.scores_output_dir("s") / "pairwise_scores.safetensors")
+    assert torch.equal(loaded["all_modules"], scores["all_modules"])
+    with pytest.raises(FileNotFoundError):
+        Analyzer.load_file(tmp_path / "nope.safetensors")
