@@ -1367,8 +1367,13 @@ class Analyzer:
         path = self.scores_output_dir(scores_name) / "self_scores.safetensors"
         return io.load_file(path) if path.exists() else None
 
-    def get_module_summary(self) -> str:
-        lines = ["Tracked modules:"]
-        for module in tracked_modules(self.model):
-            lines.append(f"  {module.name}: {module.original_module}")
+    @staticmethod
+    def get_module_summary(model: nn.Module) -> str:
+        """One line per leaf module that has parameters (analyzer.py:222-242 of the reference): the names to pass to
+        `Task.get_influence_tracked_modules`.  Works on a plain or a prepared model."""
+        lines = ["==Model Summary=="]
+        for name, module in model.named_modules():
+            if any(True for _ in module.children()) or not any(True for _ in module.parameters()):
+                continue
+            lines.append(f"Module Name: `{name}`, Module: {module!r}")
         return "\n".join(lines)
