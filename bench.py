@@ -179,7 +179,7 @@ def _import_reference():
         return None
     for path in (os.path.join(ROOT, "oracle", "shims"), ref):
         if path not in sys.path:
-            sys.path.insert(0, path)
+            sys.path.append(path)  # appended: baseline/_ref also holds the reference's `tests` package, ours must win
     import kronfluence  # noqa: F401  pylint: disable=import-error
     from kronfluence.analyzer import Analyzer, prepare_model  # pylint: disable=import-error
     from kronfluence.arguments import FactorArguments, ScoreArguments  # pylint: disable=import-error

@@ -44,11 +44,17 @@ def test_score_presets():
 @pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "kronfluence")),
                     reason="the reference is not installed under baseline/_ref")
 def test_presets_match_the_installed_reference():
-    for path in (os.path.join(ROOT, "oracle", "shims"), os.path.join(ROOT, "baseline", "_ref")):
-        if path not in sys.path:
-            sys.path.insert(0, path)
-    from kronfluence.utils.common import factor_arguments as ref_f  # pylint: disable=import-error
-    from kronfluence.utils.common import score_arguments as ref_s  # pylint: disable=import-error
+    # appended, and removed again: baseline/_ref also holds the reference's own `tests` package, which must never shadow
+    # ours (spawned workers of the distributed tests inherit sys.path)
+    added = [path for path in (os.path.join(ROOT, "oracle", "shims"), os.path.join(ROOT, "baseline", "_ref"))
+             if path not in sys.path]
+    sys.path.extend(added)
+    try:
+        from kronfluence.utils.common import factor_arguments as ref_f  # pylint: disable=import-error
+        from kronfluence.utils.common import score_arguments as ref_s  # pylint: disable=import-error
+    finally:
+        for path in added:
+            sys.path.remove(path)
 
     for name in ("default", "pytest", "smart_low_precision", "all_low_precision", "reduce_memory", "extreme_reduce_memory"):
         ours = getattr(common, f"{name}_factor_arguments")().to_dict()
