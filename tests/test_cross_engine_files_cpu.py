@@ -104,3 +104,80 @@ def test_factors_of_this_engine_feed_the_reference(reference, tmp_path):
                                 score_args=ref_arguments.ScoreArguments(damping_factor=None))
     got = ref.load_pairwise_scores("s_ref")["all_modules"].numpy()
     assert rel(got, want) < 5e-5
+
+
+def _describe(directory):
+    """{file: layout} of one factors_/scores_ directory: tensor names with dtype and shape, safetensors metadata keys,
+    JSON keys."""
+    import json
+
+    from safetensors import safe_open
+
+    out = {}
+    for name in sorted(os.listdir(directory)):
+        path = os.path.join(directory, name)
+        if name.endswith(".safetensors"):
+            with safe_open(path, "pt") as handle:
+                tensors = {key: handle.get_tensor(key) for key in handle.keys()}
+                out[name] = (sorted((handle.metadata() or {}).keys()),
+                             {key: (str(t.dtype), tuple(t.shape)) for key, t in tensors.items()})
+        elif name.endswith(".json"):
+            with open(path, encoding="utf-8") as handle:
+                out[name] = sorted(json.load(handle).keys())
+        else:
+            out[name] = None
+    return out
+
+
+@pytest.mark.parametrize("partitions", [1, 2])
+def test_directory_layout_matches_the_reference(partitions, reference, tmp_path):
+    """Same file names (partition files included), tensor names, dtypes, shapes, metadata keys and JSON keys in
+    factors_* and scores_*."""
+    ref_analyzer, ref_arguments, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+
+    factor_kwargs = dict(use_empirical_fisher=True, covariance_data_partitions=partitions,
+                         covariance_module_partitions=partitions, lambda_data_partitions=partitions,
+                         lambda_module_partitions=partitions)
+    score_kwargs = dict(data_partitions=partitions, module_partitions=partitions)
+
+    case = "mlp"
+    _, _, _, _, train_bs, query_bs = fixtures.CASES[case]
+    model, train_set, query_set = fixtures.make_case(case)
+    task = fixtures.make_tasks(ref_task.Task)[case]()
+    ref = ref_analyzer.Analyzer("shared", ref_analyzer.prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path),
+                                disable_tqdm=True)
+    ref.fit_all_factors("ref", train_set, per_device_batch_size=train_bs,
+                        factor_args=ref_arguments.FactorArguments(**factor_kwargs))
+    ref.compute_pairwise_scores("ref", "ref", query_set, train_set, per_device_query_batch_size=query_bs,
+                                per_device_train_batch_size=train_bs, score_args=ref_arguments.ScoreArguments(**score_kwargs))
+    ref.compute_self_scores("ref_self", "ref", train_set, per_device_train_batch_size=train_bs,
+                            score_args=ref_arguments.ScoreArguments(**score_kwargs))
+
+    ours_model, _, _ = fixtures.make_case(case)
+    ours_task = fixtures.make_tasks(Task)[case]()
+    with oracle_backend():
+        ours = Analyzer("shared", prepare_model(ours_model, ours_task), ours_task, cpu=True, output_dir=str(tmp_path),
+                        disable_tqdm=True)
+        ours.fit_all_factors("ours", train_set, per_device_batch_size=train_bs,
+                             factor_args=FactorArguments(**factor_kwargs))
+        ours.compute_pairwise_scores("ours", "ours", query_set, train_set, per_device_query_batch_size=query_bs,
+                                     per_device_train_batch_size=train_bs, score_args=ScoreArguments(**score_kwargs))
+        ours.compute_self_scores("ours_self", "ours", train_set, per_device_train_batch_size=train_bs,
+                                 score_args=ScoreArguments(**score_kwargs))
+
+    base = tmp_path / "shared"
+    for theirs, mine in (("factors_ref", "factors_ours"), ("scores_ref", "scores_ours"), ("scores_ref_self", "scores_ours_self")):
+        want, got = _describe(base / theirs), _describe(base / mine)
+        assert sorted(want) == sorted(got), (theirs, mine)
+        for name, layout in want.items():
+            if name.endswith(".safetensors"):
+                # tensors identical in name / dtype / shape; the reference drops the argument metadata from the files
+                # its aggregate_* calls write, this engine keeps it there too (a superset, ignored on load)
+                assert layout[1] == got[name][1], name
+                assert set(layout[0]) <= set(got[name][0]), name
+                assert partitions > 1 or layout[0] == got[name][0], name
+            else:
+                assert layout == got[name], name
