@@ -14,9 +14,7 @@ execution model that follow from that, all invisible in the results:
     gather of score columns per query chunk, over NCCL.
 """
 
-import logging
 import math
-import time
 from pathlib import Path
 from typing import Any, Callable, Dict, List, Optional, Sequence, Union
 
@@ -78,6 +76,8 @@ from kronfluence_b200.utils.dataset import (
     make_indices_partition,
 )
 from kronfluence_b200.utils.exceptions import FactorsNotFoundError
+from kronfluence_b200.utils.logger import Profiler, get_logger
+from kronfluence_b200.utils.model import unwrap_data_parallel
 from kronfluence_b200.utils.state import State, release_memory
 
 FACTOR_TYPE = Dict[str, Dict[str, torch.Tensor]]
@@ -120,39 +120,6 @@ def _find_batch_size(batch: Any) -> Optional[int]:
     return None
 
 
-class Profiler:
-    """Wall-clock per named action, synchronised on the device (utils/logger.py:57-154 of the reference)."""
-
-    def __init__(self, state: State, enabled: bool) -> None:
-        self.state, self.enabled = state, enabled
-        self.durations: Dict[str, List[float]] = {}
-
-    class _Span:
-        def __init__(self, prof: "Profiler", name: str) -> None:
-            self.prof, self.name = prof, name
-
-        def __enter__(self):
-            if self.prof.enabled and self.prof.state.device.type == "cuda":
-                torch.cuda.synchronize(self.prof.state.device)
-            self.start = time.monotonic()
-            return self
-
-        def __exit__(self, *exc):
-            if self.prof.enabled and self.prof.state.device.type == "cuda":
-                torch.cuda.synchronize(self.prof.state.device)
-            self.prof.durations.setdefault(self.name, []).append(time.monotonic() - self.start)
-            return False
-
-    def profile(self, name: str) -> "Profiler._Span":
-        return Profiler._Span(self, name)
-
-    def summary(self) -> str:
-        lines = ["Action | Total time (s) | Calls"]
-        for name, values in sorted(self.durations.items(), key=lambda kv: -sum(kv[1])):
-            lines.append(f"{name} | {sum(values):.4f} | {len(values)}")
-        return "\n".join(lines)
-
-
 class Analyzer:
     """Fits EK-FAC factors and computes pairwise influence scores for a prepared model."""
 
@@ -160,18 +127,18 @@ class Analyzer:
                  log_level: Optional[int] = None, log_main_process_only: bool = True, profile: bool = False,
                  disable_tqdm: bool = False, output_dir: str = "./influence_results",
                  disable_model_save: bool = True) -> None:
-        del log_main_process_only, disable_model_save
         get_tracked_module_names(model)  # raises TrackedModuleNotFoundError if prepare_model was skipped
         self.state = State(cpu=cpu)
         if self.state.device.type != "cuda" and ops.BACKEND == "cuda":
             raise RuntimeError(
                 "kronfluence_b200 computes factors and scores with sm_100a CUDA kernels only; there is no CPU "
                 "path (cpu=True / no visible GPU is not supported).")
-        self.model = model
+        # A DDP wrapper (scripts written for the reference apply one) is removed: ranks exchange factors, queries and score
+        # tiles explicitly and the frozen replicas need no gradient all-reduce.
+        self.model = unwrap_data_parallel(model)
         self.task = task
-        self.logger = logging.getLogger("kronfluence_b200")
-        if log_level is not None:
-            self.logger.setLevel(log_level)
+        self.logger = get_logger("kronfluence_b200", log_level=log_level, state=self.state)
+        self.logger.main_process_only = log_main_process_only
         self.disable_tqdm = disable_tqdm
         self.model.to(self.state.device)
         self.output_dir = Path(output_dir).joinpath(analysis_name).resolve()
@@ -183,6 +150,26 @@ class Analyzer:
         # chunks (0 disables; see TrainOperandCache).  `last_train_operand_cache` reports what the last run did.
         self.train_operand_cache_fraction = 0.5
         self.last_train_operand_cache: Optional[Dict[str, Any]] = None
+        if self.state.is_main_process and not disable_model_save:
+            self._save_model()
+        self.state.wait_for_everyone()
+
+    @torch.no_grad()
+    def _save_model(self) -> None:
+        """`disable_model_save=False` (analyzer.py:106-142 of the reference): the first Analyzer of an analysis writes
+        `model.safetensors`; later ones must bring the same weights or fail, so factors are never mixed across models."""
+        path = self.output_dir / "model.safetensors"
+        state_dict = self.model.state_dict()
+        if path.exists():
+            if not io.verify_models_equivalence(io.load_file(path), state_dict):
+                message = (f"Detected a difference between the current model and the one saved at `{path}`. "
+                           "Consider using a different `analysis_name` to avoid conflicts.")
+                self.logger.error(message)
+                raise ValueError(message)
+            self.logger.info("Model matches the one saved at `%s`.", path)
+        else:
+            io.save_tensors({name: tensor.detach().clone() for name, tensor in state_dict.items()}, path)
+            self.logger.info("Saved model at `%s`.", path)
 
     # ------------------------------------------------------------------------------------------
     # small helpers

@@ -83,3 +83,15 @@ def save_scores(output_dir: Path, scores: Dict[str, torch.Tensor], partition: Op
                 metadata: Optional[Dict[str, str]] = None) -> None:
     Path(output_dir).mkdir(parents=True, exist_ok=True)
     save_tensors(scores, scores_path(output_dir, partition), metadata)
+
+
+def verify_models_equivalence(state_dict1: Dict[str, torch.Tensor], state_dict2: Dict[str, torch.Tensor]) -> bool:
+    """Same parameter / buffer names and, compared as float32 on the host, values equal within rtol 1.3e-6 / atol 1e-5
+    (utils/save.py:67-101 of the reference): guards an analysis directory against being reused with another model."""
+    if set(state_dict1) != set(state_dict2):
+        return False
+    for name, tensor in state_dict1.items():
+        lhs, rhs = (t.detach().to(device="cpu", dtype=torch.float32) for t in (tensor, state_dict2[name]))
+        if lhs.shape != rhs.shape or not torch.allclose(lhs, rhs, rtol=1.3e-6, atol=1e-5):
+            return False
+    return True

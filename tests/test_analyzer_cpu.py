@@ -599,3 +599,59 @@ def test_argument_and_file_loaders(tmp_path):
     assert torch.equal(loaded["all_modules"], scores["all_modules"])
     with pytest.raises(FileNotFoundError):
         Analyzer.load_file(tmp_path / "nope.safetensors")
+
+
+def test_model_save_guards_the_analysis_directory(tmp_path):
+    """analyzer.py:106-142 of the reference: `disable_model_save=False` writes model.safetensors once and refuses a
+    different model under the same analysis name."""
+    from kronfluence_b200.utils.save import load_file, verify_models_equivalence
+
+    model, _, _ = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    model = prepare_model(model, task)
+    with oracle_backend():
+        analyzer = Analyzer("guard", model, task, cpu=True, output_dir=str(tmp_path), disable_model_save=False)
+        saved = analyzer.output_dir / "model.safetensors"
+        assert saved.exists() and verify_models_equivalence(load_file(saved), model.state_dict())
+        Analyzer("guard", model, task, cpu=True, output_dir=str(tmp_path), disable_model_save=False)  # same weights: fine
+        other, _, _ = fixtures.make_case("mlp")
+        with torch.no_grad():
+            next(other.parameters()).add_(1e-2)
+        other = prepare_model(other, task)
+        with pytest.raises(ValueError, match="different `analysis_name`"):
+            Analyzer("guard", other, task, cpu=True, output_dir=str(tmp_path), disable_model_save=False)
+        Analyzer("guard", other, task, cpu=True, output_dir=str(tmp_path))  # the default skips the check
+    state = model.state_dict()
+    assert not verify_models_equivalence(state, {k: v for k, v in list(state.items())[1:]})
+
+
+def test_logger_and_profiler_helpers(tmp_path, caplog):
+    """utils/logger.py of the reference: rank-aware logger, device-synchronised clock, per-action profile summary."""
+    import logging
+
+    from kronfluence_b200.utils.logger import PassThroughProfiler, Profiler, get_logger, get_time
+    from kronfluence_b200.utils.state import State
+
+    state = State(cpu=True)
+    logger = get_logger("kfb_test_logger", log_level=logging.INFO, state=state)
+    with caplog.at_level(logging.INFO, logger="kfb_test_logger"):
+        logger.info("hello %d", 1)
+        state.process_index = 1  # a non-main rank stays silent unless asked
+        logger.info("muted")
+        logger.main_process_only = False
+        logger.info("every rank")
+    assert [r.getMessage() for r in caplog.records] == ["hello 1", "every rank"]
+    state.process_index = 0
+    assert abs(get_time(state) - __import__("time").time()) < 5.0
+    profiler = Profiler(state)
+    with profiler.profile("stage"):
+        pass
+    assert "stage" in profiler.summary() and PassThroughProfiler(state).summary() == ""
+
+    model, train_set, _ = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    with oracle_backend():
+        analyzer = Analyzer("prof", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), profile=True,
+                            disable_tqdm=True)
+        analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8)
+    assert "Action" in analyzer.profiler.summary() and len(analyzer.profiler.durations) > 0

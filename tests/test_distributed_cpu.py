@@ -134,6 +134,49 @@ def test_two_ranks_match_reference(case, tmp_path):
     assert abs(agg - ref_agg).max() / abs(ref_agg).max() < 5e-5
 
 
+def _ddp_worker(rank, world, port, out_dir):
+    """A script written for the reference: joins the process group itself and hands the Analyzer a DDP-wrapped model."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world), GLOO_SOCKET_IFNAME="lo")
+    sys.path.insert(0, ROOT)
+    torch.set_num_threads(1)
+    from torch.nn.parallel.distributed import DistributedDataParallel
+
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+    from tests import fixtures
+    from tests.cpu_backend import oracle_backend
+
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    model, train_set, query_set = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    wrapped = DistributedDataParallel(prepare_model(model, task))
+    with oracle_backend():
+        analyzer = Analyzer("ddp", wrapped, task, cpu=True, output_dir=out_dir, disable_tqdm=True)
+        assert not isinstance(analyzer.model, DistributedDataParallel) and analyzer.state.num_processes == world
+        analyzer.fit_all_factors("f", train_set, per_device_batch_size=4,
+                                 factor_args=FactorArguments(use_empirical_fisher=True))
+        scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                  per_device_train_batch_size=4,
+                                                  score_args=ScoreArguments(damping_factor=None))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "scores.npy"), scores["all_modules"].numpy())
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_ddp_wrapped_model_is_unwrapped(tmp_path):
+    """utils/model.py:17-55 of the reference: user scripts wrap the prepared model in DDP before building the Analyzer."""
+    tmp_path = _spawn_with_retries(_ddp_worker, (), tmp_path)
+    scores = np.load(tmp_path / "scores.npy")
+    ref = dict(np.load(os.path.join(GOLDEN, "e2e_mlp.npz")))["f32/scores"]
+    assert scores.shape == ref.shape
+    # eigenvectors come from this run's own solve here (not the golden ones): compare at the tolerance of the
+    # end-to-end tests
+    assert np.linalg.norm(scores - ref) / np.linalg.norm(ref) < 1e-3
+
+
 def test_samplers():
     """tests/test_dataset_utils.py:14-70 of the reference: coverage and chunking semantics."""
     from kronfluence_b200.utils.dataset import (DistributedEvalSampler, DistributedQuerySampler,
