@@ -1,9 +1,10 @@
 """Process / device state: one process per GPU under torchrun, NCCL over NVLink for the collectives
 (the role of utils/state.py:12-165 in the reference, without its accelerate dependency)."""
 
+import contextlib
 import gc
 import os
-from typing import Optional
+from typing import Iterator, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -47,6 +48,18 @@ class State:
     def is_main_process(self) -> bool:
         return self.process_index == 0
 
+    @property
+    def is_local_main_process(self) -> bool:
+        return self.local_process_index == 0
+
+    @property
+    def is_last_process(self) -> bool:
+        return self.process_index == self.num_processes - 1
+
+    @property
+    def default_device(self) -> torch.device:
+        return torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
     def wait_for_everyone(self) -> None:
         if self.use_distributed:
             dist.barrier()
@@ -60,3 +73,28 @@ def release_memory() -> None:
     gc.collect()
     if torch.cuda.is_available():
         torch.cuda.empty_cache()
+
+
+def get_active_tensors() -> List[Tuple[type, torch.Size]]:
+    """(type, shape) of every tensor the garbage collector can see: a leak-hunting aid between stages."""
+    import warnings
+
+    found = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # isinstance() on deprecated module attributes warns
+        for obj in gc.get_objects():
+            try:
+                if torch.is_tensor(obj):
+                    found.append((type(obj), obj.size()))
+            except Exception:  # pylint: disable=broad-exception-caught  # objects with hostile __class__ / __getattr__
+                continue
+    return found
+
+
+@contextlib.contextmanager
+def no_sync(model: torch.nn.Module, state: State) -> Iterator[None]:
+    """Backward passes inside this block skip a data-parallel wrapper's gradient all-reduce, when there is one.  The
+    Analyzer unwraps DDP, so this only matters to callers that drive a wrapped model themselves."""
+    enter = getattr(model, "no_sync", None) if state.use_distributed else None
+    with (enter() if callable(enter) else contextlib.nullcontext()):
+        yield

@@ -1,0 +1,114 @@
+"""Hook behaviour under the autograd variants the reference tests (tests/factors/test_covariances.py:393-520,
+tests/factors/test_lambdas.py:394-520, tests/scores/*): activation checkpointing (forward hooks fire twice per batch),
+in-place activations right after a tracked layer, and `per_device_batch_size=None` (largest executable batch size).
+Host logic only: the CUDA ops are replaced by the oracle double."""
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+from torch.utils.checkpoint import checkpoint_sequential
+
+from kronfluence_b200.analyzer import Analyzer, prepare_model
+from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+from kronfluence_b200.task import Task
+from tests import fixtures
+from tests.cpu_backend import oracle_backend
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def run_everything(model, task, train_set, query_set, out_dir, train_bs, query_bs):
+    """Covariances, Lambda, pairwise and self scores of one model / task."""
+    with oracle_backend():
+        analyzer = Analyzer("variant", prepare_model(model, task), task, cpu=True, output_dir=str(out_dir), disable_tqdm=True)
+        analyzer.fit_all_factors("f", train_set, per_device_batch_size=train_bs,
+                                 factor_args=FactorArguments(use_empirical_fisher=True))
+        factors = analyzer.load_all_factors("f")
+        pairwise = analyzer.compute_pairwise_scores("p", "f", query_set, train_set, per_device_query_batch_size=query_bs,
+                                                    per_device_train_batch_size=train_bs,
+                                                    score_args=ScoreArguments(damping_factor=None))["all_modules"]
+        own = analyzer.compute_self_scores("s", "f", train_set, per_device_train_batch_size=train_bs,
+                                           score_args=ScoreArguments(damping_factor=None))["all_modules"]
+    return factors, pairwise.numpy(), own.numpy()
+
+
+def test_activation_checkpointing(tmp_path):
+    """checkpoint_sequential re-runs the forward of each segment inside backward: gradient covariances, Lambda and scores
+    must not change (the activation covariance may see the rows twice in the reference as well, so it is compared after
+    normalising by its own count)."""
+    base = fixtures.make_tasks(Task)["mlp"]
+
+    class CheckpointedTask(base):
+        def compute_train_loss(self, batch, model, sample=False):
+            inputs, targets = batch
+            inputs = inputs.clone().requires_grad_(True)  # non-reentrant checkpointing wants a differentiable input
+            outputs = checkpoint_sequential(model, 2, inputs, use_reentrant=False)
+            return torch.nn.functional.mse_loss(outputs, targets.to(outputs.dtype), reduction="sum")
+
+    model, train_set, query_set = fixtures.make_case("mlp")
+    plain = run_everything(model, base(), train_set, query_set, tmp_path / "plain", 8, 3)
+    model, _, _ = fixtures.make_case("mlp")
+    ckpt = run_everything(model, CheckpointedTask(), train_set, query_set, tmp_path / "ckpt", 8, 3)
+
+    for name in ("gradient_covariance", "num_gradient_covariance_processed", "lambda_matrix", "num_lambda_processed"):
+        for module in plain[0][name]:
+            assert rel(ckpt[0][name][module], plain[0][name][module]) < 1e-6, (name, module)
+    for module, cov in plain[0]["activation_covariance"].items():
+        want = cov / plain[0]["num_activation_covariance_processed"][module]
+        got = ckpt[0]["activation_covariance"][module] / ckpt[0]["num_activation_covariance_processed"][module]
+        assert rel(got, want) < 1e-6, module
+    assert rel(ckpt[1], plain[1]) < 1e-5 and rel(ckpt[2], plain[2]) < 1e-5
+
+
+def test_inplace_activation_after_tracked_layer(tmp_path):
+    """nn.ReLU(inplace=True) overwrites the tracked layer's output: factors and scores equal the out-of-place model's
+    (tests/factors/test_covariances.py:455-520 of the reference)."""
+
+    def make(inplace):
+        torch.manual_seed(0)
+        return nn.Sequential(nn.Conv2d(3, 4, 3, stride=1, padding=1), nn.ReLU(inplace=inplace),
+                             nn.Conv2d(4, 6, 3, stride=2, padding=0, bias=False), nn.ReLU(inplace=inplace), nn.Flatten(),
+                             nn.Linear(6 * 3 * 3, 5))
+
+    task_cls = fixtures.make_tasks(Task)["conv"]
+    _, train_set, query_set = fixtures.make_case("conv")
+    plain = run_everything(make(False), task_cls(), train_set, query_set, tmp_path / "plain", 5, 3)
+    inplace = run_everything(make(True), task_cls(), train_set, query_set, tmp_path / "inplace", 5, 3)
+    for name, per_module in plain[0].items():
+        for module, tensor in per_module.items():
+            if "eigen" in name:
+                continue  # bases may differ by sign; Lambda and the scores below cover them
+            assert rel(inplace[0][name][module], tensor) < 1e-6, (name, module)
+    assert rel(inplace[1], plain[1]) < 1e-5 and rel(inplace[2], plain[2]) < 1e-5
+
+
+def test_automatic_batch_size(tmp_path):
+    """per_device_batch_size=None: the largest executable batch size is searched from
+    `initial_per_device_batch_size_attempt` downwards and the results equal a fixed batch size's
+    (tests/factors/test_covariances.py:522-560 of the reference)."""
+    model, train_set, query_set = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    with oracle_backend():
+        analyzer = Analyzer("auto", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        args = FactorArguments(use_empirical_fisher=True)
+        analyzer.fit_all_factors("fixed", train_set, per_device_batch_size=8, factor_args=args)
+        analyzer.fit_all_factors("auto", train_set, per_device_batch_size=None, initial_per_device_batch_size_attempt=16,
+                                 factor_args=args)
+        fixed, auto = analyzer.load_all_factors("fixed"), analyzer.load_all_factors("auto")
+        for name in ("activation_covariance", "gradient_covariance", "lambda_matrix"):
+            for module, tensor in fixed[name].items():
+                assert rel(auto[name][module], tensor) < 1e-5, (name, module)
+        want = analyzer.compute_pairwise_scores("fixed", "fixed", query_set, train_set, per_device_query_batch_size=3,
+                                                per_device_train_batch_size=8)["all_modules"]
+        got = analyzer.compute_pairwise_scores("auto", "fixed", query_set, train_set, per_device_query_batch_size=3,
+                                               per_device_train_batch_size=None,
+                                               initial_per_device_train_batch_size_attempt=16)["all_modules"]
+        assert rel(got.numpy(), want.numpy()) < 1e-5
+        own = analyzer.compute_self_scores("auto_self", "fixed", train_set, per_device_train_batch_size=None,
+                                           initial_per_device_train_batch_size_attempt=16)["all_modules"]
+        want_own = analyzer.compute_self_scores("fixed_self", "fixed", train_set, per_device_train_batch_size=8)["all_modules"]
+        assert rel(own.numpy(), want_own.numpy()) < 1e-5
