@@ -15,6 +15,7 @@ execution model that follow from that, all invisible in the results:
 """
 
 import math
+from collections.abc import Mapping
 from pathlib import Path
 from typing import Any, Callable, Dict, List, Optional, Sequence, Union
 
@@ -95,25 +96,37 @@ def prepare_model(model: nn.Module, task: Task) -> nn.Module:
 
 
 def _send_to_device(batch: Any, device: torch.device) -> Any:
+    """Moves every tensor of a nested batch (lists, tuples, named tuples, any Mapping such as transformers'
+    BatchEncoding, objects with their own `.to`) and leaves the rest alone: the role accelerate's `send_to_device`
+    plays in score/pairwise.py:224 and factor/covariance.py:214 of the reference."""
     if isinstance(batch, torch.Tensor):
         return batch.to(device, non_blocking=True)
+    if isinstance(batch, tuple) and hasattr(batch, "_fields"):  # named tuple: positional constructor
+        return type(batch)(*(_send_to_device(item, device) for item in batch))
     if isinstance(batch, (list, tuple)):
-        return type(batch)(_send_to_device(b, device) for b in batch)
-    if isinstance(batch, dict):
-        return {k: _send_to_device(v, device) for k, v in batch.items()}
+        return type(batch)(_send_to_device(item, device) for item in batch)
+    if isinstance(batch, Mapping):
+        moved = {key: _send_to_device(value, device) for key, value in batch.items()}
+        try:
+            return type(batch)(moved)
+        except Exception:  # pylint: disable=broad-exception-caught  # a Mapping that is not built from a dict
+            return moved
+    if hasattr(batch, "to") and not isinstance(batch, (str, bytes)):
+        try:
+            return batch.to(device)
+        except TypeError:
+            return batch
     return batch
 
 
 def _find_batch_size(batch: Any) -> Optional[int]:
+    """Leading dimension of the first tensor found in a nested batch."""
     if isinstance(batch, torch.Tensor):
-        return batch.shape[0]
+        return batch.shape[0] if batch.dim() > 0 else None
+    if isinstance(batch, Mapping):
+        batch = list(batch.values())
     if isinstance(batch, (list, tuple)):
         for item in batch:
-            size = _find_batch_size(item)
-            if size is not None:
-                return size
-    if isinstance(batch, dict):
-        for item in batch.values():
             size = _find_batch_size(item)
             if size is not None:
                 return size

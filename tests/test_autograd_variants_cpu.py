@@ -112,3 +112,63 @@ def test_automatic_batch_size(tmp_path):
                                            initial_per_device_train_batch_size_attempt=16)["all_modules"]
         want_own = analyzer.compute_self_scores("fixed_self", "fixed", train_set, per_device_train_batch_size=8)["all_modules"]
         assert rel(own.numpy(), want_own.numpy()) < 1e-5
+
+
+def test_batch_containers_and_collate_fn(tmp_path):
+    """Language-model style batches: a dataset of dicts, a user collate_fn that returns a Mapping that is not a dict
+    (what transformers' BatchEncoding is) — scores equal the tuple-batch run's."""
+    import collections
+    from typing import NamedTuple
+
+    from torch.utils import data
+
+    from kronfluence_b200.analyzer import _find_batch_size, _send_to_device
+    from kronfluence_b200.utils.dataset import DataLoaderKwargs
+
+    class Pair(NamedTuple):
+        inputs: torch.Tensor
+        targets: torch.Tensor
+
+    nested = {"a": [torch.zeros(3, 2), "text"], "b": Pair(torch.ones(3), torch.ones(3, 1)), "c": None}
+    moved = _send_to_device(collections.UserDict(nested), torch.device("cpu"))
+    assert isinstance(moved, collections.UserDict) and isinstance(moved["b"], Pair) and moved["a"][1] == "text"
+    assert _find_batch_size(moved) == 3 and _find_batch_size({"n": 5, "x": torch.zeros(4, 1)}) == 4
+
+    class DictDataset(data.Dataset):
+        def __init__(self, base):
+            self.base = base
+
+        def __len__(self):
+            return len(self.base)
+
+        def __getitem__(self, index):
+            x, y = self.base[index]
+            return {"inputs": x, "targets": y}
+
+    def collate(rows):
+        return collections.UserDict(inputs=torch.stack([r["inputs"] for r in rows]),
+                                    targets=torch.stack([r["targets"] for r in rows]))
+
+    base_task = fixtures.make_tasks(Task)["mlp"]
+
+    class DictTask(base_task):
+        def compute_train_loss(self, batch, model, sample=False):
+            return super().compute_train_loss((batch["inputs"], batch["targets"]), model, sample)
+
+    model, train_set, query_set = fixtures.make_case("mlp")
+    want = run_everything(model, base_task(), train_set, query_set, tmp_path / "tuple", 8, 3)
+    model, _, _ = fixtures.make_case("mlp")
+    task = DictTask()
+    with oracle_backend():
+        analyzer = Analyzer("dict", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path / "dict"),
+                            disable_tqdm=True)
+        analyzer.set_dataloader_kwargs(DataLoaderKwargs(collate_fn=collate))
+        analyzer.fit_all_factors("f", DictDataset(train_set), per_device_batch_size=8,
+                                 factor_args=FactorArguments(use_empirical_fisher=True))
+        got = analyzer.compute_pairwise_scores("p", "f", DictDataset(query_set), DictDataset(train_set),
+                                               per_device_query_batch_size=3, per_device_train_batch_size=8,
+                                               score_args=ScoreArguments(damping_factor=None))["all_modules"].numpy()
+        own = analyzer.compute_self_scores("s", "f", DictDataset(train_set), per_device_train_batch_size=8,
+                                           dataloader_kwargs=DataLoaderKwargs(collate_fn=collate),
+                                           score_args=ScoreArguments(damping_factor=None))["all_modules"].numpy()
+    assert rel(got, want[1]) < 1e-6 and rel(own, want[2]) < 1e-6
