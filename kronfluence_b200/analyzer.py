@@ -14,6 +14,7 @@ execution model that follow from that, all invisible in the results:
     gather of score columns per query chunk, over NCCL.
 """
 
+import dataclasses
 import math
 from collections.abc import Mapping
 from pathlib import Path
@@ -228,6 +229,16 @@ class Analyzer:
             io.save_json(meta, path)
         self.state.wait_for_everyone()
 
+    def _adopt_loaded_factors(self, factors: FACTOR_TYPE, source_name: str, out_dir: Path, kind: str) -> None:
+        """`load_from_factors_name`: the factors borrowed from another factor set are copied next to the ones being
+        computed, with the arguments they were fitted with (`factor_loaded_<kind>_arguments.json`), so that the new
+        directory is complete on its own (factor_computer.py:433-444,556-567 of the reference)."""
+        if self.state.is_main_process:
+            io.save_factors(out_dir, factors)
+            io.save_json(self._load_factor_args(source_name).to_dict(),
+                         out_dir / f"{FACTOR_ARGUMENTS_NAME}_loaded_{kind}_arguments.json")
+        self.state.wait_for_everyone()
+
     def _load_factor_args(self, factors_name: str) -> FactorArguments:
         path = self.factors_output_dir(factors_name) / f"{FACTOR_ARGUMENTS_NAME}_arguments.json"
         if not path.exists():
@@ -394,8 +405,9 @@ class Analyzer:
         if per_device_batch_size is not None:
             return per_device_batch_size
         if self.state.use_distributed:
-            raise ValueError("`per_device_batch_size` must be given when running on several GPUs "
-                             "(automatic search is single-device, factor_computer.py:120-126 of the reference).")
+            # same exception type as factor_computer.py:120-126 / score_computer.py:182-188 of the reference
+            raise NotImplementedError("Automatic batch size search is not supported for multi-GPU setting. Please "
+                                      "manually configure the batch size by passing in `per_device_batch_size`.")
         return find_executable_batch_size(run, min(initial_attempt, total))
 
     # ------------------------------------------------------------------------------------------
@@ -414,10 +426,12 @@ class Analyzer:
         if self.state.is_main_process:
             out_dir.mkdir(parents=True, exist_ok=True)
         self.state.wait_for_everyone()
+        # order of factor_computer.py:200-214 of the reference: finished results are reused before anything is compared
+        if io.factors_exist(out_dir, COVARIANCE_FACTOR_NAMES) and not overwrite_output_dir:
+            self.logger.info("Found existing covariance matrices at `%s`. Skipping.", out_dir)
+            return
         self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
         if not strategy_config(factor_args.strategy)["covariance"]:
-            return
-        if io.factors_exist(out_dir, COVARIANCE_FACTOR_NAMES) and not overwrite_output_dir:
             return
         self._save_dataset_metadata("covariance", dataset, out_dir, None, overwrite_output_dir)
         update_factor_args(self.model, factor_args)
@@ -478,10 +492,11 @@ class Analyzer:
         if self.state.is_main_process:
             out_dir.mkdir(parents=True, exist_ok=True)
         self.state.wait_for_everyone()
+        if io.factors_exist(out_dir, EIGENDECOMPOSITION_FACTOR_NAMES) and not overwrite_output_dir:
+            self.logger.info("Found existing eigendecomposition results at `%s`. Skipping.", out_dir)
+            return
         self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
         if not strategy_config(factor_args.strategy)["eigen"]:
-            return
-        if io.factors_exist(out_dir, EIGENDECOMPOSITION_FACTOR_NAMES) and not overwrite_output_dir:
             return
         source = factors_name if load_from_factors_name is None else load_from_factors_name
         with self.profiler.profile("Load Covariance"):
@@ -489,6 +504,8 @@ class Analyzer:
         if covariance is None:
             raise FactorsNotFoundError(f"Covariance matrices not found at `{self.factors_output_dir(source)}`. "
                                        "To perform eigendecomposition, covariance matrices need to be fitted first.")
+        if load_from_factors_name is not None:
+            self._adopt_loaded_factors(covariance, load_from_factors_name, out_dir, "covariance")
         eigen: FACTOR_TYPE = {name: {} for name in EIGENDECOMPOSITION_FACTOR_NAMES}
         with self.profiler.profile("Perform Eigendecomposition"):
             self._eigendecompose(covariance, eigen)
@@ -585,11 +602,12 @@ class Analyzer:
         if self.state.is_main_process:
             out_dir.mkdir(parents=True, exist_ok=True)
         self.state.wait_for_everyone()
+        if io.factors_exist(out_dir, LAMBDA_FACTOR_NAMES) and not overwrite_output_dir:
+            self.logger.info("Found existing Lambda matrices at `%s`. Skipping.", out_dir)
+            return
         self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
         config = strategy_config(factor_args.strategy)
         if not config["lambda_"]:
-            return
-        if io.factors_exist(out_dir, LAMBDA_FACTOR_NAMES) and not overwrite_output_dir:
             return
         self._save_dataset_metadata("lambda", dataset, out_dir, None, overwrite_output_dir)
         update_factor_args(self.model, factor_args)
@@ -602,6 +620,8 @@ class Analyzer:
                 raise FactorsNotFoundError(
                     f"Eigendecomposition results not found at `{self.factors_output_dir(source)}`. To fit Lambda "
                     f"matrices for `{factor_args.strategy}`, eigendecomposition must be performed first.")
+            if load_from_factors_name is not None:
+                self._adopt_loaded_factors(eigen, load_from_factors_name, out_dir, "eigendecomposition")
         total = len(dataset) if factor_args.lambda_max_examples is None else min(
             factor_args.lambda_max_examples, len(dataset))
         all_names = get_tracked_module_names(self.model)
@@ -683,18 +703,24 @@ class Analyzer:
                                  dataloader_kwargs, factor_args, overwrite_output_dir=overwrite_output_dir)
 
     def load_all_factors(self, factors_name: str) -> FACTOR_TYPE:
-        """Every factor the strategy produced (computer/computer.py:387-434 of the reference)."""
-        factor_args = self._load_factor_args(factors_name)
-        config = strategy_config(factor_args.strategy)
+        """The factors the strategy's preconditioner reads (computer/computer.py:387-434 of the reference): for EK-FAC
+        the eigendecomposition and Lambda, but not the covariances -- a factor set whose covariances live under another
+        name (`load_from_factors_name`) is complete."""
+        factor_args = self.load_factor_args(factors_name)
+        if factor_args is None:
+            raise FileNotFoundError(f"Factors with name `{factors_name}` was not found at "
+                                    f"`{self.factors_output_dir(factors_name)}`.")
+        config = strategy_config(factor_args.strategy)["config"]
         out: FACTOR_TYPE = {}
-        for needed, loader in ((config["covariance"], self.load_covariance_matrices),
-                               (config["eigen"], self.load_eigendecomposition),
-                               (config["lambda_"], self.load_lambda_matrices)):
+        for needed, loader, what in (
+                (config.requires_covariance_matrices_for_precondition, self.load_covariance_matrices, "covariance matrices"),
+                (config.requires_eigendecomposition_for_precondition, self.load_eigendecomposition, "Eigendecomposition results"),
+                (config.requires_lambda_matrices_for_precondition, self.load_lambda_matrices, "Lambda matrices")):
             if needed:
                 part = loader(factors_name)
                 if part is None:
-                    raise FactorsNotFoundError(f"Factors `{factors_name}` are incomplete at "
-                                               f"`{self.factors_output_dir(factors_name)}`.")
+                    raise FactorsNotFoundError(f"Strategy `{factor_args.strategy}` requires {what}. However, the {what} "
+                                               f"were not found at `{self.factors_output_dir(factors_name)}`.")
                 out.update(part)
         return out
 
@@ -921,8 +947,6 @@ class Analyzer:
                 out_chunks[ALL_MODULE_NAME].append(shared.to(dtype=score_args.score_dtype, device="cpu"))
 
         if score_args.aggregate_train_gradients:
-            if score_args.compute_per_token_scores:
-                raise ValueError("`compute_per_token_scores` cannot be combined with `aggregate_train_gradients`.")
             train_sweep = aggregated_train_sweep  # noqa: F811
 
         if score_args.aggregate_query_gradients:
@@ -1020,9 +1044,20 @@ class Analyzer:
             out_dir.mkdir(parents=True, exist_ok=True)
         self.state.wait_for_everyone()
         if io.scores_path(out_dir).exists() and not overwrite_output_dir:
-            return None
+            self.logger.info("Found existing pairwise scores at `%s`. Skipping.", out_dir)
+            return self.load_pairwise_scores(scores_name)
         self._save_arguments(SCORE_ARGUMENTS_NAME, score_args, out_dir, overwrite_output_dir)
         self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
+        # score_computer.py:287-309 of the reference: per-token scores are switched off (with a warning, after the
+        # arguments were saved) where they have no meaning.  The caller's object is left alone.
+        for clash, why in ((score_args.aggregate_train_gradients, "`aggregate_train_gradients=True`"),
+                           (factor_args.has_shared_parameters, "`has_shared_parameters=True`"),
+                           (self.task.enable_post_process_per_sample_gradient,
+                            "tasks that require `enable_post_process_per_sample_gradient`")):
+            if score_args.compute_per_token_scores and clash:
+                self.logger.warning("Token-wise influence computation is not compatible with %s. Disabling "
+                                    "`compute_per_token_scores`.", why)
+                score_args = dataclasses.replace(score_args, compute_per_token_scores=False)
         self._save_dataset_metadata("query", query_dataset, out_dir, query_indices, overwrite_output_dir)
         self._save_dataset_metadata("train", train_dataset, out_dir, train_indices, overwrite_output_dir)
         with self.profiler.profile("Load All Factors"):
@@ -1077,7 +1112,8 @@ class Analyzer:
                         scores = part
         if partitioned:
             # every partition present: concatenate the data partitions, sum the module partitions
-            scores = self._merge_score_partitions(out_dir, len(data_parts), len(module_parts))
+            scores = self._merge_score_partitions(out_dir, len(data_parts), len(module_parts),
+                                                  score_args.aggregate_train_gradients)
             if scores is None:
                 release_memory()
                 return None  # the remaining partitions belong to another call (`target_*_partitions`)
@@ -1088,9 +1124,11 @@ class Analyzer:
         release_memory()
         return scores
 
-    def _merge_score_partitions(self, out_dir: Path, n_data: int, n_module: int) -> Optional[Dict[str, torch.Tensor]]:
+    def _merge_score_partitions(self, out_dir: Path, n_data: int, n_module: int,
+                                sum_data_partitions: bool = False) -> Optional[Dict[str, torch.Tensor]]:
         """score_computer.py:77-139 `_aggregate_scores` of the reference: module partitions add up, data partitions
-        are concatenated along the train axis; None if a partition file is missing."""
+        are concatenated along the train axis -- or, with `aggregate_train_gradients`, add up as well (each partition
+        holds the score against the sum of ITS train gradients); None if a partition file is missing."""
         blocks: List[Dict[str, torch.Tensor]] = []
         for d_idx in range(n_data):
             block: Dict[str, torch.Tensor] = {}
@@ -1101,6 +1139,8 @@ class Analyzer:
                 for key, value in io.load_file(path).items():
                     block[key] = value if key not in block else block[key] + value
             blocks.append(block)
+        if sum_data_partitions:
+            return {key: torch.stack([blk[key] for blk in blocks]).sum(dim=0) for key in blocks[0]}
         return {key: torch.cat([blk[key] for blk in blocks], dim=1) for key in blocks[0]}
 
     def aggregate_pairwise_scores(self, scores_name: str) -> None:
@@ -1113,7 +1153,8 @@ class Analyzer:
         score_args = ScoreArguments(**io.load_json(args_path))
         if score_args.data_partitions == 1 and score_args.module_partitions == 1:
             return
-        scores = self._merge_score_partitions(out_dir, score_args.data_partitions, score_args.module_partitions)
+        scores = self._merge_score_partitions(out_dir, score_args.data_partitions, score_args.module_partitions,
+                                              score_args.aggregate_train_gradients)
         if scores is None:
             self.logger.warning("Some score partitions of `%s` are missing at %s; nothing aggregated.", scores_name, out_dir)
             return
@@ -1154,7 +1195,8 @@ class Analyzer:
         self.state.wait_for_everyone()
         path = out_dir / "self_scores.safetensors"
         if path.exists() and not overwrite_output_dir:
-            return None
+            self.logger.info("Found existing self-influence scores at `%s`. Skipping.", out_dir)
+            return self.load_self_scores(scores_name)
         self._save_arguments(SCORE_ARGUMENTS_NAME, score_args, out_dir, overwrite_output_dir)
         self._save_arguments(FACTOR_ARGUMENTS_NAME, factor_args, out_dir, overwrite_output_dir)
         self._save_dataset_metadata("train", train_dataset, out_dir, train_indices, overwrite_output_dir)

@@ -57,7 +57,7 @@ def test_end_to_end_matches_reference(case, tmp_path):
     golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
     with oracle_backend():
         analyzer, scores = run_case(case, tmp_path, inject_eigen=golden)
-        factors = analyzer.load_all_factors("f")
+        factors = {**analyzer.load_covariance_matrices("f"), **analyzer.load_all_factors("f")}
     for key, ref in golden.items():
         if not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files") or key.count("/") != 2:
             continue
@@ -655,3 +655,96 @@ def test_logger_and_profiler_helpers(tmp_path, caplog):
                             disable_tqdm=True)
         analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8)
     assert "Action" in analyzer.profiler.summary() and len(analyzer.profiler.durations) > 0
+
+
+def test_error_behaviour_matches_the_reference(tmp_path):
+    """Exception types and the reuse-before-compare order of computer/factor_computer.py:195-262,350-430 and
+    score_computer.py:77-139,467-494 of the reference.  Every expectation below is what the unmodified reference does
+    for the same call sequence (checked against baseline/_ref)."""
+    from kronfluence_b200.utils.exceptions import FactorsNotFoundError
+
+    model, train_set, query_set = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    with oracle_backend():
+        analyzer = Analyzer("errors", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        # stages out of order
+        with pytest.raises(FactorsNotFoundError):
+            analyzer.perform_eigendecomposition("missing")
+        with pytest.raises(FactorsNotFoundError):
+            analyzer.compute_pairwise_scores("s", "missing2", query_set, train_set, per_device_query_batch_size=3,
+                                             per_device_train_batch_size=8)
+        with pytest.raises(FactorsNotFoundError):
+            analyzer.compute_self_scores("s", "missing3", train_set, per_device_train_batch_size=8)
+        with pytest.raises(FileNotFoundError):
+            analyzer.load_all_factors("never_made")
+        # aggregating what was never computed: the missing arguments are reported
+        for aggregate in (analyzer.aggregate_covariance_matrices, analyzer.aggregate_lambda_matrices,
+                          analyzer.aggregate_pairwise_scores, analyzer.aggregate_self_scores):
+            with pytest.raises(ValueError):
+                aggregate("never_made")
+        # partitions
+        with pytest.raises(ValueError, match="target_data_partitions"):
+            analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8, target_data_partitions=[0])
+        with pytest.raises((ValueError, IndexError)):
+            analyzer.fit_covariance_matrices("f2", train_set, per_device_batch_size=8, target_data_partitions=[2],
+                                             factor_args=FactorArguments(covariance_data_partitions=2))
+        with pytest.raises(ValueError):
+            analyzer.fit_covariance_matrices("g", train_set, per_device_batch_size=8,
+                                             factor_args=FactorArguments(covariance_module_partitions=4))  # 3 modules
+        with pytest.raises(ValueError):
+            analyzer.fit_covariance_matrices("h", train_set, per_device_batch_size=8,
+                                             factor_args=FactorArguments(covariance_data_partitions=len(train_set) + 1))
+        # finished factors are reused as they are: neither the arguments nor the dataset are compared
+        fisher = FactorArguments(use_empirical_fisher=True)
+        analyzer.fit_all_factors("ok", train_set, per_device_batch_size=8, factor_args=fisher)
+        before = analyzer.load_covariance_matrices("ok")
+        analyzer.fit_covariance_matrices("ok", train_set, per_device_batch_size=8,
+                                         factor_args=FactorArguments(use_empirical_fisher=False))
+        analyzer.fit_covariance_matrices("ok", query_set, per_device_batch_size=8, factor_args=fisher)
+        after = analyzer.load_covariance_matrices("ok")
+        assert all(torch.equal(after[name][module], tensor) for name, per in before.items() for module, tensor in per.items())
+        assert analyzer.load_factor_args("ok").use_empirical_fisher
+        # an unfinished directory refuses other arguments and another dataset
+        halves = FactorArguments(use_empirical_fisher=True, covariance_data_partitions=2)
+        analyzer.fit_covariance_matrices("half", train_set, per_device_batch_size=8, factor_args=halves,
+                                         target_data_partitions=[0])
+        with pytest.raises(ValueError, match="overwrite_output_dir"):
+            analyzer.fit_covariance_matrices("half", train_set, per_device_batch_size=8, target_data_partitions=[1],
+                                             factor_args=FactorArguments(covariance_data_partitions=2))
+        with pytest.raises(ValueError, match="overwrite_output_dir"):
+            analyzer.fit_covariance_matrices("half", query_set, per_device_batch_size=3, factor_args=halves,
+                                             target_data_partitions=[1])
+        analyzer.fit_covariance_matrices("half", train_set, per_device_batch_size=8, factor_args=halves,
+                                         target_data_partitions=[1])
+        assert analyzer.load_covariance_matrices("half") is not None  # aggregated once the last partition is in
+        assert analyzer.load_pairwise_scores("never") is None and analyzer.load_self_scores("never") is None
+        assert analyzer.load_covariance_matrices("never") is None and analyzer.load_lambda_matrices("never") is None
+
+
+def test_load_from_factors_name(tmp_path):
+    """factor_computer.py:415-444,548-567 of the reference: covariances / eigendecompositions borrowed from another factor
+    set are copied into the new directory together with the arguments they were fitted with, so the new set scores on its
+    own."""
+    model, train_set, query_set = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(Task)["mlp"]()
+    args = FactorArguments(use_empirical_fisher=True)
+    with oracle_backend():
+        analyzer = Analyzer("borrow", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        analyzer.fit_all_factors("whole", train_set, per_device_batch_size=8, factor_args=args)
+        want = analyzer.compute_pairwise_scores("whole", "whole", query_set, train_set, per_device_query_batch_size=3,
+                                                per_device_train_batch_size=8)["all_modules"]
+        analyzer.fit_covariance_matrices("a", train_set, per_device_batch_size=8, factor_args=args)
+        analyzer.perform_eigendecomposition("b", args, load_from_factors_name="a")
+        analyzer.fit_lambda_matrices("c", train_set, per_device_batch_size=8, factor_args=args, load_from_factors_name="b")
+        files_b = set(os.listdir(analyzer.factors_output_dir("b")))
+        files_c = set(os.listdir(analyzer.factors_output_dir("c")))
+        assert {"activation_covariance.safetensors", "factor_loaded_covariance_arguments.json",
+                "gradient_eigenvectors.safetensors"} <= files_b
+        assert {"activation_eigenvectors.safetensors", "factor_loaded_eigendecomposition_arguments.json",
+                "lambda_matrix.safetensors"} <= files_c and "activation_covariance.safetensors" not in files_c
+        got = analyzer.compute_pairwise_scores("c", "c", query_set, train_set, per_device_query_batch_size=3,
+                                               per_device_train_batch_size=8)["all_modules"]
+        assert set(analyzer.load_all_factors("c")) == {"activation_eigenvectors", "activation_eigenvalues",
+                                                       "gradient_eigenvectors", "gradient_eigenvalues", "lambda_matrix",
+                                                       "num_lambda_processed"}
+    assert torch.equal(got, want)

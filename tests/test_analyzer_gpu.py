@@ -49,7 +49,7 @@ def run(case, tmp_path, golden, inject, **score_kwargs):
 def test_end_to_end_with_reference_eigenbasis(case, tmp_path):
     golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
     analyzer, scores, own_eigen = run(case, tmp_path, golden, inject=True)
-    factors = analyzer.load_all_factors("f")
+    factors = {**analyzer.load_covariance_matrices("f"), **analyzer.load_all_factors("f")}
     for key, ref in golden.items():
         if (not key.startswith("f32/") or key.startswith("f32/scores") or key.startswith("f32/files") or "eigen" in key
                 or key.count("/") != 2):

@@ -27,7 +27,7 @@ def run_everything(model, task, train_set, query_set, out_dir, train_bs, query_b
         analyzer = Analyzer("variant", prepare_model(model, task), task, cpu=True, output_dir=str(out_dir), disable_tqdm=True)
         analyzer.fit_all_factors("f", train_set, per_device_batch_size=train_bs,
                                  factor_args=FactorArguments(use_empirical_fisher=True))
-        factors = analyzer.load_all_factors("f")
+        factors = {**analyzer.load_covariance_matrices("f"), **analyzer.load_all_factors("f")}
         pairwise = analyzer.compute_pairwise_scores("p", "f", query_set, train_set, per_device_query_batch_size=query_bs,
                                                     per_device_train_batch_size=train_bs,
                                                     score_args=ScoreArguments(damping_factor=None))["all_modules"]
@@ -98,7 +98,8 @@ def test_automatic_batch_size(tmp_path):
         analyzer.fit_all_factors("fixed", train_set, per_device_batch_size=8, factor_args=args)
         analyzer.fit_all_factors("auto", train_set, per_device_batch_size=None, initial_per_device_batch_size_attempt=16,
                                  factor_args=args)
-        fixed, auto = analyzer.load_all_factors("fixed"), analyzer.load_all_factors("auto")
+        fixed, auto = ({**analyzer.load_covariance_matrices(name), **analyzer.load_all_factors(name)}
+                       for name in ("fixed", "auto"))
         for name in ("activation_covariance", "gradient_covariance", "lambda_matrix"):
             for module, tensor in fixed[name].items():
                 assert rel(auto[name][module], tensor) < 1e-5, (name, module)

@@ -181,3 +181,41 @@ def test_directory_layout_matches_the_reference(partitions, reference, tmp_path)
                 assert partitions > 1 or layout[0] == got[name][0], name
             else:
                 assert layout == got[name], name
+
+
+def test_aggregated_train_gradients_over_data_partitions(reference, tmp_path):
+    """score_computer.py:120-131 of the reference: with `aggregate_train_gradients` the data partitions of a score
+    matrix ADD UP (each holds the score against the sum of its own train gradients) instead of being concatenated, and
+    `compute_per_token_scores` is switched off with a warning."""
+    ref_analyzer, ref_arguments, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+
+    case = "mlp"
+    _, _, _, _, train_bs, query_bs = fixtures.CASES[case]
+    model, train_set, query_set = fixtures.make_case(case)
+    task = fixtures.make_tasks(ref_task.Task)[case]()
+    ref = ref_analyzer.Analyzer("agg", ref_analyzer.prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path),
+                                disable_tqdm=True)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=train_bs,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+    kwargs = dict(damping_factor=None, aggregate_train_gradients=True, data_partitions=2, module_partitions=2,
+                  compute_per_token_scores=True)
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set, per_device_query_batch_size=query_bs,
+                                per_device_train_batch_size=train_bs, score_args=ref_arguments.ScoreArguments(**kwargs))
+    want = ref.load_pairwise_scores("ref")["all_modules"].numpy()
+
+    ours_model, _, _ = fixtures.make_case(case)
+    ours_task = fixtures.make_tasks(Task)[case]()
+    with oracle_backend():
+        ours = Analyzer("agg", prepare_model(ours_model, ours_task), ours_task, cpu=True, output_dir=str(tmp_path),
+                        disable_tqdm=True)
+        got = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=query_bs,
+                                           per_device_train_batch_size=train_bs,
+                                           score_args=ScoreArguments(**kwargs))["all_modules"].numpy()
+        again = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=query_bs,
+                                             per_device_train_batch_size=train_bs, score_args=ScoreArguments(**kwargs))
+    assert want.shape == got.shape == (len(query_set), 1)
+    assert rel(got, want) < 5e-5
+    assert np.array_equal(again["all_modules"].numpy(), got)  # an existing result is returned, not recomputed

@@ -160,6 +160,12 @@ def _ddp_worker(rank, world, port, out_dir):
         scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=2,
                                                   per_device_train_batch_size=4,
                                                   score_args=ScoreArguments(damping_factor=None))
+        # factor_computer.py:120-126 of the reference: the batch-size search is single-device
+        try:
+            analyzer.fit_covariance_matrices("auto", train_set, per_device_batch_size=None)
+            raise AssertionError("automatic batch size under two ranks must raise NotImplementedError")
+        except NotImplementedError:
+            pass
     if rank == 0:
         np.save(os.path.join(out_dir, "scores.npy"), scores["all_modules"].numpy())
     torch.distributed.barrier()
