@@ -1,0 +1,201 @@
+"""Differential test against the UNMODIFIED reference (baseline/_ref) on CPU: the same Analyzer call sequence with the
+same argument combination goes through both engines (here: host logic + the oracle double for the CUDA ops) and the
+results are compared.  Covers argument COMBINATIONS the golden files do not; skipped when the reference is not
+installed."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests import fixtures
+from tests.cpu_backend import oracle_backend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "kronfluence")),
+                                reason="the reference is not installed under baseline/_ref")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def reference():
+    added = [p for p in (os.path.join(ROOT, "oracle", "shims"), os.path.join(ROOT, "baseline", "_ref")) if p not in sys.path]
+    sys.path.extend(added)  # appended: the reference's own `tests` package must not shadow ours
+    try:
+        import kronfluence.analyzer as ref_analyzer  # pylint: disable=import-error
+        import kronfluence.arguments as ref_arguments  # pylint: disable=import-error
+        import kronfluence.task as ref_task  # pylint: disable=import-error
+        from kronfluence.utils.state import State  # pylint: disable=import-error
+
+        State._reset_state()
+        yield ref_analyzer, ref_arguments, ref_task
+        State._reset_state()
+    finally:
+        for p in added:
+            sys.path.remove(p)
+
+
+def both_engines(reference, case, tmp_path):
+    """(reference analyzer, this engine's analyzer, train set, query set) on identical models, sharing one directory so
+    that factors fitted by the reference (its eigenbasis included) are what both score with."""
+    ref_analyzer, _, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.task import Task
+
+    model, train_set, query_set = fixtures.make_case(case)
+    task = fixtures.make_tasks(ref_task.Task)[case]()
+    ref = ref_analyzer.Analyzer("diff", ref_analyzer.prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path),
+                                disable_tqdm=True)
+    model, _, _ = fixtures.make_case(case)
+    task = fixtures.make_tasks(Task)[case]()
+    with oracle_backend():
+        ours = Analyzer("diff", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+    return ref, ours, train_set, query_set
+
+
+SCORE_COMBINATIONS = [
+    dict(compute_per_module_scores=True, query_gradient_accumulation_steps=2),
+    dict(compute_per_module_scores=True, module_partitions=2, data_partitions=3),
+    dict(aggregate_query_gradients=True, data_partitions=2),
+    dict(aggregate_query_gradients=True, aggregate_train_gradients=True, module_partitions=3),
+    dict(query_gradient_low_rank=2, use_full_svd=True, query_gradient_accumulation_steps=2, module_partitions=2),
+    dict(query_gradient_low_rank=2, use_full_svd=True, compute_per_module_scores=True, data_partitions=2),
+    dict(damping_factor=1e-3, data_partitions=2, compute_per_module_scores=True),
+]
+
+
+@pytest.mark.parametrize("index", range(len(SCORE_COMBINATIONS)))
+def test_pairwise_score_argument_combinations(index, reference, tmp_path):
+    _, ref_arguments, _ = reference
+    from kronfluence_b200.arguments import ScoreArguments
+
+    combo = dict(damping_factor=None)
+    combo.update(SCORE_COMBINATIONS[index])
+    ref, ours, train_set, query_set = both_engines(reference, "mlp", tmp_path)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=8,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+    query_indices, train_indices = [5, 0, 3, 6, 1], list(range(3, 40, 2))
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set, per_device_query_batch_size=2,
+                                per_device_train_batch_size=5, query_indices=query_indices, train_indices=train_indices,
+                                score_args=ref_arguments.ScoreArguments(**combo))
+    want = ref.load_pairwise_scores("ref")
+    with oracle_backend():
+        got = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=2,
+                                           per_device_train_batch_size=5, query_indices=query_indices,
+                                           train_indices=train_indices, score_args=ScoreArguments(**combo))
+    assert set(got) == set(want)
+    for name, tensor in want.items():
+        assert got[name].shape == tensor.shape and got[name].dtype == tensor.dtype, name
+        assert rel(got[name].numpy(), tensor.numpy()) < 1e-4, (name, combo)
+
+
+PER_TOKEN_COMBINATIONS = [
+    dict(compute_per_token_scores=True, data_partitions=2),
+    dict(compute_per_token_scores=True, compute_per_module_scores=True, module_partitions=2,
+         query_gradient_accumulation_steps=2),
+    dict(compute_per_token_scores=True, query_gradient_low_rank=2, use_full_svd=True),
+    dict(compute_per_token_scores=True, aggregate_query_gradients=True),
+]
+
+
+@pytest.mark.parametrize("index", range(len(PER_TOKEN_COMBINATIONS)))
+def test_per_token_score_argument_combinations(index, reference, tmp_path):
+    """[Q, T, S] scores of the masked sequence model (module/linear.py:100-111 of the reference)."""
+    _, ref_arguments, _ = reference
+    from kronfluence_b200.arguments import ScoreArguments
+
+    combo = dict(damping_factor=None)
+    combo.update(PER_TOKEN_COMBINATIONS[index])
+    ref, ours, train_set, query_set = both_engines(reference, "seq", tmp_path)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=6,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set, per_device_query_batch_size=2,
+                                per_device_train_batch_size=6, score_args=ref_arguments.ScoreArguments(**combo))
+    want = ref.load_pairwise_scores("ref")
+    with oracle_backend():
+        got = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=3,
+                                           per_device_train_batch_size=4, score_args=ScoreArguments(**combo))
+    assert set(got) == set(want)
+    for name, tensor in want.items():
+        assert got[name].shape == tensor.shape and tensor.dim() == 3, name
+        assert rel(got[name].numpy(), tensor.numpy()) < 1e-4, (name, combo)
+
+
+SELF_COMBINATIONS = [
+    dict(compute_per_module_scores=True, data_partitions=2, module_partitions=2),
+    dict(use_measurement_for_self_influence=True, data_partitions=3),
+    dict(use_measurement_for_self_influence=True, compute_per_module_scores=True, module_partitions=2),
+    dict(query_gradient_low_rank=2, query_gradient_accumulation_steps=3, compute_per_token_scores=True),  # all ignored
+]
+
+
+@pytest.mark.parametrize("index", range(len(SELF_COMBINATIONS)))
+def test_self_score_argument_combinations(index, reference, tmp_path):
+    _, ref_arguments, _ = reference
+    from kronfluence_b200.arguments import ScoreArguments
+
+    combo = dict(damping_factor=None)
+    combo.update(SELF_COMBINATIONS[index])
+    ref, ours, train_set, _ = both_engines(reference, "conv", tmp_path)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=5,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+    train_indices = [0, 2, 3, 5, 8, 13, 18, 1, 4]
+    ref.compute_self_scores("ref", "f", train_set, per_device_train_batch_size=4, train_indices=train_indices,
+                            score_args=ref_arguments.ScoreArguments(**combo))
+    want = ref.load_self_scores("ref")
+    with oracle_backend():
+        got = ours.compute_self_scores("ours", "f", train_set, per_device_train_batch_size=4, train_indices=train_indices,
+                                       score_args=ScoreArguments(**combo))
+    assert set(got) == set(want)
+    for name, tensor in want.items():
+        assert got[name].shape == tensor.shape and got[name].dtype == tensor.dtype, name
+        assert rel(got[name].numpy(), tensor.numpy()) < 1e-4, (name, combo)
+
+
+FACTOR_COMBINATIONS = [
+    dict(covariance_max_examples=17, lambda_max_examples=11),
+    dict(covariance_data_partitions=2, covariance_module_partitions=2, lambda_data_partitions=3, lambda_module_partitions=2),
+    dict(use_iterative_lambda_aggregation=True, lambda_max_examples=None, covariance_max_examples=None),
+    dict(strategy="kfac", covariance_data_partitions=2),
+    dict(strategy="diagonal", lambda_data_partitions=2, lambda_module_partitions=3),
+    dict(strategy="identity"),
+]
+
+
+@pytest.mark.parametrize("index", range(len(FACTOR_COMBINATIONS)))
+def test_factor_argument_combinations(index, reference, tmp_path):
+    """Both engines fit their own factors; covariances and Lambda are compared directly for every strategy that has them,
+    scores for the strategies whose result does not depend on the choice of eigenbasis signs."""
+    _, ref_arguments, _ = reference
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+
+    combo = dict(use_empirical_fisher=True)
+    combo.update(FACTOR_COMBINATIONS[index])
+    ref, ours, train_set, query_set = both_engines(reference, "seq", tmp_path)
+    ref.fit_all_factors("ref", train_set, per_device_batch_size=6, factor_args=ref_arguments.FactorArguments(**combo))
+    with oracle_backend():
+        ours.fit_all_factors("ours", train_set, per_device_batch_size=4, factor_args=FactorArguments(**combo))
+        assert sorted(os.listdir(ours.factors_output_dir("ours"))) == sorted(os.listdir(ref.factors_output_dir("ref")))
+        for load in ("load_covariance_matrices", "load_lambda_matrices"):
+            want, got = getattr(ref, load)("ref"), getattr(ours, load)("ours")
+            assert (want is None) == (got is None), load
+            if want is None or (load == "load_lambda_matrices" and combo.get("strategy", "ekfac") == "ekfac"):
+                continue  # EK-FAC's Lambda lives in the engine's own eigenbasis: compared through the scores
+            for name, per_module in want.items():
+                for module, tensor in per_module.items():
+                    assert got[name][module].shape == tensor.shape and got[name][module].dtype == tensor.dtype
+                    assert rel(got[name][module].numpy(), tensor.numpy()) < 2e-5, (name, module)
+        ref.compute_pairwise_scores("ref", "ref", query_set, train_set, per_device_query_batch_size=2,
+                                    per_device_train_batch_size=6,
+                                    score_args=ref_arguments.ScoreArguments(damping_factor=None))
+        got = ours.compute_pairwise_scores("ours", "ours", query_set, train_set, per_device_query_batch_size=3,
+                                           per_device_train_batch_size=4,
+                                           score_args=ScoreArguments(damping_factor=None))["all_modules"].numpy()
+    want = ref.load_pairwise_scores("ref")["all_modules"].numpy()
+    assert got.shape == want.shape and rel(got, want) < 1e-3, combo
