@@ -199,3 +199,50 @@ def test_factor_argument_combinations(index, reference, tmp_path):
                                            score_args=ScoreArguments(damping_factor=None))["all_modules"].numpy()
     want = ref.load_pairwise_scores("ref")["all_modules"].numpy()
     assert got.shape == want.shape and rel(got, want) < 1e-3, combo
+
+
+DTYPE_COMBINATIONS = [
+    # (FactorArguments overrides, ScoreArguments overrides, tolerance)
+    (dict(), dict(score_dtype=torch.bfloat16), 3e-2),
+    (dict(), dict(per_sample_gradient_dtype=torch.bfloat16, precondition_dtype=torch.bfloat16,
+                  score_dtype=torch.bfloat16), 5e-2),
+    (dict(amp_dtype=torch.bfloat16), dict(amp_dtype=torch.bfloat16), 1e-4),
+    (dict(activation_covariance_dtype=torch.bfloat16, gradient_covariance_dtype=torch.bfloat16,
+          per_sample_gradient_dtype=torch.bfloat16, lambda_dtype=torch.bfloat16), dict(), 1e-1),
+    (dict(offload_activations_to_cpu=True), dict(offload_activations_to_cpu=True), 1e-4),
+]
+
+
+@pytest.mark.parametrize("index", range(len(DTYPE_COMBINATIONS)))
+def test_dtype_argument_combinations(index, reference, tmp_path):
+    """The dtype fields decide what the saved factors and the returned scores are stored as (same as the reference) and
+    which tensor-core mode a stage runs in; values agree to the precision of the lowest dtype involved."""
+    _, ref_arguments, _ = reference
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+
+    factor_overrides, score_overrides, tolerance = DTYPE_COMBINATIONS[index]
+    ref, ours, train_set, query_set = both_engines(reference, "mlp", tmp_path)
+    ref.fit_all_factors("ref", train_set, per_device_batch_size=8,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True, **factor_overrides))
+    ref.compute_pairwise_scores("ref", "ref", query_set, train_set, per_device_query_batch_size=3,
+                                per_device_train_batch_size=8,
+                                score_args=ref_arguments.ScoreArguments(damping_factor=None, **score_overrides))
+    ref.compute_self_scores("ref_self", "ref", train_set, per_device_train_batch_size=8,
+                            score_args=ref_arguments.ScoreArguments(damping_factor=None, **score_overrides))
+    with oracle_backend():
+        ours.fit_all_factors("ours", train_set, per_device_batch_size=8,
+                             factor_args=FactorArguments(use_empirical_fisher=True, **factor_overrides))
+        pairwise = ours.compute_pairwise_scores("ours", "ours", query_set, train_set, per_device_query_batch_size=3,
+                                                per_device_train_batch_size=8,
+                                                score_args=ScoreArguments(damping_factor=None, **score_overrides))
+        own = ours.compute_self_scores("ours_self", "ours", train_set, per_device_train_batch_size=8,
+                                       score_args=ScoreArguments(damping_factor=None, **score_overrides))
+        for loader in ("load_covariance_matrices", "load_eigendecomposition", "load_lambda_matrices"):
+            want, got = getattr(ref, loader)("ref"), getattr(ours, loader)("ours")
+            for name, per_module in want.items():
+                for module, tensor in per_module.items():
+                    assert got[name][module].dtype == tensor.dtype and got[name][module].shape == tensor.shape, (name, module)
+    for got, want in ((pairwise, ref.load_pairwise_scores("ref")), (own, ref.load_self_scores("ref_self"))):
+        got, want = got["all_modules"], want["all_modules"]
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert rel(got.float().numpy(), want.float().numpy()) < tolerance
