@@ -246,3 +246,32 @@ def test_dtype_argument_combinations(index, reference, tmp_path):
         got, want = got["all_modules"], want["all_modules"]
         assert got.dtype == want.dtype and got.shape == want.shape
         assert rel(got.float().numpy(), want.float().numpy()) < tolerance
+
+
+@pytest.mark.parametrize("case", ["mlp", "seq", "conv"])
+def test_sampled_fisher_consumes_the_same_random_stream(case, reference, tmp_path):
+    """`use_empirical_fisher=False` (the default): labels are sampled from the model's predictions inside
+    `Task.compute_train_loss(sample=True)` (factor/covariance.py:221-225, factor/eigen.py:420-424 of the reference).  With
+    the same seed both engines draw the same samples, batch for batch, so the fitted factors coincide."""
+    _, ref_arguments, _ = reference
+    from kronfluence_b200.arguments import FactorArguments
+
+    ref, ours, train_set, _ = both_engines(reference, case, tmp_path)
+    torch.manual_seed(123)
+    ref.fit_all_factors("ref", train_set, per_device_batch_size=6, factor_args=ref_arguments.FactorArguments())
+    with oracle_backend():
+        # eigenvectors of the reference, so that Lambda is expressed in the same basis
+        torch.manual_seed(123)
+        ours.fit_covariance_matrices("ours", train_set, per_device_batch_size=6, factor_args=FactorArguments())
+        ours.perform_eigendecomposition("ours", FactorArguments())
+        from kronfluence_b200.utils import save as io
+
+        io.save_factors(ours.factors_output_dir("ours"), ref.load_eigendecomposition("ref"))
+        ours.fit_lambda_matrices("ours", train_set, per_device_batch_size=6, factor_args=FactorArguments())
+        want, got = ref.load_covariance_matrices("ref"), ours.load_covariance_matrices("ours")
+        for name in ("activation_covariance", "gradient_covariance"):
+            for module, tensor in want[name].items():
+                assert rel(got[name][module].numpy(), tensor.numpy()) < 1e-6, (name, module)
+        want, got = ref.load_lambda_matrices("ref"), ours.load_lambda_matrices("ours")
+        for module, tensor in want["lambda_matrix"].items():
+            assert rel(got["lambda_matrix"][module].numpy(), tensor.numpy()) < 1e-5, module
