@@ -229,6 +229,31 @@ class Analyzer:
             io.save_json(meta, path)
         self.state.wait_for_everyone()
 
+    def _progress(self, iterable, desc: str):
+        """tqdm over a loader on the main process unless `disable_tqdm` (the bars of factor/covariance.py:181-187,
+        score/pairwise.py:185-192 of the reference).  Host-side only: nothing waits for the device."""
+        if self.disable_tqdm or not self.state.is_main_process:
+            return iterable
+        from tqdm import tqdm
+
+        return tqdm(iterable, desc=desc, bar_format="{desc} [{n_fmt}/{total_fmt}] {percentage:3.0f}%|{bar}{postfix} "
+                                                    "[time left: {remaining}, time spent: {elapsed}]")
+
+    def _log_profile_summary(self, name: str) -> None:
+        """`profile=True`: the per-action table goes to the log and to
+        `<output_dir>/profiler_output/<name>_summary_rank_<r>_<time>.txt` (computer/computer.py:324-334 of the reference)."""
+        summary = self.profiler.summary() if self.profiler.enabled else ""
+        if summary == "":
+            return
+        import time
+
+        directory = (self.output_dir / "profiler_output").resolve()
+        directory.mkdir(parents=True, exist_ok=True)
+        self.logger.info(summary)
+        stamp = time.strftime("%Y%m%d_%H%M%S")
+        with open(directory / f"{name}_summary_rank_{self.state.process_index}_{stamp}.txt", "a", encoding="utf-8") as f:
+            f.write(summary)
+
     def _adopt_loaded_factors(self, factors: FACTOR_TYPE, source_name: str, out_dir: Path, kind: str) -> None:
         """`load_from_factors_name`: the factors borrowed from another factor set are copied next to the ones being
         computed, with the arguments they were fitted with (`factor_loaded_<kind>_arguments.json`), so that the new
@@ -322,10 +347,9 @@ class Analyzer:
                   factor_args: FactorArguments, desc: str) -> torch.Tensor:
         """One pass over `loader` with the trackers of `mode` live: forward, (sampled) loss, backward
         (the loop of factor/covariance.py:205-236 and factor/eigen.py:404-433 of the reference)."""
-        del desc
         scaler, autocast = self._amp(factor_args.amp_dtype, factor_args.amp_scale)
         num_processed = torch.zeros(1, dtype=torch.int64)
-        for batch in loader:
+        for batch in self._progress(loader, f"Fitting {desc} matrices"):
             batch = _send_to_device(batch, self.state.device)
             set_attention_mask(self.model, self.task.get_attention_mask(batch))
             self.model.zero_grad(set_to_none=True)
@@ -474,6 +498,7 @@ class Analyzer:
             if self.state.is_main_process:
                 io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
             self.state.wait_for_everyone()
+        self._log_profile_summary(f"factors_{factors_name}_covariance")
 
     def load_covariance_matrices(self, factors_name: str) -> Optional[FACTOR_TYPE]:
         out_dir = self.factors_output_dir(factors_name)
@@ -513,6 +538,7 @@ class Analyzer:
             if self.state.is_main_process:
                 io.save_factors(out_dir, eigen, metadata=factor_args.to_str_dict())
             self.state.wait_for_everyone()
+        self._log_profile_summary(f"factors_{factors_name}_eigendecomposition")
 
     def _eigendecompose(self, covariance: FACTOR_TYPE, eigen: FACTOR_TYPE) -> None:
         """factor/eigen.py:140-224 of the reference for every module and side.  The reference decomposes one matrix at
@@ -637,7 +663,7 @@ class Analyzer:
                                     device=self.state.device)
                 set_mode(self.model, ModuleMode.LAMBDA, names, release_memory=False)
                 loader = self._loader(dataset, batch_size, range(start, end), "eval", dataloader_kwargs)
-                return self._fit_loop(loader, ModuleMode.LAMBDA, names, factor_args, "lambda")
+                return self._fit_loop(loader, ModuleMode.LAMBDA, names, factor_args, "Lambda")
 
             batch_size = self._resolve_batch_size(run, per_device_batch_size, initial_per_device_batch_size_attempt,
                                                   end - start)
@@ -661,6 +687,7 @@ class Analyzer:
             if self.state.is_main_process:
                 io.save_factors(out_dir, merged, metadata=factor_args.to_str_dict())
             self.state.wait_for_everyone()
+        self._log_profile_summary(f"factors_{factors_name}_lambda")
 
     def load_lambda_matrices(self, factors_name: str) -> Optional[FACTOR_TYPE]:
         out_dir = self.factors_output_dir(factors_name)
@@ -802,7 +829,7 @@ class Analyzer:
         for module in modules:
             module.aggregate_precondition = precondition
             module.storage[AGGREGATED_GRADIENT_NAME] = None
-        for batch in loader:
+        for batch in self._progress(loader, "Aggregating query gradients" if query_side else "Aggregating train gradients"):
             batch = _send_to_device(batch, device)
             self.model.zero_grad(set_to_none=True)
             with autocast():
@@ -891,7 +918,7 @@ class Analyzer:
             if cache is not None and cache.complete:
                 replay_sweep(num_queries, sinks)
             else:
-                for batch in train_loader:
+                for batch in self._progress(train_loader, "Computing pairwise scores (training gradient)"):
                     batch = _send_to_device(batch, device)
                     for module in modules:
                         module.score_offset = offset
@@ -981,7 +1008,7 @@ class Analyzer:
         remaining = n_query
         step = 0
         chunk_done = 0
-        for batch in query_loader:
+        for batch in self._progress(query_loader, "Computing pairwise scores (query gradient)"):
             batch = _send_to_device(batch, device)
             base = modules[0].query_count
             local_batch = _find_batch_size(batch)
@@ -1121,6 +1148,7 @@ class Analyzer:
             if self.state.is_main_process:
                 io.save_scores(out_dir, scores, metadata=score_args.to_str_dict())
             self.state.wait_for_everyone()
+        self._log_profile_summary(f"scores_{scores_name}_pairwise")
         release_memory()
         return scores
 
@@ -1227,7 +1255,7 @@ class Analyzer:
                 set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
                 for module in modules:
                     module.allocate_query_store(batch_size, device)
-                for batch in loader:
+                for batch in self._progress(loader, "Computing self-influence scores (measurement)"):
                     batch = _send_to_device(batch, device)
                     count = _find_batch_size(batch)
                     set_mode(self.model, ModuleMode.PRECONDITION_GRADIENT, names, release_memory=False)
@@ -1292,7 +1320,7 @@ class Analyzer:
                 for module in modules:
                     module.storage[SELF_SCORE_VECTOR_NAME] = sinks[module.name]
                 offset = 0
-                for batch in loader:
+                for batch in self._progress(loader, "Computing self-influence scores"):
                     batch = _send_to_device(batch, device)
                     for module in modules:
                         module.score_offset = offset
@@ -1366,6 +1394,7 @@ class Analyzer:
             if self.state.is_main_process:
                 io.save_tensors(scores, path, score_args.to_str_dict())
             self.state.wait_for_everyone()
+        self._log_profile_summary(f"scores_{scores_name}_self")
         return scores
 
     @staticmethod

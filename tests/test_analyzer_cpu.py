@@ -655,6 +655,8 @@ def test_logger_and_profiler_helpers(tmp_path, caplog):
                             disable_tqdm=True)
         analyzer.fit_covariance_matrices("f", train_set, per_device_batch_size=8)
     assert "Action" in analyzer.profiler.summary() and len(analyzer.profiler.durations) > 0
+    written = os.listdir(analyzer.output_dir / "profiler_output")  # computer/computer.py:324-334 of the reference
+    assert len(written) == 1 and written[0].startswith("factors_f_covariance_summary_rank_0_")
 
 
 def test_error_behaviour_matches_the_reference(tmp_path):
