@@ -107,7 +107,10 @@ def find_executable_batch_size(func: Callable[[int], Any], start_batch_size: int
             return batch_size
         except RuntimeError as exc:  # pylint: disable=broad-exception-caught
             message = exc.args[0] if len(exc.args) == 1 and isinstance(exc.args[0], str) else ""
-            if "CUDA out of memory." in message or "can't allocate memory" in message:
+            # the three texts accelerate's `should_reduce_batch_size` (used by the reference) treats as out-of-memory;
+            # libkfb's KFB_ERR_OOM is raised with the first one
+            if any(text in message for text in ("CUDA out of memory.", "cuDNN error: CUDNN_STATUS_NOT_SUPPORTED.",
+                                                "DefaultCPUAllocator: can't allocate memory")):
                 from kronfluence_b200.utils.state import release_memory
 
                 release_memory()

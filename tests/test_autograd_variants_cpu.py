@@ -173,3 +173,48 @@ def test_batch_containers_and_collate_fn(tmp_path):
                                            dataloader_kwargs=DataLoaderKwargs(collate_fn=collate),
                                            score_args=ScoreArguments(damping_factor=None))["all_modules"].numpy()
     assert rel(got, want[1]) < 1e-6 and rel(own, want[2]) < 1e-6
+
+
+def test_batch_size_search_recovers_from_out_of_memory(tmp_path):
+    """utils/dataset.py:66-101 of the reference: the batch size is halved while the run raises an out-of-memory error
+    (libkfb reports KFB_ERR_OOM with the same text); the trackers are reset between attempts, so the result equals a
+    fixed-batch-size run.  Other errors propagate."""
+    from kronfluence_b200.utils.dataset import find_executable_batch_size
+
+    attempts = []
+
+    def fake(batch_size):
+        attempts.append(batch_size)
+        if batch_size > 5:
+            raise RuntimeError("CUDA out of memory. Tried to allocate 1.00 GiB")
+
+    assert find_executable_batch_size(fake, 40) == 5 and attempts == [40, 20, 10, 5]
+    with pytest.raises(RuntimeError, match="reached zero"):
+        find_executable_batch_size(lambda b: (_ for _ in ()).throw(RuntimeError("CUDA out of memory.")), 4)
+    with pytest.raises(ValueError):
+        find_executable_batch_size(lambda b: (_ for _ in ()).throw(ValueError("unrelated")), 4)
+
+    base = fixtures.make_tasks(Task)["mlp"]
+    seen = []
+
+    class TightMemoryTask(base):
+        def compute_train_loss(self, batch, model, sample=False):
+            seen.append(batch[0].shape[0])
+            if batch[0].shape[0] > 6:  # the second batch of an attempt fails: state of the first must be discarded
+                if len(seen) % 2 == 0:
+                    raise RuntimeError("CUDA out of memory. Tried to allocate 2.00 GiB")
+            return super().compute_train_loss(batch, model, sample)
+
+    model, train_set, _ = fixtures.make_case("mlp")
+    with oracle_backend():
+        task = TightMemoryTask()
+        analyzer = Analyzer("oom", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        args = FactorArguments(use_empirical_fisher=True)
+        analyzer.fit_covariance_matrices("auto", train_set, per_device_batch_size=None,
+                                         initial_per_device_batch_size_attempt=24, factor_args=args)
+        analyzer.fit_covariance_matrices("fixed", train_set, per_device_batch_size=6, factor_args=args)
+        auto, fixed = analyzer.load_covariance_matrices("auto"), analyzer.load_covariance_matrices("fixed")
+    assert max(seen) == 24 and 12 in seen
+    for name, per_module in fixed.items():
+        for module, tensor in per_module.items():
+            assert rel(auto[name][module].double().numpy(), tensor.double().numpy()) < 1e-6, (name, module)
