@@ -275,3 +275,79 @@ def test_sampled_fisher_consumes_the_same_random_stream(case, reference, tmp_pat
         want, got = ref.load_lambda_matrices("ref"), ours.load_lambda_matrices("ours")
         for module, tensor in want["lambda_matrix"].items():
             assert rel(got["lambda_matrix"][module].numpy(), tensor.numpy()) < 1e-5, module
+
+
+def test_unusual_layer_shapes(reference, tmp_path):
+    """Grouped + dilated convolution, depthwise convolution with a non-square kernel and stride, a bias-free Linear that
+    sees [B, H, W, d] inputs (every middle dimension is a position, module/linear.py:30-54 of the reference)."""
+    import torch.nn.functional as F
+    from torch import nn
+    from torch.utils import data
+
+    ref_analyzer, ref_arguments, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(4, 6, 3, padding=2, dilation=2, groups=2)
+            self.tok = nn.Linear(6, 5, bias=False)
+            self.dw = nn.Conv2d(5, 5, (1, 3), stride=(1, 2), groups=5, bias=False)
+            self.head = nn.Linear(5 * 6 * 2, 3)
+
+        def forward(self, x):
+            h = torch.relu(self.conv(x))                          # [B, 6, 6, 6]
+            h = torch.tanh(self.tok(h.permute(0, 2, 3, 1)))       # Linear on [B, 6, 6, 6] -> [B, 6, 6, 5]
+            h = torch.relu(self.dw(h.permute(0, 3, 1, 2)))        # [B, 5, 6, 2]
+            return self.head(h.flatten(1))
+
+    def make_task(base):
+        class Classification(base):
+            def compute_train_loss(self, batch, model, sample=False):
+                inputs, labels = batch
+                return F.cross_entropy(model(inputs), labels, reduction="sum")
+
+            def compute_measurement(self, batch, model):
+                return self.compute_train_loss(batch, model)
+
+        return Classification()
+
+    generator = torch.Generator().manual_seed(0)
+    inputs = torch.randn(30, 4, 6, 6, generator=generator)
+    labels = torch.randint(0, 3, (30,), generator=generator)
+    train_set = data.TensorDataset(inputs[:23], labels[:23])
+    query_set = data.TensorDataset(inputs[23:], labels[23:])
+    torch.manual_seed(1)
+    theirs, mine = Net(), Net()
+    mine.load_state_dict(theirs.state_dict())
+
+    task = make_task(ref_task.Task)
+    ref = ref_analyzer.Analyzer("shapes", ref_analyzer.prepare_model(theirs, task), task, cpu=True, output_dir=str(tmp_path),
+                                disable_tqdm=True)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=7,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+    score_kwargs = dict(damping_factor=None, compute_per_module_scores=True)
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set, per_device_query_batch_size=3,
+                                per_device_train_batch_size=7, score_args=ref_arguments.ScoreArguments(**score_kwargs))
+    ref.compute_self_scores("ref_self", "f", train_set, per_device_train_batch_size=7,
+                            score_args=ref_arguments.ScoreArguments(damping_factor=None))
+    task = make_task(Task)
+    with oracle_backend():
+        ours = Analyzer("shapes", prepare_model(mine, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        pairwise = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                per_device_train_batch_size=5, score_args=ScoreArguments(**score_kwargs))
+        own = ours.compute_self_scores("ours_self", "f", train_set, per_device_train_batch_size=5,
+                                       score_args=ScoreArguments(damping_factor=None))["all_modules"]
+        ours.fit_covariance_matrices("g", train_set, per_device_batch_size=5,
+                                     factor_args=FactorArguments(use_empirical_fisher=True))
+        want, got = ref.load_covariance_matrices("f"), ours.load_covariance_matrices("g")
+    for name, per_module in want.items():
+        for module, tensor in per_module.items():
+            assert rel(got[name][module].double().numpy(), tensor.double().numpy()) < 1e-6, (name, module)
+    want = ref.load_pairwise_scores("ref")
+    assert set(want) == set(pairwise) == {"conv", "tok", "dw", "head"}
+    for module, tensor in want.items():
+        assert rel(pairwise[module].numpy(), tensor.numpy()) < 1e-5, module
+    assert rel(own.numpy(), ref.load_self_scores("ref_self")["all_modules"].numpy()) < 1e-5
