@@ -351,3 +351,78 @@ def test_unusual_layer_shapes(reference, tmp_path):
     for module, tensor in want.items():
         assert rel(pairwise[module].numpy(), tensor.numpy()) < 1e-5, module
     assert rel(own.numpy(), ref.load_self_scores("ref_self")["all_modules"].numpy()) < 1e-5
+
+
+def test_transformer_encoder_with_attention_mask(reference, tmp_path):
+    """A (tiny, randomly initialised) Hugging Face BERT classifier with dictionary batches and padding: 14 tracked Linear
+    layers, among them the pooler and classifier heads that see [B, d] inputs and must ignore the [B, S] attention mask
+    (module/linear.py:30-54 of the reference).  Mirrors tests/testable_tasks/text_classification.py of the reference."""
+    transformers = pytest.importorskip("transformers")
+    import torch.nn.functional as F
+    from torch.utils import data
+
+    ref_analyzer, ref_arguments, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+
+    config = transformers.BertConfig(hidden_size=16, num_hidden_layers=2, num_attention_heads=2, intermediate_size=24,
+                                     vocab_size=50, max_position_embeddings=16, num_labels=3, hidden_dropout_prob=0.0,
+                                     attention_probs_dropout_prob=0.0)
+    torch.manual_seed(0)
+    theirs = transformers.BertForSequenceClassification(config)
+    mine = transformers.BertForSequenceClassification(config)
+    mine.load_state_dict(theirs.state_dict())
+
+    class Padded(data.Dataset):
+        def __init__(self, count, seed):
+            generator = torch.Generator().manual_seed(seed)
+            self.ids = torch.randint(1, 50, (count, 9), generator=generator)
+            self.lengths = torch.randint(3, 10, (count,), generator=generator)
+            self.labels = torch.randint(0, 3, (count,), generator=generator)
+
+        def __len__(self):
+            return len(self.labels)
+
+        def __getitem__(self, index):
+            mask = (torch.arange(9) < self.lengths[index]).long()
+            return {"input_ids": self.ids[index] * mask, "attention_mask": mask, "labels": self.labels[index]}
+
+    def make_task(base):
+        class TextClassification(base):
+            def compute_train_loss(self, batch, model, sample=False):
+                logits = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"]).logits
+                return F.cross_entropy(logits, batch["labels"], reduction="sum")
+
+            def compute_measurement(self, batch, model):
+                return self.compute_train_loss(batch, model)
+
+            def get_attention_mask(self, batch):
+                return batch["attention_mask"]
+
+        return TextClassification()
+
+    train_set, query_set = Padded(21, 1), Padded(5, 2)
+    task = make_task(ref_task.Task)
+    ref = ref_analyzer.Analyzer("bert", ref_analyzer.prepare_model(theirs, task), task, cpu=True, output_dir=str(tmp_path),
+                                disable_tqdm=True)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=7,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+    score_kwargs = dict(damping_factor=None, compute_per_module_scores=True)
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set, per_device_query_batch_size=3,
+                                per_device_train_batch_size=7, score_args=ref_arguments.ScoreArguments(**score_kwargs))
+    want = ref.load_pairwise_scores("ref")
+    task = make_task(Task)
+    with oracle_backend():
+        ours = Analyzer("bert", prepare_model(mine, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        got = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=2,
+                                           per_device_train_batch_size=5, score_args=ScoreArguments(**score_kwargs))
+        ours.fit_covariance_matrices("g", train_set, per_device_batch_size=5,
+                                     factor_args=FactorArguments(use_empirical_fisher=True))
+        theirs_cov, mine_cov = ref.load_covariance_matrices("f"), ours.load_covariance_matrices("g")
+    assert len(want) == 14 and set(got) == set(want)
+    for module, tensor in want.items():
+        assert rel(got[module].numpy(), tensor.numpy()) < 2e-5, module
+    for name, per_module in theirs_cov.items():
+        for module, tensor in per_module.items():
+            assert rel(mine_cov[name][module].double().numpy(), tensor.double().numpy()) < 1e-6, (name, module)
