@@ -26,7 +26,12 @@ class DataLoaderKwargs:
     persistent_workers: bool = False
     pin_memory_device: str = ""
 
+    def to_dict(self) -> Dict[str, Any]:
+        """Every field (the KwargsHandler interface the reference's class inherits from accelerate)."""
+        return {f.name: getattr(self, f.name) for f in fields(self)}
+
     def to_kwargs(self) -> Dict[str, Any]:
+        """Only the fields that differ from their defaults: what is passed on to `DataLoader(...)`."""
         default = DataLoaderKwargs()
         return {f.name: getattr(self, f.name) for f in fields(self) if getattr(self, f.name) != getattr(default, f.name)}
 
