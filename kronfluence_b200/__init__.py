@@ -16,6 +16,13 @@ _LAZY = {
 }
 
 
+__all__ = [*_LAZY, "utils", "__version__"]
+
+
+def __dir__():
+    return sorted(set(globals()) | set(_LAZY))
+
+
 def __getattr__(name):
     if name in _LAZY:
         import importlib
