@@ -426,3 +426,120 @@ def test_transformer_encoder_with_attention_mask(reference, tmp_path):
     for name, per_module in theirs_cov.items():
         for module, tensor in per_module.items():
             assert rel(mine_cov[name][module].double().numpy(), tensor.double().numpy()) < 1e-6, (name, module)
+
+
+def test_shared_module_agrees_with_autograd(reference, tmp_path):
+    """A module used twice per forward pass (`has_shared_parameters`).  Covariances, Lambda and plain self-influence equal
+    the reference's.  For pairwise scores and self-influence with the measurement the reference keeps one use only (its
+    backward hook clears the pending hooks of the other uses: tracker/pairwise_score.py:85-94,
+    tracker/self_score.py:200-214) -- this engine adds every use, which is what autograd gives.
+    With the identity strategy autograd is an exact ground truth: <grad m(z_q), grad L(z_t)> on the module's parameters."""
+    import torch.nn.functional as F
+    from torch import nn
+    from torch.utils import data
+
+    ref_analyzer, ref_arguments, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+    from kronfluence_b200.utils import save as io
+
+    class Shared(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = nn.Linear(7, 7)
+            self.head = nn.Linear(7, 3)
+
+        def forward(self, x):
+            hidden = torch.relu(self.lin(x))
+            hidden = torch.relu(self.lin(hidden))  # the same parameters again
+            return self.head(hidden)
+
+    def make_task(base):
+        class Classification(base):
+            def compute_train_loss(self, batch, model, sample=False):
+                inputs, labels = batch
+                return F.cross_entropy(model(inputs), labels, reduction="sum")
+
+            def compute_measurement(self, batch, model):
+                return self.compute_train_loss(batch, model)
+
+        return Classification()
+
+    generator = torch.Generator().manual_seed(0)
+    inputs, labels = torch.randn(24, 7, generator=generator), torch.randint(0, 3, (24,), generator=generator)
+    train_set, query_set = data.TensorDataset(inputs[:19], labels[:19]), data.TensorDataset(inputs[19:], labels[19:])
+    torch.manual_seed(1)
+    plain = Shared()
+
+    def engines(name):
+        theirs, mine = Shared(), Shared()
+        theirs.load_state_dict(plain.state_dict())
+        mine.load_state_dict(plain.state_dict())
+        task = make_task(ref_task.Task)
+        ref = ref_analyzer.Analyzer(name, ref_analyzer.prepare_model(theirs, task), task, cpu=True, output_dir=str(tmp_path),
+                                    disable_tqdm=True)
+        task = make_task(Task)
+        with oracle_backend():
+            ours = Analyzer(name, prepare_model(mine, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        return ref, ours
+
+    # ---- EK-FAC: everything the reference handles for shared modules ----
+    ref, ours = engines("ekfac")
+    factor_kwargs = dict(use_empirical_fisher=True, has_shared_parameters=True)
+    score_kwargs = dict(damping_factor=None, compute_per_module_scores=True)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=6, factor_args=ref_arguments.FactorArguments(**factor_kwargs))
+    ref.compute_self_scores("ref_self", "f", train_set, per_device_train_batch_size=6,
+                            score_args=ref_arguments.ScoreArguments(**score_kwargs))
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set, per_device_query_batch_size=3,
+                                per_device_train_batch_size=6, score_args=ref_arguments.ScoreArguments(**score_kwargs))
+    with oracle_backend():
+        own = ours.compute_self_scores("ours_self", "f", train_set, per_device_train_batch_size=5,
+                                       score_args=ScoreArguments(**score_kwargs))
+        pairwise = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                per_device_train_batch_size=5, score_args=ScoreArguments(**score_kwargs))
+        ours.fit_covariance_matrices("g", train_set, per_device_batch_size=5, factor_args=FactorArguments(**factor_kwargs))
+        ours.perform_eigendecomposition("g", FactorArguments(**factor_kwargs))
+        io.save_factors(ours.factors_output_dir("g"), ref.load_eigendecomposition("f"))  # Lambda in the same basis
+        ours.fit_lambda_matrices("g", train_set, per_device_batch_size=5, factor_args=FactorArguments(**factor_kwargs))
+        for loader in ("load_covariance_matrices", "load_lambda_matrices"):
+            want, got = getattr(ref, loader)("f"), getattr(ours, loader)("g")
+            for name, per_module in want.items():
+                for module, tensor in per_module.items():
+                    assert rel(got[name][module].double().numpy(), tensor.double().numpy()) < 1e-6, (name, module)
+    want = ref.load_self_scores("ref_self")
+    for module in ("lin", "head"):
+        assert rel(own[module].numpy(), want[module].numpy()) < 1e-5, module
+    assert rel(pairwise["head"].numpy(), ref.load_pairwise_scores("ref")["head"].numpy()) < 1e-5
+
+    # ---- identity strategy: autograd is the ground truth for the shared module ----
+    ref, ours = engines("identity")
+    factor_kwargs = dict(strategy="identity", has_shared_parameters=True)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=6, factor_args=ref_arguments.FactorArguments(**factor_kwargs))
+    measurement = dict(compute_per_module_scores=True, use_measurement_for_self_influence=True)
+    ref.compute_self_scores("ref_self", "f", train_set, per_device_train_batch_size=6,
+                            score_args=ref_arguments.ScoreArguments(**measurement))
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set, per_device_query_batch_size=3,
+                                per_device_train_batch_size=6,
+                                score_args=ref_arguments.ScoreArguments(compute_per_module_scores=True))
+    with oracle_backend():
+        own = ours.compute_self_scores("ours_self", "f", train_set, per_device_train_batch_size=5,
+                                       score_args=ScoreArguments(**measurement))["lin"].numpy()
+        pairwise = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                per_device_train_batch_size=5,
+                                                score_args=ScoreArguments(compute_per_module_scores=True))["lin"].numpy()
+
+    def gradients(dataset):
+        rows = []
+        for x, y in dataset:
+            plain.zero_grad()
+            F.cross_entropy(plain(x[None]), y[None], reduction="sum").backward()
+            rows.append(torch.cat([plain.lin.weight.grad.flatten(), plain.lin.bias.grad.flatten()]).clone())
+        return torch.stack(rows)
+
+    train_gradients, query_gradients = gradients(train_set), gradients(query_set)
+    assert rel(own, (train_gradients * train_gradients).sum(dim=1).numpy()) < 1e-5
+    assert rel(pairwise, (query_gradients @ train_gradients.T).numpy()) < 1e-5
+    # the reference's one-use-only result is far from both (recorded so that a change upstream is noticed)
+    assert rel(ref.load_self_scores("ref_self")["lin"].numpy(), own) > 1e-2
+    assert rel(ref.load_pairwise_scores("ref")["lin"].numpy(), pairwise) > 1e-2
