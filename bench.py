@@ -914,10 +914,13 @@ def main() -> None:
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        cpu = cpu_reference(spec, steps, max(1, min(warmup, 2)))
+        # exactly K timed and W warm-up passes over the bounded sample (about 0.7 s each on the target layer); only an
+        # absurd K is clamped so that the arm still ends within minutes.  `n_gpus` echoes the launch (the arm itself runs
+        # on the host cores of rank 0: cpu_baseline.cores).
+        steps = max(1, min(args.steps, 100))
+        cpu = cpu_reference(spec, steps, max(0, min(warmup, 20)))
         line = {"impl": "reference", "metric": "pairwise influence scores/sec", "value": cpu["value"], "unit": "scores/s",
-                "n_gpus": 0, "steps": steps, "warmup": warmup, "ms_per_step": cpu["ms_per_step"],
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cpu["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cpu["value"], "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

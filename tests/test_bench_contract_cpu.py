@@ -10,15 +10,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(extra_env=None):
+def _run(extra_env=None, steps=1, gpus=1):
     env = dict(os.environ)
     env.update(extra_env or {})
-    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                           "--warmup", "1", "--workload", "mlp"], capture_output=True, text=True, env=env, timeout=600)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", str(steps),
+                           "--warmup", "1", "--workload", "mlp", "--gpus", str(gpus)], capture_output=True, text=True,
+                          env=env, timeout=600)
 
 
 def test_reference_arm_line():
-    res = _run()
+    res = _run(steps=7, gpus=2)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -30,6 +31,7 @@ def test_reference_arm_line():
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+    assert line["steps"] == 7 and line["warmup"] == 1 and line["n_gpus"] == 2  # K, W and N of the launch, as given
 
 
 def test_reference_arm_other_ranks_stay_silent():
