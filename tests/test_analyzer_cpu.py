@@ -180,7 +180,6 @@ def test_self_scores_match_reference(case, tmp_path):
     """Analyzer.compute_self_scores vs the reference's (tests/scores/test_self_scores.py of the reference checks
     the same quantity against diag(pairwise))."""
     golden = dict(np.load(os.path.join(GOLDEN, f"e2e_{case}.npz")))
-    tasks = fixtures.make_tasks(Task)
     with oracle_backend():
         analyzer, _ = run_case(case, tmp_path, inject_eigen=golden)
         _, train_set, _ = fixtures.make_case(case)
@@ -189,7 +188,6 @@ def test_self_scores_match_reference(case, tmp_path):
         again = analyzer.load_self_scores("self")
     assert rel(scores["all_modules"].numpy(), golden["f32/self_scores"]) < 5e-5
     assert torch.equal(again["all_modules"], scores["all_modules"])
-    del tasks
 
 
 def test_per_token_scores(tmp_path):

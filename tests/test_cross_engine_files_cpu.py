@@ -8,7 +8,6 @@ import sys
 
 import numpy as np
 import pytest
-import torch
 
 from tests import fixtures
 from tests.cpu_backend import oracle_backend

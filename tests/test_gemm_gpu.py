@@ -2,7 +2,7 @@
 operands, so the only admissible differences are the dropped lo*lo term (~2^-32 relative) and fp32
 accumulation order."""
 
-import ctypes
+
 
 import pytest
 import torch
