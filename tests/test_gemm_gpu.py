@@ -2,8 +2,6 @@
 operands, so the only admissible differences are the dropped lo*lo term (~2^-32 relative) and fp32
 accumulation order."""
 
-
-
 import pytest
 import torch
 
