@@ -969,9 +969,10 @@ class Analyzer:
                 ops.pairwise_scores_explicit(layer, store, num_queries, train_aggregate[module.name].unsqueeze(0), sink, 0,
                                              accumulate=True, precision=precision_of(score_args.score_dtype))
                 if per_module:
-                    out_chunks[module.name].append(sink.to(dtype=score_args.score_dtype, device="cpu"))
+                    out_chunks[module.name].append(select_rows(sink).to(dtype=score_args.score_dtype, device="cpu"))
             if not per_module:
-                out_chunks[ALL_MODULE_NAME].append(shared.to(dtype=score_args.score_dtype, device="cpu"))
+                # rows back in dataset order, wrap-padded duplicates of a ragged last query batch dropped (as in train_sweep)
+                out_chunks[ALL_MODULE_NAME].append(select_rows(shared).to(dtype=score_args.score_dtype, device="cpu"))
 
         if score_args.aggregate_train_gradients:
             train_sweep = aggregated_train_sweep  # noqa: F811

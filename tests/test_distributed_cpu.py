@@ -97,6 +97,14 @@ def _worker(rank, world, port, case, out_dir):
                                                       score_args=ScoreArguments(damping_factor=None,
                                                                                 aggregate_query_gradients=True,
                                                                                 aggregate_train_gradients=True))
+        # factors borrowed from another name (main process copies them, every rank waits) + aggregated train gradients
+        # over two data partitions (each partition's score adds up; score_computer.py:120-131 of the reference)
+        analyzer.fit_lambda_matrices("borrowed", train_set, per_device_batch_size=4, factor_args=fa,
+                                     load_from_factors_name="f")
+        agg_train = analyzer.compute_pairwise_scores("s_agg_train", "borrowed", query_set, train_set,
+                                                     per_device_query_batch_size=2, per_device_train_batch_size=4,
+                                                     score_args=ScoreArguments(damping_factor=None, data_partitions=2,
+                                                                               aggregate_train_gradients=True))
         own = analyzer.compute_self_scores("self", "f", train_set, per_device_train_batch_size=4,
                                            score_args=ScoreArguments(damping_factor=None))
         own_m = analyzer.compute_self_scores("self_m", "f", train_set, per_device_train_batch_size=4,
@@ -108,6 +116,7 @@ def _worker(rank, world, port, case, out_dir):
         np.save(os.path.join(out_dir, "scores.npy"), scores["all_modules"].numpy())
         np.save(os.path.join(out_dir, "scores_lowrank.npy"), lowrank["all_modules"].numpy())
         np.save(os.path.join(out_dir, "scores_aggregated.npy"), aggregated["all_modules"].numpy())
+        np.save(os.path.join(out_dir, "scores_agg_train.npy"), agg_train["all_modules"].numpy())
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -132,6 +141,10 @@ def test_two_ranks_match_reference(case, tmp_path):
     agg, ref_agg = np.load(tmp_path / "scores_aggregated.npy"), golden["f32/scores_agg_both"]
     assert agg.shape == ref_agg.shape == (1, 1)
     assert abs(agg - ref_agg).max() / abs(ref_agg).max() < 5e-5
+    # aggregated train gradients summed over two data partitions, on factors borrowed through load_from_factors_name
+    agg_train, ref_agg_train = np.load(tmp_path / "scores_agg_train.npy"), golden["f32/scores_agg_train"]
+    assert agg_train.shape == ref_agg_train.shape
+    assert np.linalg.norm(agg_train - ref_agg_train) / np.linalg.norm(ref_agg_train) < 5e-5
 
 
 def _ddp_worker(rank, world, port, out_dir):
