@@ -60,6 +60,26 @@ def _compute(out_dir, save_path):
                                                   score_args=ScoreArguments(damping_factor=None, **overrides))
             for module, tensor in scores.items():
                 results[f"self/{label}/{module}"] = tensor.double().numpy()
+        # the other strategies, a task that post-processes per-sample gradients (dense-gradient path), shared parameters
+        for strategy in ("kfac", "diagonal", "identity"):
+            analyzer.fit_all_factors(strategy, train_set, per_device_batch_size=4,
+                                     factor_args=FactorArguments(strategy=strategy, use_empirical_fisher=True))
+            scores = analyzer.compute_pairwise_scores(strategy, strategy, query_set, train_set,
+                                                      per_device_query_batch_size=2, per_device_train_batch_size=4,
+                                                      score_args=ScoreArguments(damping_factor=None))
+            results[f"strategy/{strategy}"] = scores["all_modules"].double().numpy()
+        clipped_task = fixtures.make_postprocess_tasks(Task)["seq"]()
+        model, _, _ = fixtures.make_case("seq")
+        clipped = Analyzer("world_clipped", prepare_model(model, clipped_task), clipped_task, cpu=True, output_dir=out_dir,
+                           disable_tqdm=True)
+        clipped.fit_all_factors("f", train_set, per_device_batch_size=3,
+                                factor_args=FactorArguments(use_empirical_fisher=True, has_shared_parameters=True))
+        results["postprocess/pairwise"] = clipped.compute_pairwise_scores(
+            "p", "f", query_set, train_set, per_device_query_batch_size=2, per_device_train_batch_size=3,
+            score_args=ScoreArguments(damping_factor=None))["all_modules"].double().numpy()
+        results["postprocess/self"] = clipped.compute_self_scores(
+            "s", "f", train_set, per_device_train_batch_size=3,
+            score_args=ScoreArguments(damping_factor=None))["all_modules"].double().numpy()
     if analyzer.state.is_main_process:
         np.savez(save_path, **results)
 
