@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with `-m gpu` under gpurun)")
+    # the installed reference (differential tests) still calls torch.cuda.amp.GradScaler(...): not ours to fix
+    config.addinivalue_line("filterwarnings", "ignore:.*torch.cuda.amp.GradScaler.*:FutureWarning")
 
 
 def pytest_collection_modifyitems(config, items):
