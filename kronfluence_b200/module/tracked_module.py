@@ -582,11 +582,12 @@ class PairwiseScoreTracker(BaseTracker):
                 # here in the basis of the query store (rotate the dense train gradients first)
                 if sink.per_token:
                     raise ValueError("`compute_per_token_scores` cannot be combined with `post_process_per_sample_gradient`.")
-                if isinstance(store, ops.LowRankStore):
-                    raise NotImplementedError("`query_gradient_low_rank` with `post_process_per_sample_gradient` is not "
-                                              "supported; use dense query gradients.")
                 flat = module.flat_layer()
                 precision = precision_of(module.score_args.score_dtype)
+                if isinstance(store, ops.LowRankStore):
+                    # "qki,toi,qok->qt" (tracker/pairwise_score.py:26-39 of the reference): the chunk's rank-r factors
+                    # are multiplied out for the explicit contraction (a transient dense store per train batch)
+                    store = ops.lowrank_dense_store(store, module.query_count, precision)
                 if qa is not None:
                     dense = ops.transform_gradient(flat, dense, qa, qg, None, 1.0, precision=precision)
                 ops.pairwise_scores_explicit(flat, store, module.query_count, dense, sink.get(1), module.score_offset,

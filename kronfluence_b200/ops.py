@@ -356,6 +356,17 @@ class LowRankStore:
         return torch.matmul(self.left_t.to_float().transpose(1, 2), self.right.to_float())
 
 
+def lowrank_dense_store(store: LowRankStore, count: int, precision: int = PREC_FP32) -> Split:
+    """The first `count` rank-r query gradients multiplied out into a dense operand store.  Only the explicit-gradient
+    path needs it (a task that post-processes per-sample gradients scored against low-rank queries: "qki,toi,qok->qt",
+    tracker/pairwise_score.py:26-39 of the reference); the factors stay what is kept and all-gathered."""
+    left_t = store.left_t.to_float()[:count]  # [q, r, d_out]
+    right = store.right.to_float()[:count]    # [q, r, d_in(+1)]
+    dense = make_query_store(store.rows, store.cols, count, left_t.device, precision)
+    load_query_store(dense, torch.matmul(left_t.transpose(1, 2), right).to(torch.float32), 0, precision)
+    return dense
+
+
 def make_lowrank_store(d_out: int, d_in_total: int, rank: int, capacity: int, device,
                        precision: int = PREC_FP32) -> LowRankStore:
     return LowRankStore(d_out, d_in_total, rank, capacity, device, precision)
@@ -420,7 +431,7 @@ def pairwise_scores_lowrank(layer: KfbLayer, store: LowRankStore, num_queries: i
 
 
 __all__ = [
-    "LowRankStore", "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank",
+    "LowRankStore", "make_lowrank_store", "lowrank_factorize", "pairwise_scores_lowrank", "lowrank_dense_store",
     "PREC_FP32", "PREC_BF16", "PREC_STRICT", "PRECOND_IDENTITY", "PRECOND_DIAGONAL", "PRECOND_EIGEN", "EigenOperands",
     "cov_accum_activation", "cov_accum_gradient", "eigh_sym", "lambda_accum", "lambda_invert",
     "make_query_store", "make_eigen_operands", "module_factor_dims", "load_query_store", "precondition", "pairwise_scores", "self_scores", "layer_of", "factor_dims", "workspace",

@@ -95,6 +95,8 @@ class FakeLowRankStore:
         self.rows, self.cols, self.rank, self.batch = d_out, d_in_total, rank, capacity
         self.left_t = SimpleNamespace(storage=torch.zeros(1, capacity, rank, d_out, dtype=torch.float64))
         self.right = SimpleNamespace(storage=torch.zeros(1, capacity, rank, d_in_total, dtype=torch.float64))
+        self.left_t.to_float = lambda: self.left_t.storage[0]
+        self.right.to_float = lambda: self.right.storage[0]
         self.scratch = None
 
     def scratch_for(self, batch, device):

@@ -543,3 +543,57 @@ def test_shared_module_agrees_with_autograd(reference, tmp_path):
     # the reference's one-use-only result is far from both (recorded so that a change upstream is noticed)
     assert rel(ref.load_self_scores("ref_self")["lin"].numpy(), own) > 1e-2
     assert rel(ref.load_pairwise_scores("ref")["lin"].numpy(), pairwise) > 1e-2
+
+
+POSTPROCESS_COMBINATIONS = [
+    dict(compute_per_module_scores=True, data_partitions=2),
+    dict(query_gradient_accumulation_steps=2, module_partitions=3),
+    dict(aggregate_query_gradients=True, module_partitions=2),
+    dict(aggregate_train_gradients=True),
+    dict(query_gradient_low_rank=2, use_full_svd=True),
+    dict(compute_per_token_scores=True),  # switched off with a warning by both engines
+]
+
+
+@pytest.mark.parametrize("index", range(len(POSTPROCESS_COMBINATIONS)))
+def test_post_processed_gradients_argument_combinations(index, reference, tmp_path):
+    """`Task.post_process_per_sample_gradient` (a nonlinear clipping callback, task.py:99-116 of the reference) in
+    combination with the score options: every tracker runs on materialised gradients here."""
+    ref_analyzer, ref_arguments, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import ScoreArguments
+    from kronfluence_b200.task import Task
+
+    combo = dict(damping_factor=None)
+    combo.update(POSTPROCESS_COMBINATIONS[index])
+    model, train_set, query_set = fixtures.make_case("seq")
+    task = fixtures.make_postprocess_tasks(ref_task.Task)["seq"]()
+    ref = ref_analyzer.Analyzer("clip", ref_analyzer.prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path),
+                                disable_tqdm=True)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=6,
+                        factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+    # Batch sizes the reference's dense-gradient trackers cope with: one train batch per partition (a ragged last batch is
+    # added onto the previous batch's score tile and fails on the shape, tracker/pairwise_score.py:47-48) and, with
+    # per-module scores, one query batch (a ragged last one leaves 6 score rows for 5 queries).  This engine runs the
+    # same job with ragged batches on both sides below.
+    ref.compute_pairwise_scores("ref", "f", query_set, train_set,
+                                per_device_query_batch_size=len(query_set) if combo.get("compute_per_module_scores") else 2,
+                                per_device_train_batch_size=len(train_set),
+                                score_args=ref_arguments.ScoreArguments(**combo))
+    self_kwargs = dict(damping_factor=None, use_measurement_for_self_influence=bool(index % 2))
+    ref.compute_self_scores("ref_self", "f", train_set, per_device_train_batch_size=6,
+                            score_args=ref_arguments.ScoreArguments(**self_kwargs))
+    model, _, _ = fixtures.make_case("seq")
+    task = fixtures.make_postprocess_tasks(Task)["seq"]()
+    with oracle_backend():
+        ours = Analyzer("clip", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        got = ours.compute_pairwise_scores("ours", "f", query_set, train_set, per_device_query_batch_size=3,
+                                           per_device_train_batch_size=4, score_args=ScoreArguments(**combo))
+        own = ours.compute_self_scores("ours_self", "f", train_set, per_device_train_batch_size=4,
+                                       score_args=ScoreArguments(**self_kwargs))["all_modules"]
+    want = ref.load_pairwise_scores("ref")
+    assert set(got) == set(want)
+    for name, tensor in want.items():
+        assert got[name].shape == tensor.shape, (name, combo)
+        assert rel(got[name].numpy(), tensor.numpy()) < 1e-4, (name, combo)
+    assert rel(own.numpy(), ref.load_self_scores("ref_self")["all_modules"].numpy()) < 1e-4
