@@ -962,12 +962,15 @@ class Analyzer:
             shared = None if per_module else torch.zeros(num_queries, 1, dtype=torch.float32, device=device)
             for module in modules:
                 store = module.storage[ACCUMULATED_PRECONDITIONED_GRADIENT_NAME]
+                precision = precision_of(score_args.score_dtype)
                 if isinstance(store, ops.LowRankStore):
-                    raise NotImplementedError("`aggregate_train_gradients` is not supported with `query_gradient_low_rank`.")
+                    # rank-r query factors against ONE materialised gradient: multiply the chunk's factors out
+                    # ("qki,toi,qok->qt" with t = 1, tracker/pairwise_score.py:26-39,120-132 of the reference)
+                    store = ops.lowrank_dense_store(store, num_queries, precision)
                 sink = torch.zeros(num_queries, 1, dtype=torch.float32, device=device) if per_module else shared
                 layer = module.flat_layer()
                 ops.pairwise_scores_explicit(layer, store, num_queries, train_aggregate[module.name].unsqueeze(0), sink, 0,
-                                             accumulate=True, precision=precision_of(score_args.score_dtype))
+                                             accumulate=True, precision=precision)
                 if per_module:
                     out_chunks[module.name].append(select_rows(sink).to(dtype=score_args.score_dtype, device="cpu"))
             if not per_module:

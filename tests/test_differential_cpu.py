@@ -67,6 +67,7 @@ SCORE_COMBINATIONS = [
     dict(query_gradient_low_rank=2, use_full_svd=True, query_gradient_accumulation_steps=2, module_partitions=2),
     dict(query_gradient_low_rank=2, use_full_svd=True, compute_per_module_scores=True, data_partitions=2),
     dict(damping_factor=1e-3, data_partitions=2, compute_per_module_scores=True),
+    dict(query_gradient_low_rank=2, use_full_svd=True, aggregate_train_gradients=True, compute_per_module_scores=True),
 ]
 
 
