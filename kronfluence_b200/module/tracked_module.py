@@ -142,6 +142,9 @@ class BaseTracker:
         self.cached_hooks: List[Any] = []
         self.cached_activations: List[torch.Tensor] = []
         self.cached_gradients: List[torch.Tensor] = []
+        # materialised per-sample gradients that `_processed_gradient` hands out once instead of forming them from the
+        # (activation, gradient) pair it is called with: the summed uses of a shared convolution (`_stacked_uses`)
+        self._dense_override: Optional[torch.Tensor] = None
 
     def release_hooks(self) -> None:
         self.clear_all_cache()
@@ -151,6 +154,7 @@ class BaseTracker:
     def clear_all_cache(self) -> None:
         self.cached_activations = []
         self.cached_gradients = []
+        self._dense_override = None
         while self.cached_hooks:
             self.cached_hooks.pop().remove()
 
@@ -196,8 +200,18 @@ class BaseTracker:
             self._no_cache_error()
         if len(acts) == 1:
             return acts[0].to(grads[0].device), grads[0]
-        if self.module.is_conv:
-            raise NotImplementedError("has_shared_parameters is not supported for shared Conv2d modules.")
+        if self.module.is_conv or not self.module.native:
+            # A convolution's positions come out of the im2col inside the kernels (and a plugin layer flattens its own
+            # inputs), so the uses cannot be stacked: they are summed as materialised per-sample gradients, the way the
+            # reference accumulates `cached_per_sample_gradient` (tracker/factor.py:275-302), and the caller's `_update`
+            # continues on the dense-gradient kernels.  The uses may have different spatial sizes.
+            total = None
+            for a, g in zip(acts, grads):
+                a = a.to(g.device)
+                dense = self._processed_gradient(self.module.layer_for(a), a, g, force=True)
+                total = dense.clone() if total is None else total.add_(dense)
+            self._dense_override = total
+            return acts[0].to(grads[0].device), grads[0]
         acts = [a.to(grads[0].device) for a in acts]
         flat_a = [a.reshape(a.shape[0], -1, a.shape[-1]) for a in acts]
         flat_g = [g.reshape(g.shape[0], -1, g.shape[-1]) for g in grads]
@@ -212,6 +226,9 @@ class BaseTracker:
           * `force`: a user `FactorConfig` whose `precondition_gradient` takes them.
         None otherwise: the fused paths never form these tensors."""
         module = self.module
+        if self._dense_override is not None:
+            dense, self._dense_override = self._dense_override, None
+            return dense
         if not module.native:
             grads = module.compute_per_sample_gradient(input_activation=a, output_gradient=g)
             grads = grads.to(dtype=torch.float32).contiguous()

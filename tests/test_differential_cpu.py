@@ -598,3 +598,108 @@ def test_post_processed_gradients_argument_combinations(index, reference, tmp_pa
         assert got[name].shape == tensor.shape, (name, combo)
         assert rel(got[name].numpy(), tensor.numpy()) < 1e-4, (name, combo)
     assert rel(own.numpy(), ref.load_self_scores("ref_self")["all_modules"].numpy()) < 1e-4
+
+
+def test_shared_convolution(reference, tmp_path):
+    """A Conv2d used twice per forward pass, on feature maps of different sizes (`has_shared_parameters`).  Its uses are
+    summed as materialised per-sample gradients (tracker/factor.py:275-302 of the reference).  Covariances, Lambda and
+    self-influence equal the reference's; with the identity strategy the pairwise and the aggregated scores equal
+    autograd's gradient products (where the reference keeps one use only, see test_shared_module_agrees_with_autograd)."""
+    import torch.nn.functional as F
+    from torch import nn
+    from torch.utils import data
+
+    ref_analyzer, ref_arguments, ref_task = reference
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+    from kronfluence_b200.arguments import FactorArguments, ScoreArguments
+    from kronfluence_b200.task import Task
+    from kronfluence_b200.utils import save as io
+
+    class SharedConv(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Conv2d(3, 4, 3, padding=1)
+            self.block = nn.Conv2d(4, 4, 3, padding=1, bias=False)
+            self.head = nn.Linear(4 * 4 * 4, 3)
+
+        def forward(self, x):
+            hidden = torch.relu(self.stem(x))
+            hidden = torch.relu(self.block(hidden))                    # first use: 8 x 8
+            hidden = torch.relu(self.block(F.avg_pool2d(hidden, 2)))   # second use: 4 x 4
+            return self.head(hidden.flatten(1))
+
+    def make_task(base):
+        class Classification(base):
+            def compute_train_loss(self, batch, model, sample=False):
+                inputs, labels = batch
+                return F.cross_entropy(model(inputs), labels, reduction="sum")
+
+            def compute_measurement(self, batch, model):
+                return self.compute_train_loss(batch, model)
+
+        return Classification()
+
+    generator = torch.Generator().manual_seed(0)
+    inputs, labels = torch.randn(24, 3, 8, 8, generator=generator), torch.randint(0, 3, (24,), generator=generator)
+    train_set, query_set = data.TensorDataset(inputs[:19], labels[:19]), data.TensorDataset(inputs[19:], labels[19:])
+    torch.manual_seed(1)
+    plain = SharedConv()
+
+    def engines(name):
+        theirs, mine = SharedConv(), SharedConv()
+        theirs.load_state_dict(plain.state_dict())
+        mine.load_state_dict(plain.state_dict())
+        task = make_task(ref_task.Task)
+        ref = ref_analyzer.Analyzer(name, ref_analyzer.prepare_model(theirs, task), task, cpu=True, output_dir=str(tmp_path),
+                                    disable_tqdm=True)
+        task = make_task(Task)
+        with oracle_backend():
+            ours = Analyzer(name, prepare_model(mine, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        return ref, ours
+
+    ref, ours = engines("ekfac")
+    factor_kwargs = dict(use_empirical_fisher=True, has_shared_parameters=True)
+    score_kwargs = dict(damping_factor=None, compute_per_module_scores=True)
+    ref.fit_all_factors("f", train_set, per_device_batch_size=6, factor_args=ref_arguments.FactorArguments(**factor_kwargs))
+    ref.compute_self_scores("ref_self", "f", train_set, per_device_train_batch_size=6,
+                            score_args=ref_arguments.ScoreArguments(**score_kwargs))
+    with oracle_backend():
+        own = ours.compute_self_scores("ours_self", "f", train_set, per_device_train_batch_size=5,
+                                       score_args=ScoreArguments(**score_kwargs))
+        ours.fit_covariance_matrices("g", train_set, per_device_batch_size=5, factor_args=FactorArguments(**factor_kwargs))
+        ours.perform_eigendecomposition("g", FactorArguments(**factor_kwargs))
+        io.save_factors(ours.factors_output_dir("g"), ref.load_eigendecomposition("f"))  # Lambda in the same basis
+        ours.fit_lambda_matrices("g", train_set, per_device_batch_size=5, factor_args=FactorArguments(**factor_kwargs))
+        for loader in ("load_covariance_matrices", "load_lambda_matrices"):
+            want, got = getattr(ref, loader)("f"), getattr(ours, loader)("g")
+            for name, per_module in want.items():
+                for module, tensor in per_module.items():
+                    assert rel(got[name][module].double().numpy(), tensor.double().numpy()) < 1e-6, (name, module)
+    want = ref.load_self_scores("ref_self")
+    for module in ("stem", "block", "head"):
+        assert rel(own[module].numpy(), want[module].numpy()) < 1e-5, module
+
+    # identity strategy: autograd is the ground truth for the shared convolution
+    _, ours = engines("identity")
+    with oracle_backend():
+        ours.fit_all_factors("f", train_set, per_device_batch_size=6,
+                             factor_args=FactorArguments(strategy="identity", has_shared_parameters=True))
+        pairwise = ours.compute_pairwise_scores("p", "f", query_set, train_set, per_device_query_batch_size=2,
+                                                per_device_train_batch_size=5,
+                                                score_args=ScoreArguments(compute_per_module_scores=True))["block"].numpy()
+        aggregated = ours.compute_pairwise_scores(
+            "a", "f", query_set, train_set, per_device_query_batch_size=2, per_device_train_batch_size=5,
+            score_args=ScoreArguments(compute_per_module_scores=True, aggregate_query_gradients=True,
+                                      aggregate_train_gradients=True))["block"].numpy()
+
+    def gradients(dataset):
+        rows = []
+        for x, y in dataset:
+            plain.zero_grad()
+            F.cross_entropy(plain(x[None]), y[None], reduction="sum").backward()
+            rows.append(plain.block.weight.grad.flatten().clone())
+        return torch.stack(rows)
+
+    train_gradients, query_gradients = gradients(train_set), gradients(query_set)
+    assert rel(pairwise, (query_gradients @ train_gradients.T).numpy()) < 1e-5
+    assert rel(aggregated, (query_gradients.sum(0) @ train_gradients.sum(0)).reshape(1, 1).numpy()) < 1e-5
