@@ -19,7 +19,7 @@ def _run(extra_env=None, steps=1, gpus=1):
 
 
 def test_reference_arm_line():
-    res = _run(steps=7, gpus=2)
+    res = _run(steps=3, gpus=2)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -31,7 +31,7 @@ def test_reference_arm_line():
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
-    assert line["steps"] == 7 and line["warmup"] == 1 and line["n_gpus"] == 2  # K, W and N of the launch, as given
+    assert line["steps"] == 3 and line["warmup"] == 1 and line["n_gpus"] == 2  # K, W and N of the launch, as given
 
 
 def test_reference_arm_other_ranks_stay_silent():
