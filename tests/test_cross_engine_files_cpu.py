@@ -218,3 +218,29 @@ def test_aggregated_train_gradients_over_data_partitions(reference, tmp_path):
     assert want.shape == got.shape == (len(query_set), 1)
     assert rel(got, want) < 5e-5
     assert np.array_equal(again["all_modules"].numpy(), got)  # an existing result is returned, not recomputed
+
+
+def test_reference_argument_and_task_objects_are_accepted(reference, tmp_path):
+    """A script that switches only the Analyzer import keeps kronfluence's own `Task` base class, `FactorArguments`,
+    `ScoreArguments` and `DataLoaderKwargs` objects: they are used by their attributes, not by their type."""
+    _, ref_arguments, ref_task = reference
+    from kronfluence.utils.dataset import DataLoaderKwargs as ReferenceKwargs  # pylint: disable=import-error
+
+    from kronfluence_b200.analyzer import Analyzer, prepare_model
+
+    model, train_set, query_set = fixtures.make_case("mlp")
+    task = fixtures.make_tasks(ref_task.Task)["mlp"]()
+    with oracle_backend():
+        analyzer = Analyzer("mixed", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path), disable_tqdm=True)
+        analyzer.set_dataloader_kwargs(ReferenceKwargs(num_workers=0))
+        analyzer.fit_all_factors("f", train_set, per_device_batch_size=8,
+                                 factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
+        user_args = ref_arguments.ScoreArguments(damping_factor=None, compute_per_token_scores=True,
+                                                 aggregate_train_gradients=True)
+        scores = analyzer.compute_pairwise_scores("s", "f", query_set, train_set, per_device_query_batch_size=3,
+                                                  per_device_train_batch_size=8, score_args=user_args)
+        assert scores["all_modules"].shape == (len(query_set), 1)
+        assert user_args.compute_per_token_scores  # switched off for the run (with a warning), not in the caller's object
+        own = analyzer.compute_self_scores("o", "f", train_set, per_device_train_batch_size=8,
+                                           score_args=ref_arguments.ScoreArguments(damping_factor=None))
+        assert own["all_modules"].shape == (len(train_set),)
