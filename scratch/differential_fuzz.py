@@ -30,6 +30,8 @@ def main() -> None:
     parser.add_argument("--seed", type=int, default=0)
     parser.add_argument("--case", default="mlp", choices=["mlp", "seq", "conv"])
     parser.add_argument("--count", type=int, default=20)
+    parser.add_argument("--postprocess", action="store_true",
+                        help="tasks with a gradient-clipping `post_process_per_sample_gradient` (pairwise only)")
     args = parser.parse_args()
 
     import kronfluence.analyzer as ref_analyzer  # pylint: disable=import-error
@@ -65,7 +67,21 @@ def main() -> None:
                 return
 
     if args.kind == "pairwise":
-        ref, ours, train_set, query_set = diff.both_engines(reference, args.case, pathlib.Path(tempfile.mkdtemp()))
+        if args.postprocess:
+            from kronfluence_b200.analyzer import Analyzer, prepare_model
+            from kronfluence_b200.task import Task
+
+            directory = tempfile.mkdtemp()
+            model, train_set, query_set = fixtures.make_case(args.case)
+            task = fixtures.make_postprocess_tasks(ref_task.Task)[args.case]()
+            ref = ref_analyzer.Analyzer("fuzz", ref_analyzer.prepare_model(model, task), task, cpu=True,
+                                        output_dir=directory, disable_tqdm=True)
+            model, _, _ = fixtures.make_case(args.case)
+            task = fixtures.make_postprocess_tasks(Task)[args.case]()
+            with oracle_backend():
+                ours = Analyzer("fuzz", prepare_model(model, task), task, cpu=True, output_dir=directory, disable_tqdm=True)
+        else:
+            ref, ours, train_set, query_set = diff.both_engines(reference, args.case, pathlib.Path(tempfile.mkdtemp()))
         ref.fit_all_factors("f", train_set, per_device_batch_size=6,
                             factor_args=ref_arguments.FactorArguments(use_empirical_fisher=True))
     for index in range(args.count):
@@ -91,6 +107,11 @@ def main() -> None:
             query_indices = rng.choice([None, list(reversed(range(n_query - 1)))])
             batches = dict(per_device_query_batch_size=rng.choice([1, 2, 3, 7]),
                            per_device_train_batch_size=rng.choice([3, 5, 8, 50]))
+            if args.postprocess:
+                # what the reference's dense-gradient trackers cope with: one train batch per partition, one query batch
+                # (see tests/test_differential_cpu.py::test_post_processed_gradients_argument_combinations)
+                batches = dict(per_device_query_batch_size=n_query, per_device_train_batch_size=n_train)
+                score.pop("query_gradient_accumulation_steps", None)
             try:
                 ref.compute_pairwise_scores(f"r{index}", "f", query_set, train_set, query_indices=query_indices,
                                             train_indices=train_indices, score_args=ref_arguments.ScoreArguments(**score),
