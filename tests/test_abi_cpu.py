@@ -55,3 +55,31 @@ def test_no_cpu_path():
     assert lib.kfb_pairwise_workspace_bytes(ctypes.byref(layer), 16, 1) > 0
     assert lib.kfb_eigh_workspace_bytes(128) > 2 * 128 * 128 * 8
     assert lib.kfb_eigh_jacobi_max_dim() == 512
+
+
+def test_product_never_imports_the_oracle_or_the_tests():
+    """The oracle is test infrastructure: nothing under kronfluence_b200/ or examples/ may import `oracle`, `tests` or the
+    reference package, statically (AST of every module) or at import time (sys.modules after importing the package)."""
+    import ast
+    import glob
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    forbidden = {"oracle", "tests", "kronfluence"}
+    for path in glob.glob(os.path.join(root, "kronfluence_b200", "**", "*.py"), recursive=True) + glob.glob(
+            os.path.join(root, "examples", "*.py")):
+        with open(path, encoding="utf-8") as handle:
+            tree = ast.parse(handle.read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [alias.name for alias in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.level == 0 and node.module:
+                names = [node.module]
+            assert not {name.split(".")[0] for name in names} & forbidden, (path, names)
+    code = ("import sys; import kronfluence_b200, kronfluence_b200.analyzer, kronfluence_b200.ops, kronfluence_b200.engine, "
+            "kronfluence_b200.module, kronfluence_b200.factor.config, kronfluence_b200.utils.common; "
+            "bad = [m for m in sys.modules if m.split('.')[0] in ('oracle', 'tests', 'kronfluence')]; "
+            "assert not bad, bad")
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=root, timeout=300)
