@@ -146,7 +146,8 @@ def test_shared_convolution(tmp_path):
                                load_from_factors_name="f")
     for module, tensor in on_gpu.load_lambda_matrices("g")["lambda_matrix"].items():
         assert rel(tensor.numpy(), want_lambda[module].numpy()) < 5e-4, module
-    got_pairwise = on_gpu.compute_pairwise_scores("gpu", "f", query_set, train_set, per_device_query_batch_size=3,
+    got_pairwise = on_gpu.compute_pairwise_scores("gpu", "f", query_set, train_set,
+                                                  per_device_query_batch_size=len(query_set),  # one query chunk
                                                   per_device_train_batch_size=5, score_args=ScoreArguments(**score_args))
     got_self = on_gpu.compute_self_scores("gpu_self", "f", train_set, per_device_train_batch_size=5,
                                           score_args=ScoreArguments(**score_args))
