@@ -526,8 +526,19 @@ def test_train_operand_cache_across_query_chunks(tmp_path):
         plain = analyzer.compute_pairwise_scores("s2", "f", query_set, train_set, per_device_query_batch_size=2,
                                                  per_device_train_batch_size=6, score_args=ScoreArguments(damping_factor=None))
         assert calls["train"] == 3 * n_batches
+        # a budget that overflows at once / in the middle of the recording sweep: all-or-nothing, later chunks run the model
+        overflowed = []
+        for label, budget_bytes in (("first", 1_000), ("second", 30_000)):  # one batch of the three modules is 17 160 bytes
+            analyzer.train_operand_cache_fraction = budget_bytes / float(1 << 40)
+            calls["train"] = 0
+            overflowed.append(analyzer.compute_pairwise_scores(
+                "s_" + label, "f", query_set, train_set, per_device_query_batch_size=2, per_device_train_batch_size=6,
+                score_args=ScoreArguments(damping_factor=None)))
+            assert not analyzer.last_train_operand_cache["complete"] and calls["train"] == 3 * n_batches, label
     assert rel(scores["all_modules"].numpy(), golden["f32/scores"]) < 5e-5
     assert rel(scores["all_modules"].numpy(), plain["all_modules"].numpy()) < 1e-6
+    for result in overflowed:
+        assert rel(result["all_modules"].numpy(), plain["all_modules"].numpy()) < 1e-6
 
 
 def _inject(analyzer, golden):
