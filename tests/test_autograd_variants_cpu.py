@@ -218,3 +218,48 @@ def test_batch_size_search_recovers_from_out_of_memory(tmp_path):
     for name, per_module in fixed.items():
         for module, tensor in per_module.items():
             assert rel(auto[name][module].double().numpy(), tensor.double().numpy()) < 1e-6, (name, module)
+
+
+def test_out_of_memory_during_score_computation(tmp_path):
+    """per_device_train_batch_size=None in the score stages (score_computer.py:182-216 of the reference): an attempt that
+    runs out of memory in the middle of a train sweep leaves nothing behind in the score buffers, the query stores or the
+    aggregated gradients -- the halved batch size reproduces the fixed-batch-size results."""
+    base = fixtures.make_tasks(Task)["mlp"]
+    state = {"armed": False, "seen": []}
+
+    class TightMemoryTask(base):
+        def compute_train_loss(self, batch, model, sample=False):
+            if state["armed"]:
+                state["seen"].append(batch[0].shape[0])
+                if batch[0].shape[0] > 6 and len(state["seen"]) % 2 == 0:  # the second batch of an attempt fails
+                    raise RuntimeError("CUDA out of memory. Tried to allocate 2.00 GiB")
+            return super().compute_train_loss(batch, model, sample)
+
+        def compute_measurement(self, batch, model):
+            return base.compute_train_loss(self, batch, model, sample=False)
+
+    model, train_set, query_set = fixtures.make_case("mlp")
+    with oracle_backend():
+        task = TightMemoryTask()
+        analyzer = Analyzer("oom_scores", prepare_model(model, task), task, cpu=True, output_dir=str(tmp_path),
+                            disable_tqdm=True)
+        analyzer.fit_all_factors("f", train_set, per_device_batch_size=8, factor_args=FactorArguments(use_empirical_fisher=True))
+        want = analyzer.compute_pairwise_scores("fixed", "f", query_set, train_set, per_device_query_batch_size=3,
+                                                per_device_train_batch_size=6)["all_modules"].numpy()
+        want_self = analyzer.compute_self_scores("fixed_self", "f", train_set,
+                                                 per_device_train_batch_size=6)["all_modules"].numpy()
+        for index, overrides in enumerate((dict(), dict(data_partitions=2), dict(aggregate_train_gradients=True))):
+            state.update(armed=True, seen=[])
+            got = analyzer.compute_pairwise_scores(f"auto{index}", "f", query_set, train_set, per_device_query_batch_size=3,
+                                                   per_device_train_batch_size=None,
+                                                   initial_per_device_train_batch_size_attempt=24,
+                                                   score_args=ScoreArguments(**overrides))["all_modules"].numpy()
+            state["armed"] = False
+            assert max(state["seen"]) > 6 >= min(state["seen"])  # the search really went through failing sizes
+            expected = want.sum(axis=1, keepdims=True) if overrides.get("aggregate_train_gradients") else want
+            assert rel(got, expected) < 1e-6, overrides
+        state.update(armed=True, seen=[])
+        got_self = analyzer.compute_self_scores("auto_self", "f", train_set, per_device_train_batch_size=None,
+                                                initial_per_device_train_batch_size_attempt=24)["all_modules"].numpy()
+        state["armed"] = False
+        assert rel(got_self, want_self) < 1e-6
