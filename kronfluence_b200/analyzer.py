@@ -189,12 +189,16 @@ class Analyzer:
     # small helpers
     # ------------------------------------------------------------------------------------------
     def set_dataloader_kwargs(self, dataloader_kwargs: DataLoaderKwargs) -> None:
+        """Default `DataLoader` arguments (workers, collate_fn, ...) of every later stage; a stage's own
+        `dataloader_kwargs` argument overrides them."""
         self._dataloader_params = dataloader_kwargs
 
     def factors_output_dir(self, factors_name: str) -> Path:
+        """`<output_dir>/<analysis_name>/factors_<factors_name>`."""
         return (self.output_dir / (FACTOR_SAVE_PREFIX + factors_name)).resolve()
 
     def scores_output_dir(self, scores_name: str) -> Path:
+        """`<output_dir>/<analysis_name>/scores_<scores_name>`."""
         return (self.output_dir / (SCORE_SAVE_PREFIX + scores_name)).resolve()
 
     def _save_arguments(self, name: str, args: Optional[Any], out_dir: Path, overwrite: bool) -> None:
@@ -445,6 +449,15 @@ class Analyzer:
                                 target_data_partitions: Optional[Union[Sequence[int], int]] = None,
                                 target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                                 overwrite_output_dir: bool = False) -> None:
+        """Stage 1: activation / pseudo-gradient covariance sums A^T A and G^T G of every tracked module over `dataset`
+        (at most `covariance_max_examples`), saved under `factors_<factors_name>`.
+
+        `per_device_batch_size=None` searches the largest batch size that fits, starting from
+        `initial_per_device_batch_size_attempt` (single GPU only).  With data / module partitions in `factor_args` the
+        examples / modules are processed in parts, each written to its own file (a preempted job resumes with the missing
+        ones; `target_*_partitions` restricts this call to some of them) and summed once all exist.  Existing results are
+        reused unless `overwrite_output_dir`.  Under torchrun every rank takes a strided share of the examples and the sums
+        are all-reduced once."""
         factor_args = FactorArguments() if factor_args is None else factor_args
         out_dir = self.factors_output_dir(factors_name)
         if self.state.is_main_process:
@@ -501,6 +514,7 @@ class Analyzer:
         self._log_profile_summary(f"factors_{factors_name}_covariance")
 
     def load_covariance_matrices(self, factors_name: str) -> Optional[FACTOR_TYPE]:
+        """{factor name: {module name: tensor}} of the saved covariance sums and their row counts, or None."""
         out_dir = self.factors_output_dir(factors_name)
         if not io.factors_exist(out_dir, COVARIANCE_FACTOR_NAMES):
             return None
@@ -512,6 +526,9 @@ class Analyzer:
     def perform_eigendecomposition(self, factors_name: str, factor_args: Optional[FactorArguments] = None,
                                    overwrite_output_dir: bool = False,
                                    load_from_factors_name: Optional[str] = None) -> None:
+        """Stage 2: eigenvectors / eigenvalues (ascending) of every normalised, symmetrised covariance, computed in fp64
+        on the GPUs (the jobs are spread over ranks and host threads).  `load_from_factors_name` takes the covariances of
+        another factor set and copies them next to the result."""
         factor_args = FactorArguments() if factor_args is None else factor_args
         out_dir = self.factors_output_dir(factors_name)
         if self.state.is_main_process:
@@ -606,6 +623,7 @@ class Analyzer:
                 eigen[vec_name][mname] = evecs.to(dtype=dtype, device="cpu")
 
     def load_eigendecomposition(self, factors_name: str) -> Optional[FACTOR_TYPE]:
+        """{factor name: {module name: tensor}} of the saved eigenvectors and eigenvalues, or None."""
         out_dir = self.factors_output_dir(factors_name)
         if not io.factors_exist(out_dir, EIGENDECOMPOSITION_FACTOR_NAMES):
             return None
@@ -623,6 +641,10 @@ class Analyzer:
                             target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                             overwrite_output_dir: bool = False,
                             load_from_factors_name: Optional[str] = None) -> None:
+        """Stage 3: Lambda = sum over examples of (Q_G^T G_b Q_A)^2, the corrected eigenvalues of EK-FAC (for the diagonal
+        strategy: the squared per-sample gradients themselves), over at most `lambda_max_examples` examples.  Batch size,
+        partitions, resume and multi-GPU behaviour as in `fit_covariance_matrices`; `load_from_factors_name` borrows the
+        eigendecomposition of another factor set."""
         factor_args = FactorArguments() if factor_args is None else factor_args
         out_dir = self.factors_output_dir(factors_name)
         if self.state.is_main_process:
@@ -690,6 +712,7 @@ class Analyzer:
         self._log_profile_summary(f"factors_{factors_name}_lambda")
 
     def load_lambda_matrices(self, factors_name: str) -> Optional[FACTOR_TYPE]:
+        """{factor name: {module name: tensor}} of the saved Lambda matrices and example counts, or None."""
         out_dir = self.factors_output_dir(factors_name)
         if not io.factors_exist(out_dir, LAMBDA_FACTOR_NAMES):
             return None
@@ -1068,6 +1091,15 @@ class Analyzer:
                                 target_data_partitions: Optional[Union[Sequence[int], int]] = None,
                                 target_module_partitions: Optional[Union[Sequence[int], int]] = None,
                                 overwrite_output_dir: bool = False) -> Optional[Dict[str, torch.Tensor]]:
+        """Stages 4-5: scores[q, t] = sum over modules of <H^-1 grad m(z_q), grad L(z_t)> for every query / training
+        example pair, with H^-1 the preconditioner of the factors `factors_name`; returned as {"all_modules": [Q, T]} (or
+        per module / per token / aggregated, see `ScoreArguments`) and saved under `scores_<scores_name>`.
+
+        Queries are processed in chunks of `per_device_query_batch_size x query_gradient_accumulation_steps` (x ranks):
+        their preconditioned gradients are kept on the device, the training set is swept once per chunk (its prepared
+        operands are reused across chunks while they fit).  `query_indices` / `train_indices` select subsets;
+        `per_device_train_batch_size=None` searches the largest batch size that fits (single GPU only).  Data / module
+        partitions and `target_*_partitions` as in `fit_covariance_matrices`.  Scores are not divided by the dataset size."""
         score_args = ScoreArguments() if score_args is None else score_args
         factor_args = self._load_factor_args(factors_name)
         out_dir = self.scores_output_dir(scores_name)
@@ -1195,6 +1227,7 @@ class Analyzer:
         self.state.wait_for_everyone()
 
     def load_pairwise_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:
+        """{"all_modules" or module name: scores} of a finished `compute_pairwise_scores`, or None."""
         path = io.scores_path(self.scores_output_dir(scores_name))
         return io.load_file(path) if path.exists() else None
 
@@ -1439,6 +1472,7 @@ class Analyzer:
         self.state.wait_for_everyone()
 
     def load_self_scores(self, scores_name: str) -> Optional[Dict[str, torch.Tensor]]:
+        """{"all_modules" or module name: [T] scores} of a finished `compute_self_scores`, or None."""
         path = self.scores_output_dir(scores_name) / "self_scores.safetensors"
         return io.load_file(path) if path.exists() else None
 
