@@ -20,10 +20,15 @@ class Task(ABC):
 
     @abstractmethod
     def compute_train_loss(self, batch: Any, model: nn.Module, sample: bool = False) -> torch.Tensor:
+        """The loss of `batch`, SUMMED over its examples (not averaged: every example must carry weight one in the factors
+        and scores).  `sample=True` is used while fitting factors with the true Fisher: draw the targets from the model's
+        own predictive distribution (under `torch.no_grad()`) instead of using the labels."""
         raise NotImplementedError(f"{self.__class__.__name__} must implement `compute_train_loss`.")
 
     @abstractmethod
     def compute_measurement(self, batch: Any, model: nn.Module) -> torch.Tensor:
+        """The quantity whose change is attributed to training examples, summed over the query batch: the loss itself,
+        a margin, a log-probability of some tokens, ..."""
         raise NotImplementedError(f"{self.__class__.__name__} must implement `compute_measurement`.")
 
     def get_influence_tracked_modules(self) -> Optional[List[str]]:
