@@ -83,3 +83,28 @@ def test_product_never_imports_the_oracle_or_the_tests():
             "bad = [m for m in sys.modules if m.split('.')[0] in ('oracle', 'tests', 'kronfluence')]; "
             "assert not bad, bad")
     subprocess.run([sys.executable, "-c", code], check=True, cwd=root, timeout=300)
+
+
+def test_integration_md_binding_stub_matches_the_library():
+    """The ctypes stub INTEGRATION.md tells a kronfluence maintainer to add (struct kfb_layer / kfb_split field lists,
+    the error helper) is executed as written against the built library: struct sizes and field names must be the ones of
+    include/kfb.h, and every `kfb_*` entry point the mapping table names must be exported."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8") as handle:
+        text = handle.read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(block for block in blocks if "class Layer(ctypes.Structure)" in block)
+    library = engine.load_library()
+    stub = stub.replace('ctypes.CDLL("libkfb.so")', "_the_library")
+    namespace = {"_the_library": library}
+    exec(compile(stub, "INTEGRATION.md", "exec"), namespace)  # pylint: disable=exec-used
+    sizes = [ctypes.c_int() for _ in range(3)]
+    library.kfb_struct_sizes(*[ctypes.byref(x) for x in sizes])
+    assert ctypes.sizeof(namespace["Layer"]) == sizes[0].value == ctypes.sizeof(engine.KfbLayer)
+    assert ctypes.sizeof(namespace["Split"]) == sizes[1].value == ctypes.sizeof(engine.KfbSplit)
+    assert [name for name, _ in namespace["Layer"]._fields_] == [name for name, _ in engine.KfbLayer._fields_]
+    assert [name for name, _ in namespace["Split"]._fields_] == [name for name, _ in engine.KfbSplit._fields_]
+    for symbol in sorted(set(re.findall(r"\bkfb_[a-z0-9_]+\b", text))):
+        if symbol in ("kfb_layer", "kfb_split", "kfb_status", "kfb_comm_"):
+            continue  # struct / enum names and the deliberately absent communicator wrappers
+        assert hasattr(library, symbol), symbol
