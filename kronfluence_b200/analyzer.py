@@ -738,7 +738,7 @@ class Analyzer:
                                 "covariance_module_partitions")
 
     def aggregate_lambda_matrices(self, factors_name: str) -> None:
-        """Sums the partition files into `lambda_matrix.safetensors` (factor_computer.py:715-736 of the reference)."""
+        """Sums the partition files into `lambda_matrix.safetensors` (factor_computer.py:704-732 of the reference)."""
         self._aggregate_factors(factors_name, LAMBDA_FACTOR_NAMES, "lambda_data_partitions", "lambda_module_partitions")
 
     def fit_all_factors(self, factors_name: str, dataset: data.Dataset, per_device_batch_size: Optional[int] = None,
@@ -1455,7 +1455,7 @@ class Analyzer:
         return {key: torch.cat([blk[key] for blk in blocks], dim=0) for key in blocks[0]}
 
     def aggregate_self_scores(self, scores_name: str) -> None:
-        """Aggregates the partition files into `self_scores.safetensors` (score_computer.py:772-799 of the reference)."""
+        """Aggregates the partition files into `self_scores.safetensors` (score_computer.py:773-798 of the reference)."""
         out_dir = self.scores_output_dir(scores_name)
         args_path = out_dir / f"{SCORE_ARGUMENTS_NAME}_arguments.json"
         if not args_path.exists():

@@ -490,7 +490,7 @@ class PreconditionTracker(BaseTracker):
 
 
 class GradientAggregationTracker(BaseTracker):
-    """Sums the gradients of every example seen into one fp32 matrix (tracker/gradient.py:11-95 of the reference).
+    """Sums the gradients of every example seen into one fp32 matrix (tracker/gradient.py:11-93 of the reference).
 
     The sum is kept in the basis of the query store: with an eigen strategy every batch is rotated into the
     Kronecker factors' eigenbases before it is added, and on the QUERY side (`module.aggregate_precondition`) it is

@@ -464,7 +464,7 @@ def aggregate_gradient(layer: KfbLayer, a: torch.Tensor, g: torch.Tensor, acc: t
                        lambda_inv: Optional[torch.Tensor] = None, scale: float = 1.0,
                        precision: int = PREC_FP32) -> None:
     """acc[d_out, d_in(+1)] += scale * [Q_G^T (sum over the batch and its positions of g a^T) Q_A] o lambda_inv
-    (tracker/gradient.py:14-95 of the reference; rotation and factor are optional)."""
+    (tracker/gradient.py:14-93 of the reference; rotation and factor are optional)."""
     lib = engine.load_library()
     a, g = _contig(a), _contig(g)
     batch, seq = _batch_seq(layer, a)

@@ -1,4 +1,4 @@
-"""`FactorArguments` presets with the names and meaning of utils/common/factor_arguments.py:6-64 of the reference.
+"""`FactorArguments` presets with the names and meaning of utils/common/factor_arguments.py:6-62 of the reference.
 
 Each preset is the default configuration plus a set of field overrides; the dtype fields select the tensor-core mode of
 the corresponding stage here (float32 / float64: 3-MMA fp32 parity, bfloat16 / float16: single MMA), see arguments.py."""

@@ -1,4 +1,4 @@
-"""`ScoreArguments` presets with the names and meaning of utils/common/score_arguments.py:8-89 of the reference."""
+"""`ScoreArguments` presets with the names and meaning of utils/common/score_arguments.py:8-84 of the reference."""
 
 from typing import Optional
 

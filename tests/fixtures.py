@@ -1,7 +1,7 @@
 """Small seeded models / datasets / tasks shared by the golden-vector generator (oracle/make_golden.py,
 which runs them through the UNMODIFIED reference) and by the parity tests (which run them through
 kronfluence_b200).  Modelled on the reference's offline-runnable fixtures
-(tests/testable_tasks/regression.py:18-26, classification.py:17-62) but sized to exercise ragged
+(tests/testable_tasks/regression.py:18-26, tests/testable_tasks/classification.py:17-62) but sized to exercise ragged
 tiles: odd feature counts, a sequence model with an attention mask, strided/padded convolutions."""
 
 from typing import Tuple

@@ -1,6 +1,6 @@
 """The argument presets every kronfluence example uses (utils/common of the reference) produce the same field values as
 the reference's own functions.  The expected values were read off the unmodified reference (utils/common/
-factor_arguments.py:6-64, score_arguments.py:8-89) and are cross-checked against it when baseline/_ref is installed."""
+factor_arguments.py:6-62, score_arguments.py:8-84) and are cross-checked against it when baseline/_ref is installed."""
 
 import os
 import sys

@@ -1,5 +1,5 @@
-"""Hook behaviour under the autograd variants the reference tests (tests/factors/test_covariances.py:393-520,
-tests/factors/test_lambdas.py:394-520, tests/scores/*): activation checkpointing (forward hooks fire twice per batch),
+"""Hook behaviour under the autograd variants the reference tests (tests/factors/test_covariances.py:292-511,
+tests/factors/test_lambdas.py:333-502, tests/scores/*): activation checkpointing (forward hooks fire twice per batch),
 in-place activations right after a tracked layer, and `per_device_batch_size=None` (largest executable batch size).
 Host logic only: the CUDA ops are replaced by the oracle double."""
 
@@ -66,7 +66,7 @@ def test_activation_checkpointing(tmp_path):
 
 def test_inplace_activation_after_tracked_layer(tmp_path):
     """nn.ReLU(inplace=True) overwrites the tracked layer's output: factors and scores equal the out-of-place model's
-    (tests/factors/test_covariances.py:455-520 of the reference)."""
+    (tests/factors/test_covariances.py:457-511 of the reference)."""
 
     def make(inplace):
         torch.manual_seed(0)
@@ -89,7 +89,7 @@ def test_inplace_activation_after_tracked_layer(tmp_path):
 def test_automatic_batch_size(tmp_path):
     """per_device_batch_size=None: the largest executable batch size is searched from
     `initial_per_device_batch_size_attempt` downwards and the results equal a fixed batch size's
-    (tests/factors/test_covariances.py:522-560 of the reference)."""
+    (tests/factors/test_covariances.py:292-345 of the reference)."""
     model, train_set, query_set = fixtures.make_case("mlp")
     task = fixtures.make_tasks(Task)["mlp"]()
     with oracle_backend():
